@@ -1,0 +1,132 @@
+/*
+ * go1_oracle.h -- CPU oracle for the Go1 gait-planning MPC hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a dependency-free C restatement of the
+ * reference's CPU algorithm (jtdingx/quadrupedal_loco), used as the checker by
+ * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs.  Nothing under quadrupedal_loco_b200/ may include, link or
+ * call it: the product path is CUDA-only and fails loudly without its
+ * extension.
+ *
+ * Parity status: the reference ships no tests or golden vectors for this path
+ * (SURVEY.md section 4), and Eigen 3 -- the un-vendored, version-unpinned
+ * system package whose LLT / triangular solves / dot products the reference
+ * calls -- is absent from this image.  The pin that exists is
+ * oracle/_ref: the UNMODIFIED reference sources (EiQuadProg.cpp,
+ * QPBaseClass.cpp, Kinematics.cpp) compiled against oracle/eigen_shim (a
+ * minimal stand-in for the Eigen headers written for this repo) and compared
+ * bit-for-bit with this restatement in tests/test_oracle_vs_ref.py (run in the
+ * authoring container, golden outputs committed under tests/golden/).  That
+ * pins control flow, tie-breaking, tolerances and every reference quirk; it
+ * cannot pin Eigen's own floating-point summation order, which is stated in
+ * DESIGN.md ("parity pinned up to Eigen's summation order").
+ *
+ * Conventions (same as the reference, RT/src/utils/EiQuadProg/EiQuadProg.hpp:15-32):
+ *     min 0.5 x'Gx + g0'x   s.t.  CE'x + ce0 = 0,  CI'x + ci0 >= 0
+ * All matrices column-major double; CE is n x p, CI is n x m (one constraint
+ * per column).
+ */
+#ifndef GO1_ORACLE_H
+#define GO1_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes shared with include/go1mpc.h (kept numerically identical) */
+enum {
+    ORC_OK = 0,            /* converged, cost finite                         */
+    ORC_NOT_PD = 1,        /* LLT failed: x untouched, cost = +inf           */
+    ORC_INFEASIBLE = 2,    /* t = +inf in step 2c: cost = +inf, x is garbage */
+    ORC_ITER_CAP = 3,      /* safety cap hit (reference has no cap)          */
+    ORC_NAN = 4,           /* NaN in x after the solve (solveQP() == false)  */
+    ORC_EQ_DEPENDENT = 5   /* equality add failed; early return as reference */
+};
+
+/* iteration counters written to iters[4] */
+enum { ORC_IT_OUTER = 0, ORC_IT_ADD = 1, ORC_IT_DROP = 2, ORC_IT_DEGEN = 3 };
+
+/*
+ * Goldfarb-Idnani dual active-set solve.
+ * Follows Eigen::QP::solve_quadprog / solve_quadprog2 / add_constraint /
+ * delete_constraint, RT/src/utils/EiQuadProg/EiQuadProg.cpp:30-513.
+ *   x        in/out, n (left untouched when G is not PD, like the reference)
+ *   cost     out, objective value or +inf
+ *   active   out, m+p ints: final working set A[0..nactive) (equalities are
+ *            stored as -i-1, inequalities by column index)
+ *   iters    out, 4 counters (ORC_IT_*)
+ * returns a status code (ORC_*).
+ */
+int orc_qp_solve(int n, int p, int m,
+                 const double *G, const double *g0,
+                 const double *CE, const double *ce0,
+                 const double *CI, const double *ci0,
+                 double *x, double *cost,
+                 int *active, int *nactive, int *iters);
+
+/* ------------------------------------------------------------------------
+ * Body-inclination MPC (PRMPCClass), horizon-parametrised.
+ * Follows RT/src/FastMPC/PRMPCClass.cpp:46-374 (model part), 379-849.
+ * --------------------------------------------------------------------- */
+#define ORC_FOOTSTEPS 27
+#define ORC_BODY_NH_MAX 40
+
+typedef struct {
+    int nh;                 /* horizon (reference: 4)                        */
+    double dt_mpc;          /* 0.01                                          */
+    double dt_slow;         /* 0.025 (used to round _tx)                     */
+    double tstep;           /* 0.7                                           */
+    double height_offset_time; /* 1.0                                        */
+    double g, mass, j_ini;  /* 9.8, 12, 0.12                                 */
+    double foot_length, foot_width; /* 0.02, 0.02 (PRMPC members)            */
+    double theta_lim;       /* 10 deg                                        */
+    double torque_lim;      /* 20 (divided by j_ini as in the reference)     */
+    double Rtheta, alphatheta, beltatheta, gama_zmp; /* 100, 10, 5e9, 5000   */
+    double lamda[4];        /* feedback gains lamdax, lamdavx, lamday, lamdavy (0) */
+} orc_body_cfg;
+
+typedef struct {
+    orc_body_cfg cfg;
+    /* model matrices (column-major nh x nh / nh x 2) */
+    double pps[ORC_BODY_NH_MAX * 2], pvs[ORC_BODY_NH_MAX * 2];
+    double ppu[ORC_BODY_NH_MAX * ORC_BODY_NH_MAX], pvu[ORC_BODY_NH_MAX * ORC_BODY_NH_MAX];
+    double ppu_2[ORC_BODY_NH_MAX * ORC_BODY_NH_MAX], pvu_2[ORC_BODY_NH_MAX * ORC_BODY_NH_MAX];
+    int nstepx, nsum_mpc;
+    /* per-instance state */
+    double tx[ORC_FOOTSTEPS];
+    double thetaxk[2], thetayk[2];
+    double V_ini[2 * ORC_BODY_NH_MAX];
+    /* rolled-out members that survive between ticks (gated ticks return them) */
+    double thetax[ORC_BODY_NH_MAX], thetay[ORC_BODY_NH_MAX];
+    double zmpx_real[ORC_BODY_NH_MAX], zmpy_real[ORC_BODY_NH_MAX];
+    double torquex_real0, torquey_real0;
+    int bjx1, bjx2;
+    int qp_solution;
+    /* diagnostics of the last solve */
+    int status, nactive, iters[4];
+    int active[12 * ORC_BODY_NH_MAX];
+    double cost;
+} orc_body_mpc;
+
+void orc_body_cfg_default(orc_body_cfg *c, int nh);
+void orc_body_init(orc_body_mpc *s, const orc_body_cfg *c);
+/* refs are row-major-by-signal: zmp_ref[2*nh] = row0 (x) then row1 (y), etc.
+ * comacc_z_ref[nh] is row 2 of the reference's 3 x nh comacc matrix.        */
+void orc_body_theta_mpc(orc_body_mpc *s, int i, const double bodyangle_state[4],
+                        const double *zmp_ref, const double *bodyangle_ref,
+                        const double *rfoot_ref, const double *lfoot_ref,
+                        const double *comacc_z_ref, double out14[14]);
+
+/* flat batch helper used by the CPU baseline: B independent instances, each
+ * with its own state; single thread. Layouts documented in body_mpc.c.      */
+void orc_body_step_batch(const orc_body_cfg *c, int B, const int *tick,
+                         const double *tx, double *theta_state /*B*4*/,
+                         const double *bodyangle_state /*B*4*/,
+                         const double *refs /*B*9*nh*/, double *out14 /*B*14*/,
+                         double *x_out /*B*2nh*/, int *active /*B*12nh*/,
+                         int *nactive, int *iters /*B*4*/, int *status);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
