@@ -1,0 +1,180 @@
+/*
+ * go1mpc.h -- C ABI of libgo1mpc.so: batched, B200-native (sm_100a, FP64)
+ * implementation of the Go1 gait-planning MPC hot path of
+ * jtdingx/quadrupedal_loco.  Plain pointers and sizes only; no C++ or torch
+ * types cross this boundary.  Every entry point returns 0 on success or a
+ * negative GO1MPC_E_* code; go1mpc_last_error() gives the text.  There is no
+ * CPU fallback: without a CUDA device every compute call fails.
+ *
+ * Reference abbreviations (paths under the reference repository):
+ *   RT  = unitree_ros/rt_mpc_qp/src        NLP = unitree_ros/mosek_nlp_kmp/src
+ *   GO1 = unitree_ros/go1_rt_control/src
+ *
+ * The reference has no FFI: its seams are C++ classes.  Each function below
+ * names the class method(s) it replaces; the C++ mirror of those classes that
+ * binds to this ABI is in quadrupedal_loco_b200/host/ and INTEGRATION.md shows
+ * the binding a maintainer of the reference would add.
+ *
+ * QP convention (RT/utils/EiQuadProg/EiQuadProg.hpp:15-32):
+ *     min 0.5 x'Gx + g0'x   s.t.  CE'x + ce0 = 0,  CI'x + ci0 >= 0
+ * Matrices are column-major double, one constraint per column of CE / CI.
+ *
+ * Batch layout ("field arrays of per-problem blocks"): every argument is one
+ * array per field; problem b owns the contiguous block [b*stride, (b+1)*stride).
+ * A warp (or thread) works on one problem, so a block is read with fully
+ * coalesced 128-byte lines or one TMA bulk copy; blocks that are TMA sources
+ * are documented as 16-byte aligned with an even number of doubles.
+ * Pointers suffixed _d are DEVICE pointers owned by the caller; the *_host
+ * variants take HOST pointers and do the staging copies inside the call.
+ * `stream` is a cudaStream_t passed as void* (NULL = the handle's own stream).
+ * A handle is thread-compatible, not thread-safe; use one per host thread/GPU.
+ */
+#ifndef GO1MPC_H
+#define GO1MPC_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GO1MPC_VERSION_STRING "0.1.0"
+#define GO1MPC_FOOTSTEPS 27          /* _footstepsnumber, RT/FastMPC/PRMPCClass.h:30 */
+#define GO1MPC_BODY_NH_MAX 40
+
+/* error codes (function return values) */
+enum {
+    GO1MPC_OK = 0,
+    GO1MPC_E_INVALID = -1,     /* bad argument (size, NULL, alignment)        */
+    GO1MPC_E_CUDA = -2,        /* CUDA runtime error, see go1mpc_last_error   */
+    GO1MPC_E_NO_DEVICE = -3,   /* no usable CUDA device: there is no fallback */
+    GO1MPC_E_UNSUPPORTED = -4  /* size outside what the kernels are built for */
+};
+
+/* per-problem solver status (status_d[b]); numerically = oracle's ORC_* */
+enum {
+    GO1MPC_QP_OK = 0,            /* converged                                  */
+    GO1MPC_QP_NOT_PD = 1,        /* LLT failed: x untouched, cost = +inf       */
+    GO1MPC_QP_INFEASIBLE = 2,    /* no step possible: cost = +inf              */
+    GO1MPC_QP_ITER_CAP = 3,      /* safety cap hit (reference has no cap)      */
+    GO1MPC_QP_NAN = 4,           /* NaN in x  (reference: solveQP() == false)  */
+    GO1MPC_QP_EQ_DEPENDENT = 5,  /* dependent equalities: early return         */
+    GO1MPC_QP_SKIPPED = -1       /* front-end gated this tick: no solve ran    */
+};
+/* iters_d[b*4 + k] */
+enum { GO1MPC_IT_OUTER = 0, GO1MPC_IT_ADD = 1, GO1MPC_IT_DROP = 2, GO1MPC_IT_DEGEN = 3 };
+
+/* Constants of the body-inclination MPC.  Defaults = the reference's
+ * compile-time values: RT/Robotpara/robot_const_para_config.cpp:8-47,
+ * RT/FastMPC/PRMPCClass.cpp:157-170,227-261,280-287. */
+typedef struct {
+    double dt_mpc;               /* 0.01   gait::dt_mpc_fast                   */
+    double dt_slow;              /* 0.025  gait::dt_mpc_slow                   */
+    double tstep;                /* 0.7    gait::t_period                      */
+    double height_offset_time;   /* 1.0                                        */
+    double g, mass, j_ini;       /* 9.8, 12, 12*0.1*0.1                        */
+    double foot_length, foot_width; /* 0.02, 0.02                              */
+    double theta_lim;            /* 10 deg in rad                              */
+    double torque_lim;           /* 20 (the reference divides it by j_ini)     */
+    double Rtheta, alphatheta, beltatheta, gama_zmp; /* 100, 10, 5e9, 5000     */
+    double lamda[4];             /* state feedback gains (all 0 as shipped)    */
+} Go1BodyMpcConfig;
+
+typedef struct {
+    Go1BodyMpcConfig body;
+    int qp_iter_cap_scale;       /* cap on step-2a passes = scale*(n+m+p)+50; default 20 */
+    int reserved[7];
+} Go1MpcConfig;
+
+typedef struct go1mpc go1mpc_t;
+
+const char *go1mpc_version(void);
+int go1mpc_config_default(Go1MpcConfig *cfg);
+/* device < 0 selects the current CUDA device */
+int go1mpc_create(const Go1MpcConfig *cfg, int device, go1mpc_t **out);
+void go1mpc_destroy(go1mpc_t *h);
+const char *go1mpc_last_error(const go1mpc_t *h);
+int go1mpc_device(const go1mpc_t *h);
+/* number of kernels this handle has launched so far (bench's gpu_launches) */
+long long go1mpc_launch_count(const go1mpc_t *h);
+/* wait for the handle's stream */
+int go1mpc_synchronize(go1mpc_t *h);
+
+/* ---------------------------------------------------------------------------
+ * Generic dense QP batch.  Replaces, for B independent problems of one shape,
+ *   QPBaseClass::solveQP            RT/QP/QPBaseClass.cpp:126-153
+ *   Eigen::QP::solve_quadprog       RT/utils/EiQuadProg/EiQuadProg.cpp:493-513
+ * Strides (doubles): G n*n, g0 n, CE n*p, ce0 p, CI n*m, ci0 m, x n, cost 1;
+ * (ints): active m+p, nactive 1, iters 4, status 1.  CE_d/ce0_d may be NULL
+ * when p == 0.  x_d is in/out (left untouched when G is not PD, as the
+ * reference does).  active_d/nactive_d/iters_d/cost_d may be NULL.
+ * Limits: n <= 96, m + p <= 1024.
+ * ------------------------------------------------------------------------ */
+int go1mpc_qp_solve_batch(go1mpc_t *h, int n, int p, int m, int B,
+                          const double *G_d, const double *g0_d,
+                          const double *CE_d, const double *ce0_d,
+                          const double *CI_d, const double *ci0_d,
+                          double *x_d, double *cost_d,
+                          int *active_d, int *nactive_d, int *iters_d, int *status_d,
+                          void *stream);
+int go1mpc_qp_solve_batch_host(go1mpc_t *h, int n, int p, int m, int B,
+                               const double *G, const double *g0,
+                               const double *CE, const double *ce0,
+                               const double *CI, const double *ci0,
+                               double *x, double *cost,
+                               int *active, int *nactive, int *iters, int *status);
+
+/* ---------------------------------------------------------------------------
+ * Body-inclination MPC tick for B independent instances, horizon nh.
+ * Replaces PRMPCClass::body_theta_mpc (condensation + QP + clamp + roll-out)
+ *   RT/FastMPC/PRMPCClass.cpp:379-714, solve_body_rotation/Solve :799-849,
+ *   Indexfind :716-738, with the model of Initialize :198-261,280-287.
+ * One launch: condensation, the 2nh-variable / 12nh-row QP and the
+ * post-processing are fused; the QP matrices never exist in HBM.
+ *
+ * in_d   [B][go1mpc_body_in_stride(nh)] doubles, 16-byte aligned, per problem:
+ *          [0,27)      tx        step-cycle start times (_tx)
+ *          [27]        tick      i, stored as a double (exact integer)
+ *          [28,32)     theta     (thetaxk0, thetaxk1, thetayk0, thetayk1)
+ *          [32,36)     bodyangle_state (only used with non-zero lamda)
+ *          [36,36+2nh) x_warm    _V_ini (kept when G is not PD / tick gated)
+ *          then 9 rows of nh:  zmp_x, zmp_y, ang_x, ang_y, rfoot_x, rfoot_y,
+ *                              lfoot_x, lfoot_y, comacc_z
+ *          (+1 pad double when the count is odd)
+ * out_d  [B][go1mpc_body_out_stride(nh)] doubles, in/out (a gated tick keeps
+ *        its out14, as the reference returns its stale members):
+ *          [0,14)      out14     = the Vec14 body_theta_mpc returns (:696-709)
+ *          [14,18)     theta     updated state
+ *          [18,18+2nh) x         _V_ini after the tick
+ *          [18+2nh]    cost
+ *          (+pad to an even count)
+ * diag_d [B][go1mpc_body_diag_stride(nh)] ints (may be NULL):
+ *          [0] status  [1] nactive  [2,6) iters  [6] bjx1  [7] bjx2
+ *          [8, 8+2nh) final active set (constraint indices, Appendix E of SURVEY.md)
+ * Supported nh: 3..40 (the reference compiles nh = 4).
+ * ------------------------------------------------------------------------ */
+int go1mpc_body_in_stride(int nh);
+int go1mpc_body_out_stride(int nh);
+int go1mpc_body_diag_stride(int nh);
+int go1mpc_body_mpc_step_batch(go1mpc_t *h, int nh, int B,
+                               const double *in_d, double *out_d, int *diag_d,
+                               void *stream);
+int go1mpc_body_mpc_step_batch_host(go1mpc_t *h, int nh, int B,
+                                    const double *in, double *out, int *diag);
+/* Model matrices the handle condenses with, for inspection/tests (host
+ * buffers, column-major): pps,pvs nh x 2; ppu,pvu,ppu_2,pvu_2 nh x nh.
+ * Replaces PRMPCClass::Matrix_ps / Matrix_pu, RT/FastMPC/PRMPCClass.cpp:741-796. */
+int go1mpc_body_model(go1mpc_t *h, int nh, double *pps, double *pvs,
+                      double *ppu, double *pvu, double *ppu_2, double *pvu_2);
+/* default step table _tx of PRMPCClass::Initialize (:174-178), 27 doubles */
+int go1mpc_body_default_tx(go1mpc_t *h, double *tx27);
+
+/* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
+ * register-resident DFMA loop: the roofline denominator bench.py reports
+ * against.  Runs ~`ms` milliseconds. */
+int go1mpc_measure_dfma_peak(go1mpc_t *h, int ms, double *gflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GO1MPC_H */

@@ -1,0 +1,211 @@
+"""ctypes binding of include/go1mpc.h.  Mirrors the C ABI one to one."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _build
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+# every symbol include/go1mpc.h declares (tests check the .so exports all of them)
+EXPORTED_SYMBOLS = [
+    "go1mpc_version", "go1mpc_config_default", "go1mpc_create", "go1mpc_destroy",
+    "go1mpc_last_error", "go1mpc_device", "go1mpc_launch_count", "go1mpc_synchronize",
+    "go1mpc_qp_solve_batch", "go1mpc_qp_solve_batch_host",
+    "go1mpc_body_in_stride", "go1mpc_body_out_stride", "go1mpc_body_diag_stride",
+    "go1mpc_body_mpc_step_batch", "go1mpc_body_mpc_step_batch_host",
+    "go1mpc_body_model", "go1mpc_body_default_tx", "go1mpc_measure_dfma_peak",
+]
+
+
+class Go1MpcError(RuntimeError):
+    pass
+
+
+class BodyCfg(ctypes.Structure):
+    _fields_ = [
+        ("dt_mpc", ctypes.c_double), ("dt_slow", ctypes.c_double), ("tstep", ctypes.c_double),
+        ("height_offset_time", ctypes.c_double), ("g", ctypes.c_double), ("mass", ctypes.c_double),
+        ("j_ini", ctypes.c_double), ("foot_length", ctypes.c_double), ("foot_width", ctypes.c_double),
+        ("theta_lim", ctypes.c_double), ("torque_lim", ctypes.c_double), ("Rtheta", ctypes.c_double),
+        ("alphatheta", ctypes.c_double), ("beltatheta", ctypes.c_double), ("gama_zmp", ctypes.c_double),
+        ("lamda", ctypes.c_double * 4),
+    ]
+
+
+class Cfg(ctypes.Structure):
+    _fields_ = [("body", BodyCfg), ("qp_iter_cap_scale", ctypes.c_int), ("reserved", ctypes.c_int * 7)]
+
+
+_LIB = None
+
+
+def library_path():
+    return _build.LIB
+
+
+def load_library():
+    """Load libgo1mpc.so (never builds implicitly on a GPU box: the .so ships in-tree)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise Go1MpcError(
+            f"{path} is missing: build it with `python -m quadrupedal_loco_b200._build` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = ctypes.CDLL(path)
+    lib.go1mpc_version.restype = ctypes.c_char_p
+    lib.go1mpc_last_error.restype = ctypes.c_char_p
+    lib.go1mpc_last_error.argtypes = [ctypes.c_void_p]
+    lib.go1mpc_launch_count.restype = ctypes.c_longlong
+    lib.go1mpc_launch_count.argtypes = [ctypes.c_void_p]
+    lib.go1mpc_create.argtypes = [ctypes.POINTER(Cfg), ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.go1mpc_destroy.argtypes = [ctypes.c_void_p]
+    lib.go1mpc_destroy.restype = None
+    lib.go1mpc_device.argtypes = [ctypes.c_void_p]
+    lib.go1mpc_synchronize.argtypes = [ctypes.c_void_p]
+    vp = ctypes.c_void_p
+    lib.go1mpc_qp_solve_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 12 + [vp]
+    lib.go1mpc_qp_solve_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 12
+    lib.go1mpc_body_mpc_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
+    lib.go1mpc_body_mpc_step_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
+    lib.go1mpc_body_model.argtypes = [vp, ctypes.c_int] + [vp] * 6
+    lib.go1mpc_body_default_tx.argtypes = [vp, vp]
+    lib.go1mpc_measure_dfma_peak.argtypes = [vp, ctypes.c_int, c_double_p]
+    _LIB = lib
+    return lib
+
+
+def body_in_stride(nh):
+    s = 36 + 11 * nh
+    return (s + 1) & ~1
+
+
+def body_out_stride(nh):
+    s = 18 + 2 * nh + 1
+    return (s + 1) & ~1
+
+
+def body_diag_stride(nh):
+    return 8 + 2 * nh
+
+
+def pack_body_inputs(nh, tick, tx, theta, bodyangle_state, x_warm, refs):
+    """Pack per-instance arrays into the in-record layout of go1mpc_body_mpc_step_batch.
+
+    tick [B] int, tx [B,27], theta [B,4], bodyangle_state [B,4], x_warm [B,2nh],
+    refs [B,9,nh] (zmp x,y | bodyangle x,y | rfoot x,y | lfoot x,y | comacc_z).
+    """
+    B = len(tick)
+    rec = np.zeros((B, body_in_stride(nh)), dtype=np.float64)
+    rec[:, 0:27] = tx
+    rec[:, 27] = np.asarray(tick, dtype=np.float64)
+    rec[:, 28:32] = theta
+    rec[:, 32:36] = bodyangle_state
+    rec[:, 36:36 + 2 * nh] = x_warm
+    rec[:, 36 + 2 * nh:36 + 11 * nh] = np.asarray(refs).reshape(B, 9 * nh)
+    return rec
+
+
+def _ptr(a):
+    """Raw address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        if not a.flags["C_CONTIGUOUS"]:
+            raise Go1MpcError("array must be C-contiguous")
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        if not a.is_contiguous():
+            raise Go1MpcError("tensor must be contiguous")
+        return a.data_ptr()
+    raise Go1MpcError(f"cannot take the address of {type(a)}")
+
+
+class Go1Mpc:
+    """Handle wrapper: one per host thread / GPU."""
+
+    def __init__(self, device=-1, cfg=None):
+        self.lib = load_library()
+        self.cfg = Cfg()
+        self.lib.go1mpc_config_default(ctypes.byref(self.cfg))
+        if cfg:
+            for k, v in cfg.items():
+                if k == "lamda":
+                    for i in range(4):
+                        self.cfg.body.lamda[i] = v[i]
+                elif k == "qp_iter_cap_scale":
+                    self.cfg.qp_iter_cap_scale = v
+                else:
+                    setattr(self.cfg.body, k, v)
+        self.h = ctypes.c_void_p()
+        rc = self.lib.go1mpc_create(ctypes.byref(self.cfg), device, ctypes.byref(self.h))
+        if rc != 0:
+            raise Go1MpcError(f"go1mpc_create failed with {rc} (no usable CUDA device? there is no CPU fallback)")
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.go1mpc_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise Go1MpcError(f"{what} failed ({rc}): {self.lib.go1mpc_last_error(self.h).decode()}")
+
+    @property
+    def launch_count(self):
+        return int(self.lib.go1mpc_launch_count(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.go1mpc_synchronize(self.h), "synchronize")
+
+    # --- body-inclination MPC ---
+    def body_mpc_step(self, nh, B, in_d, out_d, diag_d=None, stream=None):
+        """Device-pointer entry (torch CUDA tensors or raw addresses)."""
+        self._check(self.lib.go1mpc_body_mpc_step_batch(self.h, nh, B, _ptr(in_d), _ptr(out_d), _ptr(diag_d), stream),
+                    "body_mpc_step_batch")
+
+    def body_mpc_step_host(self, nh, B, in_h, out_h, diag_h=None):
+        """Host-buffer entry: H2D, launch, D2H and a stream sync inside the call."""
+        self._check(self.lib.go1mpc_body_mpc_step_batch_host(self.h, nh, B, _ptr(in_h), _ptr(out_h), _ptr(diag_h)),
+                    "body_mpc_step_batch_host")
+
+    def body_model(self, nh):
+        out = {k: np.zeros((2, nh) if k in ("pps", "pvs") else (nh, nh)) for k in ("pps", "pvs", "ppu", "pvu", "ppu_2", "pvu_2")}
+        self._check(self.lib.go1mpc_body_model(self.h, nh, *[_ptr(out[k]) for k in ("pps", "pvs", "ppu", "pvu", "ppu_2", "pvu_2")]),
+                    "body_model")
+        return {k: v.T.copy() for k, v in out.items()}   # column-major -> [row, col]
+
+    def body_default_tx(self):
+        tx = np.zeros(27)
+        self._check(self.lib.go1mpc_body_default_tx(self.h, _ptr(tx)), "body_default_tx")
+        return tx
+
+    # --- generic dense QP ---
+    def qp_solve(self, n, p, m, B, G, g0, CE, ce0, CI, ci0, x, cost=None, active=None, nactive=None, iters=None,
+                 status=None, stream=None):
+        self._check(self.lib.go1mpc_qp_solve_batch(self.h, n, p, m, B, _ptr(G), _ptr(g0), _ptr(CE), _ptr(ce0), _ptr(CI),
+                                                   _ptr(ci0), _ptr(x), _ptr(cost), _ptr(active), _ptr(nactive),
+                                                   _ptr(iters), _ptr(status), stream), "qp_solve_batch")
+
+    def qp_solve_host(self, n, p, m, B, G, g0, CE, ce0, CI, ci0, x, cost=None, active=None, nactive=None, iters=None,
+                      status=None):
+        self._check(self.lib.go1mpc_qp_solve_batch_host(self.h, n, p, m, B, _ptr(G), _ptr(g0), _ptr(CE), _ptr(ce0),
+                                                        _ptr(CI), _ptr(ci0), _ptr(x), _ptr(cost), _ptr(active),
+                                                        _ptr(nactive), _ptr(iters), _ptr(status)), "qp_solve_batch_host")
+
+    def measure_dfma_peak(self, ms=200):
+        g = ctypes.c_double(0.0)
+        self._check(self.lib.go1mpc_measure_dfma_peak(self.h, ms, ctypes.byref(g)), "measure_dfma_peak")
+        return g.value

@@ -1,0 +1,427 @@
+// api.cu -- C ABI of libgo1mpc.so (include/go1mpc.h): handle, model tables, launches.
+//
+// Host side of the boundary.  No CPU compute path exists here: every entry point
+// either launches the sm_100a kernels or fails with an error code.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
+#include "../../include/go1mpc.h"
+#include "kernels.h"
+
+using namespace go1;
+
+namespace {
+
+struct BodyModel {
+  int nh = 0, tab_doubles = 0;
+  std::vector<double> pps, pvs, ppu, pvu, ppu2, pvu2;   // host copies (column-major)
+  double* tab_d = nullptr;
+  int nstepx = 0, nsum_mpc = 0, gate = 0;
+  double tx0[GO1MPC_FOOTSTEPS];
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+}  // namespace
+
+struct go1mpc {
+  int device = 0;
+  int sms = 0;
+  size_t smem_optin = 0;
+  cudaStream_t stream = nullptr;
+  Go1MpcConfig cfg;
+  std::string err;
+  long long launches = 0;
+  std::map<int, BodyModel> body_models;
+  DevBuf stage[16];   // device staging for the *_host entry points
+};
+
+namespace {
+
+int fail(go1mpc* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+int cuda_fail(go1mpc* h, cudaError_t e, const char* what) {
+  return fail(h, GO1MPC_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(h, call)                                        \
+  do {                                                     \
+    cudaError_t e_ = (call);                               \
+    if (e_ != cudaSuccess) return cuda_fail(h, e_, #call); \
+  } while (0)
+
+// C = A(m x k) * B(k x n), column-major, ascending inner index
+void mm(const double* A, const double* B, double* C, int m, int k, int n) {
+  for (int j = 0; j < n; j++)
+    for (int i = 0; i < m; i++) {
+      double acc = 0.0;
+      for (int t = 0; t < k; t++) acc += A[t * m + i] * B[j * k + t];
+      C[j * m + i] = acc;
+    }
+}
+
+// Horizon model of the double-integrator body-angle dynamics.
+// Replaces PRMPCClass::Initialize (model part, RT/src/FastMPC/PRMPCClass.cpp:168-220)
+// and Matrix_ps / Matrix_pu (:741-796): the same power recurrences, so the tables are
+// what the reference would hold for this nh.
+int build_body_model(go1mpc* h, int nh, BodyModel& M) {
+  const Go1BodyMpcConfig& c = h->cfg.body;
+  M.nh = nh;
+  M.pps.assign(nh * 2, 0.0); M.pvs.assign(nh * 2, 0.0);
+  M.ppu.assign(nh * nh, 0.0); M.pvu.assign(nh * nh, 0.0);
+  M.ppu2.assign(nh * nh, 0.0); M.pvu2.assign(nh * nh, 0.0);
+  const double a[4] = {1, 0, c.dt_mpc, 1};
+  const double b[2] = {pow(c.dt_mpc, 2) / 2, c.dt_mpc};
+  const double cp[2] = {1, 0}, cv[2] = {0, 1};
+  for (int sel = 0; sel < 2; sel++) {
+    const double* cx = sel ? cv : cp;
+    std::vector<double>& ps = sel ? M.pvs : M.pps;
+    std::vector<double>& pu = sel ? M.pvu : M.ppu;
+    for (int i = 0; i < nh; i++) {           // row i of Pps: cx * a^(i+1)
+      double A[4] = {1, 0, 0, 1}, T[4], r[2];
+      for (int j = 1; j < i + 2; j++) { mm(A, a, T, 2, 2, 2); memcpy(A, T, sizeof A); }
+      mm(cx, A, r, 1, 2, 2);
+      ps[i] = r[0]; ps[nh + i] = r[1];
+    }
+    for (int i = 1; i <= nh; i++)            // Ppu(i,j) = cx * a^(i-j) * b, lower triangular
+      for (int j = 1; j <= i; j++) {
+        double A[4] = {1, 0, 0, 1}, T[4], r[2], v[1];
+        for (int k = 1; k < i - j + 1; k++) { mm(A, a, T, 2, 2, 2); memcpy(A, T, sizeof A); }
+        mm(cx, A, r, 1, 2, 2);
+        mm(r, b, v, 1, 2, 1);
+        pu[(j - 1) * nh + (i - 1)] = v[0];
+      }
+  }
+  std::vector<double> T(nh * nh);
+  for (int j = 0; j < nh; j++) for (int i = 0; i < nh; i++) T[j * nh + i] = M.pvu[i * nh + j];
+  mm(T.data(), M.pvu.data(), M.pvu2.data(), nh, nh, nh);
+  for (int j = 0; j < nh; j++) for (int i = 0; i < nh; i++) T[j * nh + i] = M.ppu[i * nh + j];
+  mm(T.data(), M.ppu.data(), M.ppu2.data(), nh, nh, nh);
+
+  // step tables (PRMPCClass.cpp:168-185)
+  M.nstepx = (int)round(c.tstep / c.dt_mpc);
+  M.tx0[0] = 0.0;
+  for (int i = 1; i < GO1MPC_FOOTSTEPS; i++) {
+    M.tx0[i] = M.tx0[i - 1] + c.tstep;
+    M.tx0[i] = round(M.tx0[i] / c.dt_slow) * c.dt_slow - 0.00001;
+  }
+  M.nsum_mpc = (int)floor(M.tx0[GO1MPC_FOOTSTEPS - 1] / c.dt_mpc);
+  M.gate = (int)round(c.height_offset_time / c.dt_mpc);
+
+  // device table: ppu | gc0 | s2 | m1 | m2 | pps   (see body_mpc.cu)
+  int td = 3 * nh * nh + 6 * nh;
+  td = (td + 1) & ~1;
+  M.tab_doubles = td;
+  std::vector<double> tab(td, 0.0);
+  double* ppu = tab.data();
+  double* gc0 = ppu + nh * nh;
+  double* s2 = gc0 + nh * nh;
+  double* m1 = s2 + nh * nh;
+  double* m2 = m1 + 2 * nh;
+  double* pps = m2 + 2 * nh;
+  std::vector<double> s1(nh * nh);
+  for (int j = 0; j < nh; j++)
+    for (int i = 0; i < nh; i++) {
+      ppu[j * nh + i] = M.ppu[j * nh + i];
+      double unit = (i == j) ? 1.0 : 0.0;
+      // PRMPCClass.cpp:511: the three tick-independent terms of _WthetaX, in the reference's order
+      gc0[j * nh + i] = c.Rtheta / 2 * unit + c.alphatheta / 2 * M.pvu2[j * nh + i] + c.beltatheta / 2 * M.ppu2[j * nh + i];
+      s1[j * nh + i] = c.alphatheta * M.pvu[i * nh + j];   // alpha * Pvu'
+      s2[j * nh + i] = c.beltatheta * M.ppu[i * nh + j];   // beta  * Ppu'
+    }
+  mm(s1.data(), M.pvs.data(), m1, nh, nh, 2);   // (alpha Pvu') Pvs   (cpp:523)
+  mm(s2, M.pps.data(), m2, nh, nh, 2);          // (beta  Ppu') Pps
+  memcpy(pps, M.pps.data(), sizeof(double) * 2 * nh);
+
+  CU(h, cudaMalloc(&M.tab_d, sizeof(double) * td));
+  CU(h, cudaMemcpyAsync(M.tab_d, tab.data(), sizeof(double) * td, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return GO1MPC_OK;
+}
+
+int get_body_model(go1mpc* h, int nh, BodyModel** out) {
+  auto it = h->body_models.find(nh);
+  if (it == h->body_models.end()) {
+    BodyModel M;
+    int rc = build_body_model(h, nh, M);
+    if (rc) return rc;
+    it = h->body_models.emplace(nh, std::move(M)).first;
+  }
+  *out = &it->second;
+  return GO1MPC_OK;
+}
+
+int stage_buf(go1mpc* h, int slot, size_t bytes, void** out) {
+  DevBuf& b = h->stage[slot];
+  if (bytes > b.cap) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr; b.cap = 0;
+    size_t cap = bytes + bytes / 4 + 256;
+    CU(h, cudaMalloc(&b.p, cap));
+    b.cap = cap;
+  }
+  *out = b.p;
+  return GO1MPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* go1mpc_version(void) { return GO1MPC_VERSION_STRING " (sm_100a, fp64)"; }
+
+int go1mpc_config_default(Go1MpcConfig* cfg) {
+  if (!cfg) return GO1MPC_E_INVALID;
+  memset(cfg, 0, sizeof *cfg);
+  Go1BodyMpcConfig& b = cfg->body;
+  b.dt_mpc = 0.01; b.dt_slow = 0.025; b.tstep = 0.7; b.height_offset_time = 1.0;
+  b.g = 9.8; b.mass = 12.0; b.j_ini = 12 * 0.1 * 0.1;
+  b.foot_length = 0.02; b.foot_width = 0.02;
+  b.theta_lim = 10 * M_PI / 180; b.torque_lim = 20.0;
+  b.Rtheta = 100.0; b.alphatheta = 10.0; b.beltatheta = 5000000000.0; b.gama_zmp = 5000.0;
+  cfg->qp_iter_cap_scale = 20;
+  return GO1MPC_OK;
+}
+
+int go1mpc_create(const Go1MpcConfig* cfg, int device, go1mpc_t** out) {
+  if (!out) return GO1MPC_E_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return GO1MPC_E_NO_DEVICE;
+  go1mpc* h = new go1mpc();
+  if (cfg) h->cfg = *cfg; else go1mpc_config_default(&h->cfg);
+  if (h->cfg.qp_iter_cap_scale <= 0) h->cfg.qp_iter_cap_scale = 20;
+  if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) { delete h; return GO1MPC_E_NO_DEVICE; } }
+  if (device >= ndev) { delete h; return GO1MPC_E_INVALID; }
+  h->device = device;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete h;
+    return GO1MPC_E_CUDA;
+  }
+  h->sms = prop.multiProcessorCount;
+  h->smem_optin = prop.sharedMemPerBlockOptin;
+  *out = h;
+  return GO1MPC_OK;
+}
+
+void go1mpc_destroy(go1mpc_t* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  for (auto& kv : h->body_models) if (kv.second.tab_d) cudaFree(kv.second.tab_d);
+  for (DevBuf& b : h->stage) if (b.p) cudaFree(b.p);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* go1mpc_last_error(const go1mpc_t* h) { return h ? h->err.c_str() : "null handle"; }
+int go1mpc_device(const go1mpc_t* h) { return h ? h->device : -1; }
+long long go1mpc_launch_count(const go1mpc_t* h) { return h ? h->launches : 0; }
+int go1mpc_synchronize(go1mpc_t* h) {
+  if (!h) return GO1MPC_E_INVALID;
+  CU(h, cudaStreamSynchronize(h->stream));
+  return GO1MPC_OK;
+}
+
+// ------------------------------------------------------------------ dense QP
+int go1mpc_qp_solve_batch(go1mpc_t* h, int n, int p, int m, int B, const double* G_d, const double* g0_d,
+                          const double* CE_d, const double* ce0_d, const double* CI_d, const double* ci0_d,
+                          double* x_d, double* cost_d, int* active_d, int* nactive_d, int* iters_d,
+                          int* status_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (n < 1 || p < 0 || m < 0 || B < 0 || !G_d || !g0_d || !x_d || (m && (!CI_d || !ci0_d)) || (p && (!CE_d || !ce0_d)))
+    return fail(h, GO1MPC_E_INVALID, "qp_solve_batch: bad argument");
+  if (n > 96 || m + p > 1024 || p > n) return fail(h, GO1MPC_E_UNSUPPORTED, "qp_solve_batch: n <= 96, m + p <= 1024, p <= n");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  int wpc = 4;
+  size_t smem = dense_smem_bytes(n, m, wpc);
+  while (wpc > 1 && smem > h->smem_optin / 2) { wpc >>= 1; smem = dense_smem_bytes(n, m, wpc); }
+  if (smem > h->smem_optin) return fail(h, GO1MPC_E_UNSUPPORTED, "qp_solve_batch: workspace exceeds shared memory");
+  int occ = 0;
+  CU(h, dense_qp_occupancy(wpc, smem, &occ));
+  if (occ < 1) return fail(h, GO1MPC_E_UNSUPPORTED, "qp_solve_batch: kernel does not fit on an SM");
+  int grid = (B + wpc - 1) / wpc;
+  if (grid > h->sms * occ) grid = h->sms * occ;
+  DenseKParams P;
+  P.n = n; P.p = p; P.m = m; P.B = B; P.cap = h->cfg.qp_iter_cap_scale * (m + p + n) + 50;
+  P.G = G_d; P.g0 = g0_d; P.CE = CE_d; P.ce0 = ce0_d; P.CI = CI_d; P.ci0 = ci0_d;
+  P.x = x_d; P.cost = cost_d; P.active = active_d; P.nactive = nactive_d; P.iters = iters_d; P.status = status_d;
+  CU(h, dense_qp_launch(P, wpc, grid, smem, st));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
+int go1mpc_qp_solve_batch_host(go1mpc_t* h, int n, int p, int m, int B, const double* G, const double* g0,
+                               const double* CE, const double* ce0, const double* CI, const double* ci0,
+                               double* x, double* cost, int* active, int* nactive, int* iters, int* status) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  const size_t szd = sizeof(double), szi = sizeof(int), b = (size_t)B;
+  void *dG, *dg0, *dCE = nullptr, *dce0 = nullptr, *dCI = nullptr, *dci0 = nullptr, *dx, *dcost, *dact, *dna, *dit, *dst;
+  int rc;
+  if ((rc = stage_buf(h, 0, b * n * n * szd, &dG))) return rc;
+  if ((rc = stage_buf(h, 1, b * n * szd, &dg0))) return rc;
+  if (p) { if ((rc = stage_buf(h, 2, b * n * p * szd, &dCE))) return rc; if ((rc = stage_buf(h, 3, b * p * szd, &dce0))) return rc; }
+  if (m) { if ((rc = stage_buf(h, 4, b * n * m * szd, &dCI))) return rc; if ((rc = stage_buf(h, 5, b * m * szd, &dci0))) return rc; }
+  if ((rc = stage_buf(h, 6, b * n * szd, &dx))) return rc;
+  if ((rc = stage_buf(h, 7, b * szd, &dcost))) return rc;
+  if ((rc = stage_buf(h, 8, b * (m + p + 1) * szi, &dact))) return rc;
+  if ((rc = stage_buf(h, 9, b * szi, &dna))) return rc;
+  if ((rc = stage_buf(h, 10, b * 4 * szi, &dit))) return rc;
+  if ((rc = stage_buf(h, 11, b * szi, &dst))) return rc;
+  cudaStream_t st = h->stream;
+  CU(h, cudaMemcpyAsync(dG, G, b * n * n * szd, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(dg0, g0, b * n * szd, cudaMemcpyHostToDevice, st));
+  if (p) { CU(h, cudaMemcpyAsync(dCE, CE, b * n * p * szd, cudaMemcpyHostToDevice, st)); CU(h, cudaMemcpyAsync(dce0, ce0, b * p * szd, cudaMemcpyHostToDevice, st)); }
+  if (m) { CU(h, cudaMemcpyAsync(dCI, CI, b * n * m * szd, cudaMemcpyHostToDevice, st)); CU(h, cudaMemcpyAsync(dci0, ci0, b * m * szd, cudaMemcpyHostToDevice, st)); }
+  CU(h, cudaMemcpyAsync(dx, x, b * n * szd, cudaMemcpyHostToDevice, st));
+  rc = go1mpc_qp_solve_batch(h, n, p, m, B, (double*)dG, (double*)dg0, (double*)dCE, (double*)dce0, (double*)dCI,
+                             (double*)dci0, (double*)dx, (double*)dcost, (int*)dact, (int*)dna, (int*)dit, (int*)dst, st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(x, dx, b * n * szd, cudaMemcpyDeviceToHost, st));
+  if (cost) CU(h, cudaMemcpyAsync(cost, dcost, b * szd, cudaMemcpyDeviceToHost, st));
+  if (active) CU(h, cudaMemcpyAsync(active, dact, b * (m + p) * szi, cudaMemcpyDeviceToHost, st));
+  if (nactive) CU(h, cudaMemcpyAsync(nactive, dna, b * szi, cudaMemcpyDeviceToHost, st));
+  if (iters) CU(h, cudaMemcpyAsync(iters, dit, b * 4 * szi, cudaMemcpyDeviceToHost, st));
+  if (status) CU(h, cudaMemcpyAsync(status, dst, b * szi, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return GO1MPC_OK;
+}
+
+// ------------------------------------------------------------------ body MPC
+int go1mpc_body_in_stride(int nh) { int s = 36 + 11 * nh; return (s + 1) & ~1; }
+int go1mpc_body_out_stride(int nh) { int s = 18 + 2 * nh + 1; return (s + 1) & ~1; }
+int go1mpc_body_diag_stride(int nh) { return 8 + 2 * nh; }
+
+int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, double* out_d, int* diag_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !in_d || !out_d) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch: bad argument");
+  if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "body_mpc_step_batch: 3 <= nh <= 40");
+  if (((uintptr_t)in_d & 15) || ((uintptr_t)out_d & 15)) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch: in/out must be 16-byte aligned");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  BodyModel* M;
+  int rc = get_body_model(h, nh, &M);
+  if (rc) return rc;
+  const int is = go1mpc_body_in_stride(nh), os = go1mpc_body_out_stride(nh);
+  int wpc = 4, wd = 0;
+  size_t smem = body_smem_bytes(nh, wpc, is, os, M->tab_doubles, &wd);
+  while (wpc > 1 && smem > h->smem_optin / 2) { wpc >>= 1; smem = body_smem_bytes(nh, wpc, is, os, M->tab_doubles, &wd); }
+  if (smem > h->smem_optin) return fail(h, GO1MPC_E_UNSUPPORTED, "body_mpc_step_batch: workspace exceeds shared memory");
+  int occ = 0;
+  CU(h, body_mpc_occupancy(wpc, smem, &occ));
+  if (occ < 1) return fail(h, GO1MPC_E_UNSUPPORTED, "body_mpc_step_batch: kernel does not fit on an SM");
+  int grid = (B + wpc - 1) / wpc;
+  if (grid > h->sms * occ) grid = h->sms * occ;
+  const Go1BodyMpcConfig& c = h->cfg.body;
+  BodyKParams P;
+  P.nh = nh; P.B = B; P.in_stride = is; P.out_stride = os; P.diag_stride = go1mpc_body_diag_stride(nh);
+  P.tab_doubles = M->tab_doubles; P.warp_doubles = wd;
+  P.cap_scale = h->cfg.qp_iter_cap_scale; P.gate = M->gate; P.nstepx = M->nstepx; P.nsum_mpc = M->nsum_mpc;
+  P.in = in_d; P.out = out_d; P.diag = diag_d; P.tab = M->tab_d;
+  P.dt_mpc = c.dt_mpc; P.j_ini = c.j_ini; P.mass = c.mass; P.g = c.g; P.gama = c.gama_zmp;
+  P.theta_lim = c.theta_lim; P.torque_lim = c.torque_lim;
+  for (int k = 0; k < 4; k++) P.lamda[k] = c.lamda[k];
+  CU(h, body_mpc_launch(P, wpc, grid, smem, st));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
+int go1mpc_body_mpc_step_batch_host(go1mpc_t* h, int nh, int B, const double* in, double* out, int* diag) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!in || !out) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch_host: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t ib = (size_t)B * go1mpc_body_in_stride(nh) * sizeof(double);
+  const size_t ob = (size_t)B * go1mpc_body_out_stride(nh) * sizeof(double);
+  const size_t db = (size_t)B * go1mpc_body_diag_stride(nh) * sizeof(int);
+  void *din, *dout, *ddiag = nullptr;
+  int rc;
+  if ((rc = stage_buf(h, 12, ib, &din))) return rc;
+  if ((rc = stage_buf(h, 13, ob, &dout))) return rc;
+  if (diag && (rc = stage_buf(h, 14, db, &ddiag))) return rc;
+  cudaStream_t st = h->stream;
+  CU(h, cudaMemcpyAsync(din, in, ib, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(dout, out, ob, cudaMemcpyHostToDevice, st));   // out14 is in/out (gated ticks)
+  rc = go1mpc_body_mpc_step_batch(h, nh, B, (const double*)din, (double*)dout, (int*)ddiag, st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, st));
+  if (diag) CU(h, cudaMemcpyAsync(diag, ddiag, db, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return GO1MPC_OK;
+}
+
+int go1mpc_body_model(go1mpc_t* h, int nh, double* pps, double* pvs, double* ppu, double* pvu, double* ppu_2, double* pvu_2) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (nh < 1 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "body_model: 1 <= nh <= 40");
+  CU(h, cudaSetDevice(h->device));
+  BodyModel* M;
+  int rc = get_body_model(h, nh, &M);
+  if (rc) return rc;
+  if (pps) memcpy(pps, M->pps.data(), sizeof(double) * 2 * nh);
+  if (pvs) memcpy(pvs, M->pvs.data(), sizeof(double) * 2 * nh);
+  if (ppu) memcpy(ppu, M->ppu.data(), sizeof(double) * nh * nh);
+  if (pvu) memcpy(pvu, M->pvu.data(), sizeof(double) * nh * nh);
+  if (ppu_2) memcpy(ppu_2, M->ppu2.data(), sizeof(double) * nh * nh);
+  if (pvu_2) memcpy(pvu_2, M->pvu2.data(), sizeof(double) * nh * nh);
+  return GO1MPC_OK;
+}
+
+int go1mpc_body_default_tx(go1mpc_t* h, double* tx27) {
+  if (!h || !tx27) return GO1MPC_E_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  BodyModel* M;
+  int rc = get_body_model(h, 4, &M);
+  if (rc) return rc;
+  memcpy(tx27, M->tx0, sizeof M->tx0);
+  return GO1MPC_OK;
+}
+
+int go1mpc_measure_dfma_peak(go1mpc_t* h, int ms, double* gflops) {
+  if (!h || !gflops) return GO1MPC_E_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  double* sink;
+  CU(h, cudaMalloc(&sink, sizeof(double)));
+  cudaEvent_t e0, e1;
+  CU(h, cudaEventCreate(&e0));
+  CU(h, cudaEventCreate(&e1));
+  const int grid = h->sms * 8, block = 256;
+  int iters = 2000;
+  double best = 0.0, elapsed_total = 0.0;
+  CU(h, dfma_peak_launch(grid, block, 200, sink, h->stream));   // warm-up
+  h->launches++;
+  for (int rep = 0; rep < 64 && elapsed_total < ms; rep++) {
+    CU(h, cudaEventRecord(e0, h->stream));
+    CU(h, dfma_peak_launch(grid, block, iters, sink, h->stream));
+    CU(h, cudaEventRecord(e1, h->stream));
+    CU(h, cudaEventSynchronize(e1));
+    h->launches++;
+    float t_ms = 0.f;
+    CU(h, cudaEventElapsedTime(&t_ms, e0, e1));
+    elapsed_total += t_ms;
+    double flops = (double)grid * block * (double)iters * 64.0 * 2.0;
+    double gf = flops / (t_ms * 1e-3) * 1e-9;
+    if (gf > best) best = gf;
+    if (t_ms < 2.0f) iters *= 4;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+  *gflops = best;
+  return GO1MPC_OK;
+}
+
+}  // extern "C"

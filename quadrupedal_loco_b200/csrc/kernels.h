@@ -1,0 +1,37 @@
+// kernels.h -- internal interface between the C-ABI host layer (api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace go1 {
+
+struct BodyKParams {
+  int nh, B;
+  int in_stride, out_stride, diag_stride;   // doubles, doubles, ints
+  int tab_doubles, warp_doubles;
+  int cap_scale, gate, nstepx, nsum_mpc;
+  const double* in;
+  double* out;
+  int* diag;
+  const double* tab;
+  double dt_mpc, j_ini, mass, g, gama, theta_lim, torque_lim;
+  double lamda[4];
+};
+size_t body_smem_bytes(int nh, int wpc, int in_stride, int out_stride, int tab_doubles, int* warp_doubles);
+cudaError_t body_mpc_launch(BodyKParams P, int wpc, int grid, size_t smem, cudaStream_t st);
+cudaError_t body_mpc_occupancy(int wpc, size_t smem, int* blocks_per_sm);
+
+struct DenseKParams {
+  int n, p, m, B, cap;
+  const double *G, *g0, *CE, *ce0, *CI, *ci0;
+  double *x, *cost;
+  int *active, *nactive, *iters, *status;
+};
+size_t dense_smem_bytes(int n, int m, int wpc);
+cudaError_t dense_qp_launch(DenseKParams P, int wpc, int grid, size_t smem, cudaStream_t st);
+cudaError_t dense_qp_occupancy(int wpc, size_t smem, int* blocks_per_sm);
+
+// register-resident DFMA loop: flops executed are returned through *flops
+cudaError_t dfma_peak_launch(int grid, int block, int iters, double* sink, cudaStream_t st);
+
+}  // namespace go1

@@ -1,0 +1,90 @@
+"""Synthetic, seeded workloads for tests and bench.py.
+
+All generators use numpy's counter-based Philox with the seed of the config they
+serve, so the CPU oracle, the GPU path and the reference arm see identical inputs.
+"""
+import numpy as np
+
+SEED_CFG2 = 0xB2000002
+SEED_CFG3 = 0xB2000003
+SEED_CFG4 = 0xB2000004
+SEED_CFG5 = 0xB2000005
+
+HALF_HIP = 0.12675
+
+
+def default_tx(tstep=0.7, dt_slow=0.025, n=27):
+    """_tx of PRMPCClass::Initialize (RT/src/FastMPC/PRMPCClass.cpp:174-178)."""
+    tx = np.zeros(n)
+    for i in range(1, n):
+        tx[i] = tx[i - 1] + tstep
+        tx[i] = np.round(tx[i] / dt_slow) * dt_slow - 0.00001
+    return tx
+
+
+def body_mpc_inputs(B, nh, seed=SEED_CFG2, scale=1.0, tick_lo=100, tick_hi=1700):
+    """cfg2-style body-MPC batch: randomised body-angle state, tick and reference windows.
+
+    Returns dict(tick [B] i32, tx [B,27], theta [B,4], bstate [B,4], x_warm [B,2nh], refs [B,9,nh]).
+    theta ~ U(+-0.12 rad), theta_dot ~ U(+-1.0 rad/s) (times `scale`), zmp_ref = support-foot
+    centre + U(+-0.01), bodyangle_ref ~ U(+-0.05) (smooth over the window), comacc_z ~ U(+-2).
+    """
+    rng = np.random.Generator(np.random.Philox(seed))
+    tick = rng.integers(tick_lo, tick_hi + 1, size=B).astype(np.int32)
+    tx = np.tile(default_tx(), (B, 1))
+    theta = np.empty((B, 4))
+    theta[:, 0] = rng.uniform(-0.12, 0.12, B) * scale
+    theta[:, 1] = rng.uniform(-1.0, 1.0, B) * scale
+    theta[:, 2] = rng.uniform(-0.12, 0.12, B) * scale
+    theta[:, 3] = rng.uniform(-1.0, 1.0, B) * scale
+    bstate = theta + rng.uniform(-0.01, 0.01, (B, 4))
+    x_warm = np.zeros((B, 2 * nh))
+    refs = np.zeros((B, 9, nh))
+    # feet: a walking stance around a forward-moving body; constant over the short window
+    xc = rng.uniform(0.0, 1.0, B)
+    step = rng.uniform(-0.05, 0.15, B)
+    lf = np.stack([xc + 0.5 * step, np.full(B, HALF_HIP)], 1) + rng.uniform(-0.01, 0.01, (B, 2))
+    rf = np.stack([xc - 0.5 * step, np.full(B, -HALF_HIP)], 1) + rng.uniform(-0.01, 0.01, (B, 2))
+    refs[:, 4, :] = rf[:, 0:1]; refs[:, 5, :] = rf[:, 1:2]
+    refs[:, 6, :] = lf[:, 0:1]; refs[:, 7, :] = lf[:, 1:2]
+    # zmp reference: under a foot, with the velocity-command perturbation
+    use_l = rng.integers(0, 2, B).astype(bool)
+    zc = np.where(use_l[:, None], lf, rf)
+    refs[:, 0, :] = zc[:, 0:1] + rng.uniform(-0.01, 0.01, (B, nh)) * scale
+    refs[:, 1, :] = zc[:, 1:2] + rng.uniform(-0.01, 0.01, (B, nh)) * scale
+    # body-angle reference: offset + slope over the window
+    a0 = rng.uniform(-0.05, 0.05, (B, 2)) * scale
+    a1 = rng.uniform(-0.02, 0.02, (B, 2)) * scale
+    ramp = np.linspace(0.0, 1.0, nh)[None, :]
+    refs[:, 2, :] = a0[:, 0:1] + a1[:, 0:1] * ramp
+    refs[:, 3, :] = a0[:, 1:2] + a1[:, 1:2] * ramp
+    refs[:, 8, :] = rng.uniform(-2.0, 2.0, (B, nh)) * scale
+    return dict(tick=tick, tx=tx, theta=theta, bstate=bstate, x_warm=x_warm, refs=refs)
+
+
+def random_qp(B, n, p, m, seed=1, paired=False, dup=False, infeasible_frac=0.0):
+    """Random strictly convex QPs, feasible around a random point (column-major per problem)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    G = np.empty((B, n * n)); g0 = rng.standard_normal((B, n)) * 3
+    CE = np.zeros((B, max(1, n * p))); ce0 = np.zeros((B, max(1, p)))
+    CI = np.empty((B, n * m)); ci0 = np.empty((B, m))
+    for b in range(B):
+        A = rng.standard_normal((n, n))
+        Gm = A @ A.T + 0.1 * np.eye(n)
+        G[b] = Gm.ravel(order="F")
+        x0 = rng.standard_normal(n) * 0.1
+        if p:
+            CEm = rng.standard_normal((n, p))
+            CE[b, :n * p] = CEm.ravel(order="F"); ce0[b, :p] = -(CEm.T @ x0)
+        CIm = rng.standard_normal((n, m))
+        c0 = -(CIm.T @ x0) + np.abs(rng.standard_normal(m)) * 0.3
+        if paired:
+            h = m // 2
+            CIm[:, h:2 * h] = -CIm[:, :h]
+            c0[h:2 * h] = (CIm[:, :h].T @ x0) + np.abs(rng.standard_normal(h)) * 0.3
+        if dup and m >= 2:
+            CIm[:, 1] = CIm[:, 0]; c0[1] = c0[0]
+        if rng.uniform() < infeasible_frac and m >= 2:
+            CIm[:, 1] = -CIm[:, 0]; c0[1] = -c0[0] - 1.0
+        CI[b] = CIm.ravel(order="F"); ci0[b] = c0
+    return dict(G=G, g0=g0, CE=CE, ce0=ce0, CI=CI, ci0=ci0)

@@ -1,0 +1,95 @@
+"""ctypes access to the CPU oracle (oracle/liboracle.so) and, when present, to the
+reference build (oracle/_ref/*.so).  Test infrastructure: nothing in the product
+package imports this module."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORC_DIR = os.path.join(ROOT, "oracle")
+dp = ctypes.POINTER(ctypes.c_double)
+ip = ctypes.POINTER(ctypes.c_int)
+
+
+def P(a):
+    return a.ctypes.data_as(dp)
+
+
+def PI(a):
+    return a.ctypes.data_as(ip)
+
+
+class BodyCfg(ctypes.Structure):
+    _fields_ = [("nh", ctypes.c_int), ("dt_mpc", ctypes.c_double), ("dt_slow", ctypes.c_double),
+                ("tstep", ctypes.c_double), ("height_offset_time", ctypes.c_double), ("g", ctypes.c_double),
+                ("mass", ctypes.c_double), ("j_ini", ctypes.c_double), ("foot_length", ctypes.c_double),
+                ("foot_width", ctypes.c_double), ("theta_lim", ctypes.c_double), ("torque_lim", ctypes.c_double),
+                ("Rtheta", ctypes.c_double), ("alphatheta", ctypes.c_double), ("beltatheta", ctypes.c_double),
+                ("gama_zmp", ctypes.c_double), ("lamda", ctypes.c_double * 4)]
+
+
+def build_oracle():
+    so = os.path.join(ORC_DIR, "liboracle.so")
+    srcs = [os.path.join(ORC_DIR, f) for f in os.listdir(ORC_DIR) if f.endswith((".c", ".h"))]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+        subprocess.run(["make", "-C", ORC_DIR, "liboracle.so"], check=True, env=env, capture_output=True)
+    return so
+
+
+def ref_path(name):
+    p = os.path.join(ORC_DIR, "_ref", name)
+    return p if os.path.exists(p) else None
+
+
+class Oracle:
+    def __init__(self):
+        self.lib = ctypes.CDLL(build_oracle())
+
+    def qp_solve(self, n, p, m, G, g0, CE, ce0, CI, ci0, x0=None):
+        """Column-major flat inputs for ONE problem.  Returns dict."""
+        x = np.zeros(n) if x0 is None else np.array(x0, dtype=float)
+        cost = np.zeros(1); act = np.zeros(m + p + 1, np.int32); na = np.zeros(1, np.int32); it = np.zeros(4, np.int32)
+        z = np.zeros(1)
+        st = self.lib.orc_qp_solve(n, p, m, P(np.ascontiguousarray(G, dtype=float)), P(np.ascontiguousarray(g0, dtype=float)),
+                                   P(np.ascontiguousarray(CE, dtype=float)) if p else P(z),
+                                   P(np.ascontiguousarray(ce0, dtype=float)) if p else P(z),
+                                   P(np.ascontiguousarray(CI, dtype=float)) if m else P(z),
+                                   P(np.ascontiguousarray(ci0, dtype=float)) if m else P(z),
+                                   P(x), P(cost), PI(act), PI(na), PI(it))
+        return dict(status=st, x=x, cost=cost[0], active=act[:na[0]].copy(), nactive=int(na[0]), iters=it)
+
+    def qp_solve_batch(self, n, p, m, d, x0=None):
+        B = d["G"].shape[0]
+        xs = np.zeros((B, n)); cost = np.zeros(B); status = np.zeros(B, np.int32)
+        nact = np.zeros(B, np.int32); iters = np.zeros((B, 4), np.int32); active = np.zeros((B, m + p), np.int32)
+        for b in range(B):
+            r = self.qp_solve(n, p, m, d["G"][b], d["g0"][b], d["CE"][b], d["ce0"][b], d["CI"][b], d["ci0"][b],
+                              None if x0 is None else x0[b])
+            xs[b] = r["x"]; cost[b] = r["cost"]; status[b] = r["status"]; nact[b] = r["nactive"]
+            iters[b] = r["iters"]; active[b, :r["nactive"]] = r["active"]
+        return dict(x=xs, cost=cost, status=status, nactive=nact, iters=iters, active=active)
+
+    def body_cfg(self, nh, **over):
+        c = BodyCfg()
+        self.lib.orc_body_cfg_default(ctypes.byref(c), nh)
+        for k, v in over.items():
+            if k == "lamda":
+                for i in range(4):
+                    c.lamda[i] = v[i]
+            else:
+                setattr(c, k, v)
+        return c
+
+    def body_step_batch(self, cfg, tick, tx, theta, bstate, refs, out14, x):
+        """In/out arrays as in orc_body_step_batch; returns diagnostics."""
+        B = len(tick); nh = cfg.nh
+        tick = np.ascontiguousarray(tick, np.int32)
+        act = np.zeros((B, 12 * nh), np.int32); na = np.zeros(B, np.int32); it = np.zeros((B, 4), np.int32)
+        st = np.zeros(B, np.int32)
+        refs = np.ascontiguousarray(refs.reshape(B, 9 * nh))
+        self.lib.orc_body_step_batch(ctypes.byref(cfg), B, PI(tick), P(tx), P(theta), P(bstate), P(refs), P(out14), P(x),
+                                     PI(act), PI(na), PI(it), PI(st))
+        return dict(active=act, nactive=na, iters=it, status=st)
