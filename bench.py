@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched Go1 MPC QP hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (own arm; torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm, host cores)
+
+A "step" is one pass of the fused body-inclination MPC tick (condensation -> Goldfarb-Idnani
+QP -> clamp -> roll-out; one QP solve per instance) over one batch of synthetic instances.
+Workload at every N: BASELINE.json configs[1] -- Go1 MPC, batch 4096 randomised states and
+references per GPU, horizon 10 (seed 0xB2000002 + rank); weak
+scaling: every rank owns its own 4096 instances, no collective inside the step.
+
+Timing: CUDA events on the stream the kernels are launched on, W untimed steps, then exactly K
+timed steps bracketed by barrier + synchronize; max over ranks.  The steps rotate through
+enough distinct input batches that the input footprint exceeds 2x L2 (126 MB), so no step
+re-reads a cache-resident batch.  The `e2e` leg calls the host-buffer C-ABI entry (pinned
+host memory, H2D + kernel + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "batched MPC QP solves/sec"
+UNIT = "solves/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="instances per GPU per step")
+    ap.add_argument("--nh", type=int, default=10, help="body-MPC horizon")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep", action="store_true", help="also print per-batch-size throughput (stderr)")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {"workload": f"cfg2: Go1 body-inclination MPC tick (1 QP solve/instance: n={2 * a.nh}, m={12 * a.nh}), "
+                        f"horizon {a.nh}, batch {a.batch} randomised states+references per GPU",
+            "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus, "horizon": a.nh,
+            "qp_shape": [2 * a.nh, 0, 12 * a.nh], "seed": "0xB2000002+rank",
+            "parallelism": f"batch-sharded x{n_gpus}, no collective",
+            "l2": "inputs rotate through distinct batches totalling > 2x L2 (no flush needed)"}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_body_runner(a, threads):
+    """Returns (run_once, B): run_once() solves one batch of a.batch instances with `threads`
+    host threads through the oracle port (-O3 -march=native build), returns seconds."""
+    from tests import oracle_lib
+    from quadrupedal_loco_b200 import synth
+    orc = oracle_lib.Oracle(fast=True)
+    nh, B = a.nh, a.batch
+    d = synth.body_mpc_inputs(B, nh, seed=synth.SEED_CFG2)
+    cfg = orc.body_cfg(nh)
+    bounds = np.linspace(0, B, threads + 1).astype(int)
+
+    def work(lo, hi):
+        theta = d["theta"][lo:hi].copy(); x = d["x_warm"][lo:hi].copy(); o14 = np.zeros((hi - lo, 14))
+        orc.body_step_batch(cfg, d["tick"][lo:hi], np.ascontiguousarray(d["tx"][lo:hi]), theta,
+                            np.ascontiguousarray(d["bstate"][lo:hi]), np.ascontiguousarray(d["refs"][lo:hi]), o14, x)
+
+    def run_once():
+        t0 = time.perf_counter()
+        if threads == 1:
+            work(0, B)
+        else:
+            ts = [threading.Thread(target=work, args=(bounds[i], bounds[i + 1])) for i in range(threads)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        return time.perf_counter() - t0
+    return run_once, B
+
+
+def cpu_baseline(a, budget_s=8.0):
+    cores = os.cpu_count() or 1
+    out = {}
+    for label, thr in (("1thread", 1), ("all", cores)):
+        run, B = cpu_body_runner(a, thr)
+        run()
+        n, el = 0, 0.0
+        while el < budget_s / 2 and n < 200:
+            el += run(); n += 1
+        out[label] = (B * n / el, n)
+    return {"value": out["all"][0], "unit": UNIT, "cores": cores, "kind": "port",
+            "value_1thread": out["1thread"][0],
+            "sample": f"{out['all'][1]} passes over the same {a.batch}-instance cfg2 batch with {cores} host threads "
+                      f"({out['1thread'][1]} passes single-threaded); oracle/ C restatement of PRMPCClass::body_theta_mpc + "
+                      f"EiQuadProg at -O3 -march=native (the reference compiles only at horizon 4 and needs Eigen, absent here)"}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    run, B = cpu_body_runner(a, cores)
+    steps = min(a.steps, 200)
+    for _ in range(min(a.warmup, 5)):
+        run()
+    times = [run() for _ in range(steps)]
+    tot = sum(times)
+    v = B * steps / tot
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": min(a.warmup, 5), "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, 1),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"each step = one pass over the {B}-instance cfg2 batch split over {cores} host threads "
+                                       f"(oracle/ C port at -O3 -march=native; host CPU only, GPU count does not apply)"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Polls NVML (SM clock, power, clock-event reasons) every few ms from a thread while the
+    timed region runs; only samples taken between start() and stop() are kept."""
+    REASONS = {8: "hw_slowdown", 64: "hw_thermal_slowdown", 32: "sw_thermal_slowdown", 4: "sw_power_cap"}
+
+    def __init__(self, index):
+        self.index, self.samples, self.run, self.t, self.h = index, [], False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.h = None
+
+    def _poll(self):
+        nv = self.nv
+        while self.run:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.h is None:
+            return
+        self.run = True
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
+
+    def stop(self):
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "note": "NVML unavailable"}
+        self.run = False
+        self.t.join()
+        sm = [x[0] for x in self.samples]
+        reasons = set()
+        for _, _, rs in self.samples:
+            for bit, nm in self.REASONS.items():
+                if rs & bit:
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.max_sm),
+                "power_w_max": max((x[1] for x in self.samples), default=None), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_b200(a):
+    import torch
+    import quadrupedal_loco_b200 as q
+    from quadrupedal_loco_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    nh, B, K, W = a.nh, a.batch, a.steps, max(a.warmup, 3)
+    mpc = q.Go1Mpc(local)
+    stream = torch.cuda.ExternalStream(mpc.stream, device=dev)
+    in_s, out_s, dg_s = q.body_in_stride(nh), q.body_out_stride(nh), q.body_diag_stride(nh)
+
+    # distinct input batches: footprint > 2x L2
+    nrot = max(4, int(np.ceil(2.2 * L2_BYTES / (B * in_s * 8))))
+    nrot = min(nrot, 512)
+    big = synth.body_mpc_inputs(B * nrot, nh, seed=synth.SEED_CFG2 + rank)
+    rec = q.pack_body_inputs(nh, big["tick"], big["tx"], big["theta"], big["bstate"], big["x_warm"], big["refs"])
+    rec_h = torch.from_numpy(rec).pin_memory()
+    in_d = rec_h.to(dev).view(nrot, B, in_s)
+    out_d = torch.zeros(nrot, B, out_s, dtype=torch.float64, device=dev)
+    diag_d = torch.zeros(nrot, B, dg_s, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step(i):
+        r = i % nrot
+        mpc.body_mpc_step(nh, B, in_d[r], out_d[r], diag_d[r])
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (also fills every diag record once: algorithmic flops per batch)
+    for i in range(max(W, nrot)):
+        step(i)
+    mpc.synchronize()
+    diag_all = diag_d.cpu().numpy()
+    assert (diag_all[:, :, 0] == 0).all(), "a warm-up solve did not converge"
+    flops_per_batch = diag_all[:, :, 9].astype(np.float64).sum(axis=1)          # [nrot]
+    mean_iters = diag_all[:, :, 2:6].reshape(-1, 4).mean(axis=0)
+    mean_l2a = diag_all[:, :, 8].mean()
+
+    dfma_gflops = mpc.measure_dfma_peak(300)
+
+    # ---- device-resident leg ----
+    clocks = ClockSampler(local)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    clocks.start()
+    l0 = mpc.launch_count
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        for i in range(K):
+            step(i)
+            ev[i + 1].record(stream)
+    mpc.synchronize()
+    barrier()
+    launches = mpc.launch_count - l0
+    per_step_ms = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(K)])
+    total_ms = ev[0].elapsed_time(ev[K])
+
+    # kernel-only duration: the same K launches, each timed alone (sync between launches so the
+    # events bracket exactly one kernel); feeds the roofline figure and the latency percentiles
+    lat_ms = []
+    k_lat = min(K, 400)
+    for i in range(k_lat):
+        with torch.cuda.stream(stream):
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(stream); step(i); e1.record(stream)
+        e1.synchronize()
+        lat_ms.append(e0.elapsed_time(e1))
+    lat_ms = np.array(lat_ms)
+    clk = clocks.stop()
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * B * K / (total_ms_max * 1e-3)
+
+    # ---- e2e leg: host buffers through the *_host C-ABI entry ----
+    e2e = None
+    if not a.no_e2e:
+        Ke = min(K, 200)
+        in_h = rec_h.view(nrot, B, in_s)
+        out_h = torch.zeros(nrot, B, out_s, dtype=torch.float64).pin_memory()
+        diag_h = torch.zeros(nrot, B, dg_s, dtype=torch.int32).pin_memory()
+        in_np, out_np, diag_np = in_h.numpy(), out_h.numpy(), diag_h.numpy()
+        for i in range(3):
+            mpc.body_mpc_step_host(nh, B, in_np[i % nrot], out_np[i % nrot], diag_np[i % nrot])
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(Ke):
+            r = i % nrot
+            mpc.body_mpc_step_host(nh, B, in_np[r], out_np[r], diag_np[r])
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        assert (diag_np[:min(Ke, nrot), :, 0] == 0).all()
+        e2e = {"value": world * B * Ke / (float(te.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": B * (in_s + out_s) * 8, "d2h_bytes_per_step": B * (out_s * 8 + dg_s * 4),
+               "steps": Ke, "api": "go1mpc_body_mpc_step_batch_host (pinned host buffers; H2D, kernel, D2H, stream sync per call)"}
+
+    if rank == 0:
+        kern_ms = float(np.mean(lat_ms))
+        fl = float(np.mean(flops_per_batch[np.arange(k_lat) % nrot]))
+        achieved_tf = fl / (kern_ms * 1e-3) / 1e12
+        peak_tf = dfma_gflops / 1e3
+        io_bytes = B * ((in_s + out_s) * 8 + dg_s * 4)
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]; hbm_src = "measured"
+        except Exception:
+            hbm_peak = 6650.0; hbm_src = "fallback"
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, nrot),
+            "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
+            "latency_ms": {"p50": float(np.percentile(lat_ms, 50)), "p99": float(np.percentile(lat_ms, 99)),
+                           "max": float(lat_ms.max()), "what": f"one {B}-instance batch, one launch, CUDA events, {k_lat} samples"},
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "kernel": "body_mpc_kernel", "kernel_ms": kern_ms,
+                         "flops_per_launch": fl, "flops_per_solve": fl / B,
+                         "flops_def": "algorithmic flops of the dense reference algorithm along each problem's path "
+                                      "(SURVEY.md 8d formula, counted per problem in-kernel)",
+                         "peak_source": "measured live on this GPU: register-resident DFMA loop (go1mpc_measure_dfma_peak); "
+                                        "MEASURED_PEAKS.json has no FP64 figure",
+                         "hbm": {"achieved": io_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "peak_source": f"{hbm_src} (MEASURED_PEAKS.json)", "bytes_per_launch": io_bytes}},
+            "solver": {"mean_outer": float(mean_iters[0]), "mean_add": float(mean_iters[1]), "mean_drop": float(mean_iters[2]),
+                       "mean_degen": float(mean_iters[3]), "mean_l2a": float(mean_l2a)},
+            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(a)
+        print(json.dumps(line), flush=True)
+
+    if a.sweep and rank == 0:
+        for Bs in (256, 1024, 4096, 16384, 65536):
+            d = synth.body_mpc_inputs(Bs, nh, seed=1)
+            r = torch.from_numpy(q.pack_body_inputs(nh, d["tick"], d["tx"], d["theta"], d["bstate"], d["x_warm"], d["refs"])).to(dev)
+            o = torch.zeros(Bs, out_s, dtype=torch.float64, device=dev)
+            torch.cuda.synchronize()
+            for _ in range(3):
+                mpc.body_mpc_step(nh, Bs, r, o, None)
+            mpc.synchronize()
+            with torch.cuda.stream(stream):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for _ in range(20):
+                    mpc.body_mpc_step(nh, Bs, r, o, None)
+                e1.record(stream)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(f"sweep B={Bs}: {ms * 1e3:.1f} us/launch, {Bs / ms * 1e3:.3e} solves/s", file=sys.stderr)
+    mpc.close()
+    if dist:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

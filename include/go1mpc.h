@@ -61,8 +61,13 @@ enum {
     GO1MPC_QP_EQ_DEPENDENT = 5,  /* dependent equalities: early return         */
     GO1MPC_QP_SKIPPED = -1       /* front-end gated this tick: no solve ran    */
 };
-/* iters_d[b*4 + k] */
-enum { GO1MPC_IT_OUTER = 0, GO1MPC_IT_ADD = 1, GO1MPC_IT_DROP = 2, GO1MPC_IT_DEGEN = 3 };
+/* iters_d[b*GO1MPC_ITERS + k]: outer passes (step 1), constraints added, dropped,
+ * degenerate restarts, passes through step 2a, and the ALGORITHMIC flop count of the
+ * dense reference algorithm along the path this problem took (SURVEY.md section 8d:
+ * what the roofline figure uses; saturates at INT_MAX). */
+#define GO1MPC_ITERS 6
+enum { GO1MPC_IT_OUTER = 0, GO1MPC_IT_ADD = 1, GO1MPC_IT_DROP = 2, GO1MPC_IT_DEGEN = 3,
+       GO1MPC_IT_L2A = 4, GO1MPC_IT_FLOPS = 5 };
 
 /* Constants of the body-inclination MPC.  Defaults = the reference's
  * compile-time values: RT/Robotpara/robot_const_para_config.cpp:8-47,
@@ -97,6 +102,10 @@ const char *go1mpc_last_error(const go1mpc_t *h);
 int go1mpc_device(const go1mpc_t *h);
 /* number of kernels this handle has launched so far (bench's gpu_launches) */
 long long go1mpc_launch_count(const go1mpc_t *h);
+/* the handle's own cudaStream_t (as void*), e.g. to record timing events on it */
+void *go1mpc_stream(const go1mpc_t *h);
+/* multiprocessor count of the handle's device */
+int go1mpc_sm_count(const go1mpc_t *h);
 /* wait for the handle's stream */
 int go1mpc_synchronize(go1mpc_t *h);
 
@@ -105,7 +114,7 @@ int go1mpc_synchronize(go1mpc_t *h);
  *   QPBaseClass::solveQP            RT/QP/QPBaseClass.cpp:126-153
  *   Eigen::QP::solve_quadprog       RT/utils/EiQuadProg/EiQuadProg.cpp:493-513
  * Strides (doubles): G n*n, g0 n, CE n*p, ce0 p, CI n*m, ci0 m, x n, cost 1;
- * (ints): active m+p, nactive 1, iters 4, status 1.  CE_d/ce0_d may be NULL
+ * (ints): active m+p, nactive 1, iters GO1MPC_ITERS, status 1.  CE_d/ce0_d may be NULL
  * when p == 0.  x_d is in/out (left untouched when G is not PD, as the
  * reference does).  active_d/nactive_d/iters_d/cost_d may be NULL.
  * Limits: n <= 96, m + p <= 1024.
@@ -150,7 +159,8 @@ int go1mpc_qp_solve_batch_host(go1mpc_t *h, int n, int p, int m, int B,
  *          (+pad to an even count)
  * diag_d [B][go1mpc_body_diag_stride(nh)] ints (may be NULL):
  *          [0] status  [1] nactive  [2,6) iters  [6] bjx1  [7] bjx2
- *          [8, 8+2nh) final active set (constraint indices, Appendix E of SURVEY.md)
+ *          [8] passes through step 2a  [9] algorithmic flops (GO1MPC_IT_FLOPS)
+ *          [10, 10+2nh) final active set (constraint indices, Appendix E of SURVEY.md)
  * Supported nh: 3..40 (the reference compiles nh = 4).
  * ------------------------------------------------------------------------ */
 int go1mpc_body_in_stride(int nh);

@@ -13,11 +13,16 @@ c_int_p = ctypes.POINTER(ctypes.c_int)
 EXPORTED_SYMBOLS = [
     "go1mpc_version", "go1mpc_config_default", "go1mpc_create", "go1mpc_destroy",
     "go1mpc_last_error", "go1mpc_device", "go1mpc_launch_count", "go1mpc_synchronize",
+    "go1mpc_stream", "go1mpc_sm_count",
     "go1mpc_qp_solve_batch", "go1mpc_qp_solve_batch_host",
     "go1mpc_body_in_stride", "go1mpc_body_out_stride", "go1mpc_body_diag_stride",
     "go1mpc_body_mpc_step_batch", "go1mpc_body_mpc_step_batch_host",
     "go1mpc_body_model", "go1mpc_body_default_tx", "go1mpc_measure_dfma_peak",
 ]
+
+
+QP_ITERS = 6           # GO1MPC_ITERS
+BODY_DIAG_ACTIVE = 10  # first int of the final active set in a body-MPC diag record
 
 
 class Go1MpcError(RuntimeError):
@@ -67,6 +72,9 @@ def load_library():
     lib.go1mpc_destroy.restype = None
     lib.go1mpc_device.argtypes = [ctypes.c_void_p]
     lib.go1mpc_synchronize.argtypes = [ctypes.c_void_p]
+    lib.go1mpc_stream.argtypes = [ctypes.c_void_p]
+    lib.go1mpc_stream.restype = ctypes.c_void_p
+    lib.go1mpc_sm_count.argtypes = [ctypes.c_void_p]
     vp = ctypes.c_void_p
     lib.go1mpc_qp_solve_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 12 + [vp]
     lib.go1mpc_qp_solve_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 12
@@ -90,7 +98,7 @@ def body_out_stride(nh):
 
 
 def body_diag_stride(nh):
-    return 8 + 2 * nh
+    return BODY_DIAG_ACTIVE + 2 * nh
 
 
 def pack_body_inputs(nh, tick, tx, theta, bodyangle_state, x_warm, refs):
@@ -166,6 +174,15 @@ class Go1Mpc:
     @property
     def launch_count(self):
         return int(self.lib.go1mpc_launch_count(self.h))
+
+    @property
+    def stream(self):
+        """Raw cudaStream_t of the handle (int), usable with torch.cuda.ExternalStream."""
+        return int(self.lib.go1mpc_stream(self.h) or 0)
+
+    @property
+    def sm_count(self):
+        return int(self.lib.go1mpc_sm_count(self.h))
 
     def synchronize(self):
         self._check(self.lib.go1mpc_synchronize(self.h), "synchronize")

@@ -228,6 +228,8 @@ void go1mpc_destroy(go1mpc_t* h) {
 const char* go1mpc_last_error(const go1mpc_t* h) { return h ? h->err.c_str() : "null handle"; }
 int go1mpc_device(const go1mpc_t* h) { return h ? h->device : -1; }
 long long go1mpc_launch_count(const go1mpc_t* h) { return h ? h->launches : 0; }
+void* go1mpc_stream(const go1mpc_t* h) { return h ? (void*)h->stream : nullptr; }
+int go1mpc_sm_count(const go1mpc_t* h) { return h ? h->sms : 0; }
 int go1mpc_synchronize(go1mpc_t* h) {
   if (!h) return GO1MPC_E_INVALID;
   CU(h, cudaStreamSynchronize(h->stream));
@@ -281,7 +283,7 @@ int go1mpc_qp_solve_batch_host(go1mpc_t* h, int n, int p, int m, int B, const do
   if ((rc = stage_buf(h, 7, b * szd, &dcost))) return rc;
   if ((rc = stage_buf(h, 8, b * (m + p + 1) * szi, &dact))) return rc;
   if ((rc = stage_buf(h, 9, b * szi, &dna))) return rc;
-  if ((rc = stage_buf(h, 10, b * 4 * szi, &dit))) return rc;
+  if ((rc = stage_buf(h, 10, b * 6 * szi, &dit))) return rc;
   if ((rc = stage_buf(h, 11, b * szi, &dst))) return rc;
   cudaStream_t st = h->stream;
   CU(h, cudaMemcpyAsync(dG, G, b * n * n * szd, cudaMemcpyHostToDevice, st));
@@ -296,7 +298,7 @@ int go1mpc_qp_solve_batch_host(go1mpc_t* h, int n, int p, int m, int B, const do
   if (cost) CU(h, cudaMemcpyAsync(cost, dcost, b * szd, cudaMemcpyDeviceToHost, st));
   if (active) CU(h, cudaMemcpyAsync(active, dact, b * (m + p) * szi, cudaMemcpyDeviceToHost, st));
   if (nactive) CU(h, cudaMemcpyAsync(nactive, dna, b * szi, cudaMemcpyDeviceToHost, st));
-  if (iters) CU(h, cudaMemcpyAsync(iters, dit, b * 4 * szi, cudaMemcpyDeviceToHost, st));
+  if (iters) CU(h, cudaMemcpyAsync(iters, dit, b * 6 * szi, cudaMemcpyDeviceToHost, st));
   if (status) CU(h, cudaMemcpyAsync(status, dst, b * szi, cudaMemcpyDeviceToHost, st));
   CU(h, cudaStreamSynchronize(st));
   return GO1MPC_OK;
@@ -305,7 +307,7 @@ int go1mpc_qp_solve_batch_host(go1mpc_t* h, int n, int p, int m, int B, const do
 // ------------------------------------------------------------------ body MPC
 int go1mpc_body_in_stride(int nh) { int s = 36 + 11 * nh; return (s + 1) & ~1; }
 int go1mpc_body_out_stride(int nh) { int s = 18 + 2 * nh + 1; return (s + 1) & ~1; }
-int go1mpc_body_diag_stride(int nh) { return 8 + 2 * nh; }
+int go1mpc_body_diag_stride(int nh) { return 10 + 2 * nh; }
 
 int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, double* out_d, int* diag_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;

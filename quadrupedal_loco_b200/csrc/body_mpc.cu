@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(WPC * 32) body_mpc_kernel(BodyKParams P) {
 
     int status = -1, nactive = 0, bjx1 = 0, bjx2 = 0;
     GiResult res; res.f = 0.0; res.iq = 0; res.status = -1;
-    res.it_outer = res.it_add = res.it_drop = res.it_degen = 0;
+    res.it_outer = res.it_add = res.it_drop = res.it_degen = res.it_l2a = 0;
+    res.flops = 0;
 
     bool live = false;
     int i = tick;
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(WPC * 32) body_mpc_kernel(BodyKParams P) {
       for (int t = lane; t < n * w.ld; t += 32) w.J[t] = 0.0;
       __syncwarp();
 
+      res.flops = gi_flops_setup(n, 0);
       if (!gi_llt(w, nh, lane)) {
         status = ST_NOT_PD;   // x keeps the warm start, exactly as the reference
         res.f = CUDART_INF;
@@ -298,8 +300,9 @@ __global__ void __launch_bounds__(WPC * 32) body_mpc_kernel(BodyKParams P) {
         dg[0] = status; dg[1] = nactive;
         dg[2] = res.it_outer; dg[3] = res.it_add; dg[4] = res.it_drop; dg[5] = res.it_degen;
         dg[6] = bjx1; dg[7] = bjx2;
+        dg[8] = res.it_l2a; dg[9] = (int)(res.flops > 0x7fffffffull ? 0x7fffffffull : res.flops);
       }
-      for (int k = lane; k < n; k += 32) dg[8 + k] = (k < nactive) ? w.A[k] : -1;
+      for (int k = lane; k < n; k += 32) dg[10 + k] = (k < nactive) ? w.A[k] : -1;
     }
     if (lane == 0) tma_store_wait_read();   // outrec may be overwritten by the next instance
     __syncwarp();

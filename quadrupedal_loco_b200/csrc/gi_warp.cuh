@@ -191,9 +191,9 @@ __device__ inline bool gi_add_constraint(const GiWs& w, int& iq, double& R_norm,
 }
 
 // EiQuadProg.cpp:95-170.  Returns false when l is not in A[p..iq) (UB in the reference).
-__device__ inline bool gi_delete_constraint(const GiWs& w, int& iq, int l, int lane) {
+__device__ inline bool gi_delete_constraint(const GiWs& w, int& iq, int l, int lane, int& qq) {
   const int n = w.n, ld = w.ld, p = w.p;
-  int qq = -1;
+  qq = -1;
   for (int base = p; base < iq; base += 32) {
     int i = base + lane;
     unsigned hit = __ballot_sync(FULL_MASK, i < iq && w.A[i] == l);
@@ -291,7 +291,15 @@ __device__ inline void gi_inv_lt(const GiWs& w, int nb, int off, int lane) {
 //   double eval_one(const GiWs& w, int ip, int lane)        -- CI(:,ip).x + ci0(ip), warp-uniform result
 //   void load_eq(const GiWs& w, int i, int lane, bool& allzero) -- n+ = CE(:, i)   (only used when p > 0)
 //   double ce0(int i)
-struct GiResult { double f; int iq; int status; int it_outer, it_add, it_drop, it_degen; };
+// it_l2a counts passes through step 2a; flops is the ALGORITHMIC flop count of the dense
+// reference algorithm for the path this problem took (SURVEY.md section 8d formula, one
+// multiply-add = 2 flop) -- what bench.py's roofline uses, not the instructions executed.
+struct GiResult { double f; int iq; int status; int it_outer, it_add, it_drop, it_degen, it_l2a; unsigned long long flops; };
+
+__host__ __device__ inline unsigned long long gi_flops_setup(int n, int p) {
+  unsigned long long N = n;
+  return N * N * N / 3 + N * N * N / 3 + 2 * N * N + (unsigned long long)p * 4 * N * N;
+}
 
 // Main loop.  Requires: w.J = L^-T, w.R = 0, w.x = unconstrained minimiser, res.f = its cost.
 template <class Pol>
@@ -300,7 +308,8 @@ __device__ inline void gi_loop(const GiWs& w, Pol& pol, double c1, double c2, in
   const double inf = CUDART_INF;
   double R_norm = 1.0, f_value = res.f;
   int iq = 0, status = ST_OK;
-  int it_outer = 0, it_add = 0, it_drop = 0, it_degen = 0;
+  int it_outer = 0, it_add = 0, it_drop = 0, it_degen = 0, it_l2a = 0, qq = 0;
+  unsigned long long flops = res.flops;
   unsigned inA = 0u, excl = 0u;  // bit t <-> constraint lane + 32 t
 
   for (int t = lane; t < n + 2; t += 32) { w.u[t] = 0.0; w.uold[t] = 0.0; w.A[t] = 0; w.Aold[t] = 0; w.r[t] = 0.0; }
@@ -335,6 +344,7 @@ __device__ inline void gi_loop(const GiWs& w, Pol& pol, double c1, double c2, in
       if (phase == PH_L1) {
         // EiQuadProg.cpp:282-320
         it_outer++;
+        flops += 2ull * n * m;
         for (int i = me; i < iq; i++) { int c = w.A[i]; if ((c & 31) == lane) inA |= 1u << (c >> 5); }
         excl = 0u;
         double psi = 0.0;
@@ -365,6 +375,8 @@ __device__ inline void gi_loop(const GiWs& w, Pol& pol, double c1, double c2, in
       }
       // PH_L2A: EiQuadProg.cpp:349-490
       if (++passes > cap) { status = ST_ITER_CAP; break; }
+      it_l2a++;
+      flops += 2ull * n * n + 2ull * n * (n - iq) + (unsigned long long)iq * iq + 4ull * n + 2ull * iq;
       gi_compute_d(w, klo, khi, lane);
       gi_update_z(w, iq, lane);
       gi_update_r(w, iq, lane);
@@ -387,8 +399,9 @@ __device__ inline void gi_loop(const GiWs& w, Pol& pol, double c1, double c2, in
         if (lane == 0) w.u[iq] += t;
         if ((l & 31) == lane) inA &= ~(1u << (l >> 5));
         __syncwarp();
-        if (!gi_delete_constraint(w, iq, l, lane)) { status = ST_ITER_CAP; break; }
+        if (!gi_delete_constraint(w, iq, l, lane, qq)) { status = ST_ITER_CAP; break; }
         it_drop++;
+        flops += 3ull * (iq - qq) * (iq - qq) + 6ull * n * (iq - qq);
         continue;
       }
       // case (iii): step in primal and dual space
@@ -400,11 +413,12 @@ __device__ inline void gi_loop(const GiWs& w, Pol& pol, double c1, double c2, in
       if (lane == 0) w.u[iq] = uiq + t;
       __syncwarp();
       if (t == t2) {
+        flops += 6ull * n * (n - iq - 1 > 0 ? n - iq - 1 : 0);
         if (!gi_add_constraint(w, iq, R_norm, lane)) {
           // EiQuadProg.cpp:444-462 degenerate: exclude ip, restore the state saved at l1
           it_degen++;
           if ((ip & 31) == lane) excl |= 1u << (ip >> 5);
-          if (!gi_delete_constraint(w, iq, ip, lane)) { status = ST_ITER_CAP; break; }
+          if (!gi_delete_constraint(w, iq, ip, lane, qq)) { status = ST_ITER_CAP; break; }
           inA = 0u;
           for (int t3 = lane; t3 < iq; t3 += 32) { w.A[t3] = w.Aold[t3]; w.u[t3] = w.uold[t3]; }
           for (int k = lane; k < n; k += 32) w.x[k] = w.xold[k];
@@ -420,8 +434,9 @@ __device__ inline void gi_loop(const GiWs& w, Pol& pol, double c1, double c2, in
       }
       // partial step: drop l, recompute s(ip), stay in 2a   (EiQuadProg.cpp:477-490)
       if ((l & 31) == lane) inA &= ~(1u << (l >> 5));
-      if (!gi_delete_constraint(w, iq, l, lane)) { status = ST_ITER_CAP; break; }
+      if (!gi_delete_constraint(w, iq, l, lane, qq)) { status = ST_ITER_CAP; break; }
       it_drop++;
+      flops += 3ull * (iq - qq) * (iq - qq) + 6ull * n * (iq - qq);
       {
         double sv = pol.eval_one(w, ip, lane);
         if (lane == 0) w.s[ip] = sv;
@@ -432,6 +447,7 @@ __device__ inline void gi_loop(const GiWs& w, Pol& pol, double c1, double c2, in
 done:
   res.f = f_value; res.iq = iq; res.status = status;
   res.it_outer = it_outer; res.it_add = it_add; res.it_drop = it_drop; res.it_degen = it_degen;
+  res.it_l2a = it_l2a; res.flops = flops;
 }
 
 }  // namespace go1

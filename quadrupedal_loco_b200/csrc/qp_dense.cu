@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(WPC * 32) dense_qp_kernel(DenseKParams P) {
     for (int t = lane; t < n * w.ld; t += 32) w.J[t] = 0.0;
     __syncwarp();
     GiResult res; res.f = 0.0; res.iq = 0; res.status = ST_OK;
-    res.it_outer = res.it_add = res.it_drop = res.it_degen = 0;
+    res.it_outer = res.it_add = res.it_drop = res.it_degen = res.it_l2a = 0;
+    res.flops = gi_flops_setup(n, p);
     bool pd = gi_llt(w, n, lane);
     if (!pd) {
       res.status = ST_NOT_PD; res.f = CUDART_INF;   // x untouched (EiQuadProg.cpp:507-510)
@@ -103,8 +104,9 @@ __global__ void __launch_bounds__(WPC * 32) dense_qp_kernel(DenseKParams P) {
     if (P.status && lane == 0) P.status[b] = res.status;
     if (P.nactive && lane == 0) P.nactive[b] = pd ? res.iq : 0;
     if (P.iters && lane == 0) {
-      int* it = P.iters + (size_t)b * 4;
+      int* it = P.iters + (size_t)b * 6;
       it[0] = res.it_outer; it[1] = res.it_add; it[2] = res.it_drop; it[3] = res.it_degen;
+      it[4] = res.it_l2a; it[5] = (int)(res.flops > 0x7fffffffull ? 0x7fffffffull : res.flops);
     }
     if (P.active) {
       int* ag = P.active + (size_t)b * (m + p);

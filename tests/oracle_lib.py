@@ -30,12 +30,16 @@ class BodyCfg(ctypes.Structure):
                 ("gama_zmp", ctypes.c_double), ("lamda", ctypes.c_double * 4)]
 
 
-def build_oracle():
-    so = os.path.join(ORC_DIR, "liboracle.so")
+def build_oracle(fast=False):
+    """liboracle.so: -O2 -ffp-contract=off (the checker).  fast=True: liboracle_fast.so, the same
+    sources at -O3 -march=native for the CPU-baseline timing; always rebuilt on the machine that
+    times it (it is never shipped: -march=native code may not run elsewhere)."""
+    name = "liboracle_fast.so" if fast else "liboracle.so"
+    so = os.path.join(ORC_DIR, name)
     srcs = [os.path.join(ORC_DIR, f) for f in os.listdir(ORC_DIR) if f.endswith((".c", ".h"))]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+    if fast or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-        subprocess.run(["make", "-C", ORC_DIR, "liboracle.so"], check=True, env=env, capture_output=True)
+        subprocess.run(["make", "-B" if fast else "-s", "-C", ORC_DIR, name], check=True, env=env, capture_output=True)
     return so
 
 
@@ -45,8 +49,8 @@ def ref_path(name):
 
 
 class Oracle:
-    def __init__(self):
-        self.lib = ctypes.CDLL(build_oracle())
+    def __init__(self, fast=False):
+        self.lib = ctypes.CDLL(build_oracle(fast))
 
     def qp_solve(self, n, p, m, G, g0, CE, ce0, CI, ci0, x0=None):
         """Column-major flat inputs for ONE problem.  Returns dict."""
