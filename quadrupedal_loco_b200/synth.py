@@ -22,12 +22,19 @@ def default_tx(tstep=0.7, dt_slow=0.025, n=27):
     return tx
 
 
-def body_mpc_inputs(B, nh, seed=SEED_CFG2, scale=1.0, tick_lo=100, tick_hi=1700):
+def body_mpc_inputs(B, nh, seed=SEED_CFG2, scale=1.0, tick_lo=100, tick_hi=1700, ref_amp=0.25):
     """cfg2-style body-MPC batch: randomised body-angle state, tick and reference windows.
 
     Returns dict(tick [B] i32, tx [B,27], theta [B,4], bstate [B,4], x_warm [B,2nh], refs [B,9,nh]).
     theta ~ U(+-0.12 rad), theta_dot ~ U(+-1.0 rad/s) (times `scale`), zmp_ref = support-foot
-    centre + U(+-0.01), bodyangle_ref ~ U(+-0.05) (smooth over the window), comacc_z ~ U(+-2).
+    centre + U(+-0.01), comacc_z ~ U(+-2), and the commanded body inclination
+    bodyangle_ref ~ U(+-ref_amp) (offset + slope over the window).  With the reference's weights
+    (beta = 5e9 on angle tracking) the controller is near dead-beat, so a command inside the
+    +-10 deg limit never activates a constraint (every solve ends after the unconstrained step);
+    ref_amp = 0.25 rad lets about 60 % of the instances command an inclination beyond the limit
+    or a move that saturates the torque bound, which is what exercises the active-set
+    iteration (mean ~4 constraints added, up to 16 at nh = 10).  scale > 1.5 additionally
+    starts some instances outside the angle limit (infeasible solves, status 2).
     """
     rng = np.random.Generator(np.random.Philox(seed))
     tick = rng.integers(tick_lo, tick_hi + 1, size=B).astype(np.int32)
@@ -53,7 +60,7 @@ def body_mpc_inputs(B, nh, seed=SEED_CFG2, scale=1.0, tick_lo=100, tick_hi=1700)
     refs[:, 0, :] = zc[:, 0:1] + rng.uniform(-0.01, 0.01, (B, nh)) * scale
     refs[:, 1, :] = zc[:, 1:2] + rng.uniform(-0.01, 0.01, (B, nh)) * scale
     # body-angle reference: offset + slope over the window
-    a0 = rng.uniform(-0.05, 0.05, (B, 2)) * scale
+    a0 = rng.uniform(-ref_amp, ref_amp, (B, 2)) * scale
     a1 = rng.uniform(-0.02, 0.02, (B, 2)) * scale
     ramp = np.linspace(0.0, 1.0, nh)[None, :]
     refs[:, 2, :] = a0[:, 0:1] + a1[:, 0:1] * ramp
