@@ -1,0 +1,114 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference sources compiled into
+oracle/_ref/ (recipe: oracle/Makefile; needs /root/reference, so it only runs in the
+authoring container).  The fixtures pin the oracle (tests/test_oracle_vs_ref.py) and give the
+GPU tests reference-made outputs on the box, where /root/reference does not exist.
+
+    python tests/golden/make_golden.py
+
+Inputs are regenerated from seeds by quadrupedal_loco_b200.synth (stored too, so a change of
+the generators cannot silently re-pin); outputs come from:
+  ref_qp_solve        -> Eigen::QP::solve_quadprog        RT/src/utils/EiQuadProg/EiQuadProg.cpp:493-513
+  ref_body_theta_mpc  -> PRMPCClass::body_theta_mpc       RT/src/FastMPC/PRMPCClass.cpp:379-714 (nh = 4)
+  ref_fk/_g, ref_ik/_g-> Kinematicclass                   GO1/src/kinematics/Kinematics.cpp:63-304
+"""
+import ctypes
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from quadrupedal_loco_b200 import synth  # noqa: E402
+from tests.oracle_lib import P, PI, ref_path  # noqa: E402
+
+QP_CASES = [  # (n, p, m, B, seed, kwargs)
+    (4, 1, 24, 32, 1001, dict(paired=True)),
+    (8, 0, 48, 32, 1002, dict(paired=True)),
+    (12, 2, 24, 24, 1003, dict(paired=True)),
+    (20, 0, 120, 16, 1004, dict(paired=True)),
+    (6, 0, 14, 48, 1005, dict(dup=True, infeasible_frac=0.3)),
+    (5, 0, 9, 24, 1006, dict()),
+]
+
+
+def gen_qp(lib):
+    out = {}
+    for ci, (n, p, m, B, seed, kw) in enumerate(QP_CASES):
+        d = synth.random_qp(B, n, p, m, seed=seed, **kw)
+        x = np.zeros((B, n)); cost = np.zeros(B); act = np.zeros((B, m + p + 1), np.int32); na = np.zeros(B, np.int32)
+        for b in range(B):
+            xb = np.zeros(n); cb = np.zeros(1); ab = np.zeros(m + p + 1, np.int32); nb = np.zeros(1, np.int32)
+            lib.ref_qp_solve(n, p, m, P(d["G"][b].copy()), P(d["g0"][b].copy()), P(d["CE"][b].copy()), P(d["ce0"][b].copy()),
+                             P(d["CI"][b].copy()), P(d["ci0"][b].copy()), P(xb), P(cb), PI(ab), PI(nb))
+            x[b] = xb; cost[b] = cb[0]; act[b] = ab; na[b] = nb[0]
+        for k in ("G", "g0", "CE", "ce0", "CI", "ci0"):
+            out[f"c{ci}_{k}"] = d[k]
+        out[f"c{ci}_x"] = x; out[f"c{ci}_cost"] = cost; out[f"c{ci}_active"] = act; out[f"c{ci}_nactive"] = na
+        out[f"c{ci}_shape"] = np.array([n, p, m, B, seed])
+    np.savez_compressed(os.path.join(HERE, "qp_ref.npz"), **out)
+    print("qp_ref.npz", {k: v.shape for k, v in out.items() if k.endswith("_x")})
+
+
+def gen_body(rt):
+    nh = rt.ref_body_nh()
+    assert nh == 4
+    B, T = 48, 40
+    d = synth.body_mpc_inputs(B, nh, seed=2001, scale=1.3)
+    d["tick"][:] = 150 + 37 * np.arange(B)            # spread over the walk, crossing step switches
+    d["tick"][:4] = [0, 50, 99, 100]                  # gated ticks and the first live one
+    theta = d["theta"].copy(); vini = d["x_warm"].copy()
+    o14 = np.zeros((T, B, 14)); th_t = np.zeros((T, B, 4)); v_t = np.zeros((T, B, 2 * nh)); ok = np.zeros((T, B), np.int32)
+    tick0 = d["tick"].copy()
+    rt.ref_body_new.restype = ctypes.c_void_p
+    hs = [ctypes.c_void_p(rt.ref_body_new()) for _ in range(B)]
+    for b in range(B):
+        rt.ref_body_set_state(hs[b], P(d["tx"][b].copy()), P(theta[b].copy()), P(vini[b].copy()))
+    for t in range(T):
+        for b in range(B):
+            r = d["refs"][b]
+            o = np.zeros(14); q = np.zeros(1, np.int32)
+            zmp = np.ascontiguousarray(r[0:2].ravel()); ang = np.ascontiguousarray(r[2:4].ravel())
+            rf = np.ascontiguousarray(r[4:6].ravel()); lf = np.ascontiguousarray(r[6:8].ravel()); ca = np.ascontiguousarray(r[8])
+            rt.ref_body_theta_mpc(hs[b], int(tick0[b] + t), P(d["bstate"][b].copy()), P(zmp), P(ang), P(rf), P(lf), P(ca), P(o), PI(q))
+            tx = np.zeros(27); st = np.zeros(4); vi = np.zeros(2 * nh)
+            rt.ref_body_get_state(hs[b], P(tx), P(st), P(vi))
+            o14[t, b] = o; th_t[t, b] = st; v_t[t, b] = vi; ok[t, b] = q[0]
+    for h in hs:
+        rt.ref_body_free(h)
+    np.savez_compressed(os.path.join(HERE, "body_ref_nh4.npz"), tick0=tick0, tx=d["tx"], theta0=d["theta"], bstate=d["bstate"],
+                        refs=d["refs"], out14=o14, theta=th_t, vini=v_t, qp_ok=ok)
+    print("body_ref_nh4.npz", o14.shape, "live ticks:", int((np.abs(o14).sum(axis=2) > 0).sum()))
+
+
+def gen_kin(lib):
+    rng = np.random.Generator(np.random.Philox(3001))
+    N = 64
+    q = np.stack([rng.uniform(-0.6, 0.6, N), rng.uniform(0.2, 1.4, N), rng.uniform(-2.2, -0.9, N)], 1)
+    q[0] = [0, 0.6, -1.0]          # kinematics_matlab/forward_kin_go1.m demo pose
+    q[1] = [0, 0.87, -1.5]         # homing pose, servo.cpp:767
+    q[2] = [0, 0.67, -1.3]         # stand pose, body.cpp:42-43
+    bp = rng.uniform(-0.05, 0.05, (N, 3)) + [0, 0, 0.31]; br = rng.uniform(-0.2, 0.2, (N, 3))
+    leg = (np.arange(N) % 4).astype(np.int32)
+    fk = np.zeros((N, 3)); fkJ = np.zeros((N, 9)); fkg = np.zeros((N, 3)); fkgJ = np.zeros((N, 9))
+    for i in range(N):
+        lib.ref_fk(P(q[i].copy()), int(leg[i]), P(fk[i]), P(fkJ[i]))
+        lib.ref_fk_g(P(bp[i].copy()), P(br[i].copy()), P(q[i].copy()), int(leg[i]), P(fkg[i]), P(fkgJ[i]))
+    # IK: targets = FK of the pose, start from a perturbed pose
+    qini = q + rng.uniform(-0.15, 0.15, (N, 3))
+    ik = np.zeros((N, 3)); ikJ = np.zeros((N, 9)); ikg = np.zeros((N, 3)); ikgJ = np.zeros((N, 9))
+    for i in range(N):
+        lib.ref_ik(P(fk[i].copy()), P(qini[i].copy()), int(leg[i]), P(ik[i]), P(ikJ[i]))
+        lib.ref_ik_g(P(bp[i].copy()), P(br[i].copy()), P(fkg[i].copy()), P(qini[i].copy()), int(leg[i]), P(ikg[i]), P(ikgJ[i]))
+    np.savez_compressed(os.path.join(HERE, "kin_ref.npz"), q=q, bp=bp, br=br, leg=leg, qini=qini, fk=fk, fkJ=fkJ, fkg=fkg,
+                        fkgJ=fkgJ, ik=ik, ikJ=ikJ, ikg=ikg, ikgJ=ikgJ)
+    print("kin_ref.npz", N)
+
+
+if __name__ == "__main__":
+    ref, rt = ref_path("libref.so"), ref_path("libref_rt.so")
+    if not ref or not rt:
+        raise SystemExit("oracle/_ref is missing: run `make -C oracle ref` where /root/reference exists")
+    lib = ctypes.CDLL(ref); rtl = ctypes.CDLL(rt)
+    gen_qp(lib); gen_body(rtl); gen_kin(lib)
