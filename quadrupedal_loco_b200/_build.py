@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgo1mpc.so")
-SOURCES = ["api.cu", "body_mpc.cu", "qp_dense.cu"]
+SOURCES = ["api.cu", "body_mpc.cu", "body_fast.cu", "qp_dense.cu"]
 HEADERS = ["gi_warp.cuh", "tma.cuh", "kernels.h", os.path.join("..", "..", "include", "go1mpc.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -33,7 +33,8 @@ def build(force=False, verbose=False):
     """Compile every CUDA source into quadrupedal_loco_b200/libgo1mpc.so."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    extra = os.environ.get("GO1MPC_NVCC_EXTRA", "").split()
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     # the image exports CC/CXX=/opt/gcc/bin/* whose link line picks a static libstdc++;
     # let nvcc use the PATH host compiler instead
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <map>
 #include <string>
@@ -42,7 +43,11 @@ struct go1mpc {
   long long launches = 0;
   std::map<int, BodyModel> body_models;
   DevBuf stage[16];   // device staging for the *_host entry points
+  int* sched_d = nullptr;          // ring of {next, done} counter pairs for body_fast launches
+  unsigned sched_next = 0;
+  bool force_generic = false;      // GO1MPC_FORCE_GENERIC=1: always use the run-time-sized kernel
 };
+static const int kSchedRing = 64;
 
 namespace {
 
@@ -212,6 +217,13 @@ int go1mpc_create(const Go1MpcConfig* cfg, int device, go1mpc_t** out) {
   }
   h->sms = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
+  if (cudaMalloc(&h->sched_d, sizeof(int) * 2 * kSchedRing) != cudaSuccess ||
+      cudaMemset(h->sched_d, 0, sizeof(int) * 2 * kSchedRing) != cudaSuccess) {
+    go1mpc_destroy(h);
+    return GO1MPC_E_CUDA;
+  }
+  const char* fg = getenv("GO1MPC_FORCE_GENERIC");
+  h->force_generic = fg && fg[0] == '1';
   *out = h;
   return GO1MPC_OK;
 }
@@ -221,6 +233,7 @@ void go1mpc_destroy(go1mpc_t* h) {
   cudaSetDevice(h->device);
   for (auto& kv : h->body_models) if (kv.second.tab_d) cudaFree(kv.second.tab_d);
   for (DevBuf& b : h->stage) if (b.p) cudaFree(b.p);
+  if (h->sched_d) cudaFree(h->sched_d);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -321,6 +334,21 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
   int rc = get_body_model(h, nh, &M);
   if (rc) return rc;
   const int is = go1mpc_body_in_stride(nh), os = go1mpc_body_out_stride(nh);
+  if (body_fast_supported(nh) && !h->force_generic) {
+    const Go1BodyMpcConfig& c = h->cfg.body;
+    BodyKParams P;
+    P.nh = nh; P.B = B; P.in_stride = is; P.out_stride = os; P.diag_stride = go1mpc_body_diag_stride(nh);
+    P.tab_doubles = M->tab_doubles; P.warp_doubles = 0;
+    P.cap_scale = h->cfg.qp_iter_cap_scale; P.gate = M->gate; P.nstepx = M->nstepx; P.nsum_mpc = M->nsum_mpc;
+    P.in = in_d; P.out = out_d; P.diag = diag_d; P.tab = M->tab_d;
+    P.sched = h->sched_d + 2 * (h->sched_next++ % kSchedRing);
+    P.dt_mpc = c.dt_mpc; P.j_ini = c.j_ini; P.mass = c.mass; P.g = c.g; P.gama = c.gama_zmp;
+    P.theta_lim = c.theta_lim; P.torque_lim = c.torque_lim;
+    for (int k = 0; k < 4; k++) P.lamda[k] = c.lamda[k];
+    CU(h, body_fast_launch(P, h->sms, st));
+    h->launches++;
+    return GO1MPC_OK;
+  }
   int wpc = 4, wd = 0;
   size_t smem = body_smem_bytes(nh, wpc, is, os, M->tab_doubles, &wd);
   while (wpc > 1 && smem > h->smem_optin / 2) { wpc >>= 1; smem = body_smem_bytes(nh, wpc, is, os, M->tab_doubles, &wd); }
@@ -335,7 +363,7 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
   P.nh = nh; P.B = B; P.in_stride = is; P.out_stride = os; P.diag_stride = go1mpc_body_diag_stride(nh);
   P.tab_doubles = M->tab_doubles; P.warp_doubles = wd;
   P.cap_scale = h->cfg.qp_iter_cap_scale; P.gate = M->gate; P.nstepx = M->nstepx; P.nsum_mpc = M->nsum_mpc;
-  P.in = in_d; P.out = out_d; P.diag = diag_d; P.tab = M->tab_d;
+  P.in = in_d; P.out = out_d; P.diag = diag_d; P.tab = M->tab_d; P.sched = nullptr;
   P.dt_mpc = c.dt_mpc; P.j_ini = c.j_ini; P.mass = c.mass; P.g = c.g; P.gama = c.gama_zmp;
   P.theta_lim = c.theta_lim; P.torque_lim = c.torque_lim;
   for (int k = 0; k < 4; k++) P.lamda[k] = c.lamda[k];

@@ -14,12 +14,16 @@ struct BodyKParams {
   double* out;
   int* diag;
   const double* tab;
+  int* sched;          // body_fast only: {next instance, warps finished}, zero between launches
   double dt_mpc, j_ini, mass, g, gama, theta_lim, torque_lim;
   double lamda[4];
 };
 size_t body_smem_bytes(int nh, int wpc, int in_stride, int out_stride, int tab_doubles, int* warp_doubles);
 cudaError_t body_mpc_launch(BodyKParams P, int wpc, int grid, size_t smem, cudaStream_t st);
 cudaError_t body_mpc_occupancy(int wpc, size_t smem, int* blocks_per_sm);
+// compile-time-horizon kernel (body_fast.cu); in/out strides and the table size must be the ABI's
+bool body_fast_supported(int nh);
+cudaError_t body_fast_launch(BodyKParams P, int sms, cudaStream_t st);
 
 struct DenseKParams {
   int n, p, m, B, cap;
