@@ -48,7 +48,8 @@ _LIB = None
 
 
 def library_path():
-    return _build.LIB
+    """In-tree libgo1mpc.so; GO1MPC_LIB overrides it (A/B runs of differently tuned builds)."""
+    return os.environ.get("GO1MPC_LIB") or _build.LIB
 
 
 def load_library():

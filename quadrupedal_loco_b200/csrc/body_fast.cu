@@ -28,7 +28,7 @@
 #include "kernels.h"
 
 #ifndef GO1_FAST_WARPS
-#define GO1_FAST_WARPS 24   // resident warps per SM the NH <= 10 instantiations are register-limited to
+#define GO1_FAST_WARPS 16   // resident warps per SM the NH <= 10 instantiations are register-limited to (128 regs: no spills; measured faster than 20/24/28)
 #endif
 
 namespace go1 {
