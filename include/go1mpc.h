@@ -85,8 +85,25 @@ typedef struct {
     double lamda[4];             /* state feedback gains (all 0 as shipped)    */
 } Go1BodyMpcConfig;
 
+/* Constants of the step-location / step-timing SQP.  Defaults = the reference's values:
+ * NLP/NLP/NLPClass_sqp.cpp:212-214,244-258,273-286 (go1 weights), NLP/NLP/NLPClass.h:30-38,
+ * NLP/NLPRTControl/NLPRTControlClass.cpp:35-42. */
+typedef struct {
+    double dt;                   /* 0.025  _dt                                  */
+    double Wn;                   /* sqrt(g / hcom), hcom = 0.309458             */
+    double ggg;                  /* 9.8                                         */
+    double t_min, t_max;         /* 0.5, 1.0  step-period bounds                */
+    double footx_max, footx_min; /* 0.15, -0.05                                 */
+    double footx_vmax, footx_vmin, footy_vmax, footy_vmin;  /* 3, -2.875, 2, -1 */
+    double comax_max, comax_min, comay_max, comay_min;      /* 5, -5, 6, -6     */
+    double aax, aay, aaxv, aayv, bbx, bby, rr1, rr2;        /* 5e4 5e4 1e3 5e2 2e6 1e7 1e6 1e6 */
+    double half_hip_width, foot_width;                       /* 0.12675, 0.03    */
+    double lamda[4];             /* com x, vx, y, vy feedback gains (0 as shipped) */
+} Go1StepMpcConfig;
+
 typedef struct {
     Go1BodyMpcConfig body;
+    Go1StepMpcConfig step;
     int qp_iter_cap_scale;       /* cap on step-2a passes = scale*(n+m+p)+50; default 20 */
     int reserved[7];
 } Go1MpcConfig;
@@ -178,6 +195,48 @@ int go1mpc_body_model(go1mpc_t *h, int nh, double *pps, double *pvs,
                       double *ppu, double *pvu, double *ppu_2, double *pvu_2);
 /* default step table _tx of PRMPCClass::Initialize (:174-178), 27 doubles */
 int go1mpc_body_default_tx(go1mpc_t *h, double *tx27);
+
+/* ---------------------------------------------------------------------------
+ * Step-location / step-timing SQP tick (40 Hz planner) for B independent instances.
+ * Replaces NLPClass::step_timing_opti_loop  NLP/NLP/NLPClass_sqp.cpp:693-1102 with
+ *   step_timing_object_function :1144-1173, step_timing_constraints :1175-1458,
+ *   solve_stepping_timing/Solve :1613-1653 (QP n=4, p=1, m=24), Indexfind :1105-1141.
+ * One launch runs n_sqp SQP iterations (reference: 3; 1..5 supported), the write-back of
+ * step length / width / period and of the step tables, the LIPM roll-out of samples
+ * i..i+2, the feedback blend and the integer step indices.  CoM_height_solve
+ * (:2361-2473) is not on the device yet: its vertical CoM samples are inputs.
+ *
+ * Layout: STRUCTURE OF ARRAYS, element-major / batch-minor: field f of instance b is
+ * at [f*B + b] (one thread per instance: every access of a warp is coalesced).
+ * tick_d  [B] ints         i of the reference (>= 1)
+ * state_d [201][B] doubles in/out, fields:
+ *           [0,27) ts   [27,54) tx   [54,81) footx_ref  [81,108) footy_ref
+ *           [108,135) footz_ref  [135,162) Lxx_ref  [162,189) Lyy_ref
+ *           [189,195) com x,vx,ax,y,vy,ay _feed at tick i-1
+ *           [195,199) _Vari_ini.col(i-1) = (Lx, Ly, cosh(w T), sinh(w T))
+ *           [199,201) _comvx_endref, _comvy_endref
+ * in_d    [20][B] doubles: [0,6) estimated com x,vx,ax,y,vy,ay  [6,8) right foot x,y
+ *           [8,10) left foot x,y  [10,13) comz(i..i+2)  [13,16) comaz  [16,19) Zsc  [19] comvz(i)
+ * out_d   [38][B] doubles = the Vec38 the reference returns (:1048-1090)
+ * diag_d  [60][B] ints (may be NULL): [0] period index (_periond_i; -1 = time beyond the
+ *           step table, nothing written)  [1] k_yu  [2] bjxx  [3] bjx1  [4] QPs solved;
+ *           then per SQP iteration q < 5, at 5 + 11 q: status (-1 = no solve), nactive,
+ *           iters[4], active set[5] (slot 0 = -1 is the equality)
+ * ------------------------------------------------------------------------ */
+#define GO1MPC_STEP_STATE_DOUBLES 201
+#define GO1MPC_STEP_IN_DOUBLES 20
+#define GO1MPC_STEP_OUT_DOUBLES 38
+#define GO1MPC_STEP_DIAG_INTS 60
+int go1mpc_step_timing_step_batch(go1mpc_t *h, int n_sqp, int B, const int *tick_d,
+                                  double *state_d, const double *in_d, double *out_d,
+                                  int *diag_d, void *stream);
+int go1mpc_step_timing_step_batch_host(go1mpc_t *h, int n_sqp, int B, const int *tick,
+                                       double *state, const double *in, double *out, int *diag);
+/* Initial step tables of one planner (host buffer, 201 doubles, instance-major):
+ * NLPClass::FootStepInputs :51-75 and Initialize :131-206 for the given step length,
+ * width and height (reference: 0.075, 0.2535, 0) and period tstep (0.7). */
+int go1mpc_step_default_state(go1mpc_t *h, double steplength, double stepwidth,
+                              double stepheight, double tstep, double *state201);
 
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports

@@ -126,6 +126,62 @@ void orc_body_step_batch(const orc_body_cfg *c, int B, const int *tick,
                          double *x_out /*B*2nh*/, int *active /*B*12nh*/,
                          int *nactive, int *iters /*B*4*/, int *status);
 
+
+/* ------------------------------------------------------------------------
+ * Step-location / step-timing SQP (NLPClass), one 40 Hz tick.
+ * Follows NLP/src/NLP/NLPClass_sqp.cpp (NLP = unitree_ros/mosek_nlp_kmp):
+ *   step_timing_opti_loop :693-1102 (SQP loop :776-810, write-back :886-916,
+ *   LIPM roll-out :938-955, feedback blend :1017-1022, indices :1031-1041),
+ *   Indexfind :1105-1141, step_timing_object_function :1144-1173,
+ *   step_timing_constraints :1175-1458, solve_stepping_timing :1613-1639.
+ * CoM_height_solve (:2361-2473) is NOT restated yet: the vertical CoM samples
+ * it would write are inputs (comz/comaz/zsc for ticks i..i+2, comvz at i).
+ * --------------------------------------------------------------------- */
+#define ORC_STEP_NQP_MAX 8
+typedef struct {
+    double dt, Wn, ggg;             /* 0.025, sqrt(g/hcom), 9.8                   */
+    double t_min, t_max;            /* 0.5, 1.0                                   */
+    double footx_max, footx_min;    /* 0.15, -0.05                                */
+    double footx_vmax, footx_vmin, footy_vmax, footy_vmin;   /* 3, -2.875, 2, -1  */
+    double comax_max, comax_min, comay_max, comay_min;       /* 5, -5, 6, -6      */
+    double aax, aay, aaxv, aayv, bbx, bby, rr1, rr2;         /* go1 weights       */
+    double half_hip_width, foot_width;                        /* 0.12675, 0.03     */
+    double lamda[4];                /* comx, comvx, comy, comvy feedback gains (0) */
+    int n_sqp;                      /* 3                                          */
+} orc_step_cfg;
+
+typedef struct {                    /* carried from tick to tick (201 doubles)    */
+    double ts[ORC_FOOTSTEPS], tx[ORC_FOOTSTEPS];
+    double footx[ORC_FOOTSTEPS], footy[ORC_FOOTSTEPS], footz[ORC_FOOTSTEPS];
+    double Lxx[ORC_FOOTSTEPS], Lyy[ORC_FOOTSTEPS];
+    double feed[6];                 /* com x, vx, ax, y, vy, ay _feed at tick i-1  */
+    double vari[4];                 /* _Vari_ini.col(i-1) = [Lx, Ly, tr1, tr2]     */
+    double endref[2];               /* _comvx_endref, _comvy_endref                */
+} orc_step_state;
+
+typedef struct {                    /* per-tick inputs (20 doubles)               */
+    double est[6];                  /* estimated com x, vx, ax, y, vy, ay          */
+    double rfoot_fb[2], lfoot_fb[2];/* measured foot x, y                          */
+    double comz[3], comaz[3], zsc[3], comvz0;
+} orc_step_in;
+
+typedef struct {
+    int periond_i, k_yu, bjxx, bjx1, n_solved;
+    int status[ORC_STEP_NQP_MAX], nactive[ORC_STEP_NQP_MAX], iters[ORC_STEP_NQP_MAX][4];
+    int active[ORC_STEP_NQP_MAX][25];
+    double x[ORC_STEP_NQP_MAX][4];  /* the QP increment of each SQP iteration      */
+} orc_step_diag;
+
+void orc_step_cfg_default(orc_step_cfg *c);
+/* default tables of NLPClass::FootStepInputs/Initialize (:51-75,:160-206) */
+void orc_step_state_default(orc_step_state *s, const orc_step_cfg *c, double steplength, double stepwidth,
+                            double stepheight, double tstep);
+void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const orc_step_in *in,
+                          double out38[38], orc_step_diag *diag);
+/* flat batch driver: states [B][201], ins [B][20], out [B][38], diag optional */
+void orc_step_timing_batch(const orc_step_cfg *c, int B, const int *tick, double *states, const double *ins,
+                           double *out38, orc_step_diag *diag);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,106 @@
+// C-callable wrapper around the UNMODIFIED reference step-location / step-timing planner
+// (NLP/src/NLP/NLPClass.h + NLPClass_sqp.cpp, NLP = unitree_ros/mosek_nlp_kmp), compiled from
+// /root/reference against oracle/eigen_shim and the Mosek / Armadillo / KMP stand-ins.
+// Test infrastructure only: pins oracle/step_timing.c.
+#define private public
+#define protected public
+#include <NLP/NLPClass.h>
+#undef private
+#undef protected
+
+// KMP is dead code on this path: no-op definitions for the linker.
+kmp::kmp() {}
+void kmp::kmp_initialize(mat&, int, int, int, double, double) {}
+int kmp::kernel_extend(vec, vec, mat&) { return 0; }
+int kmp::kmp_estimateMatrix() { return 0; }
+int kmp::kmp_prediction(vec, vec&) { return 0; }
+int kmp::kmp_insertPoint(vec) { return 0; }
+
+extern "C" {
+
+// same set-up as NLPRTControlClass::NLPRTControlClass (NLPRTControl/NLPRTControlClass.cpp:25-73)
+void* ref_nlp_new(double steplength, double stepwidth, double stepheight) {
+  NLPClass* p = new NLPClass();
+  p->_method_flag = 2;
+  p->_pvFlag_kmp = 1;
+  p->_robot_name = "go1";
+  p->_robot_mass = 12;
+  p->_lift_height = 0.03;
+  p->RobotPara_totalmass = 12;
+  p->RobotPara_HALF_HIP_WIDTH = 0.12675;
+  p->RobotPara_dt = 0.025;
+  p->RobotPara_Tstep = 0.7;
+  p->RobotPara_Z_C = 0.309458;
+  p->RobotPara_g = 9.8;
+  p->RobotPara_FOOT_WIDTH = 0.03;
+  p->FootStepInputs(stepwidth, steplength, stepheight);
+  p->Initialize();
+  return p;
+}
+void ref_nlp_free(void* h) { delete static_cast<NLPClass*>(h); }
+
+// constants the oracle's config is filled from (order = orc_step_cfg doubles)
+void ref_nlp_consts(void* h, double* c) {
+  NLPClass* p = static_cast<NLPClass*>(h);
+  int k = 0;
+  c[k++] = _dt; c[k++] = p->_Wn; c[k++] = p->_ggg(0);
+  c[k++] = p->_t_min; c[k++] = p->_t_max;
+  c[k++] = p->_footx_max; c[k++] = p->_footx_min;
+  c[k++] = p->_footx_vmax; c[k++] = p->_footx_vmin; c[k++] = p->_footy_vmax; c[k++] = p->_footy_vmin;
+  c[k++] = p->_comax_max; c[k++] = p->_comax_min; c[k++] = p->_comay_max; c[k++] = p->_comay_min;
+  c[k++] = p->_aax; c[k++] = p->_aay; c[k++] = p->_aaxv; c[k++] = p->_aayv;
+  c[k++] = p->_bbx; c[k++] = p->_bby; c[k++] = p->_rr1; c[k++] = p->_rr2;
+  c[k++] = p->RobotPara_HALF_HIP_WIDTH; c[k++] = p->RobotPara_FOOT_WIDTH;
+}
+
+// state the tick reads: tables (7 x 27) | feed at i-1 (6) | Vari_ini.col(i-1) (4) | endref (2)
+void ref_nlp_get_state(void* h, int i, double* s) {
+  NLPClass* p = static_cast<NLPClass*>(h);
+  int k = 0;
+  for (int j = 0; j < 27; j++) s[k++] = p->_ts(j);
+  for (int j = 0; j < 27; j++) s[k++] = p->_tx(j);
+  for (int j = 0; j < 27; j++) s[k++] = p->_footx_ref(j);
+  for (int j = 0; j < 27; j++) s[k++] = p->_footy_ref(j);
+  for (int j = 0; j < 27; j++) s[k++] = p->_footz_ref(j);
+  for (int j = 0; j < 27; j++) s[k++] = p->_Lxx_ref(j);
+  for (int j = 0; j < 27; j++) s[k++] = p->_Lyy_ref(j);
+  s[k++] = p->_comx_feed(i - 1); s[k++] = p->_comvx_feed(i - 1); s[k++] = p->_comax_feed(i - 1);
+  s[k++] = p->_comy_feed(i - 1); s[k++] = p->_comvy_feed(i - 1); s[k++] = p->_comay_feed(i - 1);
+  for (int j = 0; j < 4; j++) s[k++] = p->_Vari_ini(j, i - 1);
+  s[k++] = p->_comvx_endref(0); s[k++] = p->_comvy_endref(0);
+}
+void ref_nlp_set_state(void* h, int i, const double* s) {
+  NLPClass* p = static_cast<NLPClass*>(h);
+  int k = 0;
+  for (int j = 0; j < 27; j++) p->_ts(j) = s[k++];
+  for (int j = 0; j < 27; j++) p->_tx(j) = s[k++];
+  for (int j = 0; j < 27; j++) p->_footx_ref(j) = s[k++];
+  for (int j = 0; j < 27; j++) p->_footy_ref(j) = s[k++];
+  for (int j = 0; j < 27; j++) p->_footz_ref(j) = s[k++];
+  for (int j = 0; j < 27; j++) p->_Lxx_ref(j) = s[k++];
+  for (int j = 0; j < 27; j++) p->_Lyy_ref(j) = s[k++];
+  p->_comx_feed(i - 1) = s[k++]; p->_comvx_feed(i - 1) = s[k++]; p->_comax_feed(i - 1) = s[k++];
+  p->_comy_feed(i - 1) = s[k++]; p->_comvy_feed(i - 1) = s[k++]; p->_comay_feed(i - 1) = s[k++];
+  for (int j = 0; j < 4; j++) p->_Vari_ini(j, i - 1) = s[k++];
+  p->_comvx_endref(0) = s[k++]; p->_comvy_endref(0) = s[k++];
+  p->_td = 0.2 * p->_ts;
+}
+
+// NLPClass::step_timing_opti_loop, NLPClass_sqp.cpp:693-1102.  est18/rfoot/lfoot as the
+// reference takes them; hz receives what CoM_height_solve wrote: comz[3] comaz[3] zsc[3] comvz(i);
+// ints: periond_i, k_yu, bjxx, bjx1.
+void ref_nlp_step(void* h, int i, const double* est18, const double* rfoot3, const double* lfoot3, int stop,
+                  double* out38, double* hz, int* ints) {
+  NLPClass* p = static_cast<NLPClass*>(h);
+  Eigen::Matrix<double, 18, 1> est;
+  Eigen::Vector3d rf, lf;
+  for (int k = 0; k < 18; k++) est(k) = est18[k];
+  for (int k = 0; k < 3; k++) { rf(k) = rfoot3[k]; lf(k) = lfoot3[k]; }
+  Eigen::Matrix<double, 38, 1> o = p->step_timing_opti_loop(i, est, rf, lf, 0.0, stop != 0);
+  for (int k = 0; k < 38; k++) out38[k] = o(k);
+  for (int q = 0; q < 3; q++) { hz[q] = p->_comz(i + q); hz[3 + q] = p->_comaz(i + q); hz[6 + q] = p->_Zsc(i + q); }
+  hz[9] = p->_comvz(i);
+  ints[0] = p->_periond_i; ints[1] = p->_k_yu; ints[2] = p->_bjxx; ints[3] = p->_bjx1;
+}
+
+}  // extern "C"

@@ -1,0 +1,311 @@
+/*
+ * step_timing.c -- oracle restatement of the step-location / step-timing SQP tick.
+ *
+ * TEST INFRASTRUCTURE (see go1_oracle.h).  Restates NLPClass (NLP = unitree_ros/mosek_nlp_kmp):
+ *   step_timing_opti_loop        NLP/src/NLP/NLPClass_sqp.cpp:693-1102
+ *   Indexfind                    :1105-1141
+ *   step_timing_object_function  :1144-1173
+ *   step_timing_constraints      :1175-1458
+ *   solve_stepping_timing/Solve  :1613-1653
+ * Every expression keeps the association the reference's Eigen expression has when its
+ * products are evaluated in ascending inner index (what oracle/eigen_shim does), so this file
+ * and the unmodified NLPClass compiled against the shim agree bit for bit
+ * (tests/test_oracle_vs_ref.py).  Products with the selection rows _SS1.._SS4 (unit rows)
+ * reduce exactly to picking an entry: the other terms are exact zeros.
+ *
+ * Frozen quirks: `_vari_ini += _X` runs whatever the solver's status was (a not-PD solve
+ * leaves _X = _vari_ini, doubling it; an infeasible solve adds a partial step); the
+ * initial-velocity rows 20-23 use a.dt in the matrix and a.dt/2 in the right-hand side; the
+ * swing-velocity rows 8-11 are all-zero rows with b = 0 while k_yu == 0; the feedback blend
+ * computes ((1-l)(com - p) + l est) + p even with l = 0 (one rounding).
+ * Differences: Indexfind's unbounded while loops are clamped to the 27-entry table.
+ */
+#include <math.h>
+#include <string.h>
+#include "go1_oracle.h"
+
+#define NS ORC_FOOTSTEPS
+
+void orc_step_cfg_default(orc_step_cfg *c)
+{
+    /* NLPClass_sqp.cpp:212-214,244-258,273-286 ; NLPRTControlClass.cpp:35-42 ; NLPClass.h:30-38 */
+    memset(c, 0, sizeof *c);
+    c->dt = 0.025;
+    c->ggg = 9.8;
+    c->Wn = sqrt(9.8 / (0.309458 - 0.000));
+    c->t_min = 0.5; c->t_max = 1;
+    c->footx_max = 0.15; c->footx_min = -0.05;
+    c->footx_vmax = 3; c->footx_vmin = -2.875; c->footy_vmax = 2; c->footy_vmin = -1;
+    c->comax_max = 5; c->comax_min = -5; c->comay_max = 6; c->comay_min = -6;
+    c->aax = 50000; c->aay = 50000; c->aaxv = 1000; c->aayv = 500;
+    c->bbx = 2000000; c->bby = 10000000; c->rr1 = 1000000; c->rr2 = 1000000;
+    c->half_hip_width = 0.12675; c->foot_width = 0.03;
+    c->n_sqp = 3;
+}
+
+void orc_step_state_default(orc_step_state *s, const orc_step_cfg *c, double steplength, double stepwidth,
+                            double stepheight, double tstep)
+{
+    /* FootStepInputs :51-75, Initialize :131-206 */
+    double sl[NS], sw[NS], sh[NS];
+    memset(s, 0, sizeof *s);
+    for (int j = 0; j < NS; j++) { sl[j] = steplength; sw[j] = stepwidth; sh[j] = stepheight; }
+    sl[NS - 1] = sl[NS - 2] = sl[NS - 3] = sl[NS - 4] = sl[NS - 5] = 0;
+    sl[0] = sl[1] = sl[2] = 0; sl[3] = steplength / 2;
+    sw[0] = sw[0] / 2;
+    sl[14] = 0;
+    for (int j = 15; j <= 21; j++) sl[j] *= -1;
+    for (int j = 0; j < NS; j++) { s->Lxx[j] = sl[j]; s->Lyy[j] = (int)pow(-1, j) * sw[j]; }
+    for (int j = 1; j < NS; j++) {
+        s->footx[j] = s->footx[j - 1] + sl[j - 1];
+        s->footy[j] = s->footy[j - 1] + (int)pow(-1, j - 1) * sw[j - 1];
+        s->footz[j] = s->footz[j - 1] + sh[j - 1];
+    }
+    for (int j = 0; j < NS; j++) s->ts[j] = tstep;
+    for (int j = 1; j < NS; j++) {
+        s->tx[j] = s->tx[j - 1] + s->ts[j - 1];
+        s->tx[j] = round(s->tx[j] / c->dt) * c->dt - 0.000001;
+    }
+}
+
+void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const orc_step_in *in,
+                          double out38[38], orc_step_diag *dg)
+{
+    const double dt = c->dt, Wn = c->Wn;
+    double v[4];
+    if (dg) memset(dg, 0, sizeof *dg);
+
+    /* :702-704  Indexfind((i+1)*dt, xyz0 = -1) */
+    int j = 0;
+    while (j < NS && (i + 1) * dt > s->tx[j] + 0.0001) j++;
+    const int p = (j - 1) + 1;                      /* _periond_i */
+    const double px = s->footx[p - 1], py = s->footy[p - 1];
+    /* :714-727 */
+    const int ki = (int)round(s->tx[p - 1] / dt);
+    const int k_yu = i - ki;
+    const double Tk = s->ts[p - 1] - k_yu * dt;
+    const double Lxx_refx = s->Lxx[p - 1], Lyy_refy = s->Lyy[p - 1];
+    const double tr1_ref = cosh(Wn * Tk), tr2_ref = sinh(Wn * Tk);
+    /* :730-740 warm start */
+    if (i == 1) { v[0] = Lxx_refx; v[1] = Lyy_refy; v[2] = tr1_ref; v[3] = tr2_ref; }
+    else memcpy(v, s->vari, sizeof v);
+    /* :745-757 remaining-time bounds */
+    double tr1_min, tr2_min;
+    if ((c->t_min - k_yu * dt) >= 0.001) { tr1_min = cosh(Wn * (c->t_min - k_yu * dt)); tr2_min = sinh(Wn * (c->t_min - k_yu * dt)); }
+    else { tr1_min = cosh(Wn * (0.001)); tr2_min = sinh(Wn * (0.001)); }
+    const double tr1_max = cosh(Wn * (c->t_max - k_yu * dt)), tr2_max = sinh(Wn * (c->t_max - k_yu * dt));
+
+    const double comx_f = s->feed[0], comvx_f = s->feed[1], comy_f = s->feed[3], comvy_f = s->feed[4];
+    double endx = s->endref[0], endy = s->endref[1];
+    if (i == 1) {
+        /* :761-771 */
+        double isx = comx_f - px, esx = v[0] * 0.5, visx = (esx - isx * v[2]) / (1 / Wn * v[3]);
+        double isy = comy_f - py, esy = v[1] * 0.5, visy = (esy - isy * v[2]) / (1 / Wn * v[3]);
+        endx = Wn * isx * v[3] + visx * v[2];
+        endy = Wn * isy * v[3] + visy * v[2];
+    }
+
+    /* quantities of the objective / constraints that do not change inside the SQP loop */
+    const double AxO = comx_f - px, BxO = comvx_f / Wn, Cx = -0.5 * Lxx_refx;
+    const double Axv = Wn * BxO, Bxv = Wn * AxO, Cxv = -endx;
+    const double AyO = comy_f - py, ByO = comvy_f / Wn, Cy = -0.5 * Lyy_refy;
+    const double Ayv = Wn * ByO, Byv = Wn * AyO, Cyv = -endy;
+    const double aax = c->aax, aay = c->aay, aaxv = c->aaxv, aayv = c->aayv;
+    double SQ0[4][4];
+    memset(SQ0, 0, sizeof SQ0);
+    SQ0[0][0] = 0.5 * c->bbx;
+    SQ0[1][1] = 0.5 * c->bby;
+    SQ0[2][2] = 0.5 * (c->rr1 + aax * AxO * AxO + aay * AyO * AyO + aaxv * Axv * Axv + aayv * Ayv * Ayv);
+    SQ0[2][3] = 0.5 * (aax * AxO * BxO + aay * AyO * ByO + aaxv * Axv * Bxv + aayv * Ayv * Byv);
+    SQ0[3][2] = 0.5 * (aax * BxO * AxO + aay * ByO * AyO + aaxv * Bxv * Axv + aayv * Byv * Ayv);
+    SQ0[3][3] = 0.5 * (c->rr2 + aax * BxO * BxO + aay * ByO * ByO + aaxv * Bxv * Bxv + aayv * Byv * Byv);
+    double SQ[4][4], Sq[4];
+    for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) SQ[r][k] = (SQ0[r][k] + SQ0[k][r]) / 2.0;
+    Sq[0] = -c->bbx * Lxx_refx;
+    Sq[1] = -c->bby * Lyy_refy;
+    Sq[2] = -c->rr1 * tr1_ref + aax * AxO * Cx + aay * AyO * Cy + aaxv * Axv * Cxv + aayv * Ayv * Cyv;
+    Sq[3] = -c->rr2 * tr2_ref + aax * BxO * Cx + aay * ByO * Cy + aaxv * Bxv * Cxv + aayv * Byv * Cyv;
+
+    /* :1216-1246 lateral reachability, widened after two steps */
+    double footy_max, footy_min;
+    const int wide = (i >= (round(2 * s->ts[1] / dt)) + 1);
+    const double HW = c->half_hip_width, FW = c->foot_width;
+    if (p % 2 == 0) { footy_min = -(2 * HW + 0.03); footy_max = wide ? -(FW + 0.01) : -(HW - 0.03); }
+    else { footy_max = 2 * HW + 0.03; footy_min = wide ? FW + 0.01 : HW - 0.03; }
+
+    /* :1341-1411 coefficient rows that depend on the state only */
+    const double CCx = comx_f - px, CCy = comy_f - py;
+    const double AA = Wn * sinh(Wn * dt);
+    const double BBx = pow(Wn, 2) * CCx * cosh(Wn * dt), BBy = pow(Wn, 2) * CCy * cosh(Wn * dt);
+    const double AA1x = AA * Wn, AA2x = -2 * AA * CCx * Wn, AA3x = 2 * BBx;
+    const double AA1y = AA * Wn, AA2y = -2 * AA * CCy * Wn, AA3y = 2 * BBy;
+    const double VAA = cosh(Wn * dt);
+    const double VBBx = Wn * CCx * sinh(Wn * dt), VBBy = Wn * CCy * sinh(Wn * dt);
+    const double VAA1x = VAA * Wn, VAA2x = -2 * VAA * CCx * Wn, VAA3x = 2 * VBBx - 2 * comvx_f;
+    const double VAA1y = VAA * Wn, VAA2y = -2 * VAA * CCy * Wn, VAA3y = 2 * VBBy - 2 * comvy_f;
+    const double VAA1x1 = Wn, VAA2x1 = -2 * CCx * Wn, VAA3x1 = -2 * comvx_f;
+    const double VAA1y1 = Wn, VAA2y1 = -2 * CCy * Wn, VAA3y1 = -2 * comvy_f;
+
+    int n_solved = 0;
+    for (int it = 1; it <= c->n_sqp; it++) {
+        /* :1164-1165 */
+        double G[16], g0[4];
+        for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) G[k * 4 + r] = 2 * SQ[r][k];
+        for (int r = 0; r < 4; r++) {
+            double acc = 0.0;
+            for (int k = 0; k < 4; k++) acc += (2 * SQ[r][k]) * v[k];
+            g0[r] = acc + Sq[r];
+        }
+        /* :1188-1190 linearised tr1^2 - tr2^2 = 1 */
+        double CE[4], ce0[1];
+        {
+            double trx12[4] = { 0.0, 0.0, 2 * v[2], (-2) * v[3] };
+            double q = 0.0;
+            q += v[2] * v[2];
+            q += (v[3] * (-1)) * v[3];
+            ce0[0] = -q + 1;
+            for (int k = 0; k < 4; k++) CE[k] = trx12[k] * (-1);
+        }
+        /* rows A x <= b */
+        double A[24][4], b[24];
+        memset(A, 0, sizeof A);
+        memset(b, 0, sizeof b);
+        A[0][2] = 1;  b[0] = -(v[2]) + tr1_max;
+        A[1][2] = -1; b[1] = -((-1.0) * v[2]) - tr1_min;
+        A[2][3] = 1;  b[2] = -(v[3]) + tr2_max;
+        A[3][3] = -1; b[3] = -((-1.0) * v[3]) - tr2_min;
+        A[4][0] = 1;  b[4] = -(v[0]) + c->footx_max;
+        A[5][0] = -1; b[5] = -((-1.0) * v[0]) - c->footx_min;
+        A[6][1] = 1;  b[6] = -(v[1]) + footy_max;
+        A[7][1] = -1; b[7] = -((-1.0) * v[1]) - footy_min;
+        if (k_yu != 0) {
+            A[8][0] = 1;   b[8] = -(v[0] - s->Lxx[p - 1] - c->footx_vmax * dt);
+            A[9][0] = -1;  b[9] = v[0] - s->Lxx[p - 1] - c->footx_vmin * dt;
+            A[10][1] = 1;  b[10] = -(v[1] - s->Lyy[p - 1] - c->footy_vmax * dt);
+            A[11][1] = -1; b[11] = v[1] - s->Lyy[p - 1] - c->footy_vmin * dt;
+        }
+#define ROW3(r, i0, c0, c2, c3, d3) do { \
+            A[r][i0] = (c0); A[r][2] = (c2); A[r][3] = (c3); \
+            double acc_ = 0.0; \
+            if ((i0) == 0) { acc_ += (-(c0)) * v[0]; } else { acc_ += (-(c0)) * v[1]; } \
+            acc_ += (-(c2)) * v[2]; acc_ += (-(d3)) * v[3]; b[r] = acc_; } while (0)
+        {
+            double c3;
+            /* CoM acceleration at the next sample :1349-1363 */
+            c3 = AA3x - 2 * c->comax_max; ROW3(12, 0, AA1x, AA2x, c3, c3);
+            c3 = -(AA3x - 2 * c->comax_min); ROW3(13, 0, -AA1x, -AA2x, c3, c3);
+            c3 = AA3y - 2 * c->comay_max; ROW3(14, 1, AA1y, AA2y, c3, c3);
+            c3 = -(AA3y - 2 * c->comay_min); ROW3(15, 1, -AA1y, -AA2y, c3, c3);
+            /* CoM velocity increment over one dt :1374-1387 */
+            c3 = VAA3x - 2 * c->comax_max * dt; ROW3(16, 0, VAA1x, VAA2x, c3, c3);
+            c3 = -(VAA3x - 2 * c->comax_min * dt); ROW3(17, 0, -VAA1x, -VAA2x, c3, c3);
+            c3 = VAA3y - 2 * c->comay_max * dt; ROW3(18, 1, VAA1y, VAA2y, c3, c3);
+            c3 = -(VAA3y - 2 * c->comay_min * dt); ROW3(19, 1, -VAA1y, -VAA2y, c3, c3);
+            /* CoM initial velocity :1397-1411 -- matrix uses a dt, right-hand side a dt / 2 */
+            double d3;
+            c3 = VAA3x1 - 2 * c->comax_max * dt; d3 = VAA3x1 - 2 * c->comax_max * dt / 2.0; ROW3(20, 0, VAA1x1, VAA2x1, c3, d3);
+            c3 = -(VAA3x1 - 2 * c->comax_min * dt); d3 = -(VAA3x1 - 2 * c->comax_min * dt / 2.0); ROW3(21, 0, -VAA1x1, -VAA2x1, c3, d3);
+            c3 = VAA3y1 - 2 * c->comay_max * dt; d3 = VAA3y1 - 2 * c->comay_max * dt / 2.0; ROW3(22, 1, VAA1y1, VAA2y1, c3, d3);
+            c3 = -(VAA3y1 - 2 * c->comay_min * dt); d3 = -(VAA3y1 - 2 * c->comay_min * dt / 2.0); ROW3(23, 1, -VAA1y1, -VAA2y1, c3, d3);
+        }
+#undef ROW3
+        if (Tk >= 0.1 * s->ts[p - 1]) {
+            /* :1618-1638 */
+            double CI[96], X[4], cost;
+            for (int r = 0; r < 24; r++) for (int k = 0; k < 4; k++) CI[r * 4 + k] = A[r][k] * (-1);
+            memcpy(X, v, sizeof X);
+            int act[26], na = 0, iters[4] = { 0, 0, 0, 0 };
+            int st = orc_qp_solve(4, 1, 24, G, g0, CE, ce0, CI, b, X, &cost, act, &na, iters);
+            if (dg && n_solved < ORC_STEP_NQP_MAX) {
+                dg->status[n_solved] = st; dg->nactive[n_solved] = na;
+                memcpy(dg->iters[n_solved], iters, sizeof iters);
+                memcpy(dg->active[n_solved], act, sizeof(int) * (na < 25 ? na : 25));
+                memcpy(dg->x[n_solved], X, sizeof X);
+            }
+            n_solved++;
+            for (int k = 0; k < 4; k++) v[k] += X[k];    /* :795-798, whatever the status */
+        } else {
+            v[0] = Lxx_refx; v[1] = Lyy_refy; v[2] = tr1_ref; v[3] = tr2_ref;
+        }
+    }
+
+    /* :817, :886-888 write-back */
+    memcpy(s->vari, v, sizeof v);
+    s->Lxx[p - 1] = v[0];
+    s->Lyy[p - 1] = v[1];
+    s->ts[p - 1] = k_yu * dt + log(v[2] + v[3]) / Wn;
+    /* :896-901 */
+    const double isx = comx_f - px, esx = v[0] * 0.5, visx = (esx - isx * v[2]) / (1 / Wn * v[3]);
+    const double isy = comy_f - py, esy = v[1] * 0.5, visy = (esy - isy * v[2]) / (1 / Wn * v[3]);
+    /* :906-913 */
+    const double nTd_ts1 = s->ts[1];    /* NB: _td = 0.2*_ts was taken at the END of the previous tick; ts[1] only changes while p-1 == 1 */
+    for (int jxx = p + 1; jxx <= NS; jxx++) s->tx[jxx - 1] = s->tx[jxx - 2] + s->ts[jxx - 2];
+    if (p < NS) { s->footx[p] = s->footx[p - 1] + v[0]; s->footy[p] = s->footy[p - 1] + v[1]; }
+    s->endref[0] = Wn * isx * v[3] + visx * v[2];
+    s->endref[1] = Wn * isy * v[3] + visy * v[2];
+    (void)nTd_ts1;
+
+    /* :938-955 LIPM roll-out (samples i, i+1, i+2 are what the outputs read) */
+    double comx[3], comy[3], comvx[3], comvy[3], comax[3], comay[3], zmpx[3], zmpy[3], dcmx[3], dcmy[3];
+    for (int jxx = 1; jxx <= 3; jxx++) {
+        const int q = jxx - 1;
+        const double w = Wn * dt * jxx;
+        comx[q] = isx * cosh(w) + visx * 1 / Wn * sinh(w) + px;
+        comy[q] = isy * cosh(w) + visy * 1 / Wn * sinh(w) + py;
+        comvx[q] = Wn * isx * sinh(w) + visx * cosh(w);
+        comvy[q] = Wn * isy * sinh(w) + visy * cosh(w);
+        comax[q] = pow(Wn, 2) * isx * cosh(w) + visx * Wn * sinh(w);
+        comay[q] = pow(Wn, 2) * isy * cosh(w) + visy * Wn * sinh(w);
+        const double hz = (in->comz[q] - in->zsc[q]) / (in->comaz[q] + c->ggg);
+        zmpx[q] = comx[q] - hz * comax[q];
+        zmpy[q] = comy[q] - hz * comay[q];
+        dcmx[q] = comx[q] + comvx[q] * sqrt(hz);
+        dcmy[q] = comy[q] + comvy[q] * sqrt(hz);
+    }
+    /* :963-972, :1017-1022 feedback blend (gains 0 as shipped) */
+    double e0 = in->est[0], e3 = in->est[3];
+    if (p % 2 == 0) { e0 = e0 - in->lfoot_fb[0]; e3 = e3 - in->lfoot_fb[1]; }
+    else { e0 = e0 - in->rfoot_fb[0]; e3 = e3 - in->rfoot_fb[1]; }
+    const double lx = c->lamda[0], lvx = c->lamda[1], ly = c->lamda[2], lvy = c->lamda[3];
+    s->feed[0] = ((1 - lx) * (comx[0] - px) + (lx) * e0) + px;
+    s->feed[1] = (1 - lvx) * comvx[0] + (lvx) * in->est[1];
+    s->feed[2] = (1 - lx) * comax[0] + lx * in->est[2];
+    s->feed[3] = ((1 - ly) * (comy[0] - py) + (ly) * e3) + py;
+    s->feed[4] = (1 - lvy) * comvy[0] + (lvy) * in->est[4];
+    s->feed[5] = (1 - ly) * comay[0] + ly * in->est[5];
+
+    /* :1031-1041 integer step indices against the UPDATED table (xyz1 = 0 branch) */
+    j = 0; while (j < NS && i * dt >= s->tx[j]) j++;
+    const int bjxx = (j - 1) + 1;
+    j = 0; while (j < NS && (i + 1) * dt >= s->tx[j]) j++;
+    const int bjx1 = (j - 1) + 1;
+
+    /* :1048-1090 */
+    out38[0] = comx[0]; out38[1] = comy[0]; out38[2] = in->comz[0];
+    out38[3] = comvx[0]; out38[4] = comvy[0]; out38[5] = in->comvz0;
+    out38[6] = comax[0]; out38[7] = comay[0]; out38[8] = in->comaz[0];
+    out38[9] = zmpx[0]; out38[10] = zmpy[0]; out38[11] = dcmx[0]; out38[12] = dcmy[0];
+    out38[13] = zmpx[1]; out38[14] = zmpy[1]; out38[15] = dcmx[1]; out38[16] = dcmy[1];
+    out38[17] = zmpx[2]; out38[18] = zmpy[2]; out38[19] = dcmx[2]; out38[20] = dcmy[2];
+    out38[21] = comax[1]; out38[22] = comay[1]; out38[23] = in->comaz[1];
+    out38[24] = comax[2]; out38[25] = comay[2]; out38[26] = in->comaz[2];
+    out38[27] = bjxx;
+    const int b0 = bjxx < NS ? bjxx : NS - 1, b1 = bjxx + 1 < NS ? bjxx + 1 : NS - 1;   /* reference reads past the table at the very end */
+    out38[28] = s->footx[b0]; out38[29] = s->footx[b1];
+    out38[30] = s->footy[b0]; out38[31] = s->footy[b1];
+    out38[32] = s->footz[b0]; out38[33] = s->footz[b1];
+    out38[34] = p - 1;
+    out38[35] = s->ts[p - 1];
+    out38[36] = v[0];
+    out38[37] = v[1];
+    if (dg) { dg->periond_i = p; dg->k_yu = k_yu; dg->bjxx = bjxx; dg->bjx1 = bjx1; dg->n_solved = n_solved; }
+}
+
+void orc_step_timing_batch(const orc_step_cfg *c, int B, const int *tick, double *states, const double *ins,
+                           double *out38, orc_step_diag *diag)
+{
+    for (int bi = 0; bi < B; bi++)
+        orc_step_timing_tick(c, tick[bi], (orc_step_state *)(states + (size_t)bi * (sizeof(orc_step_state) / sizeof(double))),
+                             (const orc_step_in *)(ins + (size_t)bi * (sizeof(orc_step_in) / sizeof(double))),
+                             out38 + (size_t)bi * 38, diag ? diag + bi : NULL);
+}

@@ -6,11 +6,14 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgo1mpc.so")
-SOURCES = ["api.cu", "body_mpc.cu", "body_fast.cu", "qp_dense.cu"]
-HEADERS = ["gi_warp.cuh", "tma.cuh", "kernels.h", os.path.join("..", "..", "include", "go1mpc.h")]
+SOURCES = ["api.cu", "body_mpc.cu", "body_fast.cu", "qp_dense.cu", "step_timing.cu"]
+# per-source extra flags: the thread-per-instance kernels keep the oracle's operation order and
+# must not contract a*b+c into FMA
+EXTRA = {"step_timing.cu": ["-fmad=false"]}
+HEADERS = ["gi_warp.cuh", "gi_thread.cuh", "tma.cuh", "kernels.h", os.path.join("..", "..", "include", "go1mpc.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -30,19 +33,33 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source into quadrupedal_loco_b200/libgo1mpc.so."""
+    """Compile every CUDA source (one object each, in parallel) and link quadrupedal_loco_b200/libgo1mpc.so."""
     if not force and not needs_build():
         return LIB
+    from concurrent.futures import ThreadPoolExecutor
     extra = os.environ.get("GO1MPC_NVCC_EXTRA", "").split()
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     # the image exports CC/CXX=/opt/gcc/bin/* whose link line picks a static libstdc++;
     # let nvcc use the PATH host compiler instead
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
-    r = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + EXTRA.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
+        r = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
     if verbose:
-        print(r.stderr)
+        for _, err in results:
+            print(err)
+    r = subprocess.run([_nvcc(), "-shared", "-o", LIB] + [o for o, _ in results], cwd=CSRC, env=env, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

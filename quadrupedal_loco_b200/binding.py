@@ -18,6 +18,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_body_in_stride", "go1mpc_body_out_stride", "go1mpc_body_diag_stride",
     "go1mpc_body_mpc_step_batch", "go1mpc_body_mpc_step_batch_host",
     "go1mpc_body_model", "go1mpc_body_default_tx", "go1mpc_measure_dfma_peak",
+    "go1mpc_step_timing_step_batch", "go1mpc_step_timing_step_batch_host", "go1mpc_step_default_state",
 ]
 
 
@@ -40,8 +41,17 @@ class BodyCfg(ctypes.Structure):
     ]
 
 
+class StepCfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in (
+        "dt Wn ggg t_min t_max footx_max footx_min footx_vmax footx_vmin footy_vmax footy_vmin comax_max comax_min "
+        "comay_max comay_min aax aay aaxv aayv bbx bby rr1 rr2 half_hip_width foot_width").split()] + [("lamda", ctypes.c_double * 4)]
+
+
 class Cfg(ctypes.Structure):
-    _fields_ = [("body", BodyCfg), ("qp_iter_cap_scale", ctypes.c_int), ("reserved", ctypes.c_int * 7)]
+    _fields_ = [("body", BodyCfg), ("step", StepCfg), ("qp_iter_cap_scale", ctypes.c_int), ("reserved", ctypes.c_int * 7)]
+
+
+STEP_STATE, STEP_IN, STEP_OUT, STEP_DIAG = 201, 20, 38, 60
 
 
 _LIB = None
@@ -84,6 +94,9 @@ def load_library():
     lib.go1mpc_body_model.argtypes = [vp, ctypes.c_int] + [vp] * 6
     lib.go1mpc_body_default_tx.argtypes = [vp, vp]
     lib.go1mpc_measure_dfma_peak.argtypes = [vp, ctypes.c_int, c_double_p]
+    lib.go1mpc_step_timing_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    lib.go1mpc_step_timing_step_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
+    lib.go1mpc_step_default_state.argtypes = [vp] + [ctypes.c_double] * 4 + [vp]
     _LIB = lib
     return lib
 
@@ -150,6 +163,13 @@ class Go1Mpc:
                         self.cfg.body.lamda[i] = v[i]
                 elif k == "qp_iter_cap_scale":
                     self.cfg.qp_iter_cap_scale = v
+                elif k == "step":
+                    for sk, sv in v.items():
+                        if sk == "lamda":
+                            for i in range(4):
+                                self.cfg.step.lamda[i] = sv[i]
+                        else:
+                            setattr(self.cfg.step, sk, sv)
                 else:
                     setattr(self.cfg.body, k, v)
         self.h = ctypes.c_void_p()
@@ -222,6 +242,21 @@ class Go1Mpc:
         self._check(self.lib.go1mpc_qp_solve_batch_host(self.h, n, p, m, B, _ptr(G), _ptr(g0), _ptr(CE), _ptr(ce0),
                                                         _ptr(CI), _ptr(ci0), _ptr(x), _ptr(cost), _ptr(active),
                                                         _ptr(nactive), _ptr(iters), _ptr(status)), "qp_solve_batch_host")
+
+    # --- step-location / step-timing SQP (SoA buffers: [field][B]) ---
+    def step_timing_step(self, n_sqp, B, tick_d, state_d, in_d, out_d, diag_d=None, stream=None):
+        self._check(self.lib.go1mpc_step_timing_step_batch(self.h, n_sqp, B, _ptr(tick_d), _ptr(state_d), _ptr(in_d),
+                                                           _ptr(out_d), _ptr(diag_d), stream), "step_timing_step_batch")
+
+    def step_timing_step_host(self, n_sqp, B, tick, state, inp, out, diag=None):
+        self._check(self.lib.go1mpc_step_timing_step_batch_host(self.h, n_sqp, B, _ptr(tick), _ptr(state), _ptr(inp),
+                                                                _ptr(out), _ptr(diag)), "step_timing_step_batch_host")
+
+    def step_default_state(self, steplength=0.075, stepwidth=0.2535, stepheight=0.0, tstep=0.7):
+        s = np.zeros(STEP_STATE)
+        self._check(self.lib.go1mpc_step_default_state(self.h, steplength, stepwidth, stepheight, tstep, _ptr(s)),
+                    "step_default_state")
+        return s
 
     def measure_dfma_peak(self, ms=200):
         g = ctypes.c_double(0.0)

@@ -193,6 +193,15 @@ int go1mpc_config_default(Go1MpcConfig* cfg) {
   b.foot_length = 0.02; b.foot_width = 0.02;
   b.theta_lim = 10 * M_PI / 180; b.torque_lim = 20.0;
   b.Rtheta = 100.0; b.alphatheta = 10.0; b.beltatheta = 5000000000.0; b.gama_zmp = 5000.0;
+  Go1StepMpcConfig& s = cfg->step;
+  s.dt = 0.025; s.ggg = 9.8; s.Wn = sqrt(9.8 / (0.309458 - 0.000));
+  s.t_min = 0.5; s.t_max = 1;
+  s.footx_max = 0.15; s.footx_min = -0.05;
+  s.footx_vmax = 3; s.footx_vmin = -2.875; s.footy_vmax = 2; s.footy_vmin = -1;
+  s.comax_max = 5; s.comax_min = -5; s.comay_max = 6; s.comay_min = -6;
+  s.aax = 50000; s.aay = 50000; s.aaxv = 1000; s.aayv = 500;
+  s.bbx = 2000000; s.bby = 10000000; s.rr1 = 1000000; s.rr2 = 1000000;
+  s.half_hip_width = 0.12675; s.foot_width = 0.03;
   cfg->qp_iter_cap_scale = 20;
   return GO1MPC_OK;
 }
@@ -419,6 +428,86 @@ int go1mpc_body_default_tx(go1mpc_t* h, double* tx27) {
   int rc = get_body_model(h, 4, &M);
   if (rc) return rc;
   memcpy(tx27, M->tx0, sizeof M->tx0);
+  return GO1MPC_OK;
+}
+
+// ------------------------------------------------------------------ step timing
+int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick_d, double* state_d, const double* in_d,
+                                  double* out_d, int* diag_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !tick_d || !state_d || !in_d || !out_d) return fail(h, GO1MPC_E_INVALID, "step_timing_step_batch: bad argument");
+  if (n_sqp < 1 || n_sqp > STEP_MAX_SQP) return fail(h, GO1MPC_E_UNSUPPORTED, "step_timing_step_batch: 1 <= n_sqp <= 5");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const Go1StepMpcConfig& c = h->cfg.step;
+  StepKParams P;
+  P.B = B; P.n_sqp = n_sqp; P.cap = h->cfg.qp_iter_cap_scale * (4 + 24 + 1) + 50;
+  P.tick = tick_d; P.state = state_d; P.in = in_d; P.out = out_d; P.diag = diag_d;
+  StepCfgDev& d = P.cfg;
+  d.dt = c.dt; d.Wn = c.Wn; d.ggg = c.ggg; d.t_min = c.t_min; d.t_max = c.t_max;
+  d.footx_max = c.footx_max; d.footx_min = c.footx_min;
+  d.footx_vmax = c.footx_vmax; d.footx_vmin = c.footx_vmin; d.footy_vmax = c.footy_vmax; d.footy_vmin = c.footy_vmin;
+  d.comax_max = c.comax_max; d.comax_min = c.comax_min; d.comay_max = c.comay_max; d.comay_min = c.comay_min;
+  d.aax = c.aax; d.aay = c.aay; d.aaxv = c.aaxv; d.aayv = c.aayv; d.bbx = c.bbx; d.bby = c.bby; d.rr1 = c.rr1; d.rr2 = c.rr2;
+  d.half_hip_width = c.half_hip_width; d.foot_width = c.foot_width;
+  for (int k = 0; k < 4; k++) d.lamda[k] = c.lamda[k];
+  CU(h, step_timing_launch(P, st));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
+int go1mpc_step_timing_step_batch_host(go1mpc_t* h, int n_sqp, int B, const int* tick, double* state, const double* in,
+                                       double* out, int* diag) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!tick || !state || !in || !out) return fail(h, GO1MPC_E_INVALID, "step_timing_step_batch_host: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t b = (size_t)B;
+  const size_t tb = b * sizeof(int), sb = b * STEP_STATE_DOUBLES * sizeof(double), ib = b * STEP_IN_DOUBLES * sizeof(double);
+  const size_t ob = b * STEP_OUT_DOUBLES * sizeof(double), db = b * STEP_DIAG_INTS * sizeof(int);
+  void *dt_, *ds, *di, *do_, *dd = nullptr;
+  int rc;
+  if ((rc = stage_buf(h, 0, tb, &dt_))) return rc;
+  if ((rc = stage_buf(h, 1, sb, &ds))) return rc;
+  if ((rc = stage_buf(h, 2, ib, &di))) return rc;
+  if ((rc = stage_buf(h, 3, ob, &do_))) return rc;
+  if (diag && (rc = stage_buf(h, 4, db, &dd))) return rc;
+  cudaStream_t st = h->stream;
+  CU(h, cudaMemcpyAsync(dt_, tick, tb, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(ds, state, sb, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(di, in, ib, cudaMemcpyHostToDevice, st));
+  rc = go1mpc_step_timing_step_batch(h, n_sqp, B, (const int*)dt_, (double*)ds, (const double*)di, (double*)do_, (int*)dd, st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(state, ds, sb, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaMemcpyAsync(out, do_, ob, cudaMemcpyDeviceToHost, st));
+  if (diag) CU(h, cudaMemcpyAsync(diag, dd, db, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return GO1MPC_OK;
+}
+
+// NLPClass::FootStepInputs (NLP/NLP/NLPClass_sqp.cpp:51-75) + Initialize (:131-206) step tables
+int go1mpc_step_default_state(go1mpc_t* h, double steplength, double stepwidth, double stepheight, double tstep, double* s) {
+  if (!h || !s) return GO1MPC_E_INVALID;
+  const int NS = GO1MPC_FOOTSTEPS;
+  const double dt = h->cfg.step.dt;
+  double sl[GO1MPC_FOOTSTEPS], sw[GO1MPC_FOOTSTEPS], sh[GO1MPC_FOOTSTEPS];
+  memset(s, 0, sizeof(double) * STEP_STATE_DOUBLES);
+  double *ts = s, *tx = s + 27, *fx = s + 54, *fy = s + 81, *fz = s + 108, *Lxx = s + 135, *Lyy = s + 162;
+  for (int j = 0; j < NS; j++) { sl[j] = steplength; sw[j] = stepwidth; sh[j] = stepheight; }
+  sl[NS - 1] = sl[NS - 2] = sl[NS - 3] = sl[NS - 4] = sl[NS - 5] = 0;
+  sl[0] = sl[1] = sl[2] = 0; sl[3] = steplength / 2;
+  sw[0] = sw[0] / 2;
+  sl[14] = 0;
+  for (int j = 15; j <= 21; j++) sl[j] *= -1;
+  for (int j = 0; j < NS; j++) { Lxx[j] = sl[j]; Lyy[j] = (int)pow(-1, j) * sw[j]; }
+  for (int j = 1; j < NS; j++) {
+    fx[j] = fx[j - 1] + sl[j - 1];
+    fy[j] = fy[j - 1] + (int)pow(-1, j - 1) * sw[j - 1];
+    fz[j] = fz[j - 1] + sh[j - 1];
+  }
+  for (int j = 0; j < NS; j++) ts[j] = tstep;
+  for (int j = 1; j < NS; j++) { tx[j] = tx[j - 1] + ts[j - 1]; tx[j] = round(tx[j] / dt) * dt - 0.000001; }
   return GO1MPC_OK;
 }
 

@@ -35,6 +35,26 @@ size_t dense_smem_bytes(int n, int m, int wpc);
 cudaError_t dense_qp_launch(DenseKParams P, int wpc, int grid, size_t smem, cudaStream_t st);
 cudaError_t dense_qp_occupancy(int wpc, size_t smem, int* blocks_per_sm);
 
+// ---- step-location / step-timing SQP (step_timing.cu) ----
+constexpr int STEP_STATE_DOUBLES = 201, STEP_IN_DOUBLES = 20, STEP_OUT_DOUBLES = 38;
+constexpr int STEP_MAX_SQP = 5, STEP_DIAG_HEAD = 5, STEP_DIAG_PER = 11;
+constexpr int STEP_DIAG_INTS = STEP_DIAG_HEAD + STEP_MAX_SQP * STEP_DIAG_PER;
+struct StepCfgDev {
+  double dt, Wn, ggg, t_min, t_max, footx_max, footx_min, footx_vmax, footx_vmin, footy_vmax, footy_vmin;
+  double comax_max, comax_min, comay_max, comay_min, aax, aay, aaxv, aayv, bbx, bby, rr1, rr2;
+  double half_hip_width, foot_width, lamda[4];
+};
+struct StepKParams {
+  int B, n_sqp, cap;
+  const int* tick;
+  double* state;        // [STEP_STATE_DOUBLES][B], in/out
+  const double* in;     // [STEP_IN_DOUBLES][B]
+  double* out;          // [STEP_OUT_DOUBLES][B]
+  int* diag;            // [STEP_DIAG_INTS][B] or null
+  StepCfgDev cfg;
+};
+cudaError_t step_timing_launch(StepKParams P, cudaStream_t st);
+
 // register-resident DFMA loop: flops executed are returned through *flops
 cudaError_t dfma_peak_launch(int grid, int block, int iters, double* sink, cudaStream_t st);
 

@@ -1,0 +1,283 @@
+// step_timing.cu -- step-location / step-timing SQP tick, one thread per MPC instance.
+//
+// Replaces, for a batch of independent planners, one 40 Hz tick of
+//   NLPClass::step_timing_opti_loop      NLP/src/NLP/NLPClass_sqp.cpp:693-1102
+//   step_timing_object_function          :1144-1173
+//   step_timing_constraints              :1175-1458
+//   solve_stepping_timing / Solve        :1613-1653   (QP: n = 4, p = 1, m = 24)
+//   Indexfind                            :1105-1141
+// (NLP = unitree_ros/mosek_nlp_kmp).  K SQP iterations (reference: 3), the write-back of step
+// length / width / period, the LIPM roll-out of the next three samples, the feedback blend and
+// the integer step indices run in ONE launch; the QP matrices live in the thread's local memory
+// and never touch HBM.  CoM_height_solve (:2361-2473) is not on the device yet: the vertical
+// CoM samples are inputs.
+//
+// Layout: structure of arrays, element-major / batch-minor -- field f of instance b is at
+// [f * B + b] -- so a warp's 32 instances read and write 256 contiguous bytes per field.
+// Compiled with -fmad=false: same operation order as the CPU oracle, no FMA contraction.
+#include <cuda_runtime.h>
+#include "gi_thread.cuh"
+#include "kernels.h"
+
+namespace go1 {
+
+namespace {
+constexpr int NS = 27;
+// state fields (doubles)
+constexpr int S_TS = 0, S_TX = 27, S_FX = 54, S_FY = 81, S_FZ = 108, S_LXX = 135, S_LYY = 162, S_FEED = 189, S_VARI = 195, S_END = 199;
+// input fields
+constexpr int I_EST = 0, I_RF = 6, I_LF = 8, I_CZ = 10, I_CAZ = 13, I_ZSC = 16, I_CVZ = 19;
+}  // namespace
+
+__global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.B) return;
+  const size_t B = (size_t)P.B;
+  double* S = P.state + b;
+  const double* IN = P.in + b;
+#define ST(f) S[(size_t)(f) * B]
+#define INP(f) IN[(size_t)(f) * B]
+  const StepCfgDev& c = P.cfg;
+  const double dt = c.dt, Wn = c.Wn;
+  const int i = P.tick[b];
+  double ts[NS], tx[NS];
+  for (int k = 0; k < NS; k++) { ts[k] = ST(S_TS + k); tx[k] = ST(S_TX + k); }
+
+  // :702-704 Indexfind((i+1) dt, xyz0 = -1)
+  int j = 0;
+  while (j < NS && (i + 1) * dt > tx[j] + 0.0001) j++;
+  int p = (j - 1) + 1;
+  const bool valid = (p >= 1 && p <= NS);
+  if (!valid) p = 1;   // table overrun (UB in the reference): flagged in diag, nothing is written
+  const double px = ST(S_FX + p - 1), py = ST(S_FY + p - 1);
+  const int ki = (int)round(tx[p - 1] / dt);
+  const int k_yu = i - ki;
+  const double Tk = ts[p - 1] - k_yu * dt;
+  const double Lxx_refx = ST(S_LXX + p - 1), Lyy_refy = ST(S_LYY + p - 1);
+  const double tr1_ref = cosh(Wn * Tk), tr2_ref = sinh(Wn * Tk);
+  double v[4];
+  if (i == 1) { v[0] = Lxx_refx; v[1] = Lyy_refy; v[2] = tr1_ref; v[3] = tr2_ref; }
+  else { for (int k = 0; k < 4; k++) v[k] = ST(S_VARI + k); }
+  double tr1_min, tr2_min;
+  if ((c.t_min - k_yu * dt) >= 0.001) { tr1_min = cosh(Wn * (c.t_min - k_yu * dt)); tr2_min = sinh(Wn * (c.t_min - k_yu * dt)); }
+  else { tr1_min = cosh(Wn * (0.001)); tr2_min = sinh(Wn * (0.001)); }
+  const double tr1_max = cosh(Wn * (c.t_max - k_yu * dt)), tr2_max = sinh(Wn * (c.t_max - k_yu * dt));
+
+  const double comx_f = ST(S_FEED + 0), comvx_f = ST(S_FEED + 1), comy_f = ST(S_FEED + 3), comvy_f = ST(S_FEED + 4);
+  double endx = ST(S_END + 0), endy = ST(S_END + 1);
+  if (i == 1) {
+    const double isx = comx_f - px, esx = v[0] * 0.5, visx = (esx - isx * v[2]) / (1 / Wn * v[3]);
+    const double isy = comy_f - py, esy = v[1] * 0.5, visy = (esy - isy * v[2]) / (1 / Wn * v[3]);
+    endx = Wn * isx * v[3] + visx * v[2];
+    endy = Wn * isy * v[3] + visy * v[2];
+  }
+  // objective (:1144-1173)
+  const double AxO = comx_f - px, BxO = comvx_f / Wn, Cx = -0.5 * Lxx_refx;
+  const double Axv = Wn * BxO, Bxv = Wn * AxO, Cxv = -endx;
+  const double AyO = comy_f - py, ByO = comvy_f / Wn, Cy = -0.5 * Lyy_refy;
+  const double Ayv = Wn * ByO, Byv = Wn * AyO, Cyv = -endy;
+  const double aax = c.aax, aay = c.aay, aaxv = c.aaxv, aayv = c.aayv;
+  double SQ[4][4];
+  {
+    double SQ0[4][4];
+    for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) SQ0[r][k] = 0.0;
+    SQ0[0][0] = 0.5 * c.bbx;
+    SQ0[1][1] = 0.5 * c.bby;
+    SQ0[2][2] = 0.5 * (c.rr1 + aax * AxO * AxO + aay * AyO * AyO + aaxv * Axv * Axv + aayv * Ayv * Ayv);
+    SQ0[2][3] = 0.5 * (aax * AxO * BxO + aay * AyO * ByO + aaxv * Axv * Bxv + aayv * Ayv * Byv);
+    SQ0[3][2] = 0.5 * (aax * BxO * AxO + aay * ByO * AyO + aaxv * Bxv * Axv + aayv * Byv * Ayv);
+    SQ0[3][3] = 0.5 * (c.rr2 + aax * BxO * BxO + aay * ByO * ByO + aaxv * Bxv * Bxv + aayv * Byv * Byv);
+    for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) SQ[r][k] = (SQ0[r][k] + SQ0[k][r]) / 2.0;
+  }
+  double Sq[4];
+  Sq[0] = -c.bbx * Lxx_refx;
+  Sq[1] = -c.bby * Lyy_refy;
+  Sq[2] = -c.rr1 * tr1_ref + aax * AxO * Cx + aay * AyO * Cy + aaxv * Axv * Cxv + aayv * Ayv * Cyv;
+  Sq[3] = -c.rr2 * tr2_ref + aax * BxO * Cx + aay * ByO * Cy + aaxv * Bxv * Cxv + aayv * Byv * Cyv;
+
+  // lateral reachability (:1216-1246)
+  double footy_max, footy_min;
+  const bool wide = (i >= (round(2 * ts[1] / dt)) + 1);
+  const double HW = c.half_hip_width, FW = c.foot_width;
+  if (p % 2 == 0) { footy_min = -(2 * HW + 0.03); footy_max = wide ? -(FW + 0.01) : -(HW - 0.03); }
+  else { footy_max = 2 * HW + 0.03; footy_min = wide ? FW + 0.01 : HW - 0.03; }
+
+  const double CCx = comx_f - px, CCy = comy_f - py;
+  const double AA = Wn * sinh(Wn * dt);
+  const double BBx = pow(Wn, 2) * CCx * cosh(Wn * dt), BBy = pow(Wn, 2) * CCy * cosh(Wn * dt);
+  const double AA1x = AA * Wn, AA2x = -2 * AA * CCx * Wn, AA3x = 2 * BBx;
+  const double AA1y = AA * Wn, AA2y = -2 * AA * CCy * Wn, AA3y = 2 * BBy;
+  const double VAA = cosh(Wn * dt);
+  const double VBBx = Wn * CCx * sinh(Wn * dt), VBBy = Wn * CCy * sinh(Wn * dt);
+  const double VAA1x = VAA * Wn, VAA2x = -2 * VAA * CCx * Wn, VAA3x = 2 * VBBx - 2 * comvx_f;
+  const double VAA1y = VAA * Wn, VAA2y = -2 * VAA * CCy * Wn, VAA3y = 2 * VBBy - 2 * comvy_f;
+  const double VAA1x1 = Wn, VAA2x1 = -2 * CCx * Wn, VAA3x1 = -2 * comvx_f;
+  const double VAA1y1 = Wn, VAA2y1 = -2 * CCy * Wn, VAA3y1 = -2 * comvy_f;
+
+  int* DG = P.diag ? P.diag + b : nullptr;
+#define DGW(f, val) do { if (DG) DG[(size_t)(f) * B] = (val); } while (0)
+  int n_solved = 0;
+  GiThread<4, 1, 24> qp;
+  for (int it = 1; it <= P.n_sqp; it++) {
+    double G[16], g0[4];
+    for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) G[k * 4 + r] = 2 * SQ[r][k];
+    for (int r = 0; r < 4; r++) {
+      double acc = 0.0;
+      for (int k = 0; k < 4; k++) acc += (2 * SQ[r][k]) * v[k];
+      g0[r] = acc + Sq[r];
+    }
+    double CE[4], ce0[1];
+    {
+      const double trx12[4] = {0.0, 0.0, 2 * v[2], (-2) * v[3]};
+      double q = 0.0;
+      q += v[2] * v[2];
+      q += (v[3] * (-1)) * v[3];
+      ce0[0] = -q + 1;
+      for (int k = 0; k < 4; k++) CE[k] = trx12[k] * (-1);
+    }
+    double CI[96], bb[24];   // CI(:, r) = -A(r, :)
+    for (int k = 0; k < 96; k++) CI[k] = 0.0 * (-1);
+    for (int k = 0; k < 24; k++) bb[k] = 0.0;
+#define AROW(r, k, val) CI[(r) * 4 + (k)] = (val) * (-1)
+    AROW(0, 2, 1.0);  bb[0] = -(v[2]) + tr1_max;
+    AROW(1, 2, -1.0); bb[1] = -((-1.0) * v[2]) - tr1_min;
+    AROW(2, 3, 1.0);  bb[2] = -(v[3]) + tr2_max;
+    AROW(3, 3, -1.0); bb[3] = -((-1.0) * v[3]) - tr2_min;
+    AROW(4, 0, 1.0);  bb[4] = -(v[0]) + c.footx_max;
+    AROW(5, 0, -1.0); bb[5] = -((-1.0) * v[0]) - c.footx_min;
+    AROW(6, 1, 1.0);  bb[6] = -(v[1]) + footy_max;
+    AROW(7, 1, -1.0); bb[7] = -((-1.0) * v[1]) - footy_min;
+    if (k_yu != 0) {
+      AROW(8, 0, 1.0);   bb[8] = -(v[0] - Lxx_refx - c.footx_vmax * dt);
+      AROW(9, 0, -1.0);  bb[9] = v[0] - Lxx_refx - c.footx_vmin * dt;
+      AROW(10, 1, 1.0);  bb[10] = -(v[1] - Lyy_refy - c.footy_vmax * dt);
+      AROW(11, 1, -1.0); bb[11] = v[1] - Lyy_refy - c.footy_vmin * dt;
+    }
+#define ROW3(r, i0, c0, c2, c3, d3) do { \
+      AROW(r, i0, (c0)); AROW(r, 2, (c2)); AROW(r, 3, (c3)); \
+      double acc_ = 0.0; acc_ += (-(c0)) * v[i0]; acc_ += (-(c2)) * v[2]; acc_ += (-(d3)) * v[3]; bb[r] = acc_; } while (0)
+    {
+      double c3, d3;
+      c3 = AA3x - 2 * c.comax_max; ROW3(12, 0, AA1x, AA2x, c3, c3);
+      c3 = -(AA3x - 2 * c.comax_min); ROW3(13, 0, -AA1x, -AA2x, c3, c3);
+      c3 = AA3y - 2 * c.comay_max; ROW3(14, 1, AA1y, AA2y, c3, c3);
+      c3 = -(AA3y - 2 * c.comay_min); ROW3(15, 1, -AA1y, -AA2y, c3, c3);
+      c3 = VAA3x - 2 * c.comax_max * dt; ROW3(16, 0, VAA1x, VAA2x, c3, c3);
+      c3 = -(VAA3x - 2 * c.comax_min * dt); ROW3(17, 0, -VAA1x, -VAA2x, c3, c3);
+      c3 = VAA3y - 2 * c.comay_max * dt; ROW3(18, 1, VAA1y, VAA2y, c3, c3);
+      c3 = -(VAA3y - 2 * c.comay_min * dt); ROW3(19, 1, -VAA1y, -VAA2y, c3, c3);
+      c3 = VAA3x1 - 2 * c.comax_max * dt; d3 = VAA3x1 - 2 * c.comax_max * dt / 2.0; ROW3(20, 0, VAA1x1, VAA2x1, c3, d3);
+      c3 = -(VAA3x1 - 2 * c.comax_min * dt); d3 = -(VAA3x1 - 2 * c.comax_min * dt / 2.0); ROW3(21, 0, -VAA1x1, -VAA2x1, c3, d3);
+      c3 = VAA3y1 - 2 * c.comay_max * dt; d3 = VAA3y1 - 2 * c.comay_max * dt / 2.0; ROW3(22, 1, VAA1y1, VAA2y1, c3, d3);
+      c3 = -(VAA3y1 - 2 * c.comay_min * dt); d3 = -(VAA3y1 - 2 * c.comay_min * dt / 2.0); ROW3(23, 1, -VAA1y1, -VAA2y1, c3, d3);
+    }
+#undef ROW3
+#undef AROW
+    if (Tk >= 0.1 * ts[p - 1]) {
+      double X[4];
+      for (int k = 0; k < 4; k++) X[k] = v[k];
+      const int st = qp.solve(G, g0, CE, ce0, CI, bb, X, P.cap);
+      if (n_solved < STEP_MAX_SQP) {
+        const int o = STEP_DIAG_HEAD + n_solved * STEP_DIAG_PER;
+        DGW(o + 0, st); DGW(o + 1, st == 1 ? 0 : qp.iq);
+        DGW(o + 2, qp.it_outer); DGW(o + 3, qp.it_add); DGW(o + 4, qp.it_drop); DGW(o + 5, qp.it_degen);
+        for (int k = 0; k < 5; k++) DGW(o + 6 + k, (st != 1 && k < qp.iq) ? qp.A[k] : -99);
+      }
+      n_solved++;
+      for (int k = 0; k < 4; k++) v[k] += X[k];   // :795-798, whatever the status
+    } else {
+      v[0] = Lxx_refx; v[1] = Lyy_refy; v[2] = tr1_ref; v[3] = tr2_ref;
+    }
+  }
+  for (int q = n_solved; q < STEP_MAX_SQP; q++) DGW(STEP_DIAG_HEAD + q * STEP_DIAG_PER, -1);
+
+  // write-back (:817, :886-916)
+  const double ts_new = k_yu * dt + log(v[2] + v[3]) / Wn;
+  const double isx = comx_f - px, esx = v[0] * 0.5, visx = (esx - isx * v[2]) / (1 / Wn * v[3]);
+  const double isy = comy_f - py, esy = v[1] * 0.5, visy = (esy - isy * v[2]) / (1 / Wn * v[3]);
+  ts[p - 1] = ts_new;
+  for (int jxx = p + 1; jxx <= NS; jxx++) tx[jxx - 1] = tx[jxx - 2] + ts[jxx - 2];
+  const double fx_next = px + v[0], fy_next = py + v[1];
+
+  // LIPM roll-out of samples i, i+1, i+2 (:938-955)
+  double comx[3], comy[3], comvx[3], comvy[3], comax[3], comay[3], zmpx[3], zmpy[3], dcmx[3], dcmy[3];
+  for (int jxx = 1; jxx <= 3; jxx++) {
+    const int q = jxx - 1;
+    const double w = Wn * dt * jxx;
+    const double ch = cosh(w), sh = sinh(w);
+    comx[q] = isx * ch + visx * 1 / Wn * sh + px;
+    comy[q] = isy * ch + visy * 1 / Wn * sh + py;
+    comvx[q] = Wn * isx * sh + visx * ch;
+    comvy[q] = Wn * isy * sh + visy * ch;
+    comax[q] = pow(Wn, 2) * isx * ch + visx * Wn * sh;
+    comay[q] = pow(Wn, 2) * isy * ch + visy * Wn * sh;
+    const double hz = (INP(I_CZ + q) - INP(I_ZSC + q)) / (INP(I_CAZ + q) + c.ggg);
+    zmpx[q] = comx[q] - hz * comax[q];
+    zmpy[q] = comy[q] - hz * comay[q];
+    dcmx[q] = comx[q] + comvx[q] * sqrt(hz);
+    dcmy[q] = comy[q] + comvy[q] * sqrt(hz);
+  }
+  // feedback blend (:963-972, :1017-1022)
+  double e0 = INP(I_EST + 0), e3 = INP(I_EST + 3);
+  if (p % 2 == 0) { e0 = e0 - INP(I_LF + 0); e3 = e3 - INP(I_LF + 1); }
+  else { e0 = e0 - INP(I_RF + 0); e3 = e3 - INP(I_RF + 1); }
+  const double lx = c.lamda[0], lvx = c.lamda[1], ly = c.lamda[2], lvy = c.lamda[3];
+
+  if (valid) {
+    for (int k = 0; k < 4; k++) ST(S_VARI + k) = v[k];
+    ST(S_LXX + p - 1) = v[0];
+    ST(S_LYY + p - 1) = v[1];
+    ST(S_TS + p - 1) = ts_new;
+    for (int jxx = p + 1; jxx <= NS; jxx++) ST(S_TX + jxx - 1) = tx[jxx - 1];
+    if (p < NS) { ST(S_FX + p) = fx_next; ST(S_FY + p) = fy_next; }
+    ST(S_END + 0) = Wn * isx * v[3] + visx * v[2];
+    ST(S_END + 1) = Wn * isy * v[3] + visy * v[2];
+    ST(S_FEED + 0) = ((1 - lx) * (comx[0] - px) + (lx) * e0) + px;
+    ST(S_FEED + 1) = (1 - lvx) * comvx[0] + (lvx) * INP(I_EST + 1);
+    ST(S_FEED + 2) = (1 - lx) * comax[0] + lx * INP(I_EST + 2);
+    ST(S_FEED + 3) = ((1 - ly) * (comy[0] - py) + (ly) * e3) + py;
+    ST(S_FEED + 4) = (1 - lvy) * comvy[0] + (lvy) * INP(I_EST + 4);
+    ST(S_FEED + 5) = (1 - ly) * comay[0] + ly * INP(I_EST + 5);
+  }
+  // integer step indices against the UPDATED table (:1031-1041)
+  j = 0; while (j < NS && i * dt >= tx[j]) j++;
+  const int bjxx = (j - 1) + 1;
+  j = 0; while (j < NS && (i + 1) * dt >= tx[j]) j++;
+  const int bjx1 = (j - 1) + 1;
+
+  double* O = P.out + b;
+#define OUT(f, val) O[(size_t)(f) * B] = (val)
+  OUT(0, comx[0]); OUT(1, comy[0]); OUT(2, INP(I_CZ + 0));
+  OUT(3, comvx[0]); OUT(4, comvy[0]); OUT(5, INP(I_CVZ));
+  OUT(6, comax[0]); OUT(7, comay[0]); OUT(8, INP(I_CAZ + 0));
+  OUT(9, zmpx[0]); OUT(10, zmpy[0]); OUT(11, dcmx[0]); OUT(12, dcmy[0]);
+  OUT(13, zmpx[1]); OUT(14, zmpy[1]); OUT(15, dcmx[1]); OUT(16, dcmy[1]);
+  OUT(17, zmpx[2]); OUT(18, zmpy[2]); OUT(19, dcmx[2]); OUT(20, dcmy[2]);
+  OUT(21, comax[1]); OUT(22, comay[1]); OUT(23, INP(I_CAZ + 1));
+  OUT(24, comax[2]); OUT(25, comay[2]); OUT(26, INP(I_CAZ + 2));
+  OUT(27, (double)bjxx);
+  const int q0 = bjxx < NS ? bjxx : NS - 1, q1 = bjxx + 1 < NS ? bjxx + 1 : NS - 1;
+  // the next-step entries were updated above: read the new values
+  const double fx0 = (q0 == p && valid && p < NS) ? fx_next : ST(S_FX + q0), fx1 = (q1 == p && valid && p < NS) ? fx_next : ST(S_FX + q1);
+  const double fy0 = (q0 == p && valid && p < NS) ? fy_next : ST(S_FY + q0), fy1 = (q1 == p && valid && p < NS) ? fy_next : ST(S_FY + q1);
+  OUT(28, fx0); OUT(29, fx1); OUT(30, fy0); OUT(31, fy1);
+  OUT(32, ST(S_FZ + q0)); OUT(33, ST(S_FZ + q1));
+  OUT(34, (double)(p - 1));
+  OUT(35, ts_new);
+  OUT(36, v[0]);
+  OUT(37, v[1]);
+  DGW(0, valid ? p : -1); DGW(1, k_yu); DGW(2, bjxx); DGW(3, bjx1); DGW(4, n_solved);
+#undef OUT
+#undef DGW
+#undef ST
+#undef INP
+}
+
+cudaError_t step_timing_launch(StepKParams P, cudaStream_t st) {
+  const int block = 128;
+  const int grid = (P.B + block - 1) / block;
+  step_timing_kernel<<<grid, block, 0, st>>>(P);
+  return cudaGetLastError();
+}
+
+}  // namespace go1

@@ -95,3 +95,53 @@ def random_qp(B, n, p, m, seed=1, paired=False, dup=False, infeasible_frac=0.0):
             CIm[:, 1] = -CIm[:, 0]; c0[1] = -c0[0] - 1.0
         CI[b] = CIm.ravel(order="F"); ci0[b] = c0
     return dict(G=G, g0=g0, CE=CE, ce0=ce0, CI=CI, ci0=ci0)
+
+
+def step_timing_inputs(B, base_state, seed=SEED_CFG2, dt=0.025, Wn=None, amp=1.0):
+    """cfg2-style step-timing batch: every instance is a planner somewhere
+    in its walk, its CoM on the nominal LIPM orbit of that step plus a random push.
+
+    base_state: the 201-double default planner state (step tables of FootStepInputs/Initialize).
+    Per instance: support period p ~ U{3..22}, elapsed samples k_yu ~ U{0..24}, tick
+    i = round(tx[p-1]/dt) + k_yu.  Nominal orbit relative to the support foot: start
+    -L[p-2]/2, end +L[p-1]/2 after ts (the boundary conditions step_timing_opti_loop itself
+    uses, NLPClass_sqp.cpp:896-901).  Push: position U(+-0.01) m, velocity U(+-0.08) m/s in x and
+    U(+-0.006) m, U(+-0.05) m/s in y; velocity command: Lxx_ref[p-1] += U(+-0.02); all times
+    `amp`.  amp = 1 leaves about 3/4 of the QPs feasible with 1..4 constraints active; larger
+    pushes make the reference's own formulation infeasible (its CoM-acceleration rows conflict),
+    which the status codes report.  The warm start is the reference point (Lxx, Lyy, cosh(wT),
+    sinh(wT)) of the previous tick; the end-of-step velocity reference is re-derived from it.
+    Returns tick [B] i32, state [B,201], inp [B,20] (instance-major; transpose for the SoA ABI).
+    """
+    import math
+    if Wn is None:
+        Wn = math.sqrt(9.8 / 0.309458)
+    rng = np.random.Generator(np.random.Philox(seed))
+    st = np.tile(np.asarray(base_state, dtype=np.float64), (B, 1))
+    ar = np.arange(B)
+    p = rng.integers(3, 23, B)
+    k_yu = rng.integers(0, 25, B)
+    ki = np.round(st[ar, 27 + p - 1] / dt).astype(np.int64)
+    tick = (ki + k_yu).astype(np.int32)
+    fx = st[ar, 54 + p - 1]; fy = st[ar, 81 + p - 1]
+    T = st[ar, p - 1]
+    t = k_yu * dt
+    st[ar, 135 + p - 1] += amp * rng.uniform(-0.02, 0.02, B)
+    Lx = st[ar, 135 + p - 1]; Ly = st[ar, 162 + p - 1]
+    isx = -0.5 * st[ar, 135 + p - 2]; isy = -0.5 * st[ar, 162 + p - 2]
+    visx = (0.5 * Lx - isx * np.cosh(Wn * T)) / (np.sinh(Wn * T) / Wn)
+    visy = (0.5 * Ly - isy * np.cosh(Wn * T)) / (np.sinh(Wn * T) / Wn)
+    cx = fx + isx * np.cosh(Wn * t) + visx / Wn * np.sinh(Wn * t) + amp * rng.uniform(-0.01, 0.01, B)
+    cvx = Wn * isx * np.sinh(Wn * t) + visx * np.cosh(Wn * t) + amp * rng.uniform(-0.08, 0.08, B)
+    cy = fy + isy * np.cosh(Wn * t) + visy / Wn * np.sinh(Wn * t) + amp * rng.uniform(-0.006, 0.006, B)
+    cvy = Wn * isy * np.sinh(Wn * t) + visy * np.cosh(Wn * t) + amp * rng.uniform(-0.05, 0.05, B)
+    st[:, 189] = cx; st[:, 190] = cvx; st[:, 191] = 0.0
+    st[:, 192] = cy; st[:, 193] = cvy; st[:, 194] = 0.0
+    Tk_prev = T - (k_yu - 1) * dt
+    st[:, 195] = Lx; st[:, 196] = Ly; st[:, 197] = np.cosh(Wn * Tk_prev); st[:, 198] = np.sinh(Wn * Tk_prev)
+    st[:, 199] = Wn * isx * np.sinh(Wn * T) + visx * np.cosh(Wn * T)
+    st[:, 200] = Wn * isy * np.sinh(Wn * T) + visy * np.cosh(Wn * T)
+    inp = np.zeros((B, 20))
+    inp[:, 7] = -0.12675; inp[:, 9] = 0.12675
+    inp[:, 10:13] = 0.309458
+    return tick, st, inp

@@ -10,6 +10,7 @@ the generators cannot silently re-pin); outputs come from:
   ref_qp_solve        -> Eigen::QP::solve_quadprog        RT/src/utils/EiQuadProg/EiQuadProg.cpp:493-513
   ref_body_theta_mpc  -> PRMPCClass::body_theta_mpc       RT/src/FastMPC/PRMPCClass.cpp:379-714 (nh = 4)
   ref_fk/_g, ref_ik/_g-> Kinematicclass                   GO1/src/kinematics/Kinematics.cpp:63-304
+  ref_nlp_step        -> NLPClass::step_timing_opti_loop  NLP/src/NLP/NLPClass_sqp.cpp:693-1102
 """
 import ctypes
 import os
@@ -106,9 +107,61 @@ def gen_kin(lib):
     print("kin_ref.npz", N)
 
 
+def gen_step(nl):
+    """NLPClass::step_timing_opti_loop: (a) the deterministic 671-tick replay (cfg1) sampled every
+    tick; (b) one-tick evaluations from replay states with random pushes."""
+    nl.ref_nlp_new.restype = ctypes.c_void_p
+    nl.ref_nlp_new.argtypes = [ctypes.c_double] * 3
+    S = 201
+    est = np.zeros(18); rf = np.array([0, -0.12675, 0.]); lf = np.array([0, 0.12675, 0.])
+    consts = np.zeros(25)
+
+    def step(h, i):
+        out = np.zeros(38); hz = np.zeros(10); ints = np.zeros(4, np.int32)
+        nl.ref_nlp_step(h, i, P(est), P(rf), P(lf), 0, P(out), P(hz), PI(ints))
+        inp = np.zeros(20); inp[6:8] = rf[:2]; inp[8:10] = lf[:2]; inp[10:13] = hz[0:3]; inp[13:16] = hz[3:6]
+        inp[16:19] = hz[6:9]; inp[19] = hz[9]
+        return out, inp, ints
+
+    hA = ctypes.c_void_p(nl.ref_nlp_new(0.075, 0.2535, 0.0))
+    nl.ref_nlp_consts(hA, P(consts))
+    T = 671
+    st0 = np.zeros((T + 2, S)); outs = np.zeros((T + 1, 38)); ins = np.zeros((T + 1, 20)); ints = np.zeros((T + 1, 4), np.int32)
+    for i in range(1, T + 1):
+        nl.ref_nlp_get_state(hA, i, P(st0[i]))
+        outs[i], ins[i], ints[i] = step(hA, i)
+    nl.ref_nlp_get_state(hA, T + 1, P(st0[T + 1]))
+    # pushes
+    hB = ctypes.c_void_p(nl.ref_nlp_new(0.075, 0.2535, 0.0))
+    rng = np.random.Generator(np.random.Philox(4001))
+    N = 384
+    pt = rng.integers(2, 640, N).astype(np.int32)
+    pst = st0[pt].copy()
+    amp = np.where(np.arange(N) % 4 == 3, 1.2, 0.5)
+    pst[:, 189] += amp * rng.uniform(-0.02, 0.02, N); pst[:, 190] += amp * rng.uniform(-0.25, 0.25, N)
+    pst[:, 192] += amp * rng.uniform(-0.015, 0.015, N); pst[:, 193] += amp * rng.uniform(-0.2, 0.2, N)
+    pout = np.zeros((N, 38)); pin = np.zeros((N, 20)); pints = np.zeros((N, 4), np.int32); pafter = np.zeros((N, S))
+    for k in range(N):
+        nl.ref_nlp_set_state(hB, int(pt[k]), P(pst[k].copy()))
+        pout[k], pin[k], pints[k] = step(hB, int(pt[k]))
+        nl.ref_nlp_get_state(hB, int(pt[k]) + 1, P(pafter[k]))
+    np.savez_compressed(os.path.join(HERE, "step_ref.npz"), consts=consts, replay_state=st0, replay_out=outs, replay_in=ins,
+                        replay_ints=ints, push_tick=pt, push_state=pst, push_in=pin, push_out=pout, push_ints=pints,
+                        push_state_after=pafter)
+    print("step_ref.npz replay", T, "pushes", N, "finite pushes", int(np.isfinite(pout).all(axis=1).sum()))
+
+
 if __name__ == "__main__":
-    ref, rt = ref_path("libref.so"), ref_path("libref_rt.so")
-    if not ref or not rt:
+    ref, rt, nlp = ref_path("libref.so"), ref_path("libref_rt.so"), ref_path("libref_nlp.so")
+    if not ref or not rt or not nlp:
         raise SystemExit("oracle/_ref is missing: run `make -C oracle ref` where /root/reference exists")
     lib = ctypes.CDLL(ref); rtl = ctypes.CDLL(rt)
-    gen_qp(lib); gen_body(rtl); gen_kin(lib)
+    only = sys.argv[1:]
+    if not only or "qp" in only:
+        gen_qp(lib)
+    if not only or "body" in only:
+        gen_body(rtl)
+    if not only or "kin" in only:
+        gen_kin(lib)
+    if not only or "step" in only:
+        gen_step(ctypes.CDLL(nlp))

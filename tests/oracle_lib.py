@@ -30,6 +30,22 @@ class BodyCfg(ctypes.Structure):
                 ("gama_zmp", ctypes.c_double), ("lamda", ctypes.c_double * 4)]
 
 
+class StepCfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in (
+        "dt Wn ggg t_min t_max footx_max footx_min footx_vmax footx_vmin footy_vmax footy_vmin comax_max comax_min "
+        "comay_max comay_min aax aay aaxv aayv bbx bby rr1 rr2 half_hip_width foot_width").split()] + [
+        ("lamda", ctypes.c_double * 4), ("n_sqp", ctypes.c_int)]
+
+
+class StepDiag(ctypes.Structure):
+    _fields_ = [("periond_i", ctypes.c_int), ("k_yu", ctypes.c_int), ("bjxx", ctypes.c_int), ("bjx1", ctypes.c_int),
+                ("n_solved", ctypes.c_int), ("status", ctypes.c_int * 8), ("nactive", ctypes.c_int * 8),
+                ("iters", (ctypes.c_int * 4) * 8), ("active", (ctypes.c_int * 25) * 8), ("x", (ctypes.c_double * 4) * 8)]
+
+
+STEP_STATE, STEP_IN, STEP_OUT = 201, 20, 38
+
+
 def build_oracle(fast=False):
     """liboracle.so: -O2 -ffp-contract=off (the checker).  fast=True: liboracle_fast.so, the same
     sources at -O3 -march=native for the CPU-baseline timing; always rebuilt on the machine that
@@ -97,3 +113,44 @@ class Oracle:
         self.lib.orc_body_step_batch(ctypes.byref(cfg), B, PI(tick), P(tx), P(theta), P(bstate), P(refs), P(out14), P(x),
                                      PI(act), PI(na), PI(it), PI(st))
         return dict(active=act, nactive=na, iters=it, status=st)
+
+    # ---- step-location / step-timing SQP ----
+    def step_cfg(self, n_sqp=3, **over):
+        c = StepCfg()
+        self.lib.orc_step_cfg_default(ctypes.byref(c))
+        c.n_sqp = n_sqp
+        for k, v in over.items():
+            if k == "lamda":
+                for i in range(4):
+                    c.lamda[i] = v[i]
+            else:
+                setattr(c, k, v)
+        return c
+
+    def step_default_state(self, cfg, steplength=0.075, stepwidth=0.2535, stepheight=0.0, tstep=0.7):
+        s = np.zeros(STEP_STATE)
+        self.lib.orc_step_state_default.argtypes = [ctypes.c_void_p, ctypes.c_void_p] + [ctypes.c_double] * 4
+        self.lib.orc_step_state_default(P(s), ctypes.byref(cfg), steplength, stepwidth, stepheight, tstep)
+        return s
+
+    def step_tick_batch(self, cfg, tick, states, ins):
+        """Instance-major arrays: states [B,201] (updated in place), ins [B,20].  Returns out [B,38] and
+        diagnostics in the GPU diag layout [B,60]."""
+        B = len(tick)
+        out = np.zeros((B, STEP_OUT)); diag = np.full((B, 60), -1, np.int32)
+        for b in range(B):
+            dg = StepDiag()
+            self.lib.orc_step_timing_tick(ctypes.byref(cfg), int(tick[b]), P(states[b]), P(np.ascontiguousarray(ins[b])),
+                                          P(out[b]), ctypes.byref(dg))
+            diag[b, 0:5] = [dg.periond_i, dg.k_yu, dg.bjxx, dg.bjx1, dg.n_solved]
+            for q in range(5):
+                o = 5 + 11 * q
+                if q < dg.n_solved:
+                    st = dg.status[q]
+                    diag[b, o] = st; diag[b, o + 1] = 0 if st == 1 else dg.nactive[q]
+                    diag[b, o + 2:o + 6] = list(dg.iters[q])
+                    na = 0 if st == 1 else dg.nactive[q]
+                    diag[b, o + 6:o + 11] = [dg.active[q][k] if k < na else -99 for k in range(5)]
+                else:
+                    diag[b, o] = -1
+        return out, diag

@@ -1,0 +1,153 @@
+"""GPU parity of the step-location / step-timing SQP tick (go1mpc_step_timing_step_batch,
+through the C ABI) against the CPU oracle restatement of NLPClass::step_timing_opti_loop
+(NLP/src/NLP/NLPClass_sqp.cpp:693-1102) and against outputs of the unmodified reference
+(tests/golden/step_ref.npz): planner outputs and state to 1e-9 relative, identical active sets
+and iteration counters for converged QPs, bit-exact integer step / phase indices."""
+import numpy as np
+import pytest
+
+import quadrupedal_loco_b200 as q
+from quadrupedal_loco_b200 import synth
+from tests.test_oracle_vs_ref import load
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def gpu_tick(mpc, tick, state, inp, n_sqp=3, device=False):
+    """Instance-major in, SoA through the ABI, instance-major out."""
+    B = len(tick)
+    t = np.ascontiguousarray(tick, np.int32)
+    s = np.ascontiguousarray(state.T); i_ = np.ascontiguousarray(inp.T)
+    o = np.zeros((q.STEP_OUT, B)); d = np.full((q.STEP_DIAG, B), -7, np.int32)
+    if device:
+        import torch
+        dev = torch.device("cuda", 0)
+        tt, ts, ti, to, td = (torch.from_numpy(a).to(dev) for a in (t, s, i_, o, d))
+        torch.cuda.synchronize()
+        mpc.step_timing_step(n_sqp, B, tt, ts, ti, to, td)
+        mpc.synchronize()
+        s, o, d = ts.cpu().numpy(), to.cpu().numpy(), td.cpu().numpy()
+    else:
+        mpc.step_timing_step_host(n_sqp, B, t, s, i_, o, d)
+    return o.T.copy(), s.T.copy(), d.T.copy()
+
+
+def close(a, b, label):
+    sc = np.maximum(1.0, np.abs(b))
+    err = np.abs(a - b) / sc
+    assert np.nanmax(err) < RTOL, f"{label}: rel err {np.nanmax(err):.3e} at {np.unravel_index(np.nanargmax(err), err.shape)}"
+
+
+def assert_step_parity(go, gs, gd, oo, os_, od, label=""):
+    # integer indices: bit-exact
+    assert np.array_equal(gd[:, :5], od[:, :5]), f"{label}: period / phase indices"
+    sts_g = gd[:, 5::11]; sts_o = od[:, 5::11]
+    assert np.array_equal(sts_g, sts_o), f"{label}: QP status {np.nonzero((sts_g != sts_o).any(axis=1))[0][:8]}"
+    # instances whose every QP converged: everything must agree
+    ok = ((sts_o == 0) | (sts_o == -1)).all(axis=1) & np.isfinite(oo).all(axis=1)
+    assert ok.sum() > 0
+    for qi in range(5):
+        o = 5 + 11 * qi
+        conv = od[:, o] == 0
+        assert np.array_equal(gd[conv, o + 1:o + 11], od[conv, o + 1:o + 11]), f"{label}: active set / counters of SQP iteration {qi}"
+    close(go[ok], oo[ok], label + " out38")
+    close(gs[ok], os_[ok], label + " state")
+    return ok
+
+
+@pytest.mark.parametrize("n_sqp", [1, 3, 5])
+def test_step_parity_synth(mpc, oracle, n_sqp):
+    B = 2048
+    cfg = oracle.step_cfg(n_sqp)
+    base = mpc.step_default_state()
+    np.testing.assert_array_equal(base, oracle.step_default_state(cfg))
+    tick, st, inp = synth.step_timing_inputs(B, base, seed=synth.SEED_CFG2 + n_sqp, amp=1.0)
+    go, gs, gd = gpu_tick(mpc, tick, st, inp, n_sqp)
+    os_ = st.copy()
+    oo, od = oracle.step_tick_batch(cfg, tick, os_, inp)
+    ok = assert_step_parity(go, gs, gd, oo, os_, od, f"K={n_sqp}")
+    assert ok.mean() > 0.6
+    assert (od[:, 6::11][:, :n_sqp][od[:, 5::11][:, :n_sqp] == 0] >= 3).any(), "no QP with several active constraints"
+
+
+def test_step_device_entry_large_pushes(mpc, oracle):
+    B = 4096
+    cfg = oracle.step_cfg(3)
+    tick, st, inp = synth.step_timing_inputs(B, mpc.step_default_state(), seed=synth.SEED_CFG3, amp=2.0)
+    go, gs, gd = gpu_tick(mpc, tick, st, inp, 3, device=True)
+    os_ = st.copy()
+    oo, od = oracle.step_tick_batch(cfg, tick, os_, inp)
+    assert_step_parity(go, gs, gd, oo, os_, od, "cfg3")
+    assert (od[:, 5::11][:, :3] == 2).any()
+
+
+def test_step_replay_closed_loop_vs_reference_golden(mpc):
+    """cfg1: the 671-tick replay, state carried on the GPU side only, against the unmodified
+    reference's outputs; integer indices bit-exact every tick."""
+    g = load("step_ref.npz")
+    T = g["replay_out"].shape[0] - 1
+    st = g["replay_state"][1][None, :].copy()
+    np.testing.assert_array_equal(mpc.step_default_state(), st[0][:201] * (np.arange(201) < 189))
+    for i in range(1, T + 1):
+        go, st, gd = gpu_tick(mpc, [i], st, g["replay_in"][i][None, :])
+        assert list(gd[0, :4]) == list(g["replay_ints"][i]), (i, gd[0, :4], g["replay_ints"][i])
+        close(go[0], g["replay_out"][i], f"replay out tick {i}")
+        close(st[0], g["replay_state"][i + 1], f"replay state tick {i}")
+        assert go[0, 27] == g["replay_out"][i][27] and go[0, 34] == g["replay_out"][i][34]
+
+
+def test_step_pushes_vs_reference_golden(mpc):
+    g = load("step_ref.npz")
+    go, gs, gd = gpu_tick(mpc, g["push_tick"], g["push_state"], g["push_in"])
+    fin = np.isfinite(g["push_out"]).all(axis=1)
+    assert np.array_equal(gd[fin, :4], g["push_ints"][fin])
+    conv = fin & (gd[:, 5::11][:, :3] == 0).all(axis=1)
+    assert conv.sum() > 150
+    close(go[conv], g["push_out"][conv], "push out")
+    close(gs[conv], g["push_state_after"][conv], "push state")
+
+
+def test_step_batch_of_one_and_ragged(mpc, oracle):
+    cfg = oracle.step_cfg(3)
+    for B in (1, 33, 127, 129):
+        tick, st, inp = synth.step_timing_inputs(B, mpc.step_default_state(), seed=B, amp=0.5)
+        go, gs, gd = gpu_tick(mpc, tick, st, inp)
+        os_ = st.copy()
+        oo, od = oracle.step_tick_batch(cfg, tick, os_, inp)
+        assert_step_parity(go, gs, gd, oo, os_, od, f"B={B}")
+
+
+def test_step_feedback_gains(mpc, oracle):
+    lam = [0.25, 0.001, 0.025, 0.001]     # the commented multi-push preset, NLPClass_sqp.cpp:986-993
+    h = q.Go1Mpc(0, cfg=dict(step=dict(lamda=lam)))
+    try:
+        cfg = oracle.step_cfg(3, lamda=lam)
+        tick, st, inp = synth.step_timing_inputs(512, h.step_default_state(), seed=77, amp=0.7)
+        rng = np.random.default_rng(5)
+        inp[:, 0:6] = st[:, 189:195] + rng.uniform(-0.01, 0.01, (512, 6))
+        go, gs, gd = gpu_tick(h, tick, st, inp)
+        os_ = st.copy()
+        oo, od = oracle.step_tick_batch(cfg, tick, os_, inp)
+        assert_step_parity(go, gs, gd, oo, os_, od, "lamda")
+    finally:
+        h.close()
+
+
+def test_step_full_size_properties(mpc):
+    """65536 instances: idempotent launches; converged solves respect the step-period and
+    reachability bounds; the period written back equals k_yu dt + log(tr1 + tr2) / w."""
+    B = 65536
+    tick, st, inp = synth.step_timing_inputs(B, mpc.step_default_state(), seed=synth.SEED_CFG3, amp=1.0)
+    go, gs, gd = gpu_tick(mpc, tick, st, inp)
+    go2, gs2, gd2 = gpu_tick(mpc, tick, st, inp)
+    np.testing.assert_array_equal(go, go2); np.testing.assert_array_equal(gs, gs2); np.testing.assert_array_equal(gd, gd2)
+    conv = (gd[:, 5::11][:, :3] == 0).all(axis=1)
+    assert conv.mean() > 0.6
+    v = gs[conv, 195:199]
+    assert (v[:, 0] <= 0.15 + 1e-7).all() and (v[:, 0] >= -0.05 - 1e-7).all()
+    Wn = np.sqrt(9.8 / 0.309458)
+    k_yu = gd[conv, 1]
+    ts_new = go[conv, 35]
+    np.testing.assert_allclose(ts_new, k_yu * 0.025 + np.log(v[:, 2] + v[:, 3]) / Wn, rtol=1e-12)
+    assert (ts_new <= 1.0 + 1e-6).all()

@@ -93,3 +93,69 @@ def test_oracle_qp_vs_live_reference(oracle):
                                       P(d["ce0"][b].copy()), P(d["CI"][b].copy()), P(d["ci0"][b].copy()), P(x2))
             assert ok == 1
             np.testing.assert_array_equal(x2, x)
+
+
+def _step_cfg_from_golden(oracle, g, n_sqp=3):
+    names = ("dt Wn ggg t_min t_max footx_max footx_min footx_vmax footx_vmin footy_vmax footy_vmin comax_max comax_min "
+             "comay_max comay_min aax aay aaxv aayv bbx bby rr1 rr2 half_hip_width foot_width").split()
+    cfg = oracle.step_cfg(n_sqp)
+    for n, v in zip(names, g["consts"]):
+        assert getattr(cfg, n) == v, f"default {n} differs from the reference's constant"
+    return cfg
+
+
+def test_oracle_step_replay_bit_exact_vs_reference_golden(oracle):
+    """cfg1: the deterministic 671-tick replay of NLPClass::step_timing_opti_loop -- outputs,
+    updated state and integer indices, bit for bit, every tick."""
+    g = load("step_ref.npz")
+    cfg = _step_cfg_from_golden(oracle, g)
+    T = g["replay_out"].shape[0] - 1
+    # default tables are the reference's Initialize()
+    np.testing.assert_array_equal(oracle.step_default_state(cfg)[:189], g["replay_state"][1][:189])
+    st = g["replay_state"][1].copy()
+    for i in range(1, T + 1):
+        np.testing.assert_array_equal(st, g["replay_state"][i], err_msg=f"state before tick {i}")
+        out, dg = oracle.step_tick_batch(cfg, [i], st[None, :], g["replay_in"][i][None, :])
+        # step_tick_batch updates a copy of the row when given a fresh 2-D view: redo on a real 2-D array
+        s2 = g["replay_state"][i].copy()[None, :]
+        out, dg = oracle.step_tick_batch(cfg, [i], s2, g["replay_in"][i][None, :])
+        st = s2[0]
+        np.testing.assert_array_equal(out[0], g["replay_out"][i], err_msg=f"out38 tick {i}")
+        assert list(dg[0, :4]) == list(g["replay_ints"][i]), (i, dg[0, :4], g["replay_ints"][i])
+    np.testing.assert_array_equal(st, g["replay_state"][T + 1])
+
+
+def test_oracle_step_pushes_bit_exact_vs_reference_golden(oracle):
+    g = load("step_ref.npz")
+    cfg = _step_cfg_from_golden(oracle, g)
+    st = g["push_state"].copy()
+    out, dg = oracle.step_tick_batch(cfg, g["push_tick"], st, g["push_in"])
+    fin = np.isfinite(g["push_out"]).all(axis=1)
+    assert fin.sum() > 300
+    np.testing.assert_array_equal(out[fin], g["push_out"][fin])
+    np.testing.assert_array_equal(st[fin], g["push_state_after"][fin])
+    np.testing.assert_array_equal(dg[fin, :4], g["push_ints"][fin])
+    sts = dg[:, 5::11][:, :3]
+    assert (sts == 0).any() and (sts == 2).any()       # both converged and infeasible solves are pinned
+    assert (dg[:, 6::11][:, :3][sts == 0] >= 3).any()   # with several constraints active
+
+
+@pytest.mark.skipif(ref_path("libref_nlp.so") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_step_vs_live_reference(oracle):
+    lib = ctypes.CDLL(ref_path("libref_nlp.so"))
+    lib.ref_nlp_new.restype = ctypes.c_void_p
+    lib.ref_nlp_new.argtypes = [ctypes.c_double] * 3
+    h = ctypes.c_void_p(lib.ref_nlp_new(0.06, 0.2535, 0.0))     # a different step length than the golden run
+    cfg = oracle.step_cfg(3)
+    est = np.zeros(18); rf = np.array([0, -0.12675, 0.]); lf = np.array([0, 0.12675, 0.])
+    for i in range(1, 200):
+        st = np.zeros(201); lib.ref_nlp_get_state(h, i, P(st))
+        out = np.zeros(38); hz = np.zeros(10); ints = np.zeros(4, np.int32)
+        lib.ref_nlp_step(h, i, P(est), P(rf), P(lf), 0, P(out), P(hz), PI(ints))
+        after = np.zeros(201); lib.ref_nlp_get_state(h, i + 1, P(after))
+        inp = np.zeros(20); inp[6:8] = rf[:2]; inp[8:10] = lf[:2]; inp[10:13] = hz[:3]; inp[13:16] = hz[3:6]; inp[16:19] = hz[6:9]; inp[19] = hz[9]
+        s2 = st[None, :].copy()
+        o, dg = oracle.step_tick_batch(cfg, [i], s2, inp[None, :])
+        np.testing.assert_array_equal(o[0], out); np.testing.assert_array_equal(s2[0], after)
+        assert list(dg[0, :4]) == list(ints)
+    lib.ref_nlp_free(h)
