@@ -18,7 +18,8 @@ def gpu_tick(mpc, tick, state, inp, n_sqp=3, device=False):
     """Instance-major in, SoA through the ABI, instance-major out."""
     B = len(tick)
     t = np.ascontiguousarray(tick, np.int32)
-    s = np.ascontiguousarray(state.T); i_ = np.ascontiguousarray(inp.T)
+    s = np.array(np.asarray(state).T, dtype=np.float64, order="C", copy=True)   # a (201, 1) transpose is already contiguous: force a copy
+    i_ = np.array(np.asarray(inp).T, dtype=np.float64, order="C", copy=True)
     o = np.zeros((q.STEP_OUT, B)); d = np.full((q.STEP_DIAG, B), -7, np.int32)
     if device:
         import torch
