@@ -238,6 +238,30 @@ int go1mpc_step_timing_step_batch_host(go1mpc_t *h, int n_sqp, int B, const int 
 int go1mpc_step_default_state(go1mpc_t *h, double steplength, double stepwidth,
                               double stepheight, double tstep, double *state201);
 
+/* ---------------------------------------------------------------------------
+ * Go1 leg kinematics for B independent legs.  Replaces Kinematicclass
+ * (GO1/kinematics/Kinematics.h:49-60, Kinematics.cpp:29-304):
+ *   go1mpc_leg_fk_batch  -> Forward_kinematics (body_p_d == NULL) / Forward_kinematics_g
+ *   go1mpc_leg_ik_batch  -> Inverse_kinematics (body_p_d == NULL: <= 10 updates, stop
+ *                           max(dq) < 1e-4 without abs, as the reference) / Inverse_kinematics_g
+ *                           (<= 15 updates, stop |dp|^2 <= 1e-6); lamda = 0.5
+ * The reference returns the Jacobian through the member Jacobian_kin read after each
+ * call (servo.cpp:734-741,1038-1051); here it is the output array jac_d.
+ * Layout: structure of arrays, [f*B + b].  q_d / qini_d / pdes_d / pos_d / body_p_d /
+ * body_r_d (roll, pitch, yaw): [3][B] doubles; jac_d: [9][B] doubles, row-major 3x3, may be
+ * NULL; leg_d: [B] ints, 0 FR, 1 FL, 2 RR, 3 RL; iters_d: [B] ints (Newton updates), may be NULL.
+ * ------------------------------------------------------------------------ */
+int go1mpc_leg_fk_batch(go1mpc_t *h, int B, const double *q_d, const int *leg_d,
+                        const double *body_p_d, const double *body_r_d,
+                        double *pos_d, double *jac_d, void *stream);
+int go1mpc_leg_ik_batch(go1mpc_t *h, int B, const double *pdes_d, const double *qini_d, const int *leg_d,
+                        const double *body_p_d, const double *body_r_d,
+                        double *q_d, double *jac_d, int *iters_d, void *stream);
+int go1mpc_leg_fk_batch_host(go1mpc_t *h, int B, const double *q, const int *leg,
+                             const double *body_p, const double *body_r, double *pos, double *jac);
+int go1mpc_leg_ik_batch_host(go1mpc_t *h, int B, const double *pdes, const double *qini, const int *leg,
+                             const double *body_p, const double *body_r, double *q, double *jac, int *iters);
+
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports
  * against.  Runs ~`ms` milliseconds. */

@@ -182,6 +182,18 @@ void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const
 void orc_step_timing_batch(const orc_step_cfg *c, int B, const int *tick, double *states, const double *ins,
                            double *out38, orc_step_diag *diag);
 
+/* ------------------------------------------------------------------------
+ * Go1 leg kinematics (Kinematicclass, GO1/src/kinematics/Kinematics.cpp:29-304).
+ * leg: 0 FR, 1 FL, 2 RR, 3 RL.  J is row-major 3x3 (the reference's Jacobian_kin
+ * side channel after the call).  The IK functions return the number of Newton
+ * updates applied.
+ * --------------------------------------------------------------------- */
+void orc_leg_fk(const double q[3], int leg, double pos[3], double J[9]);
+void orc_leg_fk_g(const double bp[3], const double br[3], const double q[3], int leg, double pos[3], double J[9]);
+int orc_leg_ik(const double pdes[3], const double qini[3], int leg, double q[3], double J[9]);
+int orc_leg_ik_g(const double bp[3], const double br[3], const double pdes[3], const double qini[3], int leg,
+                 double q[3], double J[9]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_body_mpc_step_batch", "go1mpc_body_mpc_step_batch_host",
     "go1mpc_body_model", "go1mpc_body_default_tx", "go1mpc_measure_dfma_peak",
     "go1mpc_step_timing_step_batch", "go1mpc_step_timing_step_batch_host", "go1mpc_step_default_state",
+    "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
 
@@ -97,6 +98,10 @@ def load_library():
     lib.go1mpc_step_timing_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     lib.go1mpc_step_timing_step_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
     lib.go1mpc_step_default_state.argtypes = [vp] + [ctypes.c_double] * 4 + [vp]
+    lib.go1mpc_leg_fk_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
+    lib.go1mpc_leg_ik_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
+    lib.go1mpc_leg_fk_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
+    lib.go1mpc_leg_ik_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 8
     _LIB = lib
     return lib
 
@@ -257,6 +262,23 @@ class Go1Mpc:
         self._check(self.lib.go1mpc_step_default_state(self.h, steplength, stepwidth, stepheight, tstep, _ptr(s)),
                     "step_default_state")
         return s
+
+    # --- leg kinematics (SoA buffers: [3][B], [9][B]) ---
+    def leg_fk(self, B, q, leg, body_p, body_r, pos, jac=None, stream=None):
+        self._check(self.lib.go1mpc_leg_fk_batch(self.h, B, _ptr(q), _ptr(leg), _ptr(body_p), _ptr(body_r), _ptr(pos),
+                                                 _ptr(jac), stream), "leg_fk_batch")
+
+    def leg_ik(self, B, pdes, qini, leg, body_p, body_r, q, jac=None, iters=None, stream=None):
+        self._check(self.lib.go1mpc_leg_ik_batch(self.h, B, _ptr(pdes), _ptr(qini), _ptr(leg), _ptr(body_p), _ptr(body_r),
+                                                 _ptr(q), _ptr(jac), _ptr(iters), stream), "leg_ik_batch")
+
+    def leg_fk_host(self, B, q, leg, body_p, body_r, pos, jac=None):
+        self._check(self.lib.go1mpc_leg_fk_batch_host(self.h, B, _ptr(q), _ptr(leg), _ptr(body_p), _ptr(body_r), _ptr(pos),
+                                                      _ptr(jac)), "leg_fk_batch_host")
+
+    def leg_ik_host(self, B, pdes, qini, leg, body_p, body_r, q, jac=None, iters=None):
+        self._check(self.lib.go1mpc_leg_ik_batch_host(self.h, B, _ptr(pdes), _ptr(qini), _ptr(leg), _ptr(body_p),
+                                                      _ptr(body_r), _ptr(q), _ptr(jac), _ptr(iters)), "leg_ik_batch_host")
 
     def measure_dfma_peak(self, ms=200):
         g = ctypes.c_double(0.0)

@@ -511,6 +511,80 @@ int go1mpc_step_default_state(go1mpc_t* h, double steplength, double stepwidth, 
   return GO1MPC_OK;
 }
 
+// ------------------------------------------------------------------ leg kinematics
+int go1mpc_leg_fk_batch(go1mpc_t* h, int B, const double* q_d, const int* leg_d, const double* body_p_d, const double* body_r_d,
+                        double* pos_d, double* jac_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !q_d || !leg_d || !pos_d || ((body_p_d == nullptr) != (body_r_d == nullptr)))
+    return fail(h, GO1MPC_E_INVALID, "leg_fk_batch: bad argument");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  LegKParams P{};
+  P.B = B; P.q_in = q_d; P.leg = leg_d; P.body_p = body_p_d; P.body_r = body_r_d; P.pos_out = pos_d; P.jac_out = jac_d;
+  CU(h, leg_fk_launch(P, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+int go1mpc_leg_ik_batch(go1mpc_t* h, int B, const double* pdes_d, const double* qini_d, const int* leg_d, const double* body_p_d,
+                        const double* body_r_d, double* q_d, double* jac_d, int* iters_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !pdes_d || !qini_d || !leg_d || !q_d || ((body_p_d == nullptr) != (body_r_d == nullptr)))
+    return fail(h, GO1MPC_E_INVALID, "leg_ik_batch: bad argument");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  LegKParams P{};
+  P.B = B; P.q_in = qini_d; P.leg = leg_d; P.body_p = body_p_d; P.body_r = body_r_d; P.pdes = pdes_d;
+  P.q_out = q_d; P.jac_out = jac_d; P.iters = iters_d;
+  CU(h, leg_ik_launch(P, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+namespace {
+// shared host staging for the two leg entries: ins[k] (bytes) up, outs[k] down
+int leg_host(go1mpc* h, int B, bool ik, const double* a3, const double* b3, const int* leg, const double* bp, const double* br,
+             double* o3, double* jac, int* iters) {
+  const size_t b = (size_t)B, v3 = b * 3 * sizeof(double), v9 = b * 9 * sizeof(double), vi = b * sizeof(int);
+  void *da, *db = nullptr, *dl, *dbp = nullptr, *dbr = nullptr, *do3, *dj = nullptr, *dit = nullptr;
+  int rc;
+  if ((rc = stage_buf(h, 0, v3, &da))) return rc;
+  if (ik && (rc = stage_buf(h, 1, v3, &db))) return rc;
+  if ((rc = stage_buf(h, 2, vi, &dl))) return rc;
+  if (bp) { if ((rc = stage_buf(h, 3, v3, &dbp))) return rc; if ((rc = stage_buf(h, 4, v3, &dbr))) return rc; }
+  if ((rc = stage_buf(h, 5, v3, &do3))) return rc;
+  if (jac && (rc = stage_buf(h, 6, v9, &dj))) return rc;
+  if (iters && (rc = stage_buf(h, 7, vi, &dit))) return rc;
+  cudaStream_t st = h->stream;
+  CU(h, cudaMemcpyAsync(da, a3, v3, cudaMemcpyHostToDevice, st));
+  if (ik) CU(h, cudaMemcpyAsync(db, b3, v3, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(dl, leg, vi, cudaMemcpyHostToDevice, st));
+  if (bp) { CU(h, cudaMemcpyAsync(dbp, bp, v3, cudaMemcpyHostToDevice, st)); CU(h, cudaMemcpyAsync(dbr, br, v3, cudaMemcpyHostToDevice, st)); }
+  if (ik) rc = go1mpc_leg_ik_batch(h, B, (double*)da, (double*)db, (int*)dl, (double*)dbp, (double*)dbr, (double*)do3, (double*)dj, (int*)dit, st);
+  else rc = go1mpc_leg_fk_batch(h, B, (double*)da, (int*)dl, (double*)dbp, (double*)dbr, (double*)do3, (double*)dj, st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(o3, do3, v3, cudaMemcpyDeviceToHost, st));
+  if (jac) CU(h, cudaMemcpyAsync(jac, dj, v9, cudaMemcpyDeviceToHost, st));
+  if (iters) CU(h, cudaMemcpyAsync(iters, dit, vi, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return GO1MPC_OK;
+}
+}  // namespace
+int go1mpc_leg_fk_batch_host(go1mpc_t* h, int B, const double* q, const int* leg, const double* body_p, const double* body_r,
+                             double* pos, double* jac) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!q || !leg || !pos || ((body_p == nullptr) != (body_r == nullptr))) return fail(h, GO1MPC_E_INVALID, "leg_fk_batch_host: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  return leg_host(h, B, false, q, nullptr, leg, body_p, body_r, pos, jac, nullptr);
+}
+int go1mpc_leg_ik_batch_host(go1mpc_t* h, int B, const double* pdes, const double* qini, const int* leg, const double* body_p,
+                             const double* body_r, double* q, double* jac, int* iters) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!pdes || !qini || !leg || !q || ((body_p == nullptr) != (body_r == nullptr))) return fail(h, GO1MPC_E_INVALID, "leg_ik_batch_host: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  return leg_host(h, B, true, pdes, qini, leg, body_p, body_r, q, jac, iters);
+}
+
 int go1mpc_measure_dfma_peak(go1mpc_t* h, int ms, double* gflops) {
   if (!h || !gflops) return GO1MPC_E_INVALID;
   CU(h, cudaSetDevice(h->device));

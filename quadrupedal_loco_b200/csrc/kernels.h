@@ -55,6 +55,22 @@ struct StepKParams {
 };
 cudaError_t step_timing_launch(StepKParams P, cudaStream_t st);
 
+// ---- leg kinematics (leg_kin.cu); all arrays SoA [field][B] ----
+struct LegKParams {
+  int B;
+  const double* q_in;     // FK: joint angles; IK: initial guess
+  const int* leg;         // 0 FR, 1 FL, 2 RR, 3 RL
+  const double* body_p;   // null = hip-frame variant
+  const double* body_r;
+  const double* pdes;     // IK target
+  double* pos_out;        // FK
+  double* q_out;          // IK
+  double* jac_out;        // [9][B] row-major 3x3, may be null
+  int* iters;             // IK updates applied, may be null
+};
+cudaError_t leg_fk_launch(LegKParams P, cudaStream_t st);
+cudaError_t leg_ik_launch(LegKParams P, cudaStream_t st);
+
 // register-resident DFMA loop: flops executed are returned through *flops
 cudaError_t dfma_peak_launch(int grid, int block, int iters, double* sink, cudaStream_t st);
 

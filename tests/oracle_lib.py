@@ -154,3 +154,24 @@ class Oracle:
                 else:
                     diag[b, o] = -1
         return out, diag
+
+    # ---- leg kinematics (instance-major arrays) ----
+    def leg_fk(self, q, leg, bp=None, br=None):
+        B = len(leg); pos = np.zeros((B, 3)); J = np.zeros((B, 9))
+        for b in range(B):
+            if bp is None:
+                self.lib.orc_leg_fk(P(np.ascontiguousarray(q[b])), int(leg[b]), P(pos[b]), P(J[b]))
+            else:
+                self.lib.orc_leg_fk_g(P(np.ascontiguousarray(bp[b])), P(np.ascontiguousarray(br[b])), P(np.ascontiguousarray(q[b])),
+                                      int(leg[b]), P(pos[b]), P(J[b]))
+        return pos, J
+
+    def leg_ik(self, pdes, qini, leg, bp=None, br=None):
+        B = len(leg); q = np.zeros((B, 3)); J = np.zeros((B, 9)); it = np.zeros(B, np.int32)
+        for b in range(B):
+            if bp is None:
+                it[b] = self.lib.orc_leg_ik(P(np.ascontiguousarray(pdes[b])), P(np.ascontiguousarray(qini[b])), int(leg[b]), P(q[b]), P(J[b]))
+            else:
+                it[b] = self.lib.orc_leg_ik_g(P(np.ascontiguousarray(bp[b])), P(np.ascontiguousarray(br[b])), P(np.ascontiguousarray(pdes[b])),
+                                              P(np.ascontiguousarray(qini[b])), int(leg[b]), P(q[b]), P(J[b]))
+        return q, J, it
