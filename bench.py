@@ -4,11 +4,14 @@
     python bench.py --gpus N --steps K --warmup W            (own arm; torchrun for N > 1)
     python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm, host cores)
 
-A "step" is one pass of the fused body-inclination MPC tick (condensation -> Goldfarb-Idnani
-QP -> clamp -> roll-out; one QP solve per instance) over one batch of synthetic instances.
+A "step" is one pass of the Go1 MPC hot path over one batch of synthetic robots: per robot one
+step-location/step-timing SQP tick (3 QP solves, n=4 p=1 m=24, plus write-back, LIPM roll-out
+and step indices) and one body-inclination MPC tick (condensation -> Goldfarb-Idnani QP ->
+clamp -> roll-out; 1 QP solve, n=2nh m=12nh) -- two kernels on two streams.  `value` counts QP
+solves (one solve = one solve_quadprog call of the reference).
 Workload at every N: BASELINE.json configs[1] -- Go1 MPC, batch 4096 randomised states and
-references per GPU, horizon 10 (seed 0xB2000002 + rank); weak
-scaling: every rank owns its own 4096 instances, no collective inside the step.
+velocity commands per GPU, horizon 10 (seed 0xB2000002 + rank); weak
+scaling: every rank owns its own 4096 robots, no collective inside the step.
 
 Timing: CUDA events on the stream the kernels are launched on, W untimed steps, then exactly K
 timed steps bracketed by barrier + synchronize; max over ranks.  The steps rotate through
@@ -50,60 +53,73 @@ def parse():
 
 
 def workload_config(a, n_gpus):
-    return {"workload": f"cfg2: Go1 body-inclination MPC tick (1 QP solve/instance: n={2 * a.nh}, m={12 * a.nh}), "
-                        f"horizon {a.nh}, batch {a.batch} randomised states+references per GPU",
-            "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus, "horizon": a.nh,
-            "qp_shape": [2 * a.nh, 0, 12 * a.nh], "seed": "0xB2000002+rank",
+    return {"workload": f"cfg2: Go1 MPC, batch {a.batch} robots per GPU with randomised CoM / body-angle states and velocity "
+                        f"commands; per robot and step: one step-location/step-timing SQP tick (3 QP solves, n=4 p=1 m=24) + "
+                        f"one body-inclination MPC tick at horizon {a.nh} (1 QP solve, n={2 * a.nh} m={12 * a.nh})",
+            "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus, "horizon": a.nh, "sqp_iterations": 3,
+            "qp_shapes": [[2 * a.nh, 0, 12 * a.nh], [4, 1, 24]], "seed": "0xB2000002+rank",
             "parallelism": f"batch-sharded x{n_gpus}, no collective",
             "l2": "inputs rotate through distinct batches totalling > 2x L2 (no flush needed)"}
 
 
 # ----------------------------------------------------------------------------- CPU arm
-def cpu_body_runner(a, threads):
-    """Returns (run_once, B): run_once() solves one batch of a.batch instances with `threads`
-    host threads through the oracle port (-O3 -march=native build), returns seconds."""
+def cpu_runner(a, threads):
+    """Returns (run_once, solves): run_once() runs one step (step-timing tick + body tick for a.batch
+    robots) with `threads` host threads through the oracle port (-O3 -march=native build), returns seconds."""
     from tests import oracle_lib
     from quadrupedal_loco_b200 import synth
     orc = oracle_lib.Oracle(fast=True)
     nh, B = a.nh, a.batch
     d = synth.body_mpc_inputs(B, nh, seed=synth.SEED_CFG2)
     cfg = orc.body_cfg(nh)
+    scfg = orc.step_cfg(3)
+    tick, st0, sin = synth.step_timing_inputs(B, orc.step_default_state(scfg), seed=synth.SEED_CFG2)
     bounds = np.linspace(0, B, threads + 1).astype(int)
+    nsolved = np.zeros(threads, np.int64)
 
-    def work(lo, hi):
+    def work(t, lo, hi):
         theta = d["theta"][lo:hi].copy(); x = d["x_warm"][lo:hi].copy(); o14 = np.zeros((hi - lo, 14))
         orc.body_step_batch(cfg, d["tick"][lo:hi], np.ascontiguousarray(d["tx"][lo:hi]), theta,
                             np.ascontiguousarray(d["bstate"][lo:hi]), np.ascontiguousarray(d["refs"][lo:hi]), o14, x)
+        st = st0[lo:hi].copy(); out = np.zeros((hi - lo, 38))
+        orc.lib.orc_step_timing_batch(ctypes.byref(scfg), int(hi - lo), oracle_lib.PI(np.ascontiguousarray(tick[lo:hi])),
+                                      oracle_lib.P(st), oracle_lib.P(np.ascontiguousarray(sin[lo:hi])), oracle_lib.P(out), None)
+
+    import ctypes
+    # solves per step: body 1 per robot + the SQP solves that actually run (the planner skips them near a step's end)
+    _, dg = orc.step_tick_batch(scfg, tick[:512], st0[:512].copy(), sin[:512])
+    solves = B + int(round(dg[:, 4].mean() * B))
 
     def run_once():
         t0 = time.perf_counter()
         if threads == 1:
-            work(0, B)
+            work(0, 0, B)
         else:
-            ts = [threading.Thread(target=work, args=(bounds[i], bounds[i + 1])) for i in range(threads)]
+            ts = [threading.Thread(target=work, args=(i, bounds[i], bounds[i + 1])) for i in range(threads)]
             for t in ts:
                 t.start()
             for t in ts:
                 t.join()
         return time.perf_counter() - t0
-    return run_once, B
+    return run_once, solves
 
 
-def cpu_baseline(a, budget_s=8.0):
+def cpu_baseline(a, budget_s=10.0):
     cores = os.cpu_count() or 1
     out = {}
     for label, thr in (("1thread", 1), ("all", cores)):
-        run, B = cpu_body_runner(a, thr)
+        run, solves = cpu_runner(a, thr)
         run()
         n, el = 0, 0.0
         while el < budget_s / 2 and n < 200:
             el += run(); n += 1
-        out[label] = (B * n / el, n)
+        out[label] = (solves * n / el, n)
     return {"value": out["all"][0], "unit": UNIT, "cores": cores, "kind": "port",
             "value_1thread": out["1thread"][0],
-            "sample": f"{out['all'][1]} passes over the same {a.batch}-instance cfg2 batch with {cores} host threads "
-                      f"({out['1thread'][1]} passes single-threaded); oracle/ C restatement of PRMPCClass::body_theta_mpc + "
-                      f"EiQuadProg at -O3 -march=native (the reference compiles only at horizon 4 and needs Eigen, absent here)"}
+            "sample": f"{out['all'][1]} passes over the same {a.batch}-robot cfg2 batch with {cores} host threads "
+                      f"({out['1thread'][1]} passes single-threaded); oracle/ C restatement of NLPClass::step_timing_opti_loop, "
+                      f"PRMPCClass::body_theta_mpc and EiQuadProg at -O3 -march=native (the reference needs Eigen, absent here, "
+                      f"and compiles the body MPC only at horizon 4)"}
 
 
 def run_reference(a):
@@ -111,18 +127,18 @@ def run_reference(a):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    run, B = cpu_body_runner(a, cores)
-    steps = min(a.steps, 200)
+    run, solves = cpu_runner(a, cores)
+    steps = min(a.steps, 100)
     for _ in range(min(a.warmup, 5)):
         run()
     times = [run() for _ in range(steps)]
     tot = sum(times)
-    v = B * steps / tot
+    v = solves * steps / tot
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": min(a.warmup, 5), "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, 1),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"each step = one pass over the {B}-instance cfg2 batch split over {cores} host threads "
+                             "sample": f"each step = one pass over the {a.batch}-robot cfg2 batch split over {cores} host threads "
                                        f"(oracle/ C port at -O3 -march=native; host CPU only, GPU count does not apply)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -203,22 +219,43 @@ def run_b200(a):
     nh, B, K, W = a.nh, a.batch, a.steps, max(a.warmup, 3)
     mpc = q.Go1Mpc(local)
     stream = torch.cuda.ExternalStream(mpc.stream, device=dev)
+    side = torch.cuda.Stream(device=dev)          # the step-timing tick runs beside the body tick
     in_s, out_s, dg_s = q.body_in_stride(nh), q.body_out_stride(nh), q.body_diag_stride(nh)
 
     # distinct input batches: footprint > 2x L2
-    nrot = max(4, int(np.ceil(2.2 * L2_BYTES / (B * in_s * 8))))
-    nrot = min(nrot, 512)
+    per_batch = B * (in_s + q.STEP_STATE + q.STEP_IN) * 8
+    nrot = min(512, max(4, int(np.ceil(2.2 * L2_BYTES / per_batch))))
     big = synth.body_mpc_inputs(B * nrot, nh, seed=synth.SEED_CFG2 + rank)
     rec = q.pack_body_inputs(nh, big["tick"], big["tx"], big["theta"], big["bstate"], big["x_warm"], big["refs"])
     rec_h = torch.from_numpy(rec).pin_memory()
     in_d = rec_h.to(dev).view(nrot, B, in_s)
     out_d = torch.zeros(nrot, B, out_s, dtype=torch.float64, device=dev)
     diag_d = torch.zeros(nrot, B, dg_s, dtype=torch.int32, device=dev)
+    # step-timing side: SoA [field][B] per rotation slot; state is double-buffered (out-of-place) so
+    # every pass sees the same inputs
+    stick, sst, sinp = synth.step_timing_inputs(B * nrot, mpc.step_default_state(), seed=synth.SEED_CFG2 + rank)
+    soa = lambda x, f: np.ascontiguousarray(x.reshape(nrot, B, f).transpose(0, 2, 1))
+    st_h = torch.from_numpy(soa(sst, q.STEP_STATE)).pin_memory(); si_h = torch.from_numpy(soa(sinp, q.STEP_IN)).pin_memory()
+    tk_h = torch.from_numpy(stick.reshape(nrot, B).copy()).pin_memory()
+    st_d, si_d, tk_d = st_h.to(dev), si_h.to(dev), tk_h.to(dev)
+    st_o = torch.zeros(B * q.STEP_STATE, dtype=torch.float64, device=dev)
+    so_d = torch.zeros(nrot, q.STEP_OUT, B, dtype=torch.float64, device=dev)
+    sd_d = torch.zeros(nrot, q.STEP_DIAG, B, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
+    ev_fork = torch.cuda.Event(); ev_join = torch.cuda.Event()
 
-    def step(i):
+    def step(i, overlap=True):
         r = i % nrot
-        mpc.body_mpc_step(nh, B, in_d[r], out_d[r], diag_d[r])
+        if overlap:
+            ev_fork.record(stream)
+            side.wait_event(ev_fork)
+            mpc.step_timing_step(3, B, tk_d[r], st_d[r], si_d[r], so_d[r], sd_d[r], stream=side.cuda_stream, state_out_d=st_o)
+            mpc.body_mpc_step(nh, B, in_d[r], out_d[r], diag_d[r])
+            ev_join.record(side)
+            stream.wait_event(ev_join)
+        else:
+            mpc.step_timing_step(3, B, tk_d[r], st_d[r], si_d[r], so_d[r], sd_d[r], state_out_d=st_o)
+            mpc.body_mpc_step(nh, B, in_d[r], out_d[r], diag_d[r])
 
     def barrier():
         torch.cuda.synchronize()
@@ -226,15 +263,20 @@ def run_b200(a):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # warm-up (also fills every diag record once: algorithmic flops per batch)
-    for i in range(max(W, nrot)):
-        step(i)
-    mpc.synchronize()
+    # warm-up (also fills every diag record once: algorithmic flops and solve counts per batch)
+    with torch.cuda.stream(stream):
+        for i in range(max(W, nrot)):
+            step(i)
+    torch.cuda.synchronize()
     diag_all = diag_d.cpu().numpy()
-    assert (diag_all[:, :, 0] == 0).all(), "a warm-up solve did not converge"
+    assert (diag_all[:, :, 0] == 0).all(), "a warm-up body-MPC solve did not converge"
     flops_per_batch = diag_all[:, :, 9].astype(np.float64).sum(axis=1)          # [nrot]
     mean_iters = diag_all[:, :, 2:6].reshape(-1, 4).mean(axis=0)
     mean_l2a = diag_all[:, :, 8].mean()
+    sdiag = sd_d.cpu().numpy()
+    sqp_solves = sdiag[:, 4, :].astype(np.int64).sum(axis=1)                     # [nrot] QPs the SQP really solved
+    sqp_status = sdiag[:, 5::11, :][:, :3, :]
+    solves_per_step = B + float(np.mean(sqp_solves))
 
     dfma_gflops = mpc.measure_dfma_peak(300)
 
@@ -249,60 +291,84 @@ def run_b200(a):
         for i in range(K):
             step(i)
             ev[i + 1].record(stream)
-    mpc.synchronize()
+    torch.cuda.synchronize()
     barrier()
     launches = mpc.launch_count - l0
-    per_step_ms = np.array([ev[i].elapsed_time(ev[i + 1]) for i in range(K)])
     total_ms = ev[0].elapsed_time(ev[K])
+    solves_timed = float(sum(B + sqp_solves[i % nrot] for i in range(K)))
 
-    # kernel-only duration: the same K launches, each timed alone (sync between launches so the
-    # events bracket exactly one kernel); feeds the roofline figure and the latency percentiles
-    lat_ms = []
+    # single-batch latency of the whole step (both kernels, one batch in flight) and the duration of
+    # each kernel alone: the same launches, a sync between them so the events bracket exactly one
     k_lat = min(K, 400)
-    for i in range(k_lat):
-        with torch.cuda.stream(stream):
-            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-            e0.record(stream); step(i); e1.record(stream)
-        e1.synchronize()
-        lat_ms.append(e0.elapsed_time(e1))
-    lat_ms = np.array(lat_ms)
+
+    def timed(fn):
+        out = []
+        for i in range(k_lat):
+            with torch.cuda.stream(stream):
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream); fn(i); e1.record(stream)
+            e1.synchronize()
+            out.append(e0.elapsed_time(e1))
+        return np.array(out)
+    lat_ms = timed(step)
+    body_ms = timed(lambda i: mpc.body_mpc_step(nh, B, in_d[i % nrot], out_d[i % nrot], diag_d[i % nrot]))
+    sqp_ms = timed(lambda i: mpc.step_timing_step(3, B, tk_d[i % nrot], st_d[i % nrot], si_d[i % nrot], so_d[i % nrot], sd_d[i % nrot],
+                                                    state_out_d=st_o))
     clk = clocks.stop()
 
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([total_ms, solves_timed], dtype=torch.float64, device=dev)
     if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms_max = float(t.item())
-    value = world * B * K / (total_ms_max * 1e-3)
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        total_ms_max, solves_all = float(tmax[0].item()), float(tsum[1].item())
+    else:
+        total_ms_max, solves_all = total_ms, solves_timed
+    value = solves_all / (total_ms_max * 1e-3)
 
-    # ---- e2e leg: host buffers through the *_host C-ABI entry ----
+    # ---- e2e leg: host buffers through the *_host C-ABI entries ----
     e2e = None
     if not a.no_e2e:
         Ke = min(K, 200)
-        in_h = rec_h.view(nrot, B, in_s)
-        out_h = torch.zeros(nrot, B, out_s, dtype=torch.float64).pin_memory()
-        diag_h = torch.zeros(nrot, B, dg_s, dtype=torch.int32).pin_memory()
-        in_np, out_np, diag_np = in_h.numpy(), out_h.numpy(), diag_h.numpy()
+        in_np = rec_h.view(nrot, B, in_s).numpy()
+        out_np = torch.zeros(nrot, B, out_s, dtype=torch.float64).pin_memory().numpy()
+        diag_np = torch.zeros(nrot, B, dg_s, dtype=torch.int32).pin_memory().numpy()
+        st_np = torch.zeros(q.STEP_STATE, B, dtype=torch.float64).pin_memory().numpy()
+        so_np = torch.zeros(nrot, q.STEP_OUT, B, dtype=torch.float64).pin_memory().numpy()
+        sd_np = torch.zeros(nrot, q.STEP_DIAG, B, dtype=torch.int32).pin_memory().numpy()
+        st_src, si_np, tk_np = st_h.numpy(), si_h.numpy(), tk_h.numpy()
+
+        def host_step(i):
+            r = i % nrot
+            np.copyto(st_np, st_src[r])     # the host entry updates the state in place: hand it a fresh copy
+            mpc.step_timing_step_host(3, B, tk_np[r], st_np, si_np[r], so_np[r], sd_np[r])
+            mpc.body_mpc_step_host(nh, B, in_np[r], out_np[r], diag_np[r])
         for i in range(3):
-            mpc.body_mpc_step_host(nh, B, in_np[i % nrot], out_np[i % nrot], diag_np[i % nrot])
+            host_step(i)
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for i in range(Ke):
-            r = i % nrot
-            mpc.body_mpc_step_host(nh, B, in_np[r], out_np[r], diag_np[r])
+            host_step(i)
         e1.record(stream)
         e1.synchronize()
         barrier()
-        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        se = float(sum(B + sqp_solves[i % nrot] for i in range(Ke)))
+        te = torch.tensor([e0.elapsed_time(e1), se], dtype=torch.float64, device=dev)
         if dist:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            tm = te.clone(); dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            tsu = te.clone(); dist.all_reduce(tsu, op=dist.ReduceOp.SUM)
+            te_ms, se_all = float(tm[0].item()), float(tsu[1].item())
+        else:
+            te_ms, se_all = float(te[0].item()), se
         assert (diag_np[:min(Ke, nrot), :, 0] == 0).all()
-        e2e = {"value": world * B * Ke / (float(te.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": B * (in_s + out_s) * 8, "d2h_bytes_per_step": B * (out_s * 8 + dg_s * 4),
-               "steps": Ke, "api": "go1mpc_body_mpc_step_batch_host (pinned host buffers; H2D, kernel, D2H, stream sync per call)"}
+        e2e = {"value": se_all / (te_ms * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": B * ((in_s + out_s) * 8 + (q.STEP_STATE + q.STEP_IN) * 8 + 4),
+               "d2h_bytes_per_step": B * (out_s * 8 + dg_s * 4 + (q.STEP_STATE + q.STEP_OUT) * 8 + q.STEP_DIAG * 4),
+               "steps": Ke, "api": "go1mpc_step_timing_step_batch_host + go1mpc_body_mpc_step_batch_host (pinned host buffers; "
+                                   "H2D, kernel, D2H, stream sync per call)"}
 
     if rank == 0:
-        kern_ms = float(np.mean(lat_ms))
+        kern_ms = float(np.mean(body_ms))
         fl = float(np.mean(flops_per_batch[np.arange(k_lat) % nrot]))
         achieved_tf = fl / (kern_ms * 1e-3) / 1e12
         peak_tf = dfma_gflops / 1e3
@@ -315,11 +381,15 @@ def run_b200(a):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, nrot),
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
+            "solves_per_step_per_gpu": solves_per_step, "robot_ticks_per_s": world * B * K / (total_ms_max * 1e-3),
             "latency_ms": {"p50": float(np.percentile(lat_ms, 50)), "p99": float(np.percentile(lat_ms, 99)),
-                           "max": float(lat_ms.max()), "what": f"one {B}-instance batch, one launch, CUDA events, {k_lat} samples"},
+                           "max": float(lat_ms.max()),
+                           "what": f"one {B}-robot batch through both ticks (2 launches on 2 streams), CUDA events, {k_lat} samples"},
+            "kernels_ms": {"body_fast_kernel": kern_ms, "step_timing_kernel": float(np.mean(sqp_ms)),
+                           "step_both_overlapped": float(np.mean(lat_ms))},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
-                         "kernel": "body_mpc_kernel", "kernel_ms": kern_ms,
+                         "kernel": "body_fast_kernel (dominant: body-inclination MPC tick)", "kernel_ms": kern_ms,
                          "flops_per_launch": fl, "flops_per_solve": fl / B,
                          "flops_def": "algorithmic flops of the dense reference algorithm along each problem's path "
                                       "(SURVEY.md 8d formula, counted per problem in-kernel)",
@@ -327,8 +397,10 @@ def run_b200(a):
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "hbm": {"achieved": io_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "peak_source": f"{hbm_src} (MEASURED_PEAKS.json)", "bytes_per_launch": io_bytes}},
-            "solver": {"mean_outer": float(mean_iters[0]), "mean_add": float(mean_iters[1]), "mean_drop": float(mean_iters[2]),
-                       "mean_degen": float(mean_iters[3]), "mean_l2a": float(mean_l2a)},
+            "solver": {"body_mean_outer": float(mean_iters[0]), "body_mean_add": float(mean_iters[1]),
+                       "body_mean_drop": float(mean_iters[2]), "body_mean_degen": float(mean_iters[3]),
+                       "body_mean_l2a": float(mean_l2a), "sqp_solves_per_robot": float(np.mean(sqp_solves)) / B,
+                       "sqp_converged_frac": float((sqp_status == 0).mean()), "sqp_infeasible_frac": float((sqp_status == 2).mean())},
             "clocks": clk, "gpu_launches": int(launches), "e2e": e2e,
         }
         if world == 1 and not a.no_cpu_baseline:
@@ -340,19 +412,27 @@ def run_b200(a):
             d = synth.body_mpc_inputs(Bs, nh, seed=1)
             r = torch.from_numpy(q.pack_body_inputs(nh, d["tick"], d["tx"], d["theta"], d["bstate"], d["x_warm"], d["refs"])).to(dev)
             o = torch.zeros(Bs, out_s, dtype=torch.float64, device=dev)
+            tk, ss, ii = synth.step_timing_inputs(Bs, mpc.step_default_state(), seed=1)
+            tkd = torch.from_numpy(tk).to(dev); ssd = torch.from_numpy(np.ascontiguousarray(ss.T)).to(dev)
+            iid = torch.from_numpy(np.ascontiguousarray(ii.T)).to(dev); sso = torch.zeros_like(ssd)
+            ood = torch.zeros(q.STEP_OUT, Bs, dtype=torch.float64, device=dev)
             torch.cuda.synchronize()
-            for _ in range(3):
-                mpc.body_mpc_step(nh, Bs, r, o, None)
-            mpc.synchronize()
-            with torch.cuda.stream(stream):
-                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                for _ in range(20):
-                    mpc.body_mpc_step(nh, Bs, r, o, None)
-                e1.record(stream)
-            e1.synchronize()
-            ms = e0.elapsed_time(e1) / 20
-            print(f"sweep B={Bs}: {ms * 1e3:.1f} us/launch, {Bs / ms * 1e3:.3e} solves/s", file=sys.stderr)
+            res = []
+            for fn in (lambda: mpc.body_mpc_step(nh, Bs, r, o, None),
+                       lambda: mpc.step_timing_step(3, Bs, tkd, ssd, iid, ood, None, state_out_d=sso)):
+                for _ in range(3):
+                    fn()
+                mpc.synchronize()
+                with torch.cuda.stream(stream):
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    for _ in range(20):
+                        fn()
+                    e1.record(stream)
+                e1.synchronize()
+                res.append(e0.elapsed_time(e1) / 20)
+            print(f"sweep B={Bs}: body {res[0] * 1e3:.1f} us ({Bs / res[0] * 1e3:.3e} solves/s), "
+                  f"step-timing SQP {res[1] * 1e3:.1f} us ({3 * Bs / res[1] * 1e3:.3e} solves/s)", file=sys.stderr)
     mpc.close()
     if dist:
         dist.destroy_process_group()

@@ -209,7 +209,9 @@ int go1mpc_body_default_tx(go1mpc_t *h, double *tx27);
  * Layout: STRUCTURE OF ARRAYS, element-major / batch-minor: field f of instance b is
  * at [f*B + b] (one thread per instance: every access of a warp is coalesced).
  * tick_d  [B] ints         i of the reference (>= 1)
- * state_d [201][B] doubles in/out, fields:
+ * state_d [201][B] doubles, the planner state before the tick; state_out_d receives the
+ *         state after it and may be the same buffer (in-place: only changed fields are
+ *         written).  Fields:
  *           [0,27) ts   [27,54) tx   [54,81) footx_ref  [81,108) footy_ref
  *           [108,135) footz_ref  [135,162) Lxx_ref  [162,189) Lyy_ref
  *           [189,195) com x,vx,ax,y,vy,ay _feed at tick i-1
@@ -228,7 +230,8 @@ int go1mpc_body_default_tx(go1mpc_t *h, double *tx27);
 #define GO1MPC_STEP_OUT_DOUBLES 38
 #define GO1MPC_STEP_DIAG_INTS 60
 int go1mpc_step_timing_step_batch(go1mpc_t *h, int n_sqp, int B, const int *tick_d,
-                                  double *state_d, const double *in_d, double *out_d,
+                                  const double *state_d, double *state_out_d,
+                                  const double *in_d, double *out_d,
                                   int *diag_d, void *stream);
 int go1mpc_step_timing_step_batch_host(go1mpc_t *h, int n_sqp, int B, const int *tick,
                                        double *state, const double *in, double *out, int *diag);

@@ -95,7 +95,7 @@ def load_library():
     lib.go1mpc_body_model.argtypes = [vp, ctypes.c_int] + [vp] * 6
     lib.go1mpc_body_default_tx.argtypes = [vp, vp]
     lib.go1mpc_measure_dfma_peak.argtypes = [vp, ctypes.c_int, c_double_p]
-    lib.go1mpc_step_timing_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    lib.go1mpc_step_timing_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.go1mpc_step_timing_step_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
     lib.go1mpc_step_default_state.argtypes = [vp] + [ctypes.c_double] * 4 + [vp]
     lib.go1mpc_leg_fk_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
@@ -249,8 +249,10 @@ class Go1Mpc:
                                                         _ptr(nactive), _ptr(iters), _ptr(status)), "qp_solve_batch_host")
 
     # --- step-location / step-timing SQP (SoA buffers: [field][B]) ---
-    def step_timing_step(self, n_sqp, B, tick_d, state_d, in_d, out_d, diag_d=None, stream=None):
-        self._check(self.lib.go1mpc_step_timing_step_batch(self.h, n_sqp, B, _ptr(tick_d), _ptr(state_d), _ptr(in_d),
+    def step_timing_step(self, n_sqp, B, tick_d, state_d, in_d, out_d, diag_d=None, stream=None, state_out_d=None):
+        """state_out_d=None updates state_d in place."""
+        so = state_d if state_out_d is None else state_out_d
+        self._check(self.lib.go1mpc_step_timing_step_batch(self.h, n_sqp, B, _ptr(tick_d), _ptr(state_d), _ptr(so), _ptr(in_d),
                                                            _ptr(out_d), _ptr(diag_d), stream), "step_timing_step_batch")
 
     def step_timing_step_host(self, n_sqp, B, tick, state, inp, out, diag=None):

@@ -432,10 +432,10 @@ int go1mpc_body_default_tx(go1mpc_t* h, double* tx27) {
 }
 
 // ------------------------------------------------------------------ step timing
-int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick_d, double* state_d, const double* in_d,
-                                  double* out_d, int* diag_d, void* stream) {
+int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick_d, const double* state_d, double* state_out_d,
+                                  const double* in_d, double* out_d, int* diag_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
-  if (B < 0 || !tick_d || !state_d || !in_d || !out_d) return fail(h, GO1MPC_E_INVALID, "step_timing_step_batch: bad argument");
+  if (B < 0 || !tick_d || !state_d || !state_out_d || !in_d || !out_d) return fail(h, GO1MPC_E_INVALID, "step_timing_step_batch: bad argument");
   if (n_sqp < 1 || n_sqp > STEP_MAX_SQP) return fail(h, GO1MPC_E_UNSUPPORTED, "step_timing_step_batch: 1 <= n_sqp <= 5");
   if (B == 0) return GO1MPC_OK;
   CU(h, cudaSetDevice(h->device));
@@ -443,7 +443,7 @@ int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick
   const Go1StepMpcConfig& c = h->cfg.step;
   StepKParams P;
   P.B = B; P.n_sqp = n_sqp; P.cap = h->cfg.qp_iter_cap_scale * (4 + 24 + 1) + 50;
-  P.tick = tick_d; P.state = state_d; P.in = in_d; P.out = out_d; P.diag = diag_d;
+  P.tick = tick_d; P.state = state_d; P.state_out = state_out_d; P.in = in_d; P.out = out_d; P.diag = diag_d;
   StepCfgDev& d = P.cfg;
   d.dt = c.dt; d.Wn = c.Wn; d.ggg = c.ggg; d.t_min = c.t_min; d.t_max = c.t_max;
   d.footx_max = c.footx_max; d.footx_min = c.footx_min;
@@ -477,7 +477,7 @@ int go1mpc_step_timing_step_batch_host(go1mpc_t* h, int n_sqp, int B, const int*
   CU(h, cudaMemcpyAsync(dt_, tick, tb, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(ds, state, sb, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(di, in, ib, cudaMemcpyHostToDevice, st));
-  rc = go1mpc_step_timing_step_batch(h, n_sqp, B, (const int*)dt_, (double*)ds, (const double*)di, (double*)do_, (int*)dd, st);
+  rc = go1mpc_step_timing_step_batch(h, n_sqp, B, (const int*)dt_, (const double*)ds, (double*)ds, (const double*)di, (double*)do_, (int*)dd, st);
   if (rc) return rc;
   CU(h, cudaMemcpyAsync(state, ds, sb, cudaMemcpyDeviceToHost, st));
   CU(h, cudaMemcpyAsync(out, do_, ob, cudaMemcpyDeviceToHost, st));

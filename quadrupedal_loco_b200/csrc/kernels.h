@@ -47,7 +47,8 @@ struct StepCfgDev {
 struct StepKParams {
   int B, n_sqp, cap;
   const int* tick;
-  double* state;        // [STEP_STATE_DOUBLES][B], in/out
+  const double* state;  // [STEP_STATE_DOUBLES][B], state before the tick
+  double* state_out;    // state after the tick; may alias `state` (in-place)
   const double* in;     // [STEP_IN_DOUBLES][B]
   double* out;          // [STEP_OUT_DOUBLES][B]
   int* diag;            // [STEP_DIAG_INTS][B] or null

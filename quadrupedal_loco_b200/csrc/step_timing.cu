@@ -33,9 +33,11 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= P.B) return;
   const size_t B = (size_t)P.B;
-  double* S = P.state + b;
+  const double* S = P.state + b;        // read side
+  double* SO = P.state_out + b;         // write side (may alias the read side: in-place update)
   const double* IN = P.in + b;
 #define ST(f) S[(size_t)(f) * B]
+#define STW(f) SO[(size_t)(f) * B]
 #define INP(f) IN[(size_t)(f) * B]
   const StepCfgDev& c = P.cfg;
   const double dt = c.dt, Wn = c.Wn;
@@ -223,27 +225,36 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
   else { e0 = e0 - INP(I_RF + 0); e3 = e3 - INP(I_RF + 1); }
   const double lx = c.lamda[0], lvx = c.lamda[1], ly = c.lamda[2], lvy = c.lamda[3];
 
-  if (valid) {
-    for (int k = 0; k < 4; k++) ST(S_VARI + k) = v[k];
-    ST(S_LXX + p - 1) = v[0];
-    ST(S_LYY + p - 1) = v[1];
-    ST(S_TS + p - 1) = ts_new;
-    for (int jxx = p + 1; jxx <= NS; jxx++) ST(S_TX + jxx - 1) = tx[jxx - 1];
-    if (p < NS) { ST(S_FX + p) = fx_next; ST(S_FY + p) = fy_next; }
-    ST(S_END + 0) = Wn * isx * v[3] + visx * v[2];
-    ST(S_END + 1) = Wn * isy * v[3] + visy * v[2];
-    ST(S_FEED + 0) = ((1 - lx) * (comx[0] - px) + (lx) * e0) + px;
-    ST(S_FEED + 1) = (1 - lvx) * comvx[0] + (lvx) * INP(I_EST + 1);
-    ST(S_FEED + 2) = (1 - lx) * comax[0] + lx * INP(I_EST + 2);
-    ST(S_FEED + 3) = ((1 - ly) * (comy[0] - py) + (ly) * e3) + py;
-    ST(S_FEED + 4) = (1 - lvy) * comvy[0] + (lvy) * INP(I_EST + 4);
-    ST(S_FEED + 5) = (1 - ly) * comay[0] + ly * INP(I_EST + 5);
-  }
   // integer step indices against the UPDATED table (:1031-1041)
   j = 0; while (j < NS && i * dt >= tx[j]) j++;
   const int bjxx = (j - 1) + 1;
   j = 0; while (j < NS && (i + 1) * dt >= tx[j]) j++;
   const int bjx1 = (j - 1) + 1;
+  // foot tables at the two entries the outputs read, taken BEFORE any write (in-place safe)
+  const int bq0 = bjxx < NS ? bjxx : NS - 1, bq1 = bjxx + 1 < NS ? bjxx + 1 : NS - 1;
+  const bool upd = valid && p < NS;
+  const double fx0 = (upd && bq0 == p) ? fx_next : ST(S_FX + bq0), fx1 = (upd && bq1 == p) ? fx_next : ST(S_FX + bq1);
+  const double fy0 = (upd && bq0 == p) ? fy_next : ST(S_FY + bq0), fy1 = (upd && bq1 == p) ? fy_next : ST(S_FY + bq1);
+  const double fz0 = ST(S_FZ + bq0), fz1 = ST(S_FZ + bq1);
+  if (SO != S) {   // out-of-place: carry the untouched fields over
+    for (int f = 0; f < STEP_STATE_DOUBLES; f++) STW(f) = ST(f);
+  }
+  if (valid) {
+    for (int k = 0; k < 4; k++) STW(S_VARI + k) = v[k];
+    STW(S_LXX + p - 1) = v[0];
+    STW(S_LYY + p - 1) = v[1];
+    STW(S_TS + p - 1) = ts_new;
+    for (int jxx = p + 1; jxx <= NS; jxx++) STW(S_TX + jxx - 1) = tx[jxx - 1];
+    if (p < NS) { STW(S_FX + p) = fx_next; STW(S_FY + p) = fy_next; }
+    STW(S_END + 0) = Wn * isx * v[3] + visx * v[2];
+    STW(S_END + 1) = Wn * isy * v[3] + visy * v[2];
+    STW(S_FEED + 0) = ((1 - lx) * (comx[0] - px) + (lx) * e0) + px;
+    STW(S_FEED + 1) = (1 - lvx) * comvx[0] + (lvx) * INP(I_EST + 1);
+    STW(S_FEED + 2) = (1 - lx) * comax[0] + lx * INP(I_EST + 2);
+    STW(S_FEED + 3) = ((1 - ly) * (comy[0] - py) + (ly) * e3) + py;
+    STW(S_FEED + 4) = (1 - lvy) * comvy[0] + (lvy) * INP(I_EST + 4);
+    STW(S_FEED + 5) = (1 - ly) * comay[0] + ly * INP(I_EST + 5);
+  }
 
   double* O = P.out + b;
 #define OUT(f, val) O[(size_t)(f) * B] = (val)
@@ -256,12 +267,8 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
   OUT(21, comax[1]); OUT(22, comay[1]); OUT(23, INP(I_CAZ + 1));
   OUT(24, comax[2]); OUT(25, comay[2]); OUT(26, INP(I_CAZ + 2));
   OUT(27, (double)bjxx);
-  const int q0 = bjxx < NS ? bjxx : NS - 1, q1 = bjxx + 1 < NS ? bjxx + 1 : NS - 1;
-  // the next-step entries were updated above: read the new values
-  const double fx0 = (q0 == p && valid && p < NS) ? fx_next : ST(S_FX + q0), fx1 = (q1 == p && valid && p < NS) ? fx_next : ST(S_FX + q1);
-  const double fy0 = (q0 == p && valid && p < NS) ? fy_next : ST(S_FY + q0), fy1 = (q1 == p && valid && p < NS) ? fy_next : ST(S_FY + q1);
   OUT(28, fx0); OUT(29, fx1); OUT(30, fy0); OUT(31, fy1);
-  OUT(32, ST(S_FZ + q0)); OUT(33, ST(S_FZ + q1));
+  OUT(32, fz0); OUT(33, fz1);
   OUT(34, (double)(p - 1));
   OUT(35, ts_new);
   OUT(36, v[0]);
@@ -270,6 +277,7 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
 #undef OUT
 #undef DGW
 #undef ST
+#undef STW
 #undef INP
 }
 

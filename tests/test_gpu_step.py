@@ -152,3 +152,24 @@ def test_step_full_size_properties(mpc):
     ts_new = go[conv, 35]
     np.testing.assert_allclose(ts_new, k_yu * 0.025 + np.log(v[:, 2] + v[:, 3]) / Wn, rtol=1e-12)
     assert (ts_new <= 1.0 + 1e-6).all()
+
+
+def test_step_out_of_place_state(mpc):
+    """state_out_d != state_d: the input state stays untouched, the output equals the in-place result."""
+    import torch
+    B = 1000
+    tick, st, inp = synth.step_timing_inputs(B, mpc.step_default_state(), seed=4, amp=1.0)
+    go, gs, gd = gpu_tick(mpc, tick, st, inp)
+    dev = torch.device("cuda", 0)
+    tt = torch.from_numpy(np.ascontiguousarray(tick, np.int32)).to(dev)
+    s_in = torch.from_numpy(np.array(st.T, order="C", copy=True)).to(dev); s_keep = s_in.clone()
+    s_out = torch.full_like(s_in, float("nan"))
+    ti = torch.from_numpy(np.array(inp.T, order="C", copy=True)).to(dev)
+    to = torch.zeros(q.STEP_OUT, B, dtype=torch.float64, device=dev); td = torch.zeros(q.STEP_DIAG, B, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    mpc.step_timing_step(3, B, tt, s_in, ti, to, td, state_out_d=s_out)
+    mpc.synchronize()
+    assert torch.equal(s_in, s_keep)
+    np.testing.assert_array_equal(s_out.cpu().numpy().T, gs)
+    np.testing.assert_array_equal(to.cpu().numpy().T, go)
+    np.testing.assert_array_equal(td.cpu().numpy().T, gd)
