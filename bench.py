@@ -243,19 +243,33 @@ def run_b200(a):
     sd_d = torch.zeros(nrot, q.STEP_DIAG, B, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
     ev_fork = torch.cuda.Event(); ev_join = torch.cuda.Event()
+    # raw device addresses per rotation slot: the launch loop is then two ctypes calls per step
+    lib, hh = mpc.lib, mpc.h
+    P_in = [in_d[r].data_ptr() for r in range(nrot)]; P_out = [out_d[r].data_ptr() for r in range(nrot)]
+    P_dg = [diag_d[r].data_ptr() for r in range(nrot)]
+    P_tk = [tk_d[r].data_ptr() for r in range(nrot)]; P_st = [st_d[r].data_ptr() for r in range(nrot)]
+    P_si = [si_d[r].data_ptr() for r in range(nrot)]; P_so = [so_d[r].data_ptr() for r in range(nrot)]
+    P_sd = [sd_d[r].data_ptr() for r in range(nrot)]; P_sto = st_o.data_ptr()
+    side_ptr = side.cuda_stream
 
-    def step(i, overlap=True):
+    def launch_body(i):
         r = i % nrot
-        if overlap:
-            ev_fork.record(stream)
-            side.wait_event(ev_fork)
-            mpc.step_timing_step(3, B, tk_d[r], st_d[r], si_d[r], so_d[r], sd_d[r], stream=side.cuda_stream, state_out_d=st_o)
-            mpc.body_mpc_step(nh, B, in_d[r], out_d[r], diag_d[r])
-            ev_join.record(side)
-            stream.wait_event(ev_join)
-        else:
-            mpc.step_timing_step(3, B, tk_d[r], st_d[r], si_d[r], so_d[r], sd_d[r], state_out_d=st_o)
-            mpc.body_mpc_step(nh, B, in_d[r], out_d[r], diag_d[r])
+        rc = lib.go1mpc_body_mpc_step_batch(hh, nh, B, P_in[r], P_out[r], P_dg[r], None)
+        assert rc == 0, rc
+
+    def launch_sqp(i, st_ptr=None):
+        r = i % nrot
+        rc = lib.go1mpc_step_timing_step_batch(hh, 3, B, P_tk[r], P_st[r], P_sto, P_si[r], P_so[r], P_sd[r], st_ptr)
+        assert rc == 0, rc
+
+    def step(i):
+        """one robot batch through both ticks: the SQP tick on the side stream beside the body tick"""
+        ev_fork.record(stream)
+        side.wait_event(ev_fork)
+        launch_sqp(i, side_ptr)
+        launch_body(i)
+        ev_join.record(side)
+        stream.wait_event(ev_join)
 
     def barrier():
         torch.cuda.synchronize()
@@ -286,11 +300,17 @@ def run_b200(a):
     barrier()
     clocks.start()
     l0 = mpc.launch_count
+    # the two ticks of a robot are independent and so are the steps: fork once, run K body ticks on the
+    # handle's stream and K SQP ticks on the side stream, join once; the timed region is start -> join
     with torch.cuda.stream(stream):
         ev[0].record(stream)
+        side.wait_event(ev[0])
         for i in range(K):
-            step(i)
-            ev[i + 1].record(stream)
+            launch_sqp(i, side_ptr)
+            launch_body(i)
+        ev_join.record(side)
+        stream.wait_event(ev_join)
+        ev[K].record(stream)
     torch.cuda.synchronize()
     barrier()
     launches = mpc.launch_count - l0
@@ -311,9 +331,8 @@ def run_b200(a):
             out.append(e0.elapsed_time(e1))
         return np.array(out)
     lat_ms = timed(step)
-    body_ms = timed(lambda i: mpc.body_mpc_step(nh, B, in_d[i % nrot], out_d[i % nrot], diag_d[i % nrot]))
-    sqp_ms = timed(lambda i: mpc.step_timing_step(3, B, tk_d[i % nrot], st_d[i % nrot], si_d[i % nrot], so_d[i % nrot], sd_d[i % nrot],
-                                                    state_out_d=st_o))
+    body_ms = timed(launch_body)
+    sqp_ms = timed(launch_sqp)
     clk = clocks.stop()
 
     t = torch.tensor([total_ms, solves_timed], dtype=torch.float64, device=dev)

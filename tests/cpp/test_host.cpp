@@ -1,0 +1,72 @@
+// Exercises the C++ mirror of the reference classes (quadrupedal_loco_b200/host/go1mpc.hpp)
+// the way the reference's callers use them, and prints the results as JSON for
+// tests/test_host_cpp.py to compare with the CPU oracle.  Needs a GPU.
+#include <cstdio>
+#include <cmath>
+#include "../../quadrupedal_loco_b200/host/go1mpc.hpp"
+
+using namespace go1host;
+
+static void arr(const char* name, const double* v, int n, bool last = false) {
+  printf("\"%s\": [", name);
+  for (int i = 0; i < n; i++) printf("%s%.17g", i ? ", " : "", v[i]);
+  printf("]%s\n", last ? "" : ",");
+}
+
+int main() {
+  printf("{\n");
+  // --- QPBaseClass seam: the QuadProg++ demo problem
+  QPBase qp;
+  qp.resizeQP(2, 1, 3);
+  qp.G(0, 0) = 4; qp.G(0, 1) = -2; qp.G(1, 0) = -2; qp.G(1, 1) = 4;
+  qp._g0[0] = 6; qp._g0[1] = 0;
+  qp.CE(0, 0) = 1; qp.CE(1, 0) = 1; qp._ce0[0] = -3;
+  qp.CI(0, 0) = 1; qp.CI(1, 0) = 0; qp.CI(0, 1) = 0; qp.CI(1, 1) = 1; qp.CI(0, 2) = 1; qp.CI(1, 2) = 1;
+  qp._ci0[0] = 0; qp._ci0[1] = 0; qp._ci0[2] = -2;
+  bool ok = qp.solveQP();
+  printf("\"qp_ok\": %d, \"qp_cost\": %.17g,\n", ok ? 1 : 0, qp._cost);
+  arr("qp_x", qp._X.data(), 2);
+
+  // --- PRMPCClass::body_theta_mpc, horizon 10, 30 closed-loop ticks
+  const int nh = 10;
+  BodyInclinationMPC body(nh);
+  body._thetaxk(0) = 0.05; body._thetaxk(1) = -0.4; body._thetayk(0) = -0.08; body._thetayk(1) = 0.6;
+  MatX zmp(2, nh), ang(2, nh), rf(2, nh), lf(2, nh), ca(3, nh);
+  for (int k = 0; k < nh; k++) {
+    zmp(0, k) = 0.30 + 0.001 * k; zmp(1, k) = 0.12; ang(0, k) = 0.21 - 0.002 * k; ang(1, k) = -0.19;
+    rf(0, k) = 0.28; rf(1, k) = -0.127; lf(0, k) = 0.31; lf(1, k) = 0.126; ca(2, k) = 0.3 * std::sin(0.7 * k);
+  }
+  Vec<4> meas; Vec<9> nrt;
+  double o14[30 * 14], th[30 * 4];
+  int idx[30 * 2];
+  for (int t = 0; t < 30; t++) {
+    Vec<14> o = body.body_theta_mpc(200 + t, meas, zmp, ang, rf, lf, ca, nrt);
+    for (int k = 0; k < 14; k++) o14[t * 14 + k] = o(k);
+    th[t * 4] = body._thetaxk(0); th[t * 4 + 1] = body._thetaxk(1); th[t * 4 + 2] = body._thetayk(0); th[t * 4 + 3] = body._thetayk(1);
+    idx[t * 2] = body._bjx1; idx[t * 2 + 1] = body._bjx2;
+  }
+  arr("body_out14", o14, 30 * 14); arr("body_theta", th, 30 * 4);
+  printf("\"body_idx\": ["); for (int i = 0; i < 60; i++) printf("%s%d", i ? ", " : "", idx[i]); printf("],\n");
+
+  // --- NLPClass::step_timing_opti_loop, the first 120 ticks of the replay
+  StepTimingMPC nlp;
+  nlp.FootStepInputs(0.2535, 0.075, 0.0); nlp.Initialize();
+  Vec<18> est; Vec<3> rfb, lfb; rfb(1) = -0.12675; lfb(1) = 0.12675;
+  double o38[120 * 38];
+  for (int i = 1; i <= 120; i++) {
+    Vec<38> o = nlp.step_timing_opti_loop(i, est, rfb, lfb, 0.0, false);
+    for (int k = 0; k < 38; k++) o38[(i - 1) * 38 + k] = o(k);
+  }
+  arr("step_out38", o38, 120 * 38);
+
+  // --- Kinematicclass: FK_g -> IK_g round trip, Jacobian side channel
+  LegKinematics kin;
+  Vec<3> bp, br, q, qi; bp(2) = 0.31; br(0) = 0.05; br(1) = -0.04; br(2) = 0.1; q(0) = 0.1; q(1) = 0.8; q(2) = -1.5;
+  qi(0) = 0.0; qi(1) = 0.87; qi(2) = -1.5;
+  Vec<3> p = kin.Forward_kinematics_g(bp, br, q, 1);
+  arr("fk_pos", p.v, 3); arr("fk_J", kin.Jacobian_kin.m, 9);
+  Vec<3> qs = kin.Inverse_kinematics_g(bp, br, p, qi, 1);
+  arr("ik_q", qs.v, 3);
+  printf("\"ik_updates\": %d\n}\n", kin.ik_updates);
+  return 0;
+}

@@ -165,7 +165,7 @@ def test_step_out_of_place_state(mpc):
     s_in = torch.from_numpy(np.array(st.T, order="C", copy=True)).to(dev); s_keep = s_in.clone()
     s_out = torch.full_like(s_in, float("nan"))
     ti = torch.from_numpy(np.array(inp.T, order="C", copy=True)).to(dev)
-    to = torch.zeros(q.STEP_OUT, B, dtype=torch.float64, device=dev); td = torch.zeros(q.STEP_DIAG, B, dtype=torch.int32, device=dev)
+    to = torch.zeros(q.STEP_OUT, B, dtype=torch.float64, device=dev); td = torch.full((q.STEP_DIAG, B), -7, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
     mpc.step_timing_step(3, B, tt, s_in, ti, to, td, state_out_d=s_out)
     mpc.synchronize()

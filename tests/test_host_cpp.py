@@ -1,0 +1,71 @@
+"""The C++ mirror of the reference classes (quadrupedal_loco_b200/host/go1mpc.hpp): it compiles
+headless with g++ against the C ABI only (CPU check), and -- on a GPU -- the calls made the way
+the reference's callers make them reproduce the CPU oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import quadrupedal_loco_b200 as q
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "test_host")
+
+
+def build_exe():
+    src = os.path.join(ROOT, "tests", "cpp", "test_host.cpp")
+    libdir = os.path.dirname(q.library_path())
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    cmd = ["g++", "-std=c++14", "-O1", "-o", EXE, src, "-L" + libdir, "-lgo1mpc", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    return EXE
+
+
+def test_host_header_compiles_headless():
+    q.load_library()
+    build_exe()
+    hdr = open(os.path.join(ROOT, "quadrupedal_loco_b200", "host", "go1mpc.hpp")).read()
+    for banned in ("#include <ros", "Eigen/", "armadillo", "boost/", "fusion.h"):
+        assert banned not in hdr
+
+
+@pytest.mark.gpu
+def test_host_classes_reproduce_oracle(oracle):
+    exe = build_exe()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout)
+    assert d["qp_ok"] == 1 and abs(d["qp_cost"] - 12) < 1e-12
+    np.testing.assert_allclose(d["qp_x"], [1, 2], atol=1e-12)
+    # body MPC, closed loop
+    nh = 10
+    cfg = oracle.body_cfg(nh)
+    k = np.arange(nh)
+    refs = np.zeros((1, 9, nh))
+    refs[0, 0] = 0.30 + 0.001 * k; refs[0, 1] = 0.12; refs[0, 2] = 0.21 - 0.002 * k; refs[0, 3] = -0.19
+    refs[0, 4] = 0.28; refs[0, 5] = -0.127; refs[0, 6] = 0.31; refs[0, 7] = 0.126; refs[0, 8] = 0.3 * np.sin(0.7 * k)
+    from quadrupedal_loco_b200 import synth
+    tx = synth.default_tx()[None, :]
+    theta = np.array([[0.05, -0.4, -0.08, 0.6]]); x = np.zeros((1, 2 * nh)); o14 = np.zeros((1, 14))
+    got14 = np.array(d["body_out14"]).reshape(30, 14); gotth = np.array(d["body_theta"]).reshape(30, 4)
+    for t in range(30):
+        oracle.body_step_batch(cfg, np.array([200 + t], np.int32), tx, theta, np.zeros((1, 4)), refs, o14, x)
+        assert np.abs(got14[t] - o14[0]).max() < 1e-9 * max(1, np.abs(o14).max()), t
+        assert np.abs(gotth[t] - theta[0]).max() < 1e-9, t
+    # step timing replay against the reference's own golden outputs
+    from tests.test_oracle_vs_ref import load
+    g = load("step_ref.npz")
+    got = np.array(d["step_out38"]).reshape(120, 38)
+    ref = g["replay_out"][1:121]
+    assert np.abs(got - ref).max() / max(1, np.abs(ref).max()) < 1e-9
+    assert np.array_equal(got[:, 27], ref[:, 27]) and np.array_equal(got[:, 34], ref[:, 34])
+    # kinematics
+    pos, J = oracle.leg_fk(np.array([[0.1, 0.8, -1.5]]), [1], np.array([[0, 0, 0.31]]), np.array([[0.05, -0.04, 0.1]]))
+    np.testing.assert_allclose(d["fk_pos"], pos[0], atol=1e-13)
+    np.testing.assert_allclose(np.array(d["fk_J"]).reshape(3, 3).T.ravel(), J[0], atol=1e-13)   # Mat is column-major
+    qs, _, it = oracle.leg_ik(pos, np.array([[0.0, 0.87, -1.5]]), [1], np.array([[0, 0, 0.31]]), np.array([[0.05, -0.04, 0.1]]))
+    np.testing.assert_allclose(d["ik_q"], qs[0], atol=1e-9)
+    assert d["ik_updates"] == it[0]
