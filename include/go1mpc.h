@@ -123,7 +123,7 @@ long long go1mpc_launch_count(const go1mpc_t *h);
 void *go1mpc_stream(const go1mpc_t *h);
 /* multiprocessor count of the handle's device */
 int go1mpc_sm_count(const go1mpc_t *h);
-/* wait for the handle's stream */
+/* wait for the handle's stream and for every pipelined *_host_async call */
 int go1mpc_synchronize(go1mpc_t *h);
 
 /* ---------------------------------------------------------------------------
@@ -188,6 +188,18 @@ int go1mpc_body_mpc_step_batch(go1mpc_t *h, int nh, int B,
                                void *stream);
 int go1mpc_body_mpc_step_batch_host(go1mpc_t *h, int nh, int B,
                                     const double *in, double *out, int *diag);
+/* Pipelined host entries: enqueue H2D copy, kernel and D2H copy on one of the handle's three
+ * internal lanes (consecutive calls use consecutive lanes, so the copies of one batch overlap
+ * the kernels of its neighbours) and return at once; go1mpc_synchronize() waits for all of
+ * them.  Host buffers should be pinned and must stay untouched until then.  The planner state
+ * of the step-timing tick stays RESIDENT ON THE DEVICE (state_d / state_out_d are device
+ * pointers, as in go1mpc_step_timing_step_batch); only the per-tick inputs and results move. */
+int go1mpc_body_mpc_step_batch_host_async(go1mpc_t *h, int nh, int B,
+                                          const double *in, double *out, int *diag);
+int go1mpc_step_timing_step_batch_host_async(go1mpc_t *h, int n_sqp, int B, const int *tick,
+                                             const double *state_d, double *state_out_d,
+                                             const double *in, double *out, int *diag);
+
 /* Model matrices the handle condenses with, for inspection/tests (host
  * buffers, column-major): pps,pvs nh x 2; ppu,pvu,ppu_2,pvu_2 nh x nh.
  * Replaces PRMPCClass::Matrix_ps / Matrix_pu, RT/FastMPC/PRMPCClass.cpp:741-796. */

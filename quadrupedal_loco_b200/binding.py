@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_body_mpc_step_batch", "go1mpc_body_mpc_step_batch_host",
     "go1mpc_body_model", "go1mpc_body_default_tx", "go1mpc_measure_dfma_peak",
     "go1mpc_step_timing_step_batch", "go1mpc_step_timing_step_batch_host", "go1mpc_step_default_state",
+    "go1mpc_body_mpc_step_batch_host_async", "go1mpc_step_timing_step_batch_host_async",
     "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
@@ -98,6 +99,8 @@ def load_library():
     lib.go1mpc_step_timing_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
     lib.go1mpc_step_timing_step_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
     lib.go1mpc_step_default_state.argtypes = [vp] + [ctypes.c_double] * 4 + [vp]
+    lib.go1mpc_body_mpc_step_batch_host_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
+    lib.go1mpc_step_timing_step_batch_host_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     lib.go1mpc_leg_fk_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
     lib.go1mpc_leg_ik_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
     lib.go1mpc_leg_fk_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
@@ -223,6 +226,19 @@ class Go1Mpc:
         """Host-buffer entry: H2D, launch, D2H and a stream sync inside the call."""
         self._check(self.lib.go1mpc_body_mpc_step_batch_host(self.h, nh, B, _ptr(in_h), _ptr(out_h), _ptr(diag_h)),
                     "body_mpc_step_batch_host")
+
+    def body_mpc_step_host_async(self, nh, B, in_h, out_h, diag_h=None):
+        """Pipelined: returns after enqueueing H2D + kernel + D2H; call synchronize() before reading out_h."""
+        self._check(self.lib.go1mpc_body_mpc_step_batch_host_async(self.h, nh, B, _ptr(in_h), _ptr(out_h), _ptr(diag_h)),
+                    "body_mpc_step_batch_host_async")
+
+    def step_timing_step_host_async(self, n_sqp, B, tick_h, state_d, in_h, out_h, diag_h=None, state_out_d=None):
+        """Pipelined; the planner state stays on the device (state_d: device buffer, updated in place
+        unless state_out_d is given)."""
+        so = state_d if state_out_d is None else state_out_d
+        self._check(self.lib.go1mpc_step_timing_step_batch_host_async(self.h, n_sqp, B, _ptr(tick_h), _ptr(state_d), _ptr(so),
+                                                                      _ptr(in_h), _ptr(out_h), _ptr(diag_h)),
+                    "step_timing_step_batch_host_async")
 
     def body_model(self, nh):
         out = {k: np.zeros((2, nh) if k in ("pps", "pvs") else (nh, nh)) for k in ("pps", "pvs", "ppu", "pvu", "ppu_2", "pvu_2")}

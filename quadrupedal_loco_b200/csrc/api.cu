@@ -42,7 +42,14 @@ struct go1mpc {
   std::string err;
   long long launches = 0;
   std::map<int, BodyModel> body_models;
-  DevBuf stage[16];   // device staging for the *_host entry points
+  DevBuf stage[16];   // device staging for the synchronous *_host entry points
+  // lanes of the asynchronous *_host_async entry points: consecutive calls go to consecutive lanes
+  // (own stream, own staging), so the H2D copy of one batch overlaps the kernel of the previous
+  // one and the D2H copy of the one before that
+  struct Lane { cudaStream_t stream = nullptr; DevBuf stage[8]; };
+  static const int kLanes = 3;
+  Lane lanes[3];
+  unsigned lane_next = 0;
   int* sched_d = nullptr;          // ring of {next, done} counter pairs for body_fast launches
   unsigned sched_next = 0;
   bool force_generic = false;      // GO1MPC_FORCE_GENERIC=1: always use the run-time-sized kernel
@@ -165,8 +172,9 @@ int get_body_model(go1mpc* h, int nh, BodyModel** out) {
   return GO1MPC_OK;
 }
 
-int stage_buf(go1mpc* h, int slot, size_t bytes, void** out) {
-  DevBuf& b = h->stage[slot];
+int stage_buf2(go1mpc* h, DevBuf& b, size_t bytes, void** out);
+int stage_buf(go1mpc* h, int slot, size_t bytes, void** out) { return stage_buf2(h, h->stage[slot], bytes, out); }
+int stage_buf2(go1mpc* h, DevBuf& b, size_t bytes, void** out) {
   if (bytes > b.cap) {
     if (b.p) cudaFree(b.p);
     b.p = nullptr; b.cap = 0;
@@ -231,6 +239,8 @@ int go1mpc_create(const Go1MpcConfig* cfg, int device, go1mpc_t** out) {
     go1mpc_destroy(h);
     return GO1MPC_E_CUDA;
   }
+  for (auto& L : h->lanes)
+    if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { go1mpc_destroy(h); return GO1MPC_E_CUDA; }
   const char* fg = getenv("GO1MPC_FORCE_GENERIC");
   h->force_generic = fg && fg[0] == '1';
   *out = h;
@@ -243,6 +253,10 @@ void go1mpc_destroy(go1mpc_t* h) {
   for (auto& kv : h->body_models) if (kv.second.tab_d) cudaFree(kv.second.tab_d);
   for (DevBuf& b : h->stage) if (b.p) cudaFree(b.p);
   if (h->sched_d) cudaFree(h->sched_d);
+  for (auto& L : h->lanes) {
+    for (DevBuf& b : L.stage) if (b.p) cudaFree(b.p);
+    if (L.stream) cudaStreamDestroy(L.stream);
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -255,6 +269,7 @@ int go1mpc_sm_count(const go1mpc_t* h) { return h ? h->sms : 0; }
 int go1mpc_synchronize(go1mpc_t* h) {
   if (!h) return GO1MPC_E_INVALID;
   CU(h, cudaStreamSynchronize(h->stream));
+  for (auto& L : h->lanes) CU(h, cudaStreamSynchronize(L.stream));
   return GO1MPC_OK;
 }
 
@@ -508,6 +523,65 @@ int go1mpc_step_default_state(go1mpc_t* h, double steplength, double stepwidth, 
   }
   for (int j = 0; j < NS; j++) ts[j] = tstep;
   for (int j = 1; j < NS; j++) { tx[j] = tx[j - 1] + ts[j - 1]; tx[j] = round(tx[j] / dt) * dt - 0.000001; }
+  return GO1MPC_OK;
+}
+
+// ------------------------------------------------------------------ pipelined host entries
+int go1mpc_body_mpc_step_batch_host_async(go1mpc_t* h, int nh, int B, const double* in, double* out, int* diag) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!in || !out) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch_host_async: bad argument");
+  if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "body_mpc_step_batch_host_async: 3 <= nh <= 40");
+  CU(h, cudaSetDevice(h->device));
+  BodyModel* M;
+  int rc = get_body_model(h, nh, &M);
+  if (rc) return rc;
+  const int is = go1mpc_body_in_stride(nh), os = go1mpc_body_out_stride(nh);
+  const size_t ib = (size_t)B * is * sizeof(double), ob = (size_t)B * os * sizeof(double);
+  const size_t db = (size_t)B * go1mpc_body_diag_stride(nh) * sizeof(int);
+  go1mpc::Lane& L = h->lanes[h->lane_next++ % go1mpc::kLanes];
+  void *din, *dout, *ddiag = nullptr;
+  if ((rc = stage_buf2(h, L.stage[0], ib, &din))) return rc;
+  if ((rc = stage_buf2(h, L.stage[1], ob, &dout))) return rc;
+  if (diag && (rc = stage_buf2(h, L.stage[2], db, &ddiag))) return rc;
+  // the previous outputs are only read by gated ticks (the reference returns its stale members):
+  // upload them only when the batch has one
+  bool gated = false;
+  for (int b = 0; b < B && !gated; b++) {
+    const int t = (int)in[(size_t)b * is + 27];
+    gated = (t < M->gate) || !(t - M->gate < M->nsum_mpc - nh);
+  }
+  CU(h, cudaMemcpyAsync(din, in, ib, cudaMemcpyHostToDevice, L.stream));
+  if (gated) CU(h, cudaMemcpyAsync(dout, out, ob, cudaMemcpyHostToDevice, L.stream));
+  rc = go1mpc_body_mpc_step_batch(h, nh, B, (const double*)din, (double*)dout, (int*)ddiag, L.stream);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, L.stream));
+  if (diag) CU(h, cudaMemcpyAsync(diag, ddiag, db, cudaMemcpyDeviceToHost, L.stream));
+  return GO1MPC_OK;
+}
+
+int go1mpc_step_timing_step_batch_host_async(go1mpc_t* h, int n_sqp, int B, const int* tick, const double* state_d,
+                                             double* state_out_d, const double* in, double* out, int* diag) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!tick || !state_d || !state_out_d || !in || !out) return fail(h, GO1MPC_E_INVALID, "step_timing_step_batch_host_async: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t b = (size_t)B;
+  const size_t tb = b * sizeof(int), ib = b * STEP_IN_DOUBLES * sizeof(double);
+  const size_t ob = b * STEP_OUT_DOUBLES * sizeof(double), db = b * STEP_DIAG_INTS * sizeof(int);
+  go1mpc::Lane& L = h->lanes[h->lane_next++ % go1mpc::kLanes];
+  void *dt_, *di, *do_, *dd = nullptr;
+  int rc;
+  if ((rc = stage_buf2(h, L.stage[3], tb, &dt_))) return rc;
+  if ((rc = stage_buf2(h, L.stage[4], ib, &di))) return rc;
+  if ((rc = stage_buf2(h, L.stage[5], ob, &do_))) return rc;
+  if (diag && (rc = stage_buf2(h, L.stage[6], db, &dd))) return rc;
+  CU(h, cudaMemcpyAsync(dt_, tick, tb, cudaMemcpyHostToDevice, L.stream));
+  CU(h, cudaMemcpyAsync(di, in, ib, cudaMemcpyHostToDevice, L.stream));
+  rc = go1mpc_step_timing_step_batch(h, n_sqp, B, (const int*)dt_, state_d, state_out_d, (const double*)di, (double*)do_, (int*)dd, L.stream);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(out, do_, ob, cudaMemcpyDeviceToHost, L.stream));
+  if (diag) CU(h, cudaMemcpyAsync(diag, dd, db, cudaMemcpyDeviceToHost, L.stream));
   return GO1MPC_OK;
 }
 

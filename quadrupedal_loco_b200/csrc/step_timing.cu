@@ -191,7 +191,10 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
       v[0] = Lxx_refx; v[1] = Lyy_refy; v[2] = tr1_ref; v[3] = tr2_ref;
     }
   }
-  for (int q = n_solved; q < STEP_MAX_SQP; q++) DGW(STEP_DIAG_HEAD + q * STEP_DIAG_PER, -1);
+  for (int q = n_solved; q < STEP_MAX_SQP; q++) {      // every diag entry is defined: unused slots read -1, 0...
+    DGW(STEP_DIAG_HEAD + q * STEP_DIAG_PER, -1);
+    for (int k = 1; k < STEP_DIAG_PER; k++) DGW(STEP_DIAG_HEAD + q * STEP_DIAG_PER + k, 0);
+  }
 
   // write-back (:817, :886-916)
   const double ts_new = k_yu * dt + log(v[2] + v[3]) / Wn;
@@ -236,8 +239,15 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
   const double fx0 = (upd && bq0 == p) ? fx_next : ST(S_FX + bq0), fx1 = (upd && bq1 == p) ? fx_next : ST(S_FX + bq1);
   const double fy0 = (upd && bq0 == p) ? fy_next : ST(S_FY + bq0), fy1 = (upd && bq1 == p) ? fy_next : ST(S_FY + bq1);
   const double fz0 = ST(S_FZ + bq0), fz1 = ST(S_FZ + bq1);
-  if (SO != S) {   // out-of-place: carry the untouched fields over
-    for (int f = 0; f < STEP_STATE_DOUBLES; f++) STW(f) = ST(f);
+  if (SO != S) {   // out-of-place: carry the untouched fields over, 32 loads in flight at a time
+#pragma unroll 1
+    for (int f0 = 0; f0 < STEP_STATE_DOUBLES; f0 += 32) {
+      double tmp[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) if (f0 + k < STEP_STATE_DOUBLES) tmp[k] = ST(f0 + k);
+#pragma unroll
+      for (int k = 0; k < 32; k++) if (f0 + k < STEP_STATE_DOUBLES) STW(f0 + k) = tmp[k];
+    }
   }
   if (valid) {
     for (int k = 0; k < 4; k++) STW(S_VARI + k) = v[k];

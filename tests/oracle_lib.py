@@ -137,7 +137,7 @@ class Oracle:
         """Instance-major arrays: states [B,201] (updated in place), ins [B,20].  Returns out [B,38] and
         diagnostics in the GPU diag layout [B,60]."""
         B = len(tick)
-        out = np.zeros((B, STEP_OUT)); diag = np.full((B, 60), -1, np.int32)
+        out = np.zeros((B, STEP_OUT)); diag = np.zeros((B, 60), np.int32)
         for b in range(B):
             dg = StepDiag()
             self.lib.orc_step_timing_tick(ctypes.byref(cfg), int(tick[b]), P(states[b]), P(np.ascontiguousarray(ins[b])),

@@ -180,3 +180,28 @@ def test_body_full_size_properties(mpc):
             assert (np.abs(x[:, half * nh:(half + 1) * nh]) * 0.12 <= 20 / 0.12 + 1e-6).all()
             viol = np.abs(ang[:, 1:]).max() - 10 * np.pi / 180
             assert viol < 2e-6, viol   # post-solve clamp of the first control moves later angles by (2k+1) x tolerance
+
+
+def test_body_pipelined_host_entry_matches_sync(mpc):
+    """go1mpc_body_mpc_step_batch_host_async: several batches in flight on the handle's lanes, one
+    synchronize; results equal the synchronous host entry (also for a batch with gated ticks)."""
+    import torch
+    nh, B, NB = 10, 1500, 7
+    recs, outs, diags, want = [], [], [], []
+    for k in range(NB):
+        d = synth.body_mpc_inputs(B, nh, seed=100 + k)
+        if k == 3:
+            d["tick"][::5] = 50          # gated ticks: the stale out14 must be uploaded
+        rec = q.pack_body_inputs(nh, d["tick"], d["tx"], d["theta"], d["bstate"], d["x_warm"], d["refs"])
+        o = np.zeros((B, q.body_out_stride(nh))); o[:, :14] = k + 1.0
+        dg = np.zeros((B, q.body_diag_stride(nh)), np.int32)
+        o2 = o.copy(); dg2 = dg.copy()
+        mpc.body_mpc_step_host(nh, B, rec, o2, dg2)
+        want.append((o2, dg2))
+        recs.append(torch.from_numpy(rec).pin_memory()); outs.append(torch.from_numpy(o).pin_memory()); diags.append(torch.from_numpy(dg).pin_memory())
+    for k in range(NB):
+        mpc.body_mpc_step_host_async(nh, B, recs[k].numpy(), outs[k].numpy(), diags[k].numpy())
+    mpc.synchronize()
+    for k in range(NB):
+        np.testing.assert_array_equal(outs[k].numpy(), want[k][0], err_msg=f"batch {k}")
+        np.testing.assert_array_equal(diags[k].numpy(), want[k][1])

@@ -173,3 +173,27 @@ def test_step_out_of_place_state(mpc):
     np.testing.assert_array_equal(s_out.cpu().numpy().T, gs)
     np.testing.assert_array_equal(to.cpu().numpy().T, go)
     np.testing.assert_array_equal(td.cpu().numpy().T, gd)
+
+
+def test_step_pipelined_host_entry_device_resident_state(mpc):
+    """go1mpc_step_timing_step_batch_host_async: state stays on the device, only tick / inputs /
+    results move; 5 closed-loop ticks equal the synchronous path."""
+    import torch
+    B = 777
+    tick, st, inp = synth.step_timing_inputs(B, mpc.step_default_state(), seed=12, amp=0.6)
+    dev = torch.device("cuda", 0)
+    s_d = torch.from_numpy(np.array(st.T, order="C", copy=True)).to(dev)
+    i_h = torch.from_numpy(np.array(inp.T, order="C", copy=True)).pin_memory()
+    st_sync = st.copy()
+    outs, ticks, diags = [], [], []
+    for t in range(5):
+        tk = torch.from_numpy((tick + t).astype(np.int32)).pin_memory()
+        o = torch.zeros(q.STEP_OUT, B, dtype=torch.float64).pin_memory(); d = torch.zeros(q.STEP_DIAG, B, dtype=torch.int32).pin_memory()
+        mpc.step_timing_step_host_async(3, B, tk.numpy(), s_d, i_h.numpy(), o.numpy(), d.numpy())
+        outs.append(o); ticks.append(tk); diags.append(d)
+    mpc.synchronize()
+    for t in range(5):
+        go, st_sync, gd = gpu_tick(mpc, tick + t, st_sync, inp)
+        np.testing.assert_array_equal(outs[t].numpy().T, go, err_msg=f"tick +{t}")
+        np.testing.assert_array_equal(diags[t].numpy().T, gd)
+    np.testing.assert_array_equal(s_d.cpu().numpy().T, st_sync)
