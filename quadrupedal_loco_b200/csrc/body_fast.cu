@@ -44,6 +44,31 @@ __device__ __forceinline__ void warp_sum2(double& a, double& b) {
   }
 }
 
+__device__ __forceinline__ void warp_sum3(double& a, double& b, double& c) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    a += __shfl_xor_sync(FULL_MASK, a, o);
+    b += __shfl_xor_sync(FULL_MASK, b, o);
+    c += __shfl_xor_sync(FULL_MASK, c, o);
+  }
+}
+
+// Arg-min over the warp of (value, index) pairs, lowest index among equal values, with three
+// integer warp reductions (REDUX) instead of a 5-step shuffle butterfly: doubles are mapped to
+// order-preserving unsigned 64-bit keys and reduced high word first.
+__device__ __forceinline__ void warp_argmin_redux(double& v, int& idx) {
+  unsigned long long k = (unsigned long long)__double_as_longlong(v);
+  k ^= (k >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull;
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mhi = __reduce_min_sync(FULL_MASK, hi);
+  const unsigned mlo = __reduce_min_sync(FULL_MASK, hi == mhi ? lo : 0xffffffffu);
+  const bool win = (hi == mhi) && (lo == mlo);
+  idx = (int)__reduce_min_sync(FULL_MASK, win ? (unsigned)idx : 0xffffffffu);
+  unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+  m ^= (m >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull;
+  v = __longlong_as_double((long long)m);
+}
+
 template <int NH>
 struct FastDims {
   static constexpr int N = 2 * NH;
@@ -319,7 +344,7 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
               if (!(blocked & 4u) && s2v < bv) { bv = s2v; bi = cbase + 4 * NH; }
               if (!(blocked & 8u) && s3 < bv) { bv = s3; bi = cbase + 5 * NH; }
             }
-            warp_argmin(bv, bi);
+            warp_argmin_redux(bv, bi);
             if (bv < ss) { ss = bv; ip = bi; }
             if (ss >= 0.0) break;
             sip = ss;
@@ -372,10 +397,10 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
           // step lengths: t1 over the working set, t2 along z
           double t1 = inf; int kmin = 0x7fffffff;
           if (lane < iq && r > 0.0) { t1 = u / r; kmin = lane; }
-          warp_argmin(t1, kmin);
+          warp_argmin_redux(t1, kmin);
           const int l = (kmin != 0x7fffffff && t1 < inf) ? __shfl_sync(FULL_MASK, A, kmin) : 0;
-          double zz = z * z, zn = z * npL;
-          warp_sum2(zz, zn);
+          double zz = z * z, zn = z * npL, dd = (act && lane >= iq) ? d * d : 0.0;
+          warp_sum3(zz, zn, dd);
           const double t2 = (fabs(zz) > EPS_D) ? (-sip / zn) : inf;
           const double t = fmin(t1, t2);
           if (t >= inf) { status = ST_INFEASIBLE; f_value = inf; break; }        // case (i)
@@ -393,63 +418,32 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
             if (lane < iq) u = fma(-t, r, u);
             if (lane == iq) u = uiq + t;
             if (t == t2) {
-              // ---- add_constraint (cpp:30-93): rotate d[iq+1:] into d[iq] ----
+              // ---- add_constraint (cpp:30-93) ----
+              // The reference zeroes d[iq+1:] with a chain of n-iq-1 Givens rotations of J's trailing
+              // columns.  Any orthogonal map that sends d2 = d[iq:] to a multiple of e_0 spans the same
+              // null-space basis, so here ONE Householder reflection H = I - tau v v' does it,
+              // v = d2 + sigma e_0, sigma = sign(d_iq) |d2|:  J2 <- J2 H = J2 - tau (J2 v) v' and
+              // J2 v = J2 d2 + sigma J(:,iq) = z + sigma J(:,iq) -- z is already in registers, so the
+              // update is a single dependency-free pass over the trailing columns.
               flops += 6u * N * (unsigned)(N - iq - 1 > 0 ? N - iq - 1 : 0);
-              const bool inrot = act && lane >= iq;            // entries that take part
-              double S = inrot ? d * d : 0.0;                   // suffix sums of d^2 from the bottom
+              const double nrm = sqrt(dd);                              // |d2|, dd reduced with zz, zn above
+              const double diq = bcast(d, iq);
+              const double sigma = (diq < 0.0) ? -nrm : nrm;
+              if (nrm != 0.0 && act) {
+                const double tau = 1.0 / (nrm * (nrm + fabs(diq)));
+                const double sw = tau * fma(sigma, J[iq * LD + lane], z);   // tau * (J2 v)_L
+                const double viq = diq + sigma;
 #pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const double up = __shfl_down_sync(FULL_MASK, S, o);
-                if (lane + o < 32) S += up;
-              }
-              // rotation j (lanes j = iq+1 .. N-1) acts on columns (j-1, j)
-              const double dm = __shfl_up_sync(FULL_MASK, d, 1);
-              const double Sprev = __shfl_up_sync(FULL_MASK, S, 1);   // S_{j-1} = S_j + d_{j-1}^2
-              const bool isrot = act && lane > iq;
-              const double h = isrot ? sqrt(Sprev) : 0.0;
-              const double hj = __shfl_down_sync(FULL_MASK, h, 1);    // h of rotation j+1 = sqrt(S_j) = |accumulated d_j|
-              double cc = 1.0, sn = 0.0, xny = 0.0;
-              const bool skip = !(h != 0.0);
-              if (isrot && !skip) {
-                // accumulated value at position j before its rotation: +-sqrt(S_j), sign of d_j
-                const double aj = (lane == N - 1) ? d : ((d < 0.0) ? -hj : hj);
-                const double ih = 1.0 / h;
-                sn = aj * ih;
-                cc = dm * ih;
-                if (cc < 0.0) { cc = -cc; sn = -sn; }
-                xny = sn / (1.0 + cc);
-              }
-              const unsigned skipmask = __ballot_sync(FULL_MASK, skip || !isrot);
-              if (isrot) { rot[3 * lane] = cc; rot[3 * lane + 1] = sn; rot[3 * lane + 2] = xny; }
-              // new d[iq] = +-|d[iq:]| with the sign of d[iq] (lane iq+1 knows it), zeros below
-              double dnew = d;
-              {
-                const double hn = __shfl_down_sync(FULL_MASK, h, 1);      // lane iq receives h of rotation iq+1
-                const bool sk = (skipmask >> ((lane + 1) & 31)) & 1u;
-                if (lane == iq && iq + 1 < N && !sk) dnew = (d < 0.0) ? -hn : hn;
-                if (act && lane > iq) dnew = 0.0;
-              }
-              d = dnew;
-              __syncwarp();
-              if (act) {
-                double carry = J[(N - 1) * LD + lane];
-#pragma unroll
-                for (int j = N - 1; j >= 1; j--) {
-                  if (j > iq) {
-                    const double t1j = J[(j - 1) * LD + lane];
-                    if ((skipmask >> j) & 1u) {
-                      J[j * LD + lane] = carry;        // h == 0: both columns untouched
-                      carry = t1j;
-                    } else {
-                      const double rc = rot[3 * j], rs_ = rot[3 * j + 1], rx = rot[3 * j + 2];
-                      const double a = fma(carry, rs_, t1j * rc);
-                      J[j * LD + lane] = fma(rx, t1j + a, -carry);
-                      carry = a;
-                    }
+                for (int j = 0; j < N; j++) {
+                  if (j >= iq) {
+                    const double vj = (j == iq) ? viq : ds[j];
+                    J[j * LD + lane] = fma(-sw, vj, J[j * LD + lane]);
                   }
                 }
-                J[iq * LD + lane] = carry;
               }
+              // H d2 = -sigma e_0
+              if (lane == iq) d = (nrm != 0.0) ? -sigma : d;
+              if (act && lane > iq) d = 0.0;
               // new column of R, its reciprocal diagonal, degeneracy test
               if (lane <= iq) Rp[iq * (iq + 3) / 2 + lane] = d;
               if (lane == iq) rinv = 1.0 / d;
@@ -603,6 +597,7 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
       if (act) outrec[18 + lane] = x;
       if (lane == 0) outrec[18 + N] = f_value;
     }
+    if (lane == 0 && D::OUT > 19 + N) outrec[19 + N] = 0.0;   // pad double of the record: defined, not stale shared memory
     // ---- write back: one TMA bulk store of the output record, diagnostics by lanes ----
     fence_proxy_async();
     __syncwarp();

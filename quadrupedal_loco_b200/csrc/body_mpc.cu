@@ -287,6 +287,7 @@ __global__ void __launch_bounds__(WPC * 32) body_mpc_kernel(BodyKParams P) {
       for (int k = lane; k < n; k += 32) outrec[18 + k] = w.x[k];
       if (lane == 0) outrec[18 + n] = res.f;
     }
+    if (lane == 0 && P.out_stride > 19 + n) outrec[19 + n] = 0.0;   // pad double of the record
     // ---- write back: one TMA bulk store of the output record, diag by lanes ----
     fence_proxy_async();   // every lane: its generic-proxy writes to outrec become visible to the async proxy
     __syncwarp();
