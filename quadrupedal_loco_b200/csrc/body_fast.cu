@@ -280,8 +280,15 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
         {
           double acc = 0.0;
           if (act) {
+            double c0 = 0.0, c1 = 0.0, c2_ = 0.0, c3 = 0.0;
 #pragma unroll
-            for (int j = 0; j < N; j++) acc = fma(J[j * LD + lane], ds[j], acc);
+            for (int j = 0; j < N; j += 4) {
+              c0 = fma(J[j * LD + lane], ds[j], c0);
+              if (j + 1 < N) c1 = fma(J[(j + 1) * LD + lane], ds[j + 1], c1);
+              if (j + 2 < N) c2_ = fma(J[(j + 2) * LD + lane], ds[j + 2], c2_);
+              if (j + 3 < N) c3 = fma(J[(j + 3) * LD + lane], ds[j + 3], c3);
+            }
+            acc = (c0 + c1) + (c2_ + c3);
           }
           x = -acc;
           double f = act ? g0 * x : 0.0;
@@ -305,10 +312,13 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
         double ip_sgn = 1.0;
 
         auto slack_angle = [&](double& up, double& low) {
-          double v = 0.0;
+          double v0 = 0.0, v1 = 0.0;       // two chains: halves the dependent-FMA latency
 #pragma unroll
-          for (int j = 0; j < NH; j++)
-            if (j <= kL) v = fma(ppu[j * NH + kL], xs[hL * NH + j], v);
+          for (int j = 0; j < NH; j += 2) {
+            if (j <= kL) v0 = fma(ppu[j * NH + kL], xs[hL * NH + j], v0);
+            if (j + 1 < NH && j + 1 <= kL) v1 = fma(ppu[(j + 1) * NH + kL], xs[hL * NH + j + 1], v1);
+          }
+          const double v = v0 + v1;
           up = (thmax - pk) - v;
           low = v + (thmax + pk);
         };
@@ -369,11 +379,13 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
           if (act) {
             const double* col = J + lane * LD + ip_h * NH;
             if (ip_blk < 4) {
-              double acc = 0.0;
+              double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-              for (int ii = 0; ii < NH; ii++)
-                if (ii <= ip_k) acc = fma(col[ii], ppu[ii * NH + ip_k], acc);
-              d = ip_sgn * acc;
+              for (int ii = 0; ii < NH; ii += 2) {
+                if (ii <= ip_k) a0 = fma(col[ii], ppu[ii * NH + ip_k], a0);
+                if (ii + 1 < NH && ii + 1 <= ip_k) a1 = fma(col[ii + 1], ppu[(ii + 1) * NH + ip_k], a1);
+              }
+              d = ip_sgn * (a0 + a1);
             } else {
               d = ip_sgn * (j_ini * col[ip_k]);
             }
@@ -383,9 +395,15 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
           // z = J[:, iq:] d[iq:]
           z = 0.0;
           if (act) {
+            double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
 #pragma unroll
-            for (int j = 0; j < N; j++)
-              if (j >= iq) z = fma(J[j * LD + lane], ds[j], z);
+            for (int j = 0; j < N; j += 4) {
+              if (j >= iq) z0 = fma(J[j * LD + lane], ds[j], z0);
+              if (j + 1 < N && j + 1 >= iq) z1 = fma(J[(j + 1) * LD + lane], ds[j + 1], z1);
+              if (j + 2 < N && j + 2 >= iq) z2 = fma(J[(j + 2) * LD + lane], ds[j + 2], z2);
+              if (j + 3 < N && j + 3 >= iq) z3 = fma(J[(j + 3) * LD + lane], ds[j + 3], z3);
+            }
+            z = (z0 + z1) + (z2 + z3);
           }
           // r = R^-1 d[0:iq)  (column-oriented back substitution, stored reciprocals)
           r = (lane < iq) ? d : 0.0;
