@@ -99,6 +99,9 @@ typedef struct {
     double aax, aay, aaxv, aayv, bbx, bby, rr1, rr2;        /* 5e4 5e4 1e3 5e2 2e6 1e7 1e6 1e6 */
     double half_hip_width, foot_width;                       /* 0.12675, 0.03    */
     double lamda[4];             /* com x, vx, y, vy feedback gains (0 as shipped) */
+    double hcom;                 /* 0.309458  RobotPara_Z_C - _height_offset    */
+    int ext_height;              /* 0: CoM_height_solve on the device; 1: comz/comaz/comvz from in_d */
+    int reserved;
 } Go1StepMpcConfig;
 
 typedef struct {
@@ -215,29 +218,30 @@ int go1mpc_body_default_tx(go1mpc_t *h, double *tx27);
  *   solve_stepping_timing/Solve :1613-1653 (QP n=4, p=1, m=24), Indexfind :1105-1141.
  * One launch runs n_sqp SQP iterations (reference: 3; 1..5 supported), the write-back of
  * step length / width / period and of the step tables, the LIPM roll-out of samples
- * i..i+2, the feedback blend and the integer step indices.  CoM_height_solve
- * (:2361-2473) is not on the device yet: its vertical CoM samples are inputs.
+ * i..i+2, the feedback blend, the integer step indices and CoM_height_solve (:2361-2473,
+ * the 6th-order vertical CoM polynomial).
  *
  * Layout: STRUCTURE OF ARRAYS, element-major / batch-minor: field f of instance b is
  * at [f*B + b] (one thread per instance: every access of a warp is coalesced).
  * tick_d  [B] ints         i of the reference (>= 1)
- * state_d [201][B] doubles, the planner state before the tick; state_out_d receives the
+ * state_d [202][B] doubles, the planner state before the tick; state_out_d receives the
  *         state after it and may be the same buffer (in-place: only changed fields are
  *         written).  Fields:
  *           [0,27) ts   [27,54) tx   [54,81) footx_ref  [81,108) footy_ref
  *           [108,135) footz_ref  [135,162) Lxx_ref  [162,189) Lyy_ref
  *           [189,195) com x,vx,ax,y,vy,ay _feed at tick i-1
  *           [195,199) _Vari_ini.col(i-1) = (Lx, Ly, cosh(w T), sinh(w T))
- *           [199,201) _comvx_endref, _comvy_endref
+ *           [199,201) _comvx_endref, _comvy_endref   [201] _bjx1 of the previous tick (exact integer)
  * in_d    [20][B] doubles: [0,6) estimated com x,vx,ax,y,vy,ay  [6,8) right foot x,y
- *           [8,10) left foot x,y  [10,13) comz(i..i+2)  [13,16) comaz  [16,19) Zsc  [19] comvz(i)
+ *           [8,10) left foot x,y  [16,19) Zsc(i..i+2) (terrain height under the CoM)
+ *           [10,13) comz(i..i+2)  [13,16) comaz  [19] comvz(i): read only when cfg.step.ext_height != 0
  * out_d   [38][B] doubles = the Vec38 the reference returns (:1048-1090)
  * diag_d  [60][B] ints (may be NULL): [0] period index (_periond_i; -1 = time beyond the
  *           step table, nothing written)  [1] k_yu  [2] bjxx  [3] bjx1  [4] QPs solved;
  *           then per SQP iteration q < 5, at 5 + 11 q: status (-1 = no solve), nactive,
  *           iters[4], active set[5] (slot 0 = -1 is the equality)
  * ------------------------------------------------------------------------ */
-#define GO1MPC_STEP_STATE_DOUBLES 201
+#define GO1MPC_STEP_STATE_DOUBLES 202
 #define GO1MPC_STEP_IN_DOUBLES 20
 #define GO1MPC_STEP_OUT_DOUBLES 38
 #define GO1MPC_STEP_DIAG_INTS 60
@@ -247,7 +251,7 @@ int go1mpc_step_timing_step_batch(go1mpc_t *h, int n_sqp, int B, const int *tick
                                   int *diag_d, void *stream);
 int go1mpc_step_timing_step_batch_host(go1mpc_t *h, int n_sqp, int B, const int *tick,
                                        double *state, const double *in, double *out, int *diag);
-/* Initial step tables of one planner (host buffer, 201 doubles, instance-major):
+/* Initial step tables of one planner (host buffer, 202 doubles, instance-major):
  * NLPClass::FootStepInputs :51-75 and Initialize :131-206 for the given step length,
  * width and height (reference: 0.075, 0.2535, 0) and period tstep (0.7). */
 int go1mpc_step_default_state(go1mpc_t *h, double steplength, double stepwidth,

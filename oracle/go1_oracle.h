@@ -134,8 +134,9 @@ void orc_body_step_batch(const orc_body_cfg *c, int B, const int *tick,
  *   LIPM roll-out :938-955, feedback blend :1017-1022, indices :1031-1041),
  *   Indexfind :1105-1141, step_timing_object_function :1144-1173,
  *   step_timing_constraints :1175-1458, solve_stepping_timing :1613-1639.
- * CoM_height_solve (:2361-2473) is NOT restated yet: the vertical CoM samples
- * it would write are inputs (comz/comaz/zsc for ticks i..i+2, comvz at i).
+ *   CoM_height_solve :2361-2473 (6th-order vertical CoM polynomial, 7x7 inverse).
+ * With cfg.ext_height != 0 the vertical CoM samples are taken from the inputs
+ * instead (comz/comaz for ticks i..i+2, comvz at i).
  * --------------------------------------------------------------------- */
 #define ORC_STEP_NQP_MAX 8
 typedef struct {
@@ -147,16 +148,19 @@ typedef struct {
     double aax, aay, aaxv, aayv, bbx, bby, rr1, rr2;         /* go1 weights       */
     double half_hip_width, foot_width;                        /* 0.12675, 0.03     */
     double lamda[4];                /* comx, comvx, comy, comvy feedback gains (0) */
+    double hcom;                    /* 0.309458 - 0 (RobotPara_Z_C - _height_offset) */
     int n_sqp;                      /* 3                                          */
+    int ext_height;                 /* 0: CoM_height_solve; 1: comz/comaz/comvz0 from the inputs */
 } orc_step_cfg;
 
-typedef struct {                    /* carried from tick to tick (201 doubles)    */
+typedef struct {                    /* carried from tick to tick (202 doubles)    */
     double ts[ORC_FOOTSTEPS], tx[ORC_FOOTSTEPS];
     double footx[ORC_FOOTSTEPS], footy[ORC_FOOTSTEPS], footz[ORC_FOOTSTEPS];
     double Lxx[ORC_FOOTSTEPS], Lyy[ORC_FOOTSTEPS];
     double feed[6];                 /* com x, vx, ax, y, vy, ay _feed at tick i-1  */
     double vari[4];                 /* _Vari_ini.col(i-1) = [Lx, Ly, tr1, tr2]     */
     double endref[2];               /* _comvx_endref, _comvy_endref                */
+    double bjx1_prev;               /* _bjx1 left by the previous tick (exact integer) */
 } orc_step_state;
 
 typedef struct {                    /* per-tick inputs (20 doubles)               */
@@ -178,7 +182,7 @@ void orc_step_state_default(orc_step_state *s, const orc_step_cfg *c, double ste
                             double stepheight, double tstep);
 void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const orc_step_in *in,
                           double out38[38], orc_step_diag *diag);
-/* flat batch driver: states [B][201], ins [B][20], out [B][38], diag optional */
+/* flat batch driver: states [B][202], ins [B][20], out [B][38], diag optional */
 void orc_step_timing_batch(const orc_step_cfg *c, int B, const int *tick, double *states, const double *ins,
                            double *out38, orc_step_diag *diag);
 

@@ -51,9 +51,11 @@ void ref_nlp_consts(void* h, double* c) {
   c[k++] = p->_aax; c[k++] = p->_aay; c[k++] = p->_aaxv; c[k++] = p->_aayv;
   c[k++] = p->_bbx; c[k++] = p->_bby; c[k++] = p->_rr1; c[k++] = p->_rr2;
   c[k++] = p->RobotPara_HALF_HIP_WIDTH; c[k++] = p->RobotPara_FOOT_WIDTH;
+  c[k++] = 0; c[k++] = 0; c[k++] = 0; c[k++] = 0;   // lamda (hard-coded 0 in the reference)
+  c[k++] = p->_hcom;
 }
 
-// state the tick reads: tables (7 x 27) | feed at i-1 (6) | Vari_ini.col(i-1) (4) | endref (2)
+// state the tick reads: tables (7 x 27) | feed at i-1 (6) | Vari_ini.col(i-1) (4) | endref (2) | _bjx1
 void ref_nlp_get_state(void* h, int i, double* s) {
   NLPClass* p = static_cast<NLPClass*>(h);
   int k = 0;
@@ -68,6 +70,7 @@ void ref_nlp_get_state(void* h, int i, double* s) {
   s[k++] = p->_comy_feed(i - 1); s[k++] = p->_comvy_feed(i - 1); s[k++] = p->_comay_feed(i - 1);
   for (int j = 0; j < 4; j++) s[k++] = p->_Vari_ini(j, i - 1);
   s[k++] = p->_comvx_endref(0); s[k++] = p->_comvy_endref(0);
+  s[k++] = p->_bjx1;
 }
 void ref_nlp_set_state(void* h, int i, const double* s) {
   NLPClass* p = static_cast<NLPClass*>(h);
@@ -83,7 +86,11 @@ void ref_nlp_set_state(void* h, int i, const double* s) {
   p->_comy_feed(i - 1) = s[k++]; p->_comvy_feed(i - 1) = s[k++]; p->_comay_feed(i - 1) = s[k++];
   for (int j = 0; j < 4; j++) p->_Vari_ini(j, i - 1) = s[k++];
   p->_comvx_endref(0) = s[k++]; p->_comvy_endref(0) = s[k++];
+  p->_bjx1 = (int)s[k++];
   p->_td = 0.2 * p->_ts;
+  // members the end of the previous tick leaves behind (NLPClass_sqp.cpp:1041-1046)
+  for (int j = 0; j < 27; j++) { p->_footxyz_real(0, j) = p->_footx_ref(j); p->_footxyz_real(1, j) = p->_footy_ref(j); p->_footxyz_real(2, j) = p->_footz_ref(j); }
+  p->_footxyz_real(1, 0) = -p->_stepwidth(0);
 }
 
 // NLPClass::step_timing_opti_loop, NLPClass_sqp.cpp:693-1102.  est18/rfoot/lfoot as the

@@ -13,6 +13,9 @@
  * (tests/test_oracle_vs_ref.py).  Products with the selection rows _SS1.._SS4 (unit rows)
  * reduce exactly to picking an entry: the other terms are exact zeros.
  *
+ *   CoM_height_solve             :2361-2473 (inverse of the 7x7 time-polynomial matrix by
+ *                                row-pivoted Gauss-Jordan, first maximal pivot wins -- what
+ *                                oracle/eigen_shim's inverse() does for n > 3)
  * Frozen quirks: `_vari_ini += _X` runs whatever the solver's status was (a not-PD solve
  * leaves _X = _vari_ini, doubling it; an infeasible solve adds a partial step); the
  * initial-velocity rows 20-23 use a.dt in the matrix and a.dt/2 in the right-hand side; the
@@ -40,6 +43,7 @@ void orc_step_cfg_default(orc_step_cfg *c)
     c->aax = 50000; c->aay = 50000; c->aaxv = 1000; c->aayv = 500;
     c->bbx = 2000000; c->bby = 10000000; c->rr1 = 1000000; c->rr2 = 1000000;
     c->half_hip_width = 0.12675; c->foot_width = 0.03;
+    c->hcom = 0.309458 - 0.000;
     c->n_sqp = 3;
 }
 
@@ -65,6 +69,63 @@ void orc_step_state_default(orc_step_state *s, const orc_step_cfg *c, double ste
     for (int j = 1; j < NS; j++) {
         s->tx[j] = s->tx[j - 1] + s->ts[j - 1];
         s->tx[j] = round(s->tx[j] / c->dt) * c->dt - 0.000001;
+    }
+}
+
+/* inverse by Gauss-Jordan with partial (row) pivoting, first maximal |pivot| wins; row-major n x n */
+static void gj_inverse(int n, double *a, double *r)
+{
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) r[i * n + j] = (i == j) ? 1.0 : 0.0;
+    for (int k = 0; k < n; k++) {
+        int piv = k;
+        double best = fabs(a[k * n + k]);
+        for (int i = k + 1; i < n; i++) if (fabs(a[i * n + k]) > best) { best = fabs(a[i * n + k]); piv = i; }
+        if (piv != k)
+            for (int j = 0; j < n; j++) {
+                double t = a[k * n + j]; a[k * n + j] = a[piv * n + j]; a[piv * n + j] = t;
+                t = r[k * n + j]; r[k * n + j] = r[piv * n + j]; r[piv * n + j] = t;
+            }
+        double d = a[k * n + k];
+        for (int j = 0; j < n; j++) { a[k * n + j] = a[k * n + j] / d; r[k * n + j] = r[k * n + j] / d; }
+        for (int i = 0; i < n; i++) {
+            if (i == k) continue;
+            double f = a[i * n + k];
+            for (int j = 0; j < n; j++) { a[i * n + j] -= f * a[k * n + j]; r[i * n + j] -= f * r[k * n + j]; }
+        }
+    }
+}
+
+/* NLPClass::CoM_height_solve :2361-2473 for the three samples the tick reads (jxx = 1..3) */
+static void com_height_solve(const orc_step_cfg *c, int i, const orc_step_state *s, int bjx1,
+                             double comz[3], double comvz[3], double comaz[3])
+{
+    if (bjx1 >= 2) {
+        double tp[3] = { 0.0001, s->ts[bjx1 - 1] / 2 + 0.0001, s->ts[bjx1 - 1] + 0.0001 };
+        double A[49], Ainv[49];
+        const int rowt[7] = { 0, 0, 0, 1, 2, 2, 2 }, kind[7] = { 1, 2, 0, 0, 0, 1, 2 };   /* 0 value, 1 velocity, 2 acceleration */
+        for (int r = 0; r < 7; r++) {
+            const double t = tp[rowt[r]];
+            double *a = A + 7 * r;
+            if (kind[r] == 0) { a[0] = pow(t, 6); a[1] = pow(t, 5); a[2] = pow(t, 4); a[3] = pow(t, 3); a[4] = pow(t, 2); a[5] = pow(t, 1); a[6] = 1; }
+            else if (kind[r] == 1) { a[0] = 6 * pow(t, 5); a[1] = 5 * pow(t, 4); a[2] = 4 * pow(t, 3); a[3] = 3 * pow(t, 2); a[4] = 2 * pow(t, 1); a[5] = 1; a[6] = 0; }
+            else { a[0] = 30 * pow(t, 4); a[1] = 20 * pow(t, 3); a[2] = 12 * pow(t, 2); a[3] = 6 * pow(t, 1); a[4] = 2; a[5] = 0; a[6] = 0; }
+        }
+        gj_inverse(7, A, Ainv);
+        const double f0 = s->footz[bjx1 - 2], f1 = s->footz[bjx1 - 1];
+        const double plan[7] = { 0, 0, f0 + c->hcom, (f0 + f1) / 2 + c->hcom, f1 + c->hcom, 0, 0 };
+        double co[7];
+        for (int r = 0; r < 7; r++) { double acc = 0.0; for (int k = 0; k < 7; k++) acc += Ainv[7 * r + k] * plan[k]; co[r] = acc; }
+        for (int jxx = 1; jxx <= 3; jxx++) {
+            const double t = (i + jxx - round(s->tx[bjx1 - 1] / c->dt)) * c->dt;
+            const double p[7] = { pow(t, 6), pow(t, 5), pow(t, 4), pow(t, 3), pow(t, 2), pow(t, 1), 1 };
+            const double v[7] = { 6 * pow(t, 5), 5 * pow(t, 4), 4 * pow(t, 3), 3 * pow(t, 2), 2 * pow(t, 1), 1, 0 };
+            const double a[7] = { 30 * pow(t, 4), 20 * pow(t, 3), 12 * pow(t, 2), 6 * pow(t, 1), 2, 0, 0 };
+            double z = 0.0, vz = 0.0, az = 0.0;
+            for (int k = 0; k < 7; k++) { z += p[k] * co[k]; vz += v[k] * co[k]; az += a[k] * co[k]; }
+            comz[jxx - 1] = z; comvz[jxx - 1] = vz; comaz[jxx - 1] = az;
+        }
+    } else {
+        for (int q = 0; q < 3; q++) { comz[q] = c->hcom; comvz[q] = 0; comaz[q] = 0; }
     }
 }
 
@@ -245,6 +306,14 @@ void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const
     s->endref[1] = Wn * isy * v[3] + visy * v[2];
     (void)nTd_ts1;
 
+    /* :936 vertical CoM samples (after the write-back of ts / tx, with the _bjx1 of the previous tick) */
+    double hz_z[3], hz_vz[3], hz_az[3];
+    if (c->ext_height) {
+        for (int q = 0; q < 3; q++) { hz_z[q] = in->comz[q]; hz_az[q] = in->comaz[q]; hz_vz[q] = 0.0; }
+        hz_vz[0] = in->comvz0;
+    } else {
+        com_height_solve(c, i, s, (int)s->bjx1_prev, hz_z, hz_vz, hz_az);
+    }
     /* :938-955 LIPM roll-out (samples i, i+1, i+2 are what the outputs read) */
     double comx[3], comy[3], comvx[3], comvy[3], comax[3], comay[3], zmpx[3], zmpy[3], dcmx[3], dcmy[3];
     for (int jxx = 1; jxx <= 3; jxx++) {
@@ -256,7 +325,7 @@ void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const
         comvy[q] = Wn * isy * sinh(w) + visy * cosh(w);
         comax[q] = pow(Wn, 2) * isx * cosh(w) + visx * Wn * sinh(w);
         comay[q] = pow(Wn, 2) * isy * cosh(w) + visy * Wn * sinh(w);
-        const double hz = (in->comz[q] - in->zsc[q]) / (in->comaz[q] + c->ggg);
+        const double hz = (hz_z[q] - in->zsc[q]) / (hz_az[q] + c->ggg);
         zmpx[q] = comx[q] - hz * comax[q];
         zmpy[q] = comy[q] - hz * comay[q];
         dcmx[q] = comx[q] + comvx[q] * sqrt(hz);
@@ -281,14 +350,14 @@ void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const
     const int bjx1 = (j - 1) + 1;
 
     /* :1048-1090 */
-    out38[0] = comx[0]; out38[1] = comy[0]; out38[2] = in->comz[0];
-    out38[3] = comvx[0]; out38[4] = comvy[0]; out38[5] = in->comvz0;
-    out38[6] = comax[0]; out38[7] = comay[0]; out38[8] = in->comaz[0];
+    out38[0] = comx[0]; out38[1] = comy[0]; out38[2] = hz_z[0];
+    out38[3] = comvx[0]; out38[4] = comvy[0]; out38[5] = hz_vz[0];
+    out38[6] = comax[0]; out38[7] = comay[0]; out38[8] = hz_az[0];
     out38[9] = zmpx[0]; out38[10] = zmpy[0]; out38[11] = dcmx[0]; out38[12] = dcmy[0];
     out38[13] = zmpx[1]; out38[14] = zmpy[1]; out38[15] = dcmx[1]; out38[16] = dcmy[1];
     out38[17] = zmpx[2]; out38[18] = zmpy[2]; out38[19] = dcmx[2]; out38[20] = dcmy[2];
-    out38[21] = comax[1]; out38[22] = comay[1]; out38[23] = in->comaz[1];
-    out38[24] = comax[2]; out38[25] = comay[2]; out38[26] = in->comaz[2];
+    out38[21] = comax[1]; out38[22] = comay[1]; out38[23] = hz_az[1];
+    out38[24] = comax[2]; out38[25] = comay[2]; out38[26] = hz_az[2];
     out38[27] = bjxx;
     const int b0 = bjxx < NS ? bjxx : NS - 1, b1 = bjxx + 1 < NS ? bjxx + 1 : NS - 1;   /* reference reads past the table at the very end */
     out38[28] = s->footx[b0]; out38[29] = s->footx[b1];
@@ -298,6 +367,7 @@ void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const
     out38[35] = s->ts[p - 1];
     out38[36] = v[0];
     out38[37] = v[1];
+    s->bjx1_prev = bjx1;
     if (dg) { dg->periond_i = p; dg->k_yu = k_yu; dg->bjxx = bjxx; dg->bjx1 = bjx1; dg->n_solved = n_solved; }
 }
 

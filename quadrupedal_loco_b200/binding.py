@@ -46,14 +46,15 @@ class BodyCfg(ctypes.Structure):
 class StepCfg(ctypes.Structure):
     _fields_ = [(n, ctypes.c_double) for n in (
         "dt Wn ggg t_min t_max footx_max footx_min footx_vmax footx_vmin footy_vmax footy_vmin comax_max comax_min "
-        "comay_max comay_min aax aay aaxv aayv bbx bby rr1 rr2 half_hip_width foot_width").split()] + [("lamda", ctypes.c_double * 4)]
+        "comay_max comay_min aax aay aaxv aayv bbx bby rr1 rr2 half_hip_width foot_width").split()] + [
+        ("lamda", ctypes.c_double * 4), ("hcom", ctypes.c_double), ("ext_height", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class Cfg(ctypes.Structure):
     _fields_ = [("body", BodyCfg), ("step", StepCfg), ("qp_iter_cap_scale", ctypes.c_int), ("reserved", ctypes.c_int * 7)]
 
 
-STEP_STATE, STEP_IN, STEP_OUT, STEP_DIAG = 201, 20, 38, 60
+STEP_STATE, STEP_IN, STEP_OUT, STEP_DIAG = 202, 20, 38, 60
 
 
 _LIB = None

@@ -210,6 +210,7 @@ int go1mpc_config_default(Go1MpcConfig* cfg) {
   s.aax = 50000; s.aay = 50000; s.aaxv = 1000; s.aayv = 500;
   s.bbx = 2000000; s.bby = 10000000; s.rr1 = 1000000; s.rr2 = 1000000;
   s.half_hip_width = 0.12675; s.foot_width = 0.03;
+  s.hcom = 0.309458 - 0.000; s.ext_height = 0;
   cfg->qp_iter_cap_scale = 20;
   return GO1MPC_OK;
 }
@@ -467,6 +468,7 @@ int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick
   d.aax = c.aax; d.aay = c.aay; d.aaxv = c.aaxv; d.aayv = c.aayv; d.bbx = c.bbx; d.bby = c.bby; d.rr1 = c.rr1; d.rr2 = c.rr2;
   d.half_hip_width = c.half_hip_width; d.foot_width = c.foot_width;
   for (int k = 0; k < 4; k++) d.lamda[k] = c.lamda[k];
+  d.hcom = c.hcom; d.ext_height = c.ext_height;
   CU(h, step_timing_launch(P, st));
   h->launches++;
   return GO1MPC_OK;

@@ -36,13 +36,14 @@ cudaError_t dense_qp_launch(DenseKParams P, int wpc, int grid, size_t smem, cuda
 cudaError_t dense_qp_occupancy(int wpc, size_t smem, int* blocks_per_sm);
 
 // ---- step-location / step-timing SQP (step_timing.cu) ----
-constexpr int STEP_STATE_DOUBLES = 201, STEP_IN_DOUBLES = 20, STEP_OUT_DOUBLES = 38;
+constexpr int STEP_STATE_DOUBLES = 202, STEP_IN_DOUBLES = 20, STEP_OUT_DOUBLES = 38;
 constexpr int STEP_MAX_SQP = 5, STEP_DIAG_HEAD = 5, STEP_DIAG_PER = 11;
 constexpr int STEP_DIAG_INTS = STEP_DIAG_HEAD + STEP_MAX_SQP * STEP_DIAG_PER;
 struct StepCfgDev {
   double dt, Wn, ggg, t_min, t_max, footx_max, footx_min, footx_vmax, footx_vmin, footy_vmax, footy_vmin;
   double comax_max, comax_min, comay_max, comay_min, aax, aay, aaxv, aayv, bbx, bby, rr1, rr2;
-  double half_hip_width, foot_width, lamda[4];
+  double half_hip_width, foot_width, lamda[4], hcom;
+  int ext_height;
 };
 struct StepKParams {
   int B, n_sqp, cap;

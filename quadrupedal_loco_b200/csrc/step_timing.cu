@@ -8,9 +8,9 @@
 //   Indexfind                            :1105-1141
 // (NLP = unitree_ros/mosek_nlp_kmp).  K SQP iterations (reference: 3), the write-back of step
 // length / width / period, the LIPM roll-out of the next three samples, the feedback blend and
-// the integer step indices run in ONE launch; the QP matrices live in the thread's local memory
-// and never touch HBM.  CoM_height_solve (:2361-2473) is not on the device yet: the vertical
-// CoM samples are inputs.
+// the integer step indices and CoM_height_solve (:2361-2473: 6th-order vertical CoM polynomial,
+// 7x7 inverse) run in ONE launch; the QP matrices live in the thread's local memory and never
+// touch HBM.
 //
 // Layout: structure of arrays, element-major / batch-minor -- field f of instance b is at
 // [f * B + b] -- so a warp's 32 instances read and write 256 contiguous bytes per field.
@@ -24,10 +24,69 @@ namespace go1 {
 namespace {
 constexpr int NS = 27;
 // state fields (doubles)
-constexpr int S_TS = 0, S_TX = 27, S_FX = 54, S_FY = 81, S_FZ = 108, S_LXX = 135, S_LYY = 162, S_FEED = 189, S_VARI = 195, S_END = 199;
+constexpr int S_TS = 0, S_TX = 27, S_FX = 54, S_FY = 81, S_FZ = 108, S_LXX = 135, S_LYY = 162, S_FEED = 189, S_VARI = 195, S_END = 199, S_BJX1 = 201;
 // input fields
 constexpr int I_EST = 0, I_RF = 6, I_LF = 8, I_CZ = 10, I_CAZ = 13, I_ZSC = 16, I_CVZ = 19;
 }  // namespace
+
+// inverse by Gauss-Jordan with partial (row) pivoting, first maximal |pivot| wins; row-major 7 x 7
+// (the elimination order of the CPU oracle: the time-polynomial matrix is badly conditioned, so
+// the order is part of the contract -- SURVEY.md Appendix B)
+__device__ void gj_inverse7(double* a, double* r) {
+  constexpr int n = 7;
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) r[i * n + j] = (i == j) ? 1.0 : 0.0;
+  for (int k = 0; k < n; k++) {
+    int piv = k;
+    double best = fabs(a[k * n + k]);
+    for (int i = k + 1; i < n; i++) if (fabs(a[i * n + k]) > best) { best = fabs(a[i * n + k]); piv = i; }
+    if (piv != k)
+      for (int j = 0; j < n; j++) {
+        double t = a[k * n + j]; a[k * n + j] = a[piv * n + j]; a[piv * n + j] = t;
+        t = r[k * n + j]; r[k * n + j] = r[piv * n + j]; r[piv * n + j] = t;
+      }
+    const double d = a[k * n + k];
+    for (int j = 0; j < n; j++) { a[k * n + j] = a[k * n + j] / d; r[k * n + j] = r[k * n + j] / d; }
+    for (int i = 0; i < n; i++) {
+      if (i == k) continue;
+      const double f = a[i * n + k];
+      for (int j = 0; j < n; j++) { a[i * n + j] -= f * a[k * n + j]; r[i * n + j] -= f * r[k * n + j]; }
+    }
+  }
+}
+
+// NLPClass::CoM_height_solve (NLPClass_sqp.cpp:2361-2473) for the samples i, i+1, i+2:
+// 6th-order polynomial through (value, velocity, acceleration) at the step's start and end and
+// the value at mid-step.  ts1 / tx1 / f0 / f1: _ts(bjx1-1), _tx(bjx1-1), footz(bjx1-2), footz(bjx1-1).
+__device__ void com_height_solve(int i, int bjx1, double ts1, double tx1, double f0, double f1, double hcom, double dt,
+                                 double comz[3], double comvz[3], double comaz[3]) {
+  if (bjx1 >= 2) {
+    const double tp[3] = {0.0001, ts1 / 2 + 0.0001, ts1 + 0.0001};
+    double A[49], Ainv[49];
+    const int rowt[7] = {0, 0, 0, 1, 2, 2, 2}, kind[7] = {1, 2, 0, 0, 0, 1, 2};
+    for (int r = 0; r < 7; r++) {
+      const double t = tp[rowt[r]];
+      double* a = A + 7 * r;
+      if (kind[r] == 0) { a[0] = pow(t, 6); a[1] = pow(t, 5); a[2] = pow(t, 4); a[3] = pow(t, 3); a[4] = pow(t, 2); a[5] = pow(t, 1); a[6] = 1; }
+      else if (kind[r] == 1) { a[0] = 6 * pow(t, 5); a[1] = 5 * pow(t, 4); a[2] = 4 * pow(t, 3); a[3] = 3 * pow(t, 2); a[4] = 2 * pow(t, 1); a[5] = 1; a[6] = 0; }
+      else { a[0] = 30 * pow(t, 4); a[1] = 20 * pow(t, 3); a[2] = 12 * pow(t, 2); a[3] = 6 * pow(t, 1); a[4] = 2; a[5] = 0; a[6] = 0; }
+    }
+    gj_inverse7(A, Ainv);
+    const double plan[7] = {0, 0, f0 + hcom, (f0 + f1) / 2 + hcom, f1 + hcom, 0, 0};
+    double co[7];
+    for (int r = 0; r < 7; r++) { double acc = 0.0; for (int k = 0; k < 7; k++) acc += Ainv[7 * r + k] * plan[k]; co[r] = acc; }
+    for (int jxx = 1; jxx <= 3; jxx++) {
+      const double t = (i + jxx - round(tx1 / dt)) * dt;
+      const double p[7] = {pow(t, 6), pow(t, 5), pow(t, 4), pow(t, 3), pow(t, 2), pow(t, 1), 1};
+      const double v[7] = {6 * pow(t, 5), 5 * pow(t, 4), 4 * pow(t, 3), 3 * pow(t, 2), 2 * pow(t, 1), 1, 0};
+      const double a[7] = {30 * pow(t, 4), 20 * pow(t, 3), 12 * pow(t, 2), 6 * pow(t, 1), 2, 0, 0};
+      double z = 0.0, vz = 0.0, az = 0.0;
+      for (int k = 0; k < 7; k++) { z += p[k] * co[k]; vz += v[k] * co[k]; az += a[k] * co[k]; }
+      comz[jxx - 1] = z; comvz[jxx - 1] = vz; comaz[jxx - 1] = az;
+    }
+  } else {
+    for (int q = 0; q < 3; q++) { comz[q] = hcom; comvz[q] = 0; comaz[q] = 0; }
+  }
+}
 
 __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -204,6 +263,16 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
   for (int jxx = p + 1; jxx <= NS; jxx++) tx[jxx - 1] = tx[jxx - 2] + ts[jxx - 2];
   const double fx_next = px + v[0], fy_next = py + v[1];
 
+  // vertical CoM samples (:936): after the write-back of ts / tx, with the _bjx1 the previous tick left
+  double hz_z[3], hz_vz[3], hz_az[3];
+  if (c.ext_height) {
+    for (int q = 0; q < 3; q++) { hz_z[q] = INP(I_CZ + q); hz_az[q] = INP(I_CAZ + q); hz_vz[q] = 0.0; }
+    hz_vz[0] = INP(I_CVZ);
+  } else {
+    const int bp = (int)ST(S_BJX1);
+    const int b1 = bp >= 1 && bp <= NS ? bp : 1, b2 = bp >= 2 && bp <= NS + 1 ? bp : 2;
+    com_height_solve(i, bp <= NS ? bp : 0, ts[b1 - 1], tx[b1 - 1], ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az);
+  }
   // LIPM roll-out of samples i, i+1, i+2 (:938-955)
   double comx[3], comy[3], comvx[3], comvy[3], comax[3], comay[3], zmpx[3], zmpy[3], dcmx[3], dcmy[3];
   for (int jxx = 1; jxx <= 3; jxx++) {
@@ -216,7 +285,7 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
     comvy[q] = Wn * isy * sh + visy * ch;
     comax[q] = pow(Wn, 2) * isx * ch + visx * Wn * sh;
     comay[q] = pow(Wn, 2) * isy * ch + visy * Wn * sh;
-    const double hz = (INP(I_CZ + q) - INP(I_ZSC + q)) / (INP(I_CAZ + q) + c.ggg);
+    const double hz = (hz_z[q] - INP(I_ZSC + q)) / (hz_az[q] + c.ggg);
     zmpx[q] = comx[q] - hz * comax[q];
     zmpy[q] = comy[q] - hz * comay[q];
     dcmx[q] = comx[q] + comvx[q] * sqrt(hz);
@@ -264,18 +333,19 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
     STW(S_FEED + 3) = ((1 - ly) * (comy[0] - py) + (ly) * e3) + py;
     STW(S_FEED + 4) = (1 - lvy) * comvy[0] + (lvy) * INP(I_EST + 4);
     STW(S_FEED + 5) = (1 - ly) * comay[0] + ly * INP(I_EST + 5);
+    STW(S_BJX1) = (double)bjx1;
   }
 
   double* O = P.out + b;
 #define OUT(f, val) O[(size_t)(f) * B] = (val)
-  OUT(0, comx[0]); OUT(1, comy[0]); OUT(2, INP(I_CZ + 0));
-  OUT(3, comvx[0]); OUT(4, comvy[0]); OUT(5, INP(I_CVZ));
-  OUT(6, comax[0]); OUT(7, comay[0]); OUT(8, INP(I_CAZ + 0));
+  OUT(0, comx[0]); OUT(1, comy[0]); OUT(2, hz_z[0]);
+  OUT(3, comvx[0]); OUT(4, comvy[0]); OUT(5, hz_vz[0]);
+  OUT(6, comax[0]); OUT(7, comay[0]); OUT(8, hz_az[0]);
   OUT(9, zmpx[0]); OUT(10, zmpy[0]); OUT(11, dcmx[0]); OUT(12, dcmy[0]);
   OUT(13, zmpx[1]); OUT(14, zmpy[1]); OUT(15, dcmx[1]); OUT(16, dcmy[1]);
   OUT(17, zmpx[2]); OUT(18, zmpy[2]); OUT(19, dcmx[2]); OUT(20, dcmy[2]);
-  OUT(21, comax[1]); OUT(22, comay[1]); OUT(23, INP(I_CAZ + 1));
-  OUT(24, comax[2]); OUT(25, comay[2]); OUT(26, INP(I_CAZ + 2));
+  OUT(21, comax[1]); OUT(22, comay[1]); OUT(23, hz_az[1]);
+  OUT(24, comax[2]); OUT(25, comay[2]); OUT(26, hz_az[2]);
   OUT(27, (double)bjxx);
   OUT(28, fx0); OUT(29, fx1); OUT(30, fy0); OUT(31, fy1);
   OUT(32, fz0); OUT(33, fz1);

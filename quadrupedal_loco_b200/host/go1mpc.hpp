@@ -182,7 +182,7 @@ class StepTimingMPC {
   void Initialize() {
     state.assign(GO1MPC_STEP_STATE_DOUBLES, 0.0);
     go1mpc_step_default_state(ctx_->get(), sl_, sw_, sh_, 0.7, state.data());
-    comz = 0.309458; _periond_i = _k_yu = _bjxx = _bjx1 = 0;
+    _periond_i = _k_yu = _bjxx = _bjx1 = 0;
   }
   Vec<38> step_timing_opti_loop(int i, const Vec<18>& estimated_state, const Vec<3>& _Rfoot_location_feedback,
                                 const Vec<3>& _Lfoot_location_feedback, double /*lamda*/, bool /*_stopwalking*/) {
@@ -191,7 +191,6 @@ class StepTimingMPC {
     for (int k = 0; k < 6; k++) in[k] = estimated_state(k);
     in[6] = _Rfoot_location_feedback(0); in[7] = _Rfoot_location_feedback(1);
     in[8] = _Lfoot_location_feedback(0); in[9] = _Lfoot_location_feedback(1);
-    in[10] = in[11] = in[12] = comz;      // flat ground: CoM_height_solve's samples are the constant height
     int rc = go1mpc_step_timing_step_batch_host(ctx_->get(), 3, 1, &i, state.data(), in, out, diag);
     if (rc != GO1MPC_OK) throw std::runtime_error(std::string("step_timing_opti_loop: ") + go1mpc_last_error(ctx_->get()));
     _periond_i = diag[0]; _k_yu = diag[1]; _bjxx = diag[2]; _bjx1 = diag[3];
@@ -200,8 +199,7 @@ class StepTimingMPC {
     for (int k = 0; k < 38; k++) r(k) = out[k];
     return r;
   }
-  std::vector<double> state;          // the 201-double planner state (layout: go1mpc.h)
-  double comz;
+  std::vector<double> state;          // the 202-double planner state (layout: go1mpc.h)
   int _periond_i, _k_yu, _bjxx, _bjx1, qp_status[5];
  private:
   double sw_ = 0.2535, sl_ = 0.075, sh_ = 0.0;

@@ -101,7 +101,7 @@ def step_timing_inputs(B, base_state, seed=SEED_CFG2, dt=0.025, Wn=None, amp=1.0
     """cfg2-style step-timing batch: every instance is a planner somewhere
     in its walk, its CoM on the nominal LIPM orbit of that step plus a random push.
 
-    base_state: the 201-double default planner state (step tables of FootStepInputs/Initialize).
+    base_state: the 202-double default planner state (step tables of FootStepInputs/Initialize).
     Per instance: support period p ~ U{3..22}, elapsed samples k_yu ~ U{0..24}, tick
     i = round(tx[p-1]/dt) + k_yu.  Nominal orbit relative to the support foot: start
     -L[p-2]/2, end +L[p-1]/2 after ts (the boundary conditions step_timing_opti_loop itself
@@ -111,7 +111,7 @@ def step_timing_inputs(B, base_state, seed=SEED_CFG2, dt=0.025, Wn=None, amp=1.0
     pushes make the reference's own formulation infeasible (its CoM-acceleration rows conflict),
     which the status codes report.  The warm start is the reference point (Lxx, Lyy, cosh(wT),
     sinh(wT)) of the previous tick; the end-of-step velocity reference is re-derived from it.
-    Returns tick [B] i32, state [B,201], inp [B,20] (instance-major; transpose for the SoA ABI).
+    Returns tick [B] i32, state [B,202], inp [B,20] (instance-major; transpose for the SoA ABI).
     """
     import math
     if Wn is None:
@@ -144,4 +144,6 @@ def step_timing_inputs(B, base_state, seed=SEED_CFG2, dt=0.025, Wn=None, amp=1.0
     inp = np.zeros((B, 20))
     inp[:, 7] = -0.12675; inp[:, 9] = 0.12675
     inp[:, 10:13] = 0.309458
+    # _bjx1 left by the previous tick: the period of time i*dt... the planner's own value is the period of (i)*dt + dt
+    st[:, 201] = p
     return tick, st, inp

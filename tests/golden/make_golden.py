@@ -112,9 +112,9 @@ def gen_step(nl):
     tick; (b) one-tick evaluations from replay states with random pushes."""
     nl.ref_nlp_new.restype = ctypes.c_void_p
     nl.ref_nlp_new.argtypes = [ctypes.c_double] * 3
-    S = 201
+    S = 202
     est = np.zeros(18); rf = np.array([0, -0.12675, 0.]); lf = np.array([0, 0.12675, 0.])
-    consts = np.zeros(25)
+    consts = np.zeros(30)
 
     def step(h, i):
         out = np.zeros(38); hz = np.zeros(10); ints = np.zeros(4, np.int32)

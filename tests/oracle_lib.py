@@ -34,7 +34,7 @@ class StepCfg(ctypes.Structure):
     _fields_ = [(n, ctypes.c_double) for n in (
         "dt Wn ggg t_min t_max footx_max footx_min footx_vmax footx_vmin footy_vmax footy_vmin comax_max comax_min "
         "comay_max comay_min aax aay aaxv aayv bbx bby rr1 rr2 half_hip_width foot_width").split()] + [
-        ("lamda", ctypes.c_double * 4), ("n_sqp", ctypes.c_int)]
+        ("lamda", ctypes.c_double * 4), ("hcom", ctypes.c_double), ("n_sqp", ctypes.c_int), ("ext_height", ctypes.c_int)]
 
 
 class StepDiag(ctypes.Structure):
@@ -43,7 +43,7 @@ class StepDiag(ctypes.Structure):
                 ("iters", (ctypes.c_int * 4) * 8), ("active", (ctypes.c_int * 25) * 8), ("x", (ctypes.c_double * 4) * 8)]
 
 
-STEP_STATE, STEP_IN, STEP_OUT = 201, 20, 38
+STEP_STATE, STEP_IN, STEP_OUT = 202, 20, 38
 
 
 def build_oracle(fast=False):
@@ -134,7 +134,7 @@ class Oracle:
         return s
 
     def step_tick_batch(self, cfg, tick, states, ins):
-        """Instance-major arrays: states [B,201] (updated in place), ins [B,20].  Returns out [B,38] and
+        """Instance-major arrays: states [B,202] (updated in place), ins [B,20].  Returns out [B,38] and
         diagnostics in the GPU diag layout [B,60]."""
         B = len(tick)
         out = np.zeros((B, STEP_OUT)); diag = np.zeros((B, 60), np.int32)

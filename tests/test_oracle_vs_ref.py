@@ -101,6 +101,7 @@ def _step_cfg_from_golden(oracle, g, n_sqp=3):
     cfg = oracle.step_cfg(n_sqp)
     for n, v in zip(names, g["consts"]):
         assert getattr(cfg, n) == v, f"default {n} differs from the reference's constant"
+    assert cfg.hcom == g["consts"][29]
     return cfg
 
 
@@ -111,7 +112,7 @@ def test_oracle_step_replay_bit_exact_vs_reference_golden(oracle):
     cfg = _step_cfg_from_golden(oracle, g)
     T = g["replay_out"].shape[0] - 1
     # default tables are the reference's Initialize()
-    np.testing.assert_array_equal(oracle.step_default_state(cfg)[:189], g["replay_state"][1][:189])
+    np.testing.assert_array_equal(oracle.step_default_state(cfg), g["replay_state"][1])
     st = g["replay_state"][1].copy()
     for i in range(1, T + 1):
         np.testing.assert_array_equal(st, g["replay_state"][i], err_msg=f"state before tick {i}")
@@ -149,10 +150,10 @@ def test_oracle_step_vs_live_reference(oracle):
     cfg = oracle.step_cfg(3)
     est = np.zeros(18); rf = np.array([0, -0.12675, 0.]); lf = np.array([0, 0.12675, 0.])
     for i in range(1, 200):
-        st = np.zeros(201); lib.ref_nlp_get_state(h, i, P(st))
+        st = np.zeros(202); lib.ref_nlp_get_state(h, i, P(st))
         out = np.zeros(38); hz = np.zeros(10); ints = np.zeros(4, np.int32)
         lib.ref_nlp_step(h, i, P(est), P(rf), P(lf), 0, P(out), P(hz), PI(ints))
-        after = np.zeros(201); lib.ref_nlp_get_state(h, i + 1, P(after))
+        after = np.zeros(202); lib.ref_nlp_get_state(h, i + 1, P(after))
         inp = np.zeros(20); inp[6:8] = rf[:2]; inp[8:10] = lf[:2]; inp[10:13] = hz[:3]; inp[13:16] = hz[3:6]; inp[16:19] = hz[6:9]; inp[19] = hz[9]
         s2 = st[None, :].copy()
         o, dg = oracle.step_tick_batch(cfg, [i], s2, inp[None, :])
