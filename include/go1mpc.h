@@ -102,6 +102,8 @@ typedef struct {
     double hcom;                 /* 0.309458  RobotPara_Z_C - _height_offset    */
     int ext_height;              /* 0: CoM_height_solve on the device; 1: comz/comaz/comvz from in_d */
     int reserved;
+    double stepwidth0;           /* 0.12675  _stepwidth(0) = stepwidthinput / 2 (NLPClass_sqp.cpp:66-67) */
+    double lift_height;          /* 0.03     _lift_height (NLPRTControlClass.cpp:48), 0 for the last two steps */
 } Go1StepMpcConfig;
 
 typedef struct {
@@ -280,6 +282,28 @@ int go1mpc_leg_fk_batch_host(go1mpc_t *h, int B, const double *q, const int *leg
                              const double *body_p, const double *body_r, double *pos, double *jac);
 int go1mpc_leg_ik_batch_host(go1mpc_t *h, int B, const double *pdes, const double *qini, const int *leg,
                              const double *body_p, const double *body_r, double *q, double *jac, int *iters);
+
+/* ---------------------------------------------------------------------------
+ * Swing-foot trajectory of the step planner for B instances; run after the step-timing tick
+ * of the same index.  Replaces NLPClass::Foot_trajectory_solve_mod2 (NLP/NLP/NLPClass_sqp.cpp:
+ * 2039-2358) and solve_AAA_inv2 (:3633-3645).  Stop-walking (_stopwalking, ticks beyond
+ * _t_end_footstep) is not covered.  SoA layout [f*B + b].
+ * state_d [202][B]  planner state AFTER go1mpc_step_timing_step_batch;  out38_d [38][B] its output
+ * foot_d  [32][B] in/out, the window of the reference's whole-walk foot arrays:
+ *           [0,6) R xyz, L xyz at tick j-1   [6,12) what the arrays hold at j   [12,18) at j-2
+ *           [18,24) at j-3   [24,30) frozen at the step's start   [30] step start index the freeze
+ *           belongs to (-1 none)   [31] _ry_left_right.  Initial value: go1mpc_foot_default_state.
+ * out18_d [18][B] = the Vec18 of the reference (R xyz, L xyz | velocities | accelerations)
+ * right_support_d [B] ints (0 left support, 1 right support, 2 double support), may be NULL
+ * ------------------------------------------------------------------------ */
+#define GO1MPC_FOOT_STATE_DOUBLES 32
+#define GO1MPC_FOOT_OUT_DOUBLES 18
+int go1mpc_foot_trajectory_batch(go1mpc_t *h, int B, const int *tick_d, const double *state_d,
+                                 const double *out38_d, double *foot_d, double *out18_d,
+                                 int *right_support_d, void *stream);
+int go1mpc_foot_trajectory_batch_host(go1mpc_t *h, int B, const int *tick, const double *state,
+                                      const double *out38, double *foot, double *out18, int *right_support);
+int go1mpc_foot_default_state(go1mpc_t *h, double *foot32);
 
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports

@@ -187,6 +187,24 @@ void orc_step_timing_batch(const orc_step_cfg *c, int B, const int *tick, double
                            double *out38, orc_step_diag *diag);
 
 /* ------------------------------------------------------------------------
+ * Swing-foot trajectory of the step planner: NLPClass::Foot_trajectory_solve_mod2
+ * (NLP/src/NLP/NLPClass_sqp.cpp:2039-2358) with solve_AAA_inv2 (:3633-3645), called
+ * right after step_timing_opti_loop with the same tick (NLPRTControlClass.cpp:470).
+ * Stop-walking (_stopwalking / ticks beyond _t_end_footstep) is not restated.
+ * The reference keeps whole-walk arrays _R/Lfoot{x,y,z}; only a sliding window
+ * is ever read, carried here as 32 doubles:
+ *   [0,6)  R xyz, L xyz at tick j-1      [6,12)  values the arrays hold at j before this tick
+ *   [12,18) at j-2   [18,24) at j-3      [24,30) value frozen at the step's start (index s-2)
+ *   [30] s the freeze belongs to (-1: none)   [31] _ry_left_right
+ * --------------------------------------------------------------------- */
+#define ORC_FOOT_STATE 32
+void orc_foot_state_default(double fs[ORC_FOOT_STATE], double stepwidth0);
+/* st: the planner state AFTER this tick's orc_step_timing_tick; bjxx: its out38[27].
+ * out18 = the Vec18 of the reference; returns right_support (0, 1 or 2). */
+int orc_foot_traj_tick(const orc_step_cfg *c, int j, const orc_step_state *st, int bjxx,
+                       double fs[ORC_FOOT_STATE], double stepwidth0, double lift_height, double out18[18]);
+
+/* ------------------------------------------------------------------------
  * Go1 leg kinematics (Kinematicclass, GO1/src/kinematics/Kinematics.cpp:29-304).
  * leg: 0 FR, 1 FL, 2 RR, 3 RL.  J is row-major 3x3 (the reference's Jacobian_kin
  * side channel after the call).  The IK functions return the number of Newton

@@ -110,4 +110,14 @@ void ref_nlp_step(void* h, int i, const double* est18, const double* rfoot3, con
   ints[0] = p->_periond_i; ints[1] = p->_k_yu; ints[2] = p->_bjxx; ints[3] = p->_bjx1;
 }
 
+// NLPClass::Foot_trajectory_solve_mod2, NLPClass_sqp.cpp:2039-2358 (call it right after ref_nlp_step
+// with the same tick, as NLPRTControlClass::rt_nlp_gait does)
+int ref_nlp_foot(void* h, int j, int stop, double* out18) {
+  NLPClass* p = static_cast<NLPClass*>(h);
+  Eigen::Matrix<double, 18, 1> o = p->Foot_trajectory_solve_mod2(j, stop != 0);
+  for (int k = 0; k < 18; k++) out18[k] = o(k);
+  return p->right_support;
+}
+double ref_nlp_stepwidth0(void* h) { return static_cast<NLPClass*>(h)->_stepwidth(0); }
+
 }  // extern "C"

@@ -379,3 +379,98 @@ void orc_step_timing_batch(const orc_step_cfg *c, int B, const int *tick, double
                              (const orc_step_in *)(ins + (size_t)bi * (sizeof(orc_step_in) / sizeof(double))),
                              out38 + (size_t)bi * 38, diag ? diag + bi : NULL);
 }
+
+/* ===================== swing-foot trajectory (NLPClass::Foot_trajectory_solve_mod2) ===================== */
+void orc_foot_state_default(double fs[ORC_FOOT_STATE], double sw0)
+{
+    /* NLPClass_sqp.cpp:496-500: _Rfooty = -stepwidth(0), _Lfooty = +stepwidth(0), the rest 0 */
+    for (int k = 0; k < 4; k++) {
+        double *p = fs + 6 * k;
+        p[0] = 0; p[1] = -sw0; p[2] = 0; p[3] = 0; p[4] = sw0; p[5] = 0;
+    }
+    for (int k = 24; k < 30; k++) fs[k] = 0.0;
+    fs[30] = -1.0;
+    fs[31] = 0.0;
+}
+
+int orc_foot_traj_tick(const orc_step_cfg *c, int j, const orc_step_state *st, int bjxx,
+                       double fs[ORC_FOOT_STATE], double sw0, double lift_height, double out18[18])
+{
+    const double dt = c->dt;
+    const int bjx1 = (int)st->bjx1_prev;             /* _bjx1 as the tick just run left it */
+    const int t_end = (int)round((st->tx[NS - 1] - 2 * 0.7) / dt);   /* :593 is evaluated at Initialize; see note */
+    double *pm1 = fs, *pj = fs + 6, *pm2 = fs + 12, *pm3 = fs + 18, *frz = fs + 24;
+    double cur[6], nxt[6], vel[6] = { 0, 0, 0, 0, 0, 0 }, acc[6] = { 0, 0, 0, 0, 0, 0 };
+    int wrote_next[6] = { 0, 0, 0, 0, 0, 0 };
+    int right_support;
+    memcpy(cur, pj, sizeof cur);
+    /* _footxyz_real: the step tables with (1,0) overwritten by -stepwidth(0) (:2050) */
+#define FXR(r, k) ((r) == 0 ? st->footx[k] : ((r) == 1 ? ((k) == 0 ? -sw0 : st->footy[k]) : st->footz[k]))
+    (void)t_end;
+    if (bjx1 >= 2) {
+        const int s = (int)round(st->tx[bjx1 - 1] / dt);
+        if ((double)s != fs[30]) {
+            /* first tick of this step: freeze the feet where they stood at index s-2 */
+            const int back = j - (s - 2);            /* 1, 2 or 3 ticks ago */
+            const double *src = (back <= 1) ? pm1 : (back == 2 ? pm2 : pm3);
+            memcpy(frz, src, sizeof(double) * 6);
+            fs[30] = (double)s;
+        }
+        const int left_support = (bjx1 % 2 == 0);
+        const int so = left_support ? 3 : 0;         /* support foot offset in the 6-vectors (L : R) */
+        const int wo = left_support ? 0 : 3;         /* swing foot offset                              */
+        right_support = left_support ? 0 : 1;
+        for (int k = 0; k < 3; k++) { cur[so + k] = frz[so + k]; nxt[so + k] = frz[so + k]; wrote_next[so + k] = 1; }
+        if ((j + 1 - s) * dt < 0.2 * st->ts[bjx1 - 1]) {
+            right_support = 2;
+            for (int k = 0; k < 3; k++) { cur[wo + k] = frz[wo + k]; nxt[wo + k] = frz[wo + k]; wrote_next[wo + k] = 1; }
+        } else {
+            const double t_des = (j + 1 - s + 1) * dt;
+            const double td1 = 0.2 * st->ts[bjx1 - 1], ts1 = st->ts[bjx1 - 1];
+            const double tp[3] = { t_des - dt, (td1 + ts1) / 2 + 0.0001, ts1 };
+            if (fabs(t_des - ts1) <= (+0.0005)) {
+                for (int k = 0; k < 3; k++) { cur[wo + k] = FXR(k, bjxx); nxt[wo + k] = FXR(k, bjxx); wrote_next[wo + k] = 1; }
+            } else {
+                double A[16], Ai[16];
+                for (int r = 0; r < 3; r++) { A[4 * r] = pow(tp[r], 3); A[4 * r + 1] = pow(tp[r], 2); A[4 * r + 2] = pow(tp[r], 1); A[4 * r + 3] = 1; }
+                A[12] = 3 * pow(tp[2], 2); A[13] = 2 * pow(tp[2], 1); A[14] = pow(tp[2], 0); A[15] = 0;
+                gj_inverse(4, A, Ai);
+                const double tap[4] = { pow(t_des, 3), pow(t_des, 2), pow(t_des, 1), 1 };
+                const double tav[4] = { 3 * pow(t_des, 2), 2 * pow(t_des, 1), 1, 0 };
+                const double taa[4] = { 6 * pow(t_des, 1), 2, 0, 0 };
+                if ((j + 1 - s) * dt < td1 + dt)
+                    fs[31] = (FXR(1, bjxx) + FXR(1, bjxx - 2)) / 2;
+                for (int k = 0; k < 3; k++) {
+                    double plan[4];
+                    plan[0] = pm1[wo + k];
+                    if (k == 0) plan[1] = (FXR(0, bjxx - 2) + FXR(0, bjxx)) / 2;
+                    else if (k == 1) plan[1] = fs[31];
+                    else plan[1] = fmax(FXR(2, bjxx - 2), FXR(2, bjxx)) + ((bjx1 - 1 >= NS - 2) ? 0.0 : lift_height);
+                    plan[2] = FXR(k, bjxx);
+                    plan[3] = 0;
+                    double co[4];
+                    for (int r = 0; r < 4; r++) { double a_ = 0.0; for (int q = 0; q < 4; q++) a_ += Ai[4 * r + q] * plan[q]; co[r] = a_; }
+                    double p_ = 0.0, v_ = 0.0, a2 = 0.0;
+                    for (int q = 0; q < 4; q++) { p_ += tap[q] * co[q]; v_ += tav[q] * co[q]; a2 += taa[q] * co[q]; }
+                    cur[wo + k] = p_; vel[wo + k] = v_; acc[wo + k] = a2;
+                    nxt[wo + k] = cur[wo + k] + dt * vel[wo + k];
+                    wrote_next[wo + k] = 1;
+                }
+            }
+        }
+    } else {
+        right_support = 2;
+        cur[1] = -sw0;      /* :2316-2317 only the lateral coordinates are set */
+        cur[4] = sw0;
+    }
+#undef FXR
+    /* :2320-2338 outputs: R xyz, L xyz | velocities | accelerations at tick j */
+    for (int k = 0; k < 6; k++) { out18[k] = cur[k]; out18[6 + k] = vel[k]; out18[12 + k] = acc[k]; }
+    /* slide the window: what the arrays hold at j+1 is this tick's extrapolation, or their initial value */
+    memcpy(pm3, pm2, sizeof(double) * 6);
+    memcpy(pm2, pm1, sizeof(double) * 6);
+    memcpy(pm1, cur, sizeof(double) * 6);
+    const double init[6] = { 0, -sw0, 0, 0, sw0, 0 };
+    for (int k = 0; k < 6; k++) pj[k] = wrote_next[k] ? nxt[k] : init[k];
+    return right_support;
+}

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_body_model", "go1mpc_body_default_tx", "go1mpc_measure_dfma_peak",
     "go1mpc_step_timing_step_batch", "go1mpc_step_timing_step_batch_host", "go1mpc_step_default_state",
     "go1mpc_body_mpc_step_batch_host_async", "go1mpc_step_timing_step_batch_host_async",
+    "go1mpc_foot_trajectory_batch", "go1mpc_foot_trajectory_batch_host", "go1mpc_foot_default_state",
     "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
@@ -47,7 +48,8 @@ class StepCfg(ctypes.Structure):
     _fields_ = [(n, ctypes.c_double) for n in (
         "dt Wn ggg t_min t_max footx_max footx_min footx_vmax footx_vmin footy_vmax footy_vmin comax_max comax_min "
         "comay_max comay_min aax aay aaxv aayv bbx bby rr1 rr2 half_hip_width foot_width").split()] + [
-        ("lamda", ctypes.c_double * 4), ("hcom", ctypes.c_double), ("ext_height", ctypes.c_int), ("reserved", ctypes.c_int)]
+        ("lamda", ctypes.c_double * 4), ("hcom", ctypes.c_double), ("ext_height", ctypes.c_int), ("reserved", ctypes.c_int),
+        ("stepwidth0", ctypes.c_double), ("lift_height", ctypes.c_double)]
 
 
 class Cfg(ctypes.Structure):
@@ -102,6 +104,9 @@ def load_library():
     lib.go1mpc_step_default_state.argtypes = [vp] + [ctypes.c_double] * 4 + [vp]
     lib.go1mpc_body_mpc_step_batch_host_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     lib.go1mpc_step_timing_step_batch_host_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    lib.go1mpc_foot_trajectory_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
+    lib.go1mpc_foot_trajectory_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
+    lib.go1mpc_foot_default_state.argtypes = [vp, vp]
     lib.go1mpc_leg_fk_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
     lib.go1mpc_leg_ik_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
     lib.go1mpc_leg_fk_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
@@ -281,6 +286,20 @@ class Go1Mpc:
         self._check(self.lib.go1mpc_step_default_state(self.h, steplength, stepwidth, stepheight, tstep, _ptr(s)),
                     "step_default_state")
         return s
+
+    # --- swing-foot trajectory of the step planner (SoA) ---
+    def foot_trajectory(self, B, tick_d, state_d, out38_d, foot_d, out18_d, right_support_d=None, stream=None):
+        self._check(self.lib.go1mpc_foot_trajectory_batch(self.h, B, _ptr(tick_d), _ptr(state_d), _ptr(out38_d), _ptr(foot_d),
+                                                          _ptr(out18_d), _ptr(right_support_d), stream), "foot_trajectory_batch")
+
+    def foot_trajectory_host(self, B, tick, state, out38, foot, out18, right_support=None):
+        self._check(self.lib.go1mpc_foot_trajectory_batch_host(self.h, B, _ptr(tick), _ptr(state), _ptr(out38), _ptr(foot),
+                                                               _ptr(out18), _ptr(right_support)), "foot_trajectory_batch_host")
+
+    def foot_default_state(self):
+        f = np.zeros(32)
+        self._check(self.lib.go1mpc_foot_default_state(self.h, _ptr(f)), "foot_default_state")
+        return f
 
     # --- leg kinematics (SoA buffers: [3][B], [9][B]) ---
     def leg_fk(self, B, q, leg, body_p, body_r, pos, jac=None, stream=None):

@@ -211,6 +211,7 @@ int go1mpc_config_default(Go1MpcConfig* cfg) {
   s.bbx = 2000000; s.bby = 10000000; s.rr1 = 1000000; s.rr2 = 1000000;
   s.half_hip_width = 0.12675; s.foot_width = 0.03;
   s.hcom = 0.309458 - 0.000; s.ext_height = 0;
+  s.stepwidth0 = 0.12675; s.lift_height = 0.03;
   cfg->qp_iter_cap_scale = 20;
   return GO1MPC_OK;
 }
@@ -525,6 +526,59 @@ int go1mpc_step_default_state(go1mpc_t* h, double steplength, double stepwidth, 
   }
   for (int j = 0; j < NS; j++) ts[j] = tstep;
   for (int j = 1; j < NS; j++) { tx[j] = tx[j - 1] + ts[j - 1]; tx[j] = round(tx[j] / dt) * dt - 0.000001; }
+  return GO1MPC_OK;
+}
+
+// ------------------------------------------------------------------ swing-foot trajectory
+int go1mpc_foot_trajectory_batch(go1mpc_t* h, int B, const int* tick_d, const double* state_d, const double* out38_d,
+                                 double* foot_d, double* out18_d, int* right_support_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !tick_d || !state_d || !out38_d || !foot_d || !out18_d) return fail(h, GO1MPC_E_INVALID, "foot_trajectory_batch: bad argument");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  FootKParams P;
+  P.B = B; P.tick = tick_d; P.state = state_d; P.out38 = out38_d; P.foot = foot_d; P.out18 = out18_d; P.right_support = right_support_d;
+  P.dt = h->cfg.step.dt; P.stepwidth0 = h->cfg.step.stepwidth0; P.lift_height = h->cfg.step.lift_height;
+  CU(h, foot_traj_launch(P, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+int go1mpc_foot_trajectory_batch_host(go1mpc_t* h, int B, const int* tick, const double* state, const double* out38,
+                                      double* foot, double* out18, int* right_support) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!tick || !state || !out38 || !foot || !out18) return fail(h, GO1MPC_E_INVALID, "foot_trajectory_batch_host: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t b = (size_t)B, tb = b * sizeof(int), sb = b * STEP_STATE_DOUBLES * sizeof(double), ob = b * STEP_OUT_DOUBLES * sizeof(double);
+  const size_t fb = b * FOOT_STATE_DOUBLES * sizeof(double), o18 = b * FOOT_OUT_DOUBLES * sizeof(double);
+  void *dt_, *ds, *do_, *df, *d18, *drs = nullptr;
+  int rc;
+  if ((rc = stage_buf(h, 0, tb, &dt_))) return rc;
+  if ((rc = stage_buf(h, 1, sb, &ds))) return rc;
+  if ((rc = stage_buf(h, 3, ob, &do_))) return rc;
+  if ((rc = stage_buf(h, 5, fb, &df))) return rc;
+  if ((rc = stage_buf(h, 6, o18, &d18))) return rc;
+  if (right_support && (rc = stage_buf(h, 7, tb, &drs))) return rc;
+  cudaStream_t st = h->stream;
+  CU(h, cudaMemcpyAsync(dt_, tick, tb, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(ds, state, sb, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(do_, out38, ob, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(df, foot, fb, cudaMemcpyHostToDevice, st));
+  rc = go1mpc_foot_trajectory_batch(h, B, (const int*)dt_, (const double*)ds, (const double*)do_, (double*)df, (double*)d18, (int*)drs, st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(foot, df, fb, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaMemcpyAsync(out18, d18, o18, cudaMemcpyDeviceToHost, st));
+  if (right_support) CU(h, cudaMemcpyAsync(right_support, drs, tb, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return GO1MPC_OK;
+}
+// initial foot window: _Rfooty = -stepwidth(0), _Lfooty = +stepwidth(0), rest 0 (NLPClass_sqp.cpp:496-500)
+int go1mpc_foot_default_state(go1mpc_t* h, double* fs) {
+  if (!h || !fs) return GO1MPC_E_INVALID;
+  const double sw0 = h->cfg.step.stepwidth0;
+  for (int k = 0; k < 4; k++) { double* p = fs + 6 * k; p[0] = 0; p[1] = -sw0; p[2] = 0; p[3] = 0; p[4] = sw0; p[5] = 0; }
+  for (int k = 24; k < 30; k++) fs[k] = 0.0;
+  fs[30] = -1.0; fs[31] = 0.0;
   return GO1MPC_OK;
 }
 

@@ -56,6 +56,18 @@ struct StepKParams {
   StepCfgDev cfg;
 };
 cudaError_t step_timing_launch(StepKParams P, cudaStream_t st);
+constexpr int FOOT_STATE_DOUBLES = 32, FOOT_OUT_DOUBLES = 18;
+struct FootKParams {
+  int B;
+  const int* tick;
+  const double* state;   // planner state AFTER the step-timing tick, [STEP_STATE_DOUBLES][B]
+  const double* out38;   // its output ([38][B]): field 27 = _bjxx
+  double* foot;          // [FOOT_STATE_DOUBLES][B], in/out
+  double* out18;         // [18][B]
+  int* right_support;    // [B] or null
+  double dt, stepwidth0, lift_height;
+};
+cudaError_t foot_traj_launch(FootKParams P, cudaStream_t st);
 
 // ---- leg kinematics (leg_kin.cu); all arrays SoA [field][B] ----
 struct LegKParams {

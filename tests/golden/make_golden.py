@@ -125,11 +125,15 @@ def gen_step(nl):
 
     hA = ctypes.c_void_p(nl.ref_nlp_new(0.075, 0.2535, 0.0))
     nl.ref_nlp_consts(hA, P(consts))
+    nl.ref_nlp_stepwidth0.restype = ctypes.c_double
+    sw0 = nl.ref_nlp_stepwidth0(hA)
     T = 671
     st0 = np.zeros((T + 2, S)); outs = np.zeros((T + 1, 38)); ins = np.zeros((T + 1, 20)); ints = np.zeros((T + 1, 4), np.int32)
+    foot = np.zeros((T + 1, 18)); foot_rs = np.zeros(T + 1, np.int32)
     for i in range(1, T + 1):
         nl.ref_nlp_get_state(hA, i, P(st0[i]))
         outs[i], ins[i], ints[i] = step(hA, i)
+        foot_rs[i] = nl.ref_nlp_foot(hA, i, 0, P(foot[i]))     # NLPClass::Foot_trajectory_solve_mod2, same tick
     nl.ref_nlp_get_state(hA, T + 1, P(st0[T + 1]))
     # pushes
     hB = ctypes.c_void_p(nl.ref_nlp_new(0.075, 0.2535, 0.0))
@@ -146,7 +150,7 @@ def gen_step(nl):
         pout[k], pin[k], pints[k] = step(hB, int(pt[k]))
         nl.ref_nlp_get_state(hB, int(pt[k]) + 1, P(pafter[k]))
     np.savez_compressed(os.path.join(HERE, "step_ref.npz"), consts=consts, replay_state=st0, replay_out=outs, replay_in=ins,
-                        replay_ints=ints, push_tick=pt, push_state=pst, push_in=pin, push_out=pout, push_ints=pints,
+                        replay_ints=ints, replay_foot=foot, replay_right_support=foot_rs, stepwidth0=np.array([sw0]), push_tick=pt, push_state=pst, push_in=pin, push_out=pout, push_ints=pints,
                         push_state_after=pafter)
     print("step_ref.npz replay", T, "pushes", N, "finite pushes", int(np.isfinite(pout).all(axis=1).sum()))
 

@@ -175,3 +175,20 @@ class Oracle:
                 it[b] = self.lib.orc_leg_ik_g(P(np.ascontiguousarray(bp[b])), P(np.ascontiguousarray(br[b])), P(np.ascontiguousarray(pdes[b])),
                                               P(np.ascontiguousarray(qini[b])), int(leg[b]), P(q[b]), P(J[b]))
         return q, J, it
+
+    # ---- swing-foot trajectory ----
+    def foot_default_state(self, sw0=0.12675):
+        f = np.zeros(32)
+        self.lib.orc_foot_state_default.argtypes = [ctypes.c_void_p, ctypes.c_double]
+        self.lib.orc_foot_state_default(P(f), sw0)
+        return f
+
+    def foot_tick_batch(self, cfg, tick, states_after, bjxx, foot, sw0=0.12675, lift=0.03):
+        """states_after [B,202] (after the step tick), bjxx [B], foot [B,32] updated in place -> out18 [B,18], right_support [B]"""
+        self.lib.orc_foot_traj_tick.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+        B = len(tick); out = np.zeros((B, 18)); rs = np.zeros(B, np.int32)
+        for b in range(B):
+            rs[b] = self.lib.orc_foot_traj_tick(ctypes.byref(cfg), int(tick[b]), P(np.ascontiguousarray(states_after[b])), int(bjxx[b]),
+                                                P(foot[b]), sw0, lift, P(out[b]))
+        return out, rs

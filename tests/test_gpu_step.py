@@ -197,3 +197,47 @@ def test_step_pipelined_host_entry_device_resident_state(mpc):
         np.testing.assert_array_equal(outs[t].numpy().T, go, err_msg=f"tick +{t}")
         np.testing.assert_array_equal(diags[t].numpy().T, gd)
     np.testing.assert_array_equal(s_d.cpu().numpy().T, st_sync)
+
+
+def test_foot_trajectory_replay_vs_reference_golden(mpc):
+    """cfg1 on the GPU: step-timing tick + swing-foot trajectory tick in closed loop for 671 ticks,
+    all state on the GPU side, against NLPClass's outputs; right_support bit-exact every tick."""
+    g = load("step_ref.npz")
+    T = g["replay_out"].shape[0] - 1
+    st = g["replay_state"][1][None, :].copy()
+    fs = mpc.foot_default_state()[None, :].copy()
+    for i in range(1, T + 1):
+        go, st, gd = gpu_tick(mpc, [i], st, g["replay_in"][i][None, :])
+        tick = np.array([i], np.int32)
+        o18 = np.zeros((18, 1)); rs = np.zeros(1, np.int32)
+        f = np.array(fs.T, order="C", copy=True)
+        mpc.foot_trajectory_host(1, tick, np.array(st.T, order="C", copy=True), np.array(go.T, order="C", copy=True), f, o18, rs)
+        fs = f.T.copy()
+        assert rs[0] == g["replay_right_support"][i], i
+        close(o18[:, 0], g["replay_foot"][i], f"foot tick {i}")
+
+
+def test_foot_trajectory_batch_vs_oracle(mpc, oracle):
+    """A batch of planners at different ticks of their walk (states from the replay), 3 consecutive ticks."""
+    g = load("step_ref.npz")
+    cfg = oracle.step_cfg(3)
+    ticks0 = np.arange(40, 640, 3, dtype=np.int32); B = len(ticks0)
+    st = g["replay_state"][ticks0].copy(); ost = st.copy()
+    fs = np.tile(oracle.foot_default_state(), (B, 1))
+    # a plausible window: feet on their nominal footholds of the running step
+    rng = np.random.default_rng(3)
+    fs[:, 0:24] += rng.uniform(-0.01, 0.01, (B, 24))
+    ofs = fs.copy()
+    for t in range(3):
+        tick = ticks0 + t
+        inp = g["replay_in"][tick]
+        go, st, gd = gpu_tick(mpc, tick, st, inp)
+        oo, od = oracle.step_tick_batch(cfg, tick, ost, inp)
+        o18 = np.zeros((18, B)); rs = np.zeros(B, np.int32)
+        f = np.array(fs.T, order="C", copy=True)
+        mpc.foot_trajectory_host(B, tick, np.array(st.T, order="C", copy=True), np.array(go.T, order="C", copy=True), f, o18, rs)
+        fs = f.T.copy()
+        want, wrs = oracle.foot_tick_batch(cfg, tick, ost, oo[:, 27].astype(int), ofs)
+        assert np.array_equal(rs, wrs)
+        close(o18.T, want, f"foot out t+{t}")
+        close(fs, ofs, f"foot window t+{t}")

@@ -160,3 +160,20 @@ def test_oracle_step_vs_live_reference(oracle):
         np.testing.assert_array_equal(o[0], out); np.testing.assert_array_equal(s2[0], after)
         assert list(dg[0, :4]) == list(ints)
     lib.ref_nlp_free(h)
+
+
+def test_oracle_foot_trajectory_bit_exact_vs_reference_golden(oracle):
+    """NLPClass::Foot_trajectory_solve_mod2 over the 671-tick replay: the oracle carries only its
+    32-double window of the reference's whole-walk foot arrays and must reproduce the Vec18 and
+    right_support of every tick bit for bit."""
+    g = load("step_ref.npz")
+    cfg = _step_cfg_from_golden(oracle, g)
+    T = g["replay_out"].shape[0] - 1
+    sw0 = float(g["stepwidth0"][0])
+    fs = oracle.foot_default_state(sw0)[None, :].copy()
+    for i in range(1, T + 1):
+        after = g["replay_state"][i + 1][None, :]
+        out, rs = oracle.foot_tick_batch(cfg, [i], after, [int(g["replay_out"][i][27])], fs, sw0)
+        np.testing.assert_array_equal(out[0], g["replay_foot"][i], err_msg=f"tick {i}")
+        assert rs[0] == g["replay_right_support"][i], i
+    assert set(np.unique(g["replay_right_support"][1:])) == {0, 1, 2}
