@@ -29,6 +29,24 @@ constexpr int S_TS = 0, S_TX = 27, S_FX = 54, S_FY = 81, S_FZ = 108, S_LXX = 135
 constexpr int I_EST = 0, I_RF = 6, I_LF = 8, I_CZ = 10, I_CAZ = 13, I_ZSC = 16, I_CVZ = 19;
 }  // namespace
 
+// t^k for k = 0..6, correctly rounded (double-double running product, one final rounding): the
+// time-polynomial systems below are badly conditioned, so a 1-2 ulp difference in a power (CUDA's
+// pow vs the host libm's, which is correctly rounded for these arguments) would show up as 1e-7 in
+// the fitted accelerations.
+__device__ __forceinline__ double powi(double t, int k) {
+  if (k == 0) return 1.0;
+  double hi = t, lo = 0.0;
+  for (int q = 1; q < k; q++) {
+    const double p = hi * t;
+    double e = fma(hi, t, -p);
+    e = fma(lo, t, e);
+    const double s = p + e;
+    lo = e - (s - p);
+    hi = s;
+  }
+  return hi + lo;
+}
+
 // inverse by Gauss-Jordan with partial (row) pivoting, first maximal |pivot| wins; row-major 7 x 7
 // (the elimination order of the CPU oracle: the time-polynomial matrix is badly conditioned, so
 // the order is part of the contract -- SURVEY.md Appendix B)
@@ -66,9 +84,9 @@ __device__ void com_height_solve(int i, int bjx1, double ts1, double tx1, double
     for (int r = 0; r < 7; r++) {
       const double t = tp[rowt[r]];
       double* a = A + 7 * r;
-      if (kind[r] == 0) { a[0] = pow(t, 6); a[1] = pow(t, 5); a[2] = pow(t, 4); a[3] = pow(t, 3); a[4] = pow(t, 2); a[5] = pow(t, 1); a[6] = 1; }
-      else if (kind[r] == 1) { a[0] = 6 * pow(t, 5); a[1] = 5 * pow(t, 4); a[2] = 4 * pow(t, 3); a[3] = 3 * pow(t, 2); a[4] = 2 * pow(t, 1); a[5] = 1; a[6] = 0; }
-      else { a[0] = 30 * pow(t, 4); a[1] = 20 * pow(t, 3); a[2] = 12 * pow(t, 2); a[3] = 6 * pow(t, 1); a[4] = 2; a[5] = 0; a[6] = 0; }
+      if (kind[r] == 0) { a[0] = powi(t, 6); a[1] = powi(t, 5); a[2] = powi(t, 4); a[3] = powi(t, 3); a[4] = powi(t, 2); a[5] = powi(t, 1); a[6] = 1; }
+      else if (kind[r] == 1) { a[0] = 6 * powi(t, 5); a[1] = 5 * powi(t, 4); a[2] = 4 * powi(t, 3); a[3] = 3 * powi(t, 2); a[4] = 2 * powi(t, 1); a[5] = 1; a[6] = 0; }
+      else { a[0] = 30 * powi(t, 4); a[1] = 20 * powi(t, 3); a[2] = 12 * powi(t, 2); a[3] = 6 * powi(t, 1); a[4] = 2; a[5] = 0; a[6] = 0; }
     }
     gj_inverse7(A, Ainv);
     const double plan[7] = {0, 0, f0 + hcom, (f0 + f1) / 2 + hcom, f1 + hcom, 0, 0};
@@ -76,9 +94,9 @@ __device__ void com_height_solve(int i, int bjx1, double ts1, double tx1, double
     for (int r = 0; r < 7; r++) { double acc = 0.0; for (int k = 0; k < 7; k++) acc += Ainv[7 * r + k] * plan[k]; co[r] = acc; }
     for (int jxx = 1; jxx <= 3; jxx++) {
       const double t = (i + jxx - round(tx1 / dt)) * dt;
-      const double p[7] = {pow(t, 6), pow(t, 5), pow(t, 4), pow(t, 3), pow(t, 2), pow(t, 1), 1};
-      const double v[7] = {6 * pow(t, 5), 5 * pow(t, 4), 4 * pow(t, 3), 3 * pow(t, 2), 2 * pow(t, 1), 1, 0};
-      const double a[7] = {30 * pow(t, 4), 20 * pow(t, 3), 12 * pow(t, 2), 6 * pow(t, 1), 2, 0, 0};
+      const double p[7] = {powi(t, 6), powi(t, 5), powi(t, 4), powi(t, 3), powi(t, 2), powi(t, 1), 1};
+      const double v[7] = {6 * powi(t, 5), 5 * powi(t, 4), 4 * powi(t, 3), 3 * powi(t, 2), 2 * powi(t, 1), 1, 0};
+      const double a[7] = {30 * powi(t, 4), 20 * powi(t, 3), 12 * powi(t, 2), 6 * powi(t, 1), 2, 0, 0};
       double z = 0.0, vz = 0.0, az = 0.0;
       for (int k = 0; k < 7; k++) { z += p[k] * co[k]; vz += v[k] * co[k]; az += a[k] * co[k]; }
       comz[jxx - 1] = z; comvz[jxx - 1] = vz; comaz[jxx - 1] = az;
@@ -435,12 +453,12 @@ __global__ void __launch_bounds__(128) foot_traj_kernel(FootKParams P) {
         for (int k = 0; k < 3; k++) { cur[wo + k] = fxr(k, bjxx); nxt[wo + k] = fxr(k, bjxx); wrote_next[wo + k] = true; }
       } else {
         double A[16], Ai[16];
-        for (int r = 0; r < 3; r++) { A[4 * r] = pow(tp[r], 3); A[4 * r + 1] = pow(tp[r], 2); A[4 * r + 2] = pow(tp[r], 1); A[4 * r + 3] = 1; }
-        A[12] = 3 * pow(tp[2], 2); A[13] = 2 * pow(tp[2], 1); A[14] = pow(tp[2], 0); A[15] = 0;
+        for (int r = 0; r < 3; r++) { A[4 * r] = powi(tp[r], 3); A[4 * r + 1] = powi(tp[r], 2); A[4 * r + 2] = powi(tp[r], 1); A[4 * r + 3] = 1; }
+        A[12] = 3 * powi(tp[2], 2); A[13] = 2 * powi(tp[2], 1); A[14] = powi(tp[2], 0); A[15] = 0;
         gj_inverse4(A, Ai);
-        const double tap[4] = {pow(t_des, 3), pow(t_des, 2), pow(t_des, 1), 1};
-        const double tav[4] = {3 * pow(t_des, 2), 2 * pow(t_des, 1), 1, 0};
-        const double taa[4] = {6 * pow(t_des, 1), 2, 0, 0};
+        const double tap[4] = {powi(t_des, 3), powi(t_des, 2), powi(t_des, 1), 1};
+        const double tav[4] = {3 * powi(t_des, 2), 2 * powi(t_des, 1), 1, 0};
+        const double taa[4] = {6 * powi(t_des, 1), 2, 0, 0};
         if ((j + 1 - s) * dt < td1 + dt) ry_lr = (fxr(1, bjxx) + fxr(1, bjxx - 2)) / 2;
         for (int k = 0; k < 3; k++) {
           double plan[4];

@@ -199,22 +199,50 @@ def test_step_pipelined_host_entry_device_resident_state(mpc):
     np.testing.assert_array_equal(s_d.cpu().numpy().T, st_sync)
 
 
-def test_foot_trajectory_replay_vs_reference_golden(mpc):
-    """cfg1 on the GPU: step-timing tick + swing-foot trajectory tick in closed loop for 671 ticks,
-    all state on the GPU side, against NLPClass's outputs; right_support bit-exact every tick."""
+def test_foot_trajectory_replay_vs_reference_golden(mpc, oracle):
+    """cfg1 on the GPU: the swing-foot tick of all 671 replay ticks against NLPClass's outputs.
+
+    The reference's cubic fit is badly conditioned at some ticks (its first node, t_des - dt,
+    comes within 1e-4 s of the mid-swing node): moving _ts by ONE ulp moves the reference's own
+    accelerations by up to 6e-6 at 23 of the 671 ticks (measured with the oracle below).  So
+    (a) tick by tick, from the reference's own state, the GPU must match to 1e-9 + 100 x that
+    1-ulp sensitivity; (b) in closed loop (GPU planner state and GPU foot window carried for all
+    671 ticks, where the planner's ts differs from the host's by libm ulps) right_support is
+    bit-exact and positions stay within 2e-6 m."""
     g = load("step_ref.npz")
+    cfg = oracle.step_cfg(3)
     T = g["replay_out"].shape[0] - 1
+    sw0 = float(g["stepwidth0"][0])
+    # (a) open loop, all ticks in one batch
+    ticks = np.arange(1, T + 1, dtype=np.int32)
+    after = g["replay_state"][2:T + 2]
+    win = np.zeros((T, 32)); sens = np.zeros(T)
+    fs = oracle.foot_default_state(sw0)[None, :].copy()
+    for k, i in enumerate(ticks):
+        win[k] = fs[0]
+        f2 = fs.copy()
+        a2 = after[k][None, :].copy(); a2[0, :27] = np.nextafter(a2[0, :27], np.inf)
+        o2, _ = oracle.foot_tick_batch(cfg, [i], a2, [int(g["replay_out"][i][27])], f2, sw0)
+        o1, _ = oracle.foot_tick_batch(cfg, [i], after[k][None, :], [int(g["replay_out"][i][27])], fs, sw0)
+        sens[k] = np.abs(o2 - o1).max()
+    o18 = np.zeros((18, T)); rs = np.zeros(T, np.int32)
+    f = np.array(win.T, order="C", copy=True)
+    mpc.foot_trajectory_host(T, ticks, np.array(after.T, order="C", copy=True), np.array(g["replay_out"][1:T + 1].T, order="C", copy=True), f, o18, rs)
+    assert np.array_equal(rs, g["replay_right_support"][1:T + 1])
+    err = np.abs(o18.T - g["replay_foot"][1:T + 1]).max(axis=1)
+    assert (err <= 1e-9 + 100 * sens).all(), (err.max(), np.nonzero(err > 1e-9 + 100 * sens)[0][:5])
+    assert (err[sens < 1e-12] < 1e-9).all()
+    # (b) closed loop
     st = g["replay_state"][1][None, :].copy()
     fs = mpc.foot_default_state()[None, :].copy()
     for i in range(1, T + 1):
         go, st, gd = gpu_tick(mpc, [i], st, g["replay_in"][i][None, :])
-        tick = np.array([i], np.int32)
-        o18 = np.zeros((18, 1)); rs = np.zeros(1, np.int32)
+        o1 = np.zeros((18, 1)); r1 = np.zeros(1, np.int32)
         f = np.array(fs.T, order="C", copy=True)
-        mpc.foot_trajectory_host(1, tick, np.array(st.T, order="C", copy=True), np.array(go.T, order="C", copy=True), f, o18, rs)
+        mpc.foot_trajectory_host(1, np.array([i], np.int32), np.array(st.T, order="C", copy=True), np.array(go.T, order="C", copy=True), f, o1, r1)
         fs = f.T.copy()
-        assert rs[0] == g["replay_right_support"][i], i
-        close(o18[:, 0], g["replay_foot"][i], f"foot tick {i}")
+        assert r1[0] == g["replay_right_support"][i], i
+        assert np.abs(o1[:6, 0] - g["replay_foot"][i][:6]).max() < 2e-6, i
 
 
 def test_foot_trajectory_batch_vs_oracle(mpc, oracle):
