@@ -198,7 +198,8 @@ int go1mpc_body_mpc_step_batch_host(go1mpc_t *h, int nh, int B,
  * the kernels of its neighbours) and return at once; go1mpc_synchronize() waits for all of
  * them.  Host buffers should be pinned and must stay untouched until then.  The planner state
  * of the step-timing tick stays RESIDENT ON THE DEVICE (state_d / state_out_d are device
- * pointers, as in go1mpc_step_timing_step_batch); only the per-tick inputs and results move. */
+ * pointers, as in go1mpc_step_timing_step_batch); only the per-tick inputs and results move.
+ * Calls that write a state buffer an earlier pipelined call wrote are ordered after it. */
 int go1mpc_body_mpc_step_batch_host_async(go1mpc_t *h, int nh, int B,
                                           const double *in, double *out, int *diag);
 int go1mpc_step_timing_step_batch_host_async(go1mpc_t *h, int n_sqp, int B, const int *tick,

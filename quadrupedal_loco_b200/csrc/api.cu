@@ -50,6 +50,9 @@ struct go1mpc {
   static const int kLanes = 3;
   Lane lanes[3];
   unsigned lane_next = 0;
+  // device-resident buffers the pipelined calls read AND write (planner state): the last
+  // enqueued writer per buffer, so that a later call on another lane is ordered after it
+  std::map<const void*, cudaEvent_t> last_writer;
   int* sched_d = nullptr;          // ring of {next, done} counter pairs for body_fast launches
   unsigned sched_next = 0;
   bool force_generic = false;      // GO1MPC_FORCE_GENERIC=1: always use the run-time-sized kernel
@@ -255,6 +258,7 @@ void go1mpc_destroy(go1mpc_t* h) {
   for (auto& kv : h->body_models) if (kv.second.tab_d) cudaFree(kv.second.tab_d);
   for (DevBuf& b : h->stage) if (b.p) cudaFree(b.p);
   if (h->sched_d) cudaFree(h->sched_d);
+  for (auto& kv : h->last_writer) cudaEventDestroy(kv.second);
   for (auto& L : h->lanes) {
     for (DevBuf& b : L.stage) if (b.p) cudaFree(b.p);
     if (L.stream) cudaStreamDestroy(L.stream);
@@ -632,10 +636,20 @@ int go1mpc_step_timing_step_batch_host_async(go1mpc_t* h, int n_sqp, int B, cons
   if ((rc = stage_buf2(h, L.stage[4], ib, &di))) return rc;
   if ((rc = stage_buf2(h, L.stage[5], ob, &do_))) return rc;
   if (diag && (rc = stage_buf2(h, L.stage[6], db, &dd))) return rc;
+  // consecutive ticks of the same planners sit on different lanes: order them through the state buffers
+  for (const void* key : {(const void*)state_d, (const void*)state_out_d}) {
+    auto it = h->last_writer.find(key);
+    if (it != h->last_writer.end()) CU(h, cudaStreamWaitEvent(L.stream, it->second, 0));
+  }
   CU(h, cudaMemcpyAsync(dt_, tick, tb, cudaMemcpyHostToDevice, L.stream));
   CU(h, cudaMemcpyAsync(di, in, ib, cudaMemcpyHostToDevice, L.stream));
   rc = go1mpc_step_timing_step_batch(h, n_sqp, B, (const int*)dt_, state_d, state_out_d, (const double*)di, (double*)do_, (int*)dd, L.stream);
   if (rc) return rc;
+  {
+    cudaEvent_t& ev = h->last_writer[(const void*)state_out_d];
+    if (!ev) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(h, cudaEventRecord(ev, L.stream));
+  }
   CU(h, cudaMemcpyAsync(out, do_, ob, cudaMemcpyDeviceToHost, L.stream));
   if (diag) CU(h, cudaMemcpyAsync(diag, dd, db, cudaMemcpyDeviceToHost, L.stream));
   return GO1MPC_OK;
