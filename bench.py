@@ -59,7 +59,8 @@ def workload_config(a, n_gpus):
             "batch_per_gpu": a.batch, "global_batch": a.batch * n_gpus, "horizon": a.nh, "sqp_iterations": 3,
             "qp_shapes": [[2 * a.nh, 0, 12 * a.nh], [4, 1, 24]], "seed": "0xB2000002+rank",
             "parallelism": f"batch-sharded x{n_gpus}, no collective",
-            "l2": "inputs rotate through distinct batches totalling > 2x L2 (no flush needed)"}
+            "l2": "inputs rotate through distinct batches totalling > 2x L2 (no flush needed)",
+            "streams": "device-resident leg: steps dealt round-robin over 4 CUDA streams (independent robot batches in flight)"}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -238,7 +239,7 @@ def run_b200(a):
     st_h = torch.from_numpy(soa(sst, q.STEP_STATE)).pin_memory(); si_h = torch.from_numpy(soa(sinp, q.STEP_IN)).pin_memory()
     tk_h = torch.from_numpy(stick.reshape(nrot, B).copy()).pin_memory()
     st_d, si_d, tk_d = st_h.to(dev), si_h.to(dev), tk_h.to(dev)
-    st_o = torch.zeros(B * q.STEP_STATE, dtype=torch.float64, device=dev)
+    st_o = torch.zeros(nrot, B * q.STEP_STATE, dtype=torch.float64, device=dev)   # state after the tick, one buffer per slot
     so_d = torch.zeros(nrot, q.STEP_OUT, B, dtype=torch.float64, device=dev)
     sd_d = torch.zeros(nrot, q.STEP_DIAG, B, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
@@ -249,17 +250,17 @@ def run_b200(a):
     P_dg = [diag_d[r].data_ptr() for r in range(nrot)]
     P_tk = [tk_d[r].data_ptr() for r in range(nrot)]; P_st = [st_d[r].data_ptr() for r in range(nrot)]
     P_si = [si_d[r].data_ptr() for r in range(nrot)]; P_so = [so_d[r].data_ptr() for r in range(nrot)]
-    P_sd = [sd_d[r].data_ptr() for r in range(nrot)]; P_sto = st_o.data_ptr()
+    P_sd = [sd_d[r].data_ptr() for r in range(nrot)]; P_sto = [st_o[r].data_ptr() for r in range(nrot)]
     side_ptr = side.cuda_stream
 
-    def launch_body(i):
+    def launch_body(i, st_ptr=None):
         r = i % nrot
-        rc = lib.go1mpc_body_mpc_step_batch(hh, nh, B, P_in[r], P_out[r], P_dg[r], None)
+        rc = lib.go1mpc_body_mpc_step_batch(hh, nh, B, P_in[r], P_out[r], P_dg[r], st_ptr)
         assert rc == 0, rc
 
     def launch_sqp(i, st_ptr=None):
         r = i % nrot
-        rc = lib.go1mpc_step_timing_step_batch(hh, 3, B, P_tk[r], P_st[r], P_sto, P_si[r], P_so[r], P_sd[r], st_ptr)
+        rc = lib.go1mpc_step_timing_step_batch(hh, 3, B, P_tk[r], P_st[r], P_sto[r], P_si[r], P_so[r], P_sd[r], st_ptr)
         assert rc == 0, rc
 
     def step(i):
@@ -300,16 +301,25 @@ def run_b200(a):
     barrier()
     clocks.start()
     l0 = mpc.launch_count
-    # the two ticks of a robot are independent and so are the steps: fork once, run K body ticks on the
-    # handle's stream and K SQP ticks on the side stream, join once; the timed region is start -> join
+    # the two ticks of a robot are independent and so are the steps (distinct robot batches): fork once,
+    # deal the steps round-robin over NSTREAM streams (step i: SQP tick then body tick on stream i mod
+    # NSTREAM), join once; the timed region is fork -> join.  One 4096-robot batch fills 1/64 of the
+    # GPU's warp slots in the SQP kernel and 1.7 waves in the body kernel, so batches in flight on
+    # several streams are what keeps the SMs busy at this batch size.
+    NSTREAM = 4
+    lanes = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NSTREAM - 1)]
+    lane_ptr = [None] + [x.cuda_stream for x in lanes[1:]]
+    joins = [torch.cuda.Event() for _ in range(NSTREAM)]
     with torch.cuda.stream(stream):
         ev[0].record(stream)
-        side.wait_event(ev[0])
+        for x in lanes[1:]:
+            x.wait_event(ev[0])
         for i in range(K):
-            launch_sqp(i, side_ptr)
-            launch_body(i)
-        ev_join.record(side)
-        stream.wait_event(ev_join)
+            launch_sqp(i, lane_ptr[i % NSTREAM])
+            launch_body(i, lane_ptr[i % NSTREAM])
+        for k in range(1, NSTREAM):
+            joins[k].record(lanes[k])
+            stream.wait_event(joins[k])
         ev[K].record(stream)
     torch.cuda.synchronize()
     barrier()
@@ -362,27 +372,46 @@ def run_b200(a):
         H_si = [si_np[r].ctypes.data for r in range(nrot)]; H_so = [so_np[r].ctypes.data for r in range(nrot)]
         H_sd = [sd_np[r].ctypes.data for r in range(nrot)]
 
-        def host_step(i):
-            r = i % nrot
-            rc = lib.go1mpc_step_timing_step_batch_host_async(hh, 3, B, H_tk[r], P_st[r], P_sto, H_si[r], H_so[r], H_sd[r])
-            assert rc == 0, rc
-            rc = lib.go1mpc_body_mpc_step_batch_host_async(hh, nh, B, H_in[r], H_out[r], H_dg[r])
-            assert rc == 0, rc
-        for i in range(6):
-            host_step(i)
-        mpc.synchronize()
+        # one handle per host thread (handles are thread-compatible, not thread-safe): thread A feeds the
+        # planner ticks, thread B the body ticks; ctypes releases the GIL inside the C calls, so the two
+        # enqueue loops (about 40 us of driver calls per tick each) run side by side
+        mpc2 = q.Go1Mpc(local)
+        lib2, hh2 = mpc2.lib, mpc2.h
+
+        def feed_sqp(n):
+            for i in range(n):
+                r = i % nrot
+                rc = lib.go1mpc_step_timing_step_batch_host_async(hh, 3, B, H_tk[r], P_st[r], P_sto[r], H_si[r], H_so[r], H_sd[r])
+                assert rc == 0, rc
+                if r == nrot - 1:
+                    mpc.synchronize()        # a host slot is about to be reused
+            mpc.synchronize()
+
+        def feed_body(n):
+            for i in range(n):
+                r = i % nrot
+                rc = lib2.go1mpc_body_mpc_step_batch_host_async(hh2, nh, B, H_in[r], H_out[r], H_dg[r])
+                assert rc == 0, rc
+                if r == nrot - 1:
+                    mpc2.synchronize()
+            mpc2.synchronize()
+
+        def run_e2e(n):
+            ta = threading.Thread(target=feed_sqp, args=(n,)); tb = threading.Thread(target=feed_body, args=(n,))
+            ta.start(); tb.start(); ta.join(); tb.join()
+        run_e2e(8)
         barrier()
+        l1 = mpc.launch_count + mpc2.launch_count
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-        l1 = mpc.launch_count
         e0.record(stream)
-        for i in range(Ke):
-            host_step(i)
-            if i % nrot == nrot - 1:
-                mpc.synchronize()       # a host slot is about to be reused
-        mpc.synchronize()
+        t_wall = time.perf_counter()
+        run_e2e(Ke)
+        t_wall = time.perf_counter() - t_wall
         e1.record(stream)
         e1.synchronize()
         barrier()
+        e2e_launches = int(mpc.launch_count + mpc2.launch_count - l1)
+        mpc2.close()
         se = float(sum(B + sqp_solves[i % nrot] for i in range(Ke)))
         te = torch.tensor([e0.elapsed_time(e1), se], dtype=torch.float64, device=dev)
         if dist:
@@ -396,10 +425,11 @@ def run_b200(a):
         e2e = {"value": se_all / (te_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": B * (in_s * 8 + q.STEP_IN * 8 + 4),
                "d2h_bytes_per_step": B * (out_s * 8 + dg_s * 4 + q.STEP_OUT * 8 + q.STEP_DIAG * 4),
-               "steps": Ke, "ms_per_step": te_ms / Ke, "launches": int(mpc.launch_count - l1),
+               "steps": Ke, "ms_per_step": te_ms / Ke, "wall_ms_per_step": 1e3 * t_wall / Ke, "launches": e2e_launches,
                "api": "go1mpc_step_timing_step_batch_host_async + go1mpc_body_mpc_step_batch_host_async (pinned host buffers; "
-                      "H2D, kernel, D2H per call on 3 internal lanes; planner state resident on the device; "
-                      "go1mpc_synchronize before a host slot is reused and at the end)"}
+                      "H2D, kernel, D2H per call on 8 internal lanes; planner state resident on the device; two handles fed by two "
+                      "host threads; go1mpc_synchronize before a host slot is reused and at the end; timed with CUDA events "
+                      "recorded before the first enqueue and after the last synchronize)"}
 
     if rank == 0:
         kern_ms = float(np.mean(body_ms))

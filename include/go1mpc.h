@@ -193,7 +193,7 @@ int go1mpc_body_mpc_step_batch(go1mpc_t *h, int nh, int B,
                                void *stream);
 int go1mpc_body_mpc_step_batch_host(go1mpc_t *h, int nh, int B,
                                     const double *in, double *out, int *diag);
-/* Pipelined host entries: enqueue H2D copy, kernel and D2H copy on one of the handle's three
+/* Pipelined host entries: enqueue H2D copy, kernel and D2H copy on one of the handle's eight
  * internal lanes (consecutive calls use consecutive lanes, so the copies of one batch overlap
  * the kernels of its neighbours) and return at once; go1mpc_synchronize() waits for all of
  * them.  Host buffers should be pinned and must stay untouched until then.  The planner state

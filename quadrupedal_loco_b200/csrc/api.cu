@@ -43,12 +43,13 @@ struct go1mpc {
   long long launches = 0;
   std::map<int, BodyModel> body_models;
   DevBuf stage[16];   // device staging for the synchronous *_host entry points
-  // lanes of the asynchronous *_host_async entry points: consecutive calls go to consecutive lanes
+  // lanes of the asynchronous *_host_async entry points (8: a lane is busy for H2D + kernel + D2H, a few
+  // hundred microseconds at batch 4096, while the PCIe link needs a new batch every ~100 us): consecutive calls go to consecutive lanes
   // (own stream, own staging), so the H2D copy of one batch overlaps the kernel of the previous
   // one and the D2H copy of the one before that
   struct Lane { cudaStream_t stream = nullptr; DevBuf stage[8]; };
-  static const int kLanes = 3;
-  Lane lanes[3];
+  static const int kLanes = 8;
+  Lane lanes[8];
   unsigned lane_next = 0;
   // device-resident buffers the pipelined calls read AND write (planner state): the last
   // enqueued writer per buffer, so that a later call on another lane is ordered after it
