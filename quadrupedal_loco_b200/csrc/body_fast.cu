@@ -85,6 +85,7 @@ template <int NH, int WPC>
 __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / WPC) body_fast_kernel(BodyKParams P) {
   using D = FastDims<NH>;
   constexpr int N = D::N, LD = D::LD, M = 12 * NH;
+  static_assert(N <= 28, "lanes 30 and 31 carry the scalar divisions of a pass: the working set must stay below them");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -380,10 +381,12 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
             const double* col = J + lane * LD + ip_h * NH;
             if (ip_blk < 4) {
               double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-              for (int ii = 0; ii < NH; ii += 2) {
-                if (ii <= ip_k) a0 = fma(col[ii], ppu[ii * NH + ip_k], a0);
-                if (ii + 1 < NH && ii + 1 <= ip_k) a1 = fma(col[ii + 1], ppu[(ii + 1) * NH + ip_k], a1);
+              int ii = 0;
+              if (!(ip_k & 1)) { a0 = col[0] * ppu[ip_k]; ii = 1; }     // ip_k + 1 terms: peel one when odd
+#pragma unroll 2
+              for (; ii <= ip_k; ii += 2) {
+                a0 = fma(col[ii], ppu[ii * NH + ip_k], a0);
+                a1 = fma(col[ii + 1], ppu[(ii + 1) * NH + ip_k], a1);
               }
               d = ip_sgn * (a0 + a1);
             } else {
@@ -395,15 +398,16 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
           // z = J[:, iq:] d[iq:]
           z = 0.0;
           if (act) {
-            double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;
-#pragma unroll
-            for (int j = 0; j < N; j += 4) {
-              if (j >= iq) z0 = fma(J[j * LD + lane], ds[j], z0);
-              if (j + 1 < N && j + 1 >= iq) z1 = fma(J[(j + 1) * LD + lane], ds[j + 1], z1);
-              if (j + 2 < N && j + 2 >= iq) z2 = fma(J[(j + 2) * LD + lane], ds[j + 2], z2);
-              if (j + 3 < N && j + 3 >= iq) z3 = fma(J[(j + 3) * LD + lane], ds[j + 3], z3);
+            // run-time start (late passes of a long solve have few free columns left), two chains
+            double z0 = 0.0, z1 = 0.0;
+            int j = iq;
+            if ((N - j) & 1) { z0 = J[j * LD + lane] * ds[j]; j++; }
+#pragma unroll 2
+            for (; j < N; j += 2) {
+              z0 = fma(J[j * LD + lane], ds[j], z0);
+              z1 = fma(J[(j + 1) * LD + lane], ds[j + 1], z1);
             }
-            z = (z0 + z1) + (z2 + z3);
+            z = z0 + z1;
           }
           // r = R^-1 d[0:iq)  (column-oriented back substitution, stored reciprocals)
           r = (lane < iq) ? d : 0.0;
@@ -412,14 +416,25 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
             if (lane == c) r = rc;
             else if (lane < c) r = fma(-rc, Rp[c * (c + 3) / 2 + lane], r);
           }
-          // step lengths: t1 over the working set, t2 along z
-          double t1 = inf; int kmin = 0x7fffffff;
-          if (lane < iq && r > 0.0) { t1 = u / r; kmin = lane; }
-          warp_argmin_redux(t1, kmin);
-          const int l = (kmin != 0x7fffffff && t1 < inf) ? __shfl_sync(FULL_MASK, A, kmin) : 0;
+          // step lengths: t1 over the working set, t2 along z.  ONE division instruction serves the
+          // ratio test (lanes < iq: u/r), t2 (lane 31: -s_ip / z.n+) and the Householder scale of a
+          // possible add (lane 30: 1 / (|d2| (|d2| + |d_iq|))): FP64 division is a ~40-instruction
+          // dependent sequence, the longest scalar latency of a pass.
           double zz = z * z, zn = z * npL, dd = (act && lane >= iq) ? d * d : 0.0;
           warp_sum3(zz, zn, dd);
-          const double t2 = (fabs(zz) > EPS_D) ? (-sip / zn) : inf;
+          const double inrm = (dd > 0.0) ? rsqrt(dd) : 0.0;      // 1 / |d2|
+          const double nrm = dd * inrm;                           // |d2|
+          const double diq = bcast(d, iq);
+          double num = u, den = r;
+          if (lane == 31) { num = -sip; den = zn; }
+          if (lane == 30) { num = 1.0; den = nrm * (nrm + fabs(diq)); }
+          const double quo = num / den;
+          double t1 = inf; int kmin = 0x7fffffff;
+          if (lane < iq && r > 0.0) { t1 = quo; kmin = lane; }
+          warp_argmin_redux(t1, kmin);
+          const int l = (kmin != 0x7fffffff && t1 < inf) ? __shfl_sync(FULL_MASK, A, kmin) : 0;
+          const double t2 = (fabs(zz) > EPS_D) ? bcast(quo, 31) : inf;
+          const double tau = bcast(quo, 30);
           const double t = fmin(t1, t2);
           if (t >= inf) { status = ST_INFEASIBLE; f_value = inf; break; }        // case (i)
           int qq = 0;
@@ -444,28 +459,22 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
               // J2 v = J2 d2 + sigma J(:,iq) = z + sigma J(:,iq) -- z is already in registers, so the
               // update is a single dependency-free pass over the trailing columns.
               flops += 6u * N * (unsigned)(N - iq - 1 > 0 ? N - iq - 1 : 0);
-              const double nrm = sqrt(dd);                              // |d2|, dd reduced with zz, zn above
-              const double diq = bcast(d, iq);
+              // |d2| = nrm, 1/|d2| = inrm, tau: computed with the step lengths above
               const double sigma = (diq < 0.0) ? -nrm : nrm;
               if (nrm != 0.0 && act) {
-                const double tau = 1.0 / (nrm * (nrm + fabs(diq)));
                 const double sw = tau * fma(sigma, J[iq * LD + lane], z);   // tau * (J2 v)_L
                 const double viq = diq + sigma;
-#pragma unroll
-                for (int j = 0; j < N; j++) {
-                  if (j >= iq) {
-                    const double vj = (j == iq) ? viq : ds[j];
-                    J[j * LD + lane] = fma(-sw, vj, J[j * LD + lane]);
-                  }
-                }
+                J[iq * LD + lane] = fma(-sw, viq, J[iq * LD + lane]);
+#pragma unroll 4
+                for (int j = iq + 1; j < N; j++) J[j * LD + lane] = fma(-sw, ds[j], J[j * LD + lane]);
               }
               // H d2 = -sigma e_0
               if (lane == iq) d = (nrm != 0.0) ? -sigma : d;
               if (act && lane > iq) d = 0.0;
               // new column of R, its reciprocal diagonal, degeneracy test
               if (lane <= iq) Rp[iq * (iq + 3) / 2 + lane] = d;
-              if (lane == iq) rinv = 1.0 / d;
-              const double dq = bcast(d, iq);
+              if (lane == iq) rinv = (nrm != 0.0) ? ((diq < 0.0) ? inrm : -inrm) : 1.0 / d;   // 1 / (-sigma)
+              const double dq = (nrm != 0.0) ? -sigma : diq;           // new R(iq,iq), warp-uniform
               iq++;
               __syncwarp();
               if (fabs(dq) <= EPS_D * R_norm) {
