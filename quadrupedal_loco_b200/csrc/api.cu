@@ -57,6 +57,8 @@ struct go1mpc {
   int* sched_d = nullptr;          // ring of {next, done} counter pairs for body_fast launches
   unsigned sched_next = 0;
   bool force_generic = false;      // GO1MPC_FORCE_GENERIC=1: always use the run-time-sized kernel
+  int step_mode = 0;               // 0 auto, 1 thread per planner, 2 warp per planner (GO1MPC_STEP_MODE)
+  int step_warp_below = 16384;     // auto: warp per planner below this batch size
 };
 static const int kSchedRing = 64;
 
@@ -249,6 +251,9 @@ int go1mpc_create(const Go1MpcConfig* cfg, int device, go1mpc_t** out) {
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { go1mpc_destroy(h); return GO1MPC_E_CUDA; }
   const char* fg = getenv("GO1MPC_FORCE_GENERIC");
   h->force_generic = fg && fg[0] == '1';
+  const char* sm = getenv("GO1MPC_STEP_MODE");
+  if (sm && !strcmp(sm, "thread")) h->step_mode = 1;
+  if (sm && !strcmp(sm, "warp")) h->step_mode = 2;
   *out = h;
   return GO1MPC_OK;
 }
@@ -475,7 +480,15 @@ int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick
   d.half_hip_width = c.half_hip_width; d.foot_width = c.foot_width;
   for (int k = 0; k < 4; k++) d.lamda[k] = c.lamda[k];
   d.hcom = c.hcom; d.ext_height = c.ext_height;
-  CU(h, step_timing_launch(P, st));
+  // instance-independent transcendentals, evaluated once per launch by the host libm (the values the CPU reference uses)
+  d.sh_dt = sinh(c.Wn * c.dt); d.ch_dt = cosh(c.Wn * c.dt);
+  for (int jxx = 1; jxx <= 3; jxx++) { const double w = c.Wn * c.dt * jxx; d.sh_w[jxx - 1] = sinh(w); d.ch_w[jxx - 1] = cosh(w); }
+  // one thread per planner is the throughput mapping; below a few waves of threads the latency of the
+  // thread-serial tick dominates and one warp per planner is faster (GO1MPC_STEP_MODE=thread|warp forces one)
+  bool warp_mode = B < h->step_warp_below;
+  if (h->step_mode == 1) warp_mode = false;
+  if (h->step_mode == 2) warp_mode = true;
+  CU(h, step_timing_launch(P, warp_mode, st));
   h->launches++;
   return GO1MPC_OK;
 }

@@ -43,6 +43,7 @@ struct StepCfgDev {
   double dt, Wn, ggg, t_min, t_max, footx_max, footx_min, footx_vmax, footx_vmin, footy_vmax, footy_vmin;
   double comax_max, comax_min, comay_max, comay_min, aax, aay, aaxv, aayv, bbx, bby, rr1, rr2;
   double half_hip_width, foot_width, lamda[4], hcom;
+  double sh_dt, ch_dt, sh_w[3], ch_w[3];   // sinh / cosh(Wn dt) and (Wn dt jxx), jxx = 1..3: host libm, instance-independent
   int ext_height;
 };
 struct StepKParams {
@@ -55,7 +56,9 @@ struct StepKParams {
   int* diag;            // [STEP_DIAG_INTS][B] or null
   StepCfgDev cfg;
 };
-cudaError_t step_timing_launch(StepKParams P, cudaStream_t st);
+// per-warp shared memory of the warp-cooperative mode: QP workspace (n = 4, m = 24) | 7x14 matrix + 7
+constexpr int STEP_WARP_DOUBLES = 256;
+cudaError_t step_timing_launch(StepKParams P, bool warp_mode, cudaStream_t st);
 constexpr int FOOT_STATE_DOUBLES = 32, FOOT_OUT_DOUBLES = 18;
 struct FootKParams {
   int B;

@@ -17,6 +17,7 @@
 // Compiled with -fmad=false: same operation order as the CPU oracle, no FMA contraction.
 #include <cuda_runtime.h>
 #include "gi_thread.cuh"
+#include "gi_warp.cuh"
 #include "kernels.h"
 
 namespace go1 {
@@ -106,15 +107,126 @@ __device__ void com_height_solve(int i, int bjx1, double ts1, double tx1, double
   }
 }
 
+__device__ void gj_inverse7_warp(double* M, int lane);
+
+// CoM_height_solve, warp-cooperative: the 7 x 7 inverse one lane per column, the coefficient
+// vector one lane per row, the three samples one lane each; same operation order per element as
+// com_height_solve.  M: >= 7*14 + 7 doubles of the warp's shared memory.
+__device__ void com_height_solve_warp(int i, int bjx1, double ts1, double tx1, double f0, double f1, double hcom, double dt,
+                                      double comz[3], double comvz[3], double comaz[3], double* M, int lane) {
+  if (bjx1 >= 2) {
+    const double tp[3] = {0.0001, ts1 / 2 + 0.0001, ts1 + 0.0001};
+    const int rowt[7] = {0, 0, 0, 1, 2, 2, 2}, kind[7] = {1, 2, 0, 0, 0, 1, 2};
+    __syncwarp();
+    if (lane < 7) {
+      const int r = lane;
+      const double t = tp[rowt[r]];
+      double* a = M + 14 * r;
+      if (kind[r] == 0) { a[0] = powi(t, 6); a[1] = powi(t, 5); a[2] = powi(t, 4); a[3] = powi(t, 3); a[4] = powi(t, 2); a[5] = powi(t, 1); a[6] = 1; }
+      else if (kind[r] == 1) { a[0] = 6 * powi(t, 5); a[1] = 5 * powi(t, 4); a[2] = 4 * powi(t, 3); a[3] = 3 * powi(t, 2); a[4] = 2 * powi(t, 1); a[5] = 1; a[6] = 0; }
+      else { a[0] = 30 * powi(t, 4); a[1] = 20 * powi(t, 3); a[2] = 12 * powi(t, 2); a[3] = 6 * powi(t, 1); a[4] = 2; a[5] = 0; a[6] = 0; }
+    }
+    __syncwarp();
+    gj_inverse7_warp(M, lane);
+    const double plan[7] = {0, 0, f0 + hcom, (f0 + f1) / 2 + hcom, f1 + hcom, 0, 0};
+    double* co = M + 98;
+    if (lane < 7) { double acc = 0.0; for (int k = 0; k < 7; k++) acc += M[14 * lane + 7 + k] * plan[k]; co[lane] = acc; }
+    __syncwarp();
+    double z = 0.0, vz = 0.0, az = 0.0;
+    if (lane < 3) {
+      const int jxx = lane + 1;
+      const double t = (i + jxx - round(tx1 / dt)) * dt;
+      const double p[7] = {powi(t, 6), powi(t, 5), powi(t, 4), powi(t, 3), powi(t, 2), powi(t, 1), 1};
+      const double v[7] = {6 * powi(t, 5), 5 * powi(t, 4), 4 * powi(t, 3), 3 * powi(t, 2), 2 * powi(t, 1), 1, 0};
+      const double a[7] = {30 * powi(t, 4), 20 * powi(t, 3), 12 * powi(t, 2), 6 * powi(t, 1), 2, 0, 0};
+      for (int k = 0; k < 7; k++) { z += p[k] * co[k]; vz += v[k] * co[k]; az += a[k] * co[k]; }
+    }
+    for (int q = 0; q < 3; q++) {
+      comz[q] = __shfl_sync(FULL_MASK, z, q); comvz[q] = __shfl_sync(FULL_MASK, vz, q); comaz[q] = __shfl_sync(FULL_MASK, az, q);
+    }
+    __syncwarp();
+  } else {
+    for (int q = 0; q < 3; q++) { comz[q] = hcom; comvz[q] = 0; comaz[q] = 0; }
+  }
+}
+
+// Constraint policy of the warp-cooperative mode: lane r < 24 keeps column r of CI (= -row r of
+// A) and ci0_r in registers; the equality column is warp-uniform.
+struct StepPolicy {
+  double c0, c1, c2, c3, ci0v;   // this lane's constraint (lanes >= 24: unused)
+  double e0, e1, e2, e3, ce0v;
+  __device__ __forceinline__ double slack(const GiWs& w) const {
+    double acc = 0.0;
+    acc = fma(c0, w.x[0], acc); acc = fma(c1, w.x[1], acc); acc = fma(c2, w.x[2], acc); acc = fma(c3, w.x[3], acc);
+    return acc + ci0v;
+  }
+  __device__ __forceinline__ void eval_s(const GiWs& w, int lane, double& psi) const {
+    if (lane < 24) { const double sv = slack(w); w.s[lane] = sv; psi += fmin(0.0, sv); }
+  }
+  __device__ __forceinline__ void load_np(const GiWs& w, int ip, int lane, int& klo, int& khi) const {
+    const double v0 = __shfl_sync(FULL_MASK, c0, ip), v1 = __shfl_sync(FULL_MASK, c1, ip);
+    const double v2 = __shfl_sync(FULL_MASK, c2, ip), v3 = __shfl_sync(FULL_MASK, c3, ip);
+    if (lane == 0) { w.np[0] = v0; w.np[1] = v1; w.np[2] = v2; w.np[3] = v3; }
+    klo = 0; khi = 4;
+    __syncwarp();
+  }
+  __device__ __forceinline__ double eval_one(const GiWs& w, int ip, int lane) const {
+    const double sv = (lane < 24) ? slack(w) : 0.0;
+    return __shfl_sync(FULL_MASK, sv, ip);
+  }
+  __device__ __forceinline__ void load_eq(const GiWs& w, int, int lane, bool& allzero) const {
+    if (lane == 0) { w.np[0] = e0; w.np[1] = e1; w.np[2] = e2; w.np[3] = e3; }
+    allzero = (fabs(e0) <= 1e-12) && (fabs(e1) <= 1e-12) && (fabs(e2) <= 1e-12) && (fabs(e3) <= 1e-12);
+    __syncwarp();
+  }
+  __device__ __forceinline__ double ce0(int) const { return ce0v; }
+};
+
+// Row-pivoted Gauss-Jordan inverse of a 7 x 7 matrix with one lane per column of [A | I]: the same
+// element-by-element operation order as gj_inverse7 (bit-identical), 14 lanes wide.
+// M: shared memory, row-major 7 x 14, columns 0..6 = A on entry, columns 7..13 = A^-1 on exit.
+__device__ void gj_inverse7_warp(double* M, int lane) {
+  constexpr int n = 7, W = 14;
+  if (lane < W) for (int i = 0; i < n; i++) if (lane >= n) M[i * W + lane] = (lane - n == i) ? 1.0 : 0.0;
+  __syncwarp();
+  for (int k = 0; k < n; k++) {
+    int piv = k;
+    double best = fabs(M[k * W + k]);
+    for (int i = k + 1; i < n; i++) { const double v = fabs(M[i * W + k]); if (v > best) { best = v; piv = i; } }
+    __syncwarp();
+    if (piv != k && lane < W) { const double t = M[k * W + lane]; M[k * W + lane] = M[piv * W + lane]; M[piv * W + lane] = t; }
+    __syncwarp();
+    const double d = M[k * W + k];
+    double f[n];
+    for (int i = 0; i < n; i++) f[i] = M[i * W + k];
+    __syncwarp();
+    if (lane < W) {
+      const double pk = M[k * W + lane] / d;
+      M[k * W + lane] = pk;
+      for (int i = 0; i < n; i++) if (i != k) M[i * W + lane] -= f[i] * pk;
+    }
+    __syncwarp();
+  }
+}
+
+// WARP = false: one THREAD per planner (throughput mode, large batches).
+// WARP = true : one WARP per planner (latency mode): the scalar front-end runs warp-uniformly, the
+//               QP is solved by the warp-cooperative core (gi_warp.cuh) with one lane per constraint,
+//               the 7 x 7 inverse runs one lane per column, lane 0 writes the results.
+template <bool WARP>
 __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int b = WARP ? (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5) : (int)(blockIdx.x * blockDim.x + threadIdx.x);
   if (b >= P.B) return;
+  const bool wr = WARP ? (lane == 0) : true;       // who writes to global memory
+  extern __shared__ __align__(16) unsigned char step_smem_raw[];
+  double* wsm = reinterpret_cast<double*>(step_smem_raw) + (WARP ? (size_t)(threadIdx.x >> 5) * STEP_WARP_DOUBLES : 0);
   const size_t B = (size_t)P.B;
   const double* S = P.state + b;        // read side
   double* SO = P.state_out + b;         // write side (may alias the read side: in-place update)
   const double* IN = P.in + b;
 #define ST(f) S[(size_t)(f) * B]
-#define STW(f) SO[(size_t)(f) * B]
+#define STW(f) if (wr) SO[(size_t)(f) * B]
 #define INP(f) IN[(size_t)(f) * B]
   const StepCfgDev& c = P.cfg;
   const double dt = c.dt, Wn = c.Wn;
@@ -182,21 +294,21 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
   else { footy_max = 2 * HW + 0.03; footy_min = wide ? FW + 0.01 : HW - 0.03; }
 
   const double CCx = comx_f - px, CCy = comy_f - py;
-  const double AA = Wn * sinh(Wn * dt);
-  const double BBx = pow(Wn, 2) * CCx * cosh(Wn * dt), BBy = pow(Wn, 2) * CCy * cosh(Wn * dt);
+  const double sh_dt = c.sh_dt, ch_dt = c.ch_dt;      // sinh / cosh(Wn dt): instance-independent, from the host
+  const double AA = Wn * sh_dt;
+  const double BBx = (Wn * Wn) * CCx * ch_dt, BBy = (Wn * Wn) * CCy * ch_dt;
   const double AA1x = AA * Wn, AA2x = -2 * AA * CCx * Wn, AA3x = 2 * BBx;
   const double AA1y = AA * Wn, AA2y = -2 * AA * CCy * Wn, AA3y = 2 * BBy;
-  const double VAA = cosh(Wn * dt);
-  const double VBBx = Wn * CCx * sinh(Wn * dt), VBBy = Wn * CCy * sinh(Wn * dt);
+  const double VAA = ch_dt;
+  const double VBBx = Wn * CCx * sh_dt, VBBy = Wn * CCy * sh_dt;
   const double VAA1x = VAA * Wn, VAA2x = -2 * VAA * CCx * Wn, VAA3x = 2 * VBBx - 2 * comvx_f;
   const double VAA1y = VAA * Wn, VAA2y = -2 * VAA * CCy * Wn, VAA3y = 2 * VBBy - 2 * comvy_f;
   const double VAA1x1 = Wn, VAA2x1 = -2 * CCx * Wn, VAA3x1 = -2 * comvx_f;
   const double VAA1y1 = Wn, VAA2y1 = -2 * CCy * Wn, VAA3y1 = -2 * comvy_f;
 
   int* DG = P.diag ? P.diag + b : nullptr;
-#define DGW(f, val) do { if (DG) DG[(size_t)(f) * B] = (val); } while (0)
+#define DGW(f, val) do { if (DG && wr) DG[(size_t)(f) * B] = (val); } while (0)
   int n_solved = 0;
-  GiThread<4, 1, 24> qp;
   for (int it = 1; it <= P.n_sqp; it++) {
     double G[16], g0[4];
     for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) G[k * 4 + r] = 2 * SQ[r][k];
@@ -255,12 +367,56 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
     if (Tk >= 0.1 * ts[p - 1]) {
       double X[4];
       for (int k = 0; k < 4; k++) X[k] = v[k];
-      const int st = qp.solve(G, g0, CE, ce0, CI, bb, X, P.cap);
+      int st, q_iq, q_out, q_add, q_drop, q_degen, qA[5];
+      if (!WARP) {
+        GiThread<4, 1, 24> qp;
+        st = qp.solve(G, g0, CE, ce0, CI, bb, X, P.cap);
+        q_iq = qp.iq; q_out = qp.it_outer; q_add = qp.it_add; q_drop = qp.it_drop; q_degen = qp.it_degen;
+        for (int k = 0; k < 5; k++) qA[k] = qp.A[k];
+      } else {
+        // warp-cooperative solve (same sequence as dense_qp_kernel): lane r < 24 owns constraint r
+        GiWs w;
+        gi_ws_carve(w, wsm, 4, 1, 24);
+        for (int t = lane; t < 4 * w.ld; t += 32) w.J[t] = 0.0;
+        if (lane < 16) { const int jj = lane >> 2, ii = lane & 3; w.R[jj * w.ld + ii] = G[lane]; }
+        if (lane < 4) w.x[lane] = X[lane];
+        const double c1 = ((G[0] + G[5]) + G[10]) + G[15];
+        __syncwarp();
+        GiResult res; res.f = 0.0; res.iq = 0; res.status = ST_OK;
+        res.it_outer = res.it_add = res.it_drop = res.it_degen = res.it_l2a = 0; res.flops = 0;
+        if (!gi_llt(w, 4, lane)) {
+          res.status = ST_NOT_PD;
+        } else {
+          gi_inv_lt(w, 4, 0, lane);
+          double c2 = (lane < 4) ? w.J[lane * w.ld + lane] : 0.0;
+          c2 = warp_sum(c2);
+          for (int t = lane; t < 4 * w.ld; t += 32) w.R[t] = 0.0;
+          if (lane < 4) w.np[lane] = g0[lane];
+          __syncwarp();
+          gi_compute_d(w, 0, 4, lane);
+          gi_update_z(w, 0, lane);
+          double f = 0.0;
+          if (lane < 4) { const double xv = -w.z[lane]; w.x[lane] = xv; f = g0[lane] * xv; }
+          res.f = 0.5 * warp_sum(f);
+          __syncwarp();
+          StepPolicy pol;
+          const int rr = lane < 24 ? lane : 0;
+          pol.c0 = CI[rr * 4 + 0]; pol.c1 = CI[rr * 4 + 1]; pol.c2 = CI[rr * 4 + 2]; pol.c3 = CI[rr * 4 + 3]; pol.ci0v = bb[rr];
+          pol.e0 = CE[0]; pol.e1 = CE[1]; pol.e2 = CE[2]; pol.e3 = CE[3]; pol.ce0v = ce0[0];
+          gi_loop(w, pol, c1, c2, P.cap, res, lane);
+          for (int k = 0; k < 4; k++) X[k] = w.x[k];
+          bool has_nan = (X[0] != X[0]) || (X[1] != X[1]) || (X[2] != X[2]) || (X[3] != X[3]);
+          if (has_nan && res.status == ST_OK) res.status = ST_NAN;
+        }
+        st = res.status; q_iq = res.iq; q_out = res.it_outer; q_add = res.it_add; q_drop = res.it_drop; q_degen = res.it_degen;
+        for (int k = 0; k < 5; k++) qA[k] = (k < res.iq) ? w.A[k] : 0;
+        __syncwarp();
+      }
       if (n_solved < STEP_MAX_SQP) {
         const int o = STEP_DIAG_HEAD + n_solved * STEP_DIAG_PER;
-        DGW(o + 0, st); DGW(o + 1, st == 1 ? 0 : qp.iq);
-        DGW(o + 2, qp.it_outer); DGW(o + 3, qp.it_add); DGW(o + 4, qp.it_drop); DGW(o + 5, qp.it_degen);
-        for (int k = 0; k < 5; k++) DGW(o + 6 + k, (st != 1 && k < qp.iq) ? qp.A[k] : -99);
+        DGW(o + 0, st); DGW(o + 1, st == 1 ? 0 : q_iq);
+        DGW(o + 2, q_out); DGW(o + 3, q_add); DGW(o + 4, q_drop); DGW(o + 5, q_degen);
+        for (int k = 0; k < 5; k++) DGW(o + 6 + k, (st != 1 && k < q_iq) ? qA[k] : -99);
       }
       n_solved++;
       for (int k = 0; k < 4; k++) v[k] += X[k];   // :795-798, whatever the status
@@ -289,20 +445,20 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
   } else {
     const int bp = (int)ST(S_BJX1);
     const int b1 = bp >= 1 && bp <= NS ? bp : 1, b2 = bp >= 2 && bp <= NS + 1 ? bp : 2;
-    com_height_solve(i, bp <= NS ? bp : 0, ts[b1 - 1], tx[b1 - 1], ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az);
+    if (!WARP) com_height_solve(i, bp <= NS ? bp : 0, ts[b1 - 1], tx[b1 - 1], ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az);
+    else com_height_solve_warp(i, bp <= NS ? bp : 0, ts[b1 - 1], tx[b1 - 1], ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az, wsm, lane);
   }
   // LIPM roll-out of samples i, i+1, i+2 (:938-955)
   double comx[3], comy[3], comvx[3], comvy[3], comax[3], comay[3], zmpx[3], zmpy[3], dcmx[3], dcmy[3];
   for (int jxx = 1; jxx <= 3; jxx++) {
     const int q = jxx - 1;
-    const double w = Wn * dt * jxx;
-    const double ch = cosh(w), sh = sinh(w);
+    const double ch = c.ch_w[q], sh = c.sh_w[q];       // cosh / sinh(Wn dt jxx), from the host
     comx[q] = isx * ch + visx * 1 / Wn * sh + px;
     comy[q] = isy * ch + visy * 1 / Wn * sh + py;
     comvx[q] = Wn * isx * sh + visx * ch;
     comvy[q] = Wn * isy * sh + visy * ch;
-    comax[q] = pow(Wn, 2) * isx * ch + visx * Wn * sh;
-    comay[q] = pow(Wn, 2) * isy * ch + visy * Wn * sh;
+    comax[q] = (Wn * Wn) * isx * ch + visx * Wn * sh;
+    comay[q] = (Wn * Wn) * isy * ch + visy * Wn * sh;
     const double hz = (hz_z[q] - INP(I_ZSC + q)) / (hz_az[q] + c.ggg);
     zmpx[q] = comx[q] - hz * comax[q];
     zmpy[q] = comy[q] - hz * comay[q];
@@ -355,7 +511,7 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
   }
 
   double* O = P.out + b;
-#define OUT(f, val) O[(size_t)(f) * B] = (val)
+#define OUT(f, val) do { if (wr) O[(size_t)(f) * B] = (val); } while (0)
   OUT(0, comx[0]); OUT(1, comy[0]); OUT(2, hz_z[0]);
   OUT(3, comvx[0]); OUT(4, comvy[0]); OUT(5, hz_vz[0]);
   OUT(6, comax[0]); OUT(7, comay[0]); OUT(8, hz_az[0]);
@@ -502,10 +658,16 @@ cudaError_t foot_traj_launch(FootKParams P, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t step_timing_launch(StepKParams P, cudaStream_t st) {
+cudaError_t step_timing_launch(StepKParams P, bool warp_mode, cudaStream_t st) {
   const int block = 128;
-  const int grid = (P.B + block - 1) / block;
-  step_timing_kernel<<<grid, block, 0, st>>>(P);
+  if (warp_mode) {
+    const int wpc = block / 32;
+    const int grid = (P.B + wpc - 1) / wpc;
+    step_timing_kernel<true><<<grid, block, (size_t)wpc * STEP_WARP_DOUBLES * sizeof(double), st>>>(P);
+  } else {
+    const int grid = (P.B + block - 1) / block;
+    step_timing_kernel<false><<<grid, block, 0, st>>>(P);
+  }
   return cudaGetLastError();
 }
 
