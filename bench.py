@@ -239,7 +239,9 @@ def run_b200(a):
     st_h = torch.from_numpy(soa(sst, q.STEP_STATE)).pin_memory(); si_h = torch.from_numpy(soa(sinp, q.STEP_IN)).pin_memory()
     tk_h = torch.from_numpy(stick.reshape(nrot, B).copy()).pin_memory()
     st_d, si_d, tk_d = st_h.to(dev), si_h.to(dev), tk_h.to(dev)
-    st_o = torch.zeros(nrot, B * q.STEP_STATE, dtype=torch.float64, device=dev)   # state after the tick, one buffer per slot
+    # the tick updates the planner state in place; to keep every pass on the same inputs each step first
+    # refreshes its slot's working copy with a device-to-device copy (6.6 MB, inside the timed region)
+    st_o = torch.zeros(nrot, B * q.STEP_STATE, dtype=torch.float64, device=dev)
     so_d = torch.zeros(nrot, q.STEP_OUT, B, dtype=torch.float64, device=dev)
     sd_d = torch.zeros(nrot, q.STEP_DIAG, B, dtype=torch.int32, device=dev)
     torch.cuda.synchronize()
@@ -258,9 +260,13 @@ def run_b200(a):
         rc = lib.go1mpc_body_mpc_step_batch(hh, nh, B, P_in[r], P_out[r], P_dg[r], st_ptr)
         assert rc == 0, rc
 
+    st_bytes = B * q.STEP_STATE * 8
+
     def launch_sqp(i, st_ptr=None):
         r = i % nrot
-        rc = lib.go1mpc_step_timing_step_batch(hh, 3, B, P_tk[r], P_st[r], P_sto[r], P_si[r], P_so[r], P_sd[r], st_ptr)
+        rc = lib.go1mpc_copy_device_async(hh, P_sto[r], P_st[r], st_bytes, st_ptr)
+        assert rc == 0, rc
+        rc = lib.go1mpc_step_timing_step_batch(hh, 3, B, P_tk[r], P_sto[r], P_sto[r], P_si[r], P_so[r], P_sd[r], st_ptr)
         assert rc == 0, rc
 
     def step(i):
@@ -381,7 +387,7 @@ def run_b200(a):
         def feed_sqp(n):
             for i in range(n):
                 r = i % nrot
-                rc = lib.go1mpc_step_timing_step_batch_host_async(hh, 3, B, H_tk[r], P_st[r], P_sto[r], H_si[r], H_so[r], H_sd[r])
+                rc = lib.go1mpc_step_timing_step_batch_host_async(hh, 3, B, H_tk[r], P_st[r], P_sto[r], H_si[r], H_so[r], H_sd[r])   # out-of-place: the inputs stay put
                 assert rc == 0, rc
                 if r == nrot - 1:
                     mpc.synchronize()        # a host slot is about to be reused
@@ -483,7 +489,7 @@ def run_b200(a):
             torch.cuda.synchronize()
             res = []
             for fn in (lambda: mpc.body_mpc_step(nh, Bs, r, o, None),
-                       lambda: mpc.step_timing_step(3, Bs, tkd, ssd, iid, ood, None, state_out_d=sso)):
+                       lambda: (mpc.lib.go1mpc_copy_device_async(mpc.h, sso.data_ptr(), ssd.data_ptr(), ssd.numel() * 8, None), mpc.step_timing_step(3, Bs, tkd, sso, iid, ood, None))):
                 for _ in range(3):
                     fn()
                 mpc.synchronize()

@@ -128,6 +128,9 @@ long long go1mpc_launch_count(const go1mpc_t *h);
 void *go1mpc_stream(const go1mpc_t *h);
 /* multiprocessor count of the handle's device */
 int go1mpc_sm_count(const go1mpc_t *h);
+/* device-to-device copy on `stream` (NULL = the handle's): all per-instance state of this library
+ * is plain SoA / record memory, so checkpointing or restoring a batch is a memcpy */
+int go1mpc_copy_device_async(go1mpc_t *h, void *dst_d, const void *src_d, size_t bytes, void *stream);
 /* wait for the handle's stream and for every pipelined *_host_async call */
 int go1mpc_synchronize(go1mpc_t *h);
 

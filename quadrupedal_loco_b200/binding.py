@@ -13,7 +13,7 @@ c_int_p = ctypes.POINTER(ctypes.c_int)
 EXPORTED_SYMBOLS = [
     "go1mpc_version", "go1mpc_config_default", "go1mpc_create", "go1mpc_destroy",
     "go1mpc_last_error", "go1mpc_device", "go1mpc_launch_count", "go1mpc_synchronize",
-    "go1mpc_stream", "go1mpc_sm_count",
+    "go1mpc_stream", "go1mpc_sm_count", "go1mpc_copy_device_async",
     "go1mpc_qp_solve_batch", "go1mpc_qp_solve_batch_host",
     "go1mpc_body_in_stride", "go1mpc_body_out_stride", "go1mpc_body_diag_stride",
     "go1mpc_body_mpc_step_batch", "go1mpc_body_mpc_step_batch_host",
@@ -91,6 +91,7 @@ def load_library():
     lib.go1mpc_stream.argtypes = [ctypes.c_void_p]
     lib.go1mpc_stream.restype = ctypes.c_void_p
     lib.go1mpc_sm_count.argtypes = [ctypes.c_void_p]
+    lib.go1mpc_copy_device_async.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]
     vp = ctypes.c_void_p
     lib.go1mpc_qp_solve_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 12 + [vp]
     lib.go1mpc_qp_solve_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int] + [vp] * 12
