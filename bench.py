@@ -297,6 +297,10 @@ def run_b200(a):
     sdiag = sd_d.cpu().numpy()
     sqp_solves = sdiag[:, 4, :].astype(np.int64).sum(axis=1)                     # [nrot] QPs the SQP really solved
     sqp_status = sdiag[:, 5::11, :][:, :3, :]
+    # algorithmic flops of the planner tick (SURVEY.md 8d closed form for the (4,1,24) QP: 0.15 k + 0.35 k per
+    # outer pass; front-end 0.6 k per SQP iteration)
+    sqp_outer = sdiag[:, 7::11, :][:, :3, :].astype(np.float64)
+    sqp_flops_per_batch = (150.0 * (sqp_status >= 0) + 350.0 * sqp_outer * (sqp_status >= 0) + 600.0).sum(axis=(1, 2))
     solves_per_step = B + float(np.mean(sqp_solves))
 
     dfma_gflops = mpc.measure_dfma_peak(300)
@@ -466,7 +470,14 @@ def run_b200(a):
                          "peak_source": "measured live on this GPU: register-resident DFMA loop (go1mpc_measure_dfma_peak); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "hbm": {"achieved": io_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "peak_source": f"{hbm_src} (MEASURED_PEAKS.json)", "bytes_per_launch": io_bytes}},
+                                 "peak_source": f"{hbm_src} (MEASURED_PEAKS.json)", "bytes_per_launch": io_bytes},
+                         "other_kernels": {"step_timing_kernel": {
+                             "kernel_ms": float(np.mean(sqp_ms)), "flops_per_launch": float(np.mean(sqp_flops_per_batch)),
+                             "achieved": float(np.mean(sqp_flops_per_batch)) / (float(np.mean(sqp_ms)) * 1e-3) / 1e12,
+                             "frac": float(np.mean(sqp_flops_per_batch)) / (float(np.mean(sqp_ms)) * 1e-3) / 1e12 / peak_tf if peak_tf else None,
+                             "note": "thread-per-planner scalar kernel: longest launch of the step when run alone (128 warps, "
+                                     "latency-bound), but 1.4 % of the step's warp-slot time; body_fast_kernel holds 94 % of the "
+                                     "step's algorithmic flops"}}},
             "solver": {"body_mean_outer": float(mean_iters[0]), "body_mean_add": float(mean_iters[1]),
                        "body_mean_drop": float(mean_iters[2]), "body_mean_degen": float(mean_iters[3]),
                        "body_mean_l2a": float(mean_l2a), "sqp_solves_per_robot": float(np.mean(sqp_solves)) / B,
