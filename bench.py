@@ -214,6 +214,9 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's own banner / warnings on stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ["NCCL_DEBUG"] = os.environ.get("NCCL_DEBUG", "WARN") if os.environ.get("NCCL_DEBUG", "").upper() not in ("VERSION", "INFO", "TRACE") else "WARN"
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
