@@ -309,6 +309,22 @@ int go1mpc_foot_trajectory_batch_host(go1mpc_t *h, int B, const int *tick, const
                                       const double *out38, double *foot, double *out18, int *right_support);
 int go1mpc_foot_default_state(go1mpc_t *h, double *foot32);
 
+/* ---------------------------------------------------------------------------
+ * Servo kinematics tick for B robots (cfg5's fused leg IK / Jacobian stage).  Replaces the
+ * leg mapping and the four Inverse_kinematics_g calls of go1_servo's 1 kHz loop,
+ * GO1/servo_control/servo.cpp:935-1051: foot target of each leg = its homing position + the
+ * planner's virtual right / left foot displacement -+ half hip width, the virtual foot chosen
+ * by gait_mode (101 pace, 102 trot, 103 gallop; servo.h:100-102), body pose = (com x, com y *
+ * y_offset, com z; roll, pitch, yaw), initial guess = the previous joint angles.
+ * SoA [f*B + b]: com_d, theta_d, rfoot_d, lfoot_d [3][B]; homing_d [12][B] and q_d [12][B]
+ * (in/out) leg-major in the order FR, FL, RR, RL; jac_d [36][B] (row-major 3x3 per leg),
+ * foot_des_d [12][B], iters_d [4][B] may be NULL.
+ * ------------------------------------------------------------------------ */
+int go1mpc_servo_kin_tick_batch(go1mpc_t *h, int B, int gait_mode, double y_offset,
+                                const double *com_d, const double *theta_d,
+                                const double *rfoot_d, const double *lfoot_d, const double *homing_d,
+                                double *q_d, double *jac_d, double *foot_des_d, int *iters_d, void *stream);
+
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports
  * against.  Runs ~`ms` milliseconds. */

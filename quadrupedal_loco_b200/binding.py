@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_step_timing_step_batch", "go1mpc_step_timing_step_batch_host", "go1mpc_step_default_state",
     "go1mpc_body_mpc_step_batch_host_async", "go1mpc_step_timing_step_batch_host_async",
     "go1mpc_foot_trajectory_batch", "go1mpc_foot_trajectory_batch_host", "go1mpc_foot_default_state",
-    "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
+    "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
 
@@ -109,6 +109,7 @@ def load_library():
     lib.go1mpc_foot_trajectory_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
     lib.go1mpc_foot_default_state.argtypes = [vp, vp]
     lib.go1mpc_leg_fk_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
+    lib.go1mpc_servo_kin_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 10
     lib.go1mpc_leg_ik_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
     lib.go1mpc_leg_fk_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
     lib.go1mpc_leg_ik_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 8
@@ -310,6 +311,13 @@ class Go1Mpc:
     def leg_ik(self, B, pdes, qini, leg, body_p, body_r, q, jac=None, iters=None, stream=None):
         self._check(self.lib.go1mpc_leg_ik_batch(self.h, B, _ptr(pdes), _ptr(qini), _ptr(leg), _ptr(body_p), _ptr(body_r),
                                                  _ptr(q), _ptr(jac), _ptr(iters), stream), "leg_ik_batch")
+
+    def servo_kin_tick(self, B, gait_mode, y_offset, com, theta, rfoot, lfoot, homing, q, jac=None, foot_des=None, iters=None,
+                       stream=None):
+        """Device buffers (SoA).  q [12][B] is updated in place."""
+        self._check(self.lib.go1mpc_servo_kin_tick_batch(self.h, B, gait_mode, y_offset, _ptr(com), _ptr(theta), _ptr(rfoot),
+                                                         _ptr(lfoot), _ptr(homing), _ptr(q), _ptr(jac), _ptr(foot_des),
+                                                         _ptr(iters), stream), "servo_kin_tick_batch")
 
     def leg_fk_host(self, B, q, leg, body_p, body_r, pos, jac=None):
         self._check(self.lib.go1mpc_leg_fk_batch_host(self.h, B, _ptr(q), _ptr(leg), _ptr(body_p), _ptr(body_r), _ptr(pos),

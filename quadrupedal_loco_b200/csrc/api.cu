@@ -706,6 +706,22 @@ int go1mpc_leg_ik_batch(go1mpc_t* h, int B, const double* pdes_d, const double* 
   h->launches++;
   return GO1MPC_OK;
 }
+int go1mpc_servo_kin_tick_batch(go1mpc_t* h, int B, int gait_mode, double y_offset, const double* com_d, const double* theta_d,
+                                const double* rfoot_d, const double* lfoot_d, const double* homing_d, double* q_d, double* jac_d,
+                                double* foot_des_d, int* iters_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !com_d || !theta_d || !rfoot_d || !lfoot_d || !homing_d || !q_d) return fail(h, GO1MPC_E_INVALID, "servo_kin_tick_batch: bad argument");
+  if (gait_mode < 101 || gait_mode > 103) return fail(h, GO1MPC_E_UNSUPPORTED, "servo_kin_tick_batch: gait_mode 101, 102 or 103");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  ServoKParams P;
+  P.B = B; P.gait_mode = gait_mode; P.half_hip_width = h->cfg.step.half_hip_width; P.y_offset = y_offset;
+  P.com = com_d; P.theta = theta_d; P.rfoot = rfoot_d; P.lfoot = lfoot_d; P.homing = homing_d;
+  P.q = q_d; P.jac = jac_d; P.foot_des = foot_des_d; P.iters = iters_d;
+  CU(h, servo_kin_launch(P, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
 namespace {
 // shared host staging for the two leg entries: ins[k] (bytes) up, outs[k] down
 int leg_host(go1mpc* h, int B, bool ik, const double* a3, const double* b3, const int* leg, const double* bp, const double* br,

@@ -86,6 +86,17 @@ struct LegKParams {
   int* iters;             // IK updates applied, may be null
 };
 cudaError_t leg_fk_launch(LegKParams P, cudaStream_t st);
+struct ServoKParams {
+  int B, gait_mode;
+  double half_hip_width, y_offset;
+  const double *com, *theta, *rfoot, *lfoot;   // [3][B] each
+  const double* homing;                         // [12][B], leg-major (FR, FL, RR, RL)
+  double* q;                                    // [12][B] in/out: previous -> new joint angles
+  double* jac;                                  // [36][B] or null
+  double* foot_des;                             // [12][B] or null
+  int* iters;                                   // [4][B] or null
+};
+cudaError_t servo_kin_launch(ServoKParams P, cudaStream_t st);
 cudaError_t leg_ik_launch(LegKParams P, cudaStream_t st);
 
 // register-resident DFMA loop: flops executed are returned through *flops

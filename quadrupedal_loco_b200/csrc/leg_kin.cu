@@ -121,6 +121,59 @@ __global__ void __launch_bounds__(256) leg_ik_kernel(LegKParams P) {
   if (P.iters) P.iters[b] = it;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Servo kinematics tick (GO1/src/servo_control/servo.cpp:935-1051): the planner's virtual right /
+// left foot is mapped onto the four legs by gait_mode (101 pace: FR,RR <- right, FL,RL <- left;
+// 102 trot: FR,RL <- right, FL,RR <- left; 103 gallop: FR,FL <- right, RR,RL <- left), each foot
+// target = homing position + virtual foot displacement -+ half hip width, then
+// Inverse_kinematics_g per leg from the previous joint angles, Jacobian side channel included.
+// One thread per (robot, leg): 4 B threads, the body pose is shared by a robot's four threads.
+__global__ void __launch_bounds__(256) servo_kin_kernel(ServoKParams P) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 4 * P.B) return;
+  const int b = idx >> 2, leg = idx & 3;
+  const size_t B = (size_t)P.B;
+  // which virtual foot this leg follows: bit `leg` of the mask set = right foot
+  const unsigned right_mask = (P.gait_mode == 101) ? 0x5u : ((P.gait_mode == 102) ? 0x9u : 0x3u);   // FR=0, FL=1, RR=2, RL=3
+  const bool right = (right_mask >> leg) & 1u;
+  const double* vf = right ? P.rfoot : P.lfoot;
+  double pdes[3];
+  for (int k = 0; k < 3; k++) pdes[k] = P.homing[(size_t)(3 * leg + k) * B + b] + vf[(size_t)k * B + b];
+  pdes[1] = P.homing[(size_t)(3 * leg + 1) * B + b] + vf[B + b] + (right ? P.half_hip_width : -P.half_hip_width);
+  const LegC c = leg_consts(leg);
+  Body bd;
+  bd.on = true;
+  {
+    double sr, cr, sp, cp, sy, cy;
+    bd.p[0] = P.com[b]; bd.p[1] = P.com[B + b] * P.y_offset; bd.p[2] = P.com[2 * B + b];
+    sincos(P.theta[b], &sr, &cr); sincos(P.theta[B + b], &sp, &cp); sincos(P.theta[2 * B + b], &sy, &cy);
+    bd.R[0] = cp * cy; bd.R[1] = cy * sp * sr - cr * sy; bd.R[2] = sr * sy + cr * cy * sp;
+    bd.R[3] = cp * sy; bd.R[4] = cr * cy + sp * sr * sy; bd.R[5] = cr * sp * sy - cy * sr;
+    bd.R[6] = -sp;     bd.R[7] = cp * sr;                bd.R[8] = cp * cr;
+  }
+  double q[3] = {P.q[(size_t)(3 * leg) * B + b], P.q[(size_t)(3 * leg + 1) * B + b], P.q[(size_t)(3 * leg + 2) * B + b]};
+  double pc[3], J[9], dp[3], dq[3];
+  fk_any(q, c, bd, pc, J);
+  int it = 0;
+  for (int j = 0; j < 15; j++) {
+    for (int k = 0; k < 3; k++) dp[k] = pdes[k] - pc[k];
+    newton_step(J, dp, 0.5, dq);
+    if (fabs(dp[0] * dp[0] + dp[1] * dp[1] + dp[2] * dp[2]) <= 0.000001) break;
+    q[0] += dq[0]; q[1] += dq[1]; q[2] += dq[2];
+    fk_any(q, c, bd, pc, J);
+    it++;
+  }
+  for (int k = 0; k < 3; k++) P.q[(size_t)(3 * leg + k) * B + b] = q[k];
+  if (P.jac) for (int k = 0; k < 9; k++) P.jac[(size_t)(9 * leg + k) * B + b] = J[k];
+  if (P.foot_des) for (int k = 0; k < 3; k++) P.foot_des[(size_t)(3 * leg + k) * B + b] = pdes[k];
+  if (P.iters) P.iters[(size_t)leg * B + b] = it;
+}
+
+cudaError_t servo_kin_launch(ServoKParams P, cudaStream_t st) {
+  servo_kin_kernel<<<(4 * P.B + 255) / 256, 256, 0, st>>>(P);
+  return cudaGetLastError();
+}
+
 cudaError_t leg_fk_launch(LegKParams P, cudaStream_t st) {
   leg_fk_kernel<<<(P.B + 255) / 256, 256, 0, st>>>(P);
   return cudaGetLastError();

@@ -119,3 +119,43 @@ def test_gpu_kinematics_vs_oracle(mpc, oracle, B):
     back, _ = gpu_fk(mpc, qs, leg, bp, br)
     conv = it < 15
     assert conv.mean() > 0.95 and np.abs(back - posg)[conv].max() < 1.1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("gait_mode", [101, 102, 103])
+def test_gpu_servo_kin_tick_vs_oracle(mpc, oracle, gait_mode):
+    """servo.cpp:935-1051: gait_mode leg mapping + 4 x Inverse_kinematics_g from the previous joint angles,
+    against the same mapping done in numpy + the oracle IK."""
+    import torch
+    B = 3000
+    rng = np.random.Generator(np.random.Philox(gait_mode))
+    HW = 0.12675
+    com = rng.uniform(-0.03, 0.03, (B, 3)) + [0, 0, 0.3]; theta = rng.uniform(-0.15, 0.15, (B, 3))
+    rfoot = rng.uniform(-0.04, 0.04, (B, 3)); rfoot[:, 1] -= HW; rfoot[:, 2] = np.abs(rfoot[:, 2]) * 0.5
+    lfoot = rng.uniform(-0.04, 0.04, (B, 3)); lfoot[:, 1] += HW; lfoot[:, 2] = np.abs(lfoot[:, 2]) * 0.5
+    qh = np.array([0, 0.87, -1.5])                       # homing pose, servo.cpp:767
+    legs = np.arange(4)
+    hom, _ = oracle.leg_fk(np.tile(qh, (4, 1)), legs, np.tile([0, 0, 0.3], (4, 1)), np.zeros((4, 3)))
+    homing = np.tile(hom.reshape(1, 12), (B, 1))
+    q0 = np.tile(qh, (B, 4)) + rng.uniform(-0.05, 0.05, (B, 12))
+    y_off = 0.85
+    dev = torch.device("cuda", 0)
+    soa = lambda a: torch.from_numpy(np.array(a.T, order="C", copy=True)).to(dev)
+    tq = soa(q0); tj = torch.zeros(36, B, dtype=torch.float64, device=dev); tf = torch.zeros(12, B, dtype=torch.float64, device=dev)
+    ti = torch.zeros(4, B, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    mpc.servo_kin_tick(B, gait_mode, y_off, soa(com), soa(theta), soa(rfoot), soa(lfoot), soa(homing), tq, tj, tf, ti)
+    mpc.synchronize()
+    gq, gj, gf, gi = tq.cpu().numpy().T, tj.cpu().numpy().T, tf.cpu().numpy().T, ti.cpu().numpy().T
+    right = {101: [1, 0, 1, 0], 102: [1, 0, 0, 1], 103: [1, 1, 0, 0]}[gait_mode]      # FR, FL, RR, RL follow the right foot?
+    bp = com.copy(); bp[:, 1] *= y_off
+    n = 600
+    for leg in range(4):
+        vf = rfoot if right[leg] else lfoot
+        pdes = homing[:, 3 * leg:3 * leg + 3] + vf
+        pdes[:, 1] += HW if right[leg] else -HW
+        np.testing.assert_allclose(gf[:, 3 * leg:3 * leg + 3], pdes, rtol=0, atol=1e-15)
+        qo, Jo, ito = oracle.leg_ik(pdes[:n], q0[:n, 3 * leg:3 * leg + 3], np.full(n, leg, np.int32), bp[:n], theta[:n])
+        assert np.array_equal(gi[:n, leg], ito)
+        np.testing.assert_allclose(gq[:n, 3 * leg:3 * leg + 3], qo, rtol=0, atol=1e-9)
+        np.testing.assert_allclose(gj[:n, 9 * leg:9 * leg + 9], Jo, rtol=0, atol=1e-9)
