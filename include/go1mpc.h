@@ -325,6 +325,29 @@ int go1mpc_servo_kin_tick_batch(go1mpc_t *h, int B, int gait_mode, double y_offs
                                 const double *rfoot_d, const double *lfoot_d, const double *homing_d,
                                 double *q_d, double *jac_d, double *foot_des_d, int *iters_d, void *stream);
 
+/* ---------------------------------------------------------------------------
+ * Ground-reaction-force distribution of go1_servo's 1 kHz loop for B robots.  Replaces
+ * Dynamiccclass (GO1/whole_body_dynamics/dynmics_compute.cpp):
+ *   go1mpc_grf_force_distribution_batch -> force_distribution :141-261 (gait_mode 101 / 102)
+ *   go1mpc_grf_force_opt_batch          -> force_opt :265-373 + solve_grf_opt :387-427: the
+ *       12-variable QP (alpha 1e4, beta 1e3, gama 10, fz_max 160, mu 0.25 of :55-66) with 12
+ *       equality columns (identity on the legs that must carry no force, all-zero -- and
+ *       skipped by the solver -- on the others) and 24 inequalities; on a NaN solution the
+ *       closed-form guess is returned, as the reference does.
+ * force_opt records are instance-major:
+ *   in_d  [B][48]: base_p 3 | leg_p 12 (FR, FL, RR, RL xyz) | FT_total_des 6 | F_leg_guess 12 |
+ *                  previous grf_opt 12 | gait_mode | right_support | pad
+ *   out_d [B][16]: grf_opt 12 | cost | qp_solution (1/0) | pad 2
+ *   diag_d [B][32] ints (may be NULL): status, nactive, iters[4], qp_solution, 0, active set[24]
+ * force_distribution is SoA [f*B + b]: com_des [3][B], leg_des [12][B], F_force_des [6][B]
+ * (L xyz, R xyz), rfoot_des / lfoot_des [3][B] -> F_leg_ref [12][B] (= F_leg_guess).
+ * ------------------------------------------------------------------------ */
+int go1mpc_grf_force_opt_batch(go1mpc_t *h, int B, const double *in_d, double *out_d, int *diag_d, void *stream);
+int go1mpc_grf_force_distribution_batch(go1mpc_t *h, int B, int gait_mode, double y_coefficient,
+                                        const double *com_des_d, const double *leg_des_d, const double *F_force_des_d,
+                                        const double *rfoot_des_d, const double *lfoot_des_d,
+                                        double *F_leg_ref_d, void *stream);
+
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports
  * against.  Runs ~`ms` milliseconds. */

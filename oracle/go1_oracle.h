@@ -205,6 +205,24 @@ int orc_foot_traj_tick(const orc_step_cfg *c, int j, const orc_step_state *st, i
                        double fs[ORC_FOOT_STATE], double stepwidth0, double lift_height, double out18[18]);
 
 /* ------------------------------------------------------------------------
+ * Ground-reaction-force distribution of go1_servo's 1 kHz loop (Dynamiccclass,
+ * GO1/src/whole_body_dynamics/dynmics_compute.cpp:55-427): closed-form split, the
+ * 12-variable QP (12 equality columns of which the stance legs' are all-zero, 24
+ * inequalities), joint torques.  Leg order FR, FL, RR, RL.
+ * --------------------------------------------------------------------- */
+typedef struct { double qp_alpha, qp_beta, qp_gama, fz_max, mu; } orc_grf_cfg;
+void orc_grf_cfg_default(orc_grf_cfg *c);
+void orc_grf_force_distribution(const double com_des[3], const double leg_des[12], const double F[6], int mode,
+                                double yc, const double rfoot_des[3], const double lfoot_des[3],
+                                double F_leg_ref[12]);
+int orc_grf_force_opt(const orc_grf_cfg *c, const double base_p[3], const double leg_p[12], const double FT[6],
+                      const double F_leg_guess[12], int mode, int right_support, double grf[12],
+                      int *active, int *nactive, int *iters, int *qp_solution);
+void orc_grf_joint_torques(const double Jaco[9], int swing, const double p_des[3], const double p_est[3],
+                           const double pv_des[3], const double pv_est[3], const double F_ref[3],
+                           const double grav[3], double swing_kp, double swing_kd, double tau[3]);
+
+/* ------------------------------------------------------------------------
  * Go1 leg kinematics (Kinematicclass, GO1/src/kinematics/Kinematics.cpp:29-304).
  * leg: 0 FR, 1 FL, 2 RR, 3 RL.  J is row-major 3x3 (the reference's Jacobian_kin
  * side channel after the call).  The IK functions return the number of Newton

@@ -21,7 +21,8 @@ EXPORTED_SYMBOLS = [
     "go1mpc_step_timing_step_batch", "go1mpc_step_timing_step_batch_host", "go1mpc_step_default_state",
     "go1mpc_body_mpc_step_batch_host_async", "go1mpc_step_timing_step_batch_host_async",
     "go1mpc_foot_trajectory_batch", "go1mpc_foot_trajectory_batch_host", "go1mpc_foot_default_state",
-    "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
+    "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch",
+    "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
 
@@ -109,6 +110,8 @@ def load_library():
     lib.go1mpc_foot_trajectory_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
     lib.go1mpc_foot_default_state.argtypes = [vp, vp]
     lib.go1mpc_leg_fk_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
+    lib.go1mpc_grf_force_opt_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
+    lib.go1mpc_grf_force_distribution_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 7
     lib.go1mpc_servo_kin_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 10
     lib.go1mpc_leg_ik_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
     lib.go1mpc_leg_fk_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
@@ -318,6 +321,15 @@ class Go1Mpc:
         self._check(self.lib.go1mpc_servo_kin_tick_batch(self.h, B, gait_mode, y_offset, _ptr(com), _ptr(theta), _ptr(rfoot),
                                                          _ptr(lfoot), _ptr(homing), _ptr(q), _ptr(jac), _ptr(foot_des),
                                                          _ptr(iters), stream), "servo_kin_tick_batch")
+
+    def grf_force_opt(self, B, in_d, out_d, diag_d=None, stream=None):
+        """Device records: in [B,48], out [B,16], diag [B,32] ints."""
+        self._check(self.lib.go1mpc_grf_force_opt_batch(self.h, B, _ptr(in_d), _ptr(out_d), _ptr(diag_d), stream), "grf_force_opt_batch")
+
+    def grf_force_distribution(self, B, gait_mode, y_coefficient, com, leg, F, rfoot, lfoot, F_leg_ref, stream=None):
+        self._check(self.lib.go1mpc_grf_force_distribution_batch(self.h, B, gait_mode, y_coefficient, _ptr(com), _ptr(leg), _ptr(F),
+                                                                 _ptr(rfoot), _ptr(lfoot), _ptr(F_leg_ref), stream),
+                    "grf_force_distribution_batch")
 
     def leg_fk_host(self, B, q, leg, body_p, body_r, pos, jac=None):
         self._check(self.lib.go1mpc_leg_fk_batch_host(self.h, B, _ptr(q), _ptr(leg), _ptr(body_p), _ptr(body_r), _ptr(pos),

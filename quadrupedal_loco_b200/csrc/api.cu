@@ -609,6 +609,36 @@ int go1mpc_foot_default_state(go1mpc_t* h, double* fs) {
   return GO1MPC_OK;
 }
 
+// ------------------------------------------------------------------ GRF distribution
+int go1mpc_grf_force_opt_batch(go1mpc_t* h, int B, const double* in_d, double* out_d, int* diag_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !in_d || !out_d) return fail(h, GO1MPC_E_INVALID, "grf_force_opt_batch: bad argument");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  GrfKParams P;
+  P.B = B; P.cap = h->cfg.qp_iter_cap_scale * (12 + 12 + 24) + 50; P.warp_doubles = 0;
+  P.qp_alpha = 10000; P.qp_beta = 1000; P.qp_gama = 10; P.fz_max = 160; P.mu = 0.25;   // dynmics_compute.cpp:59-63
+  P.in = in_d; P.out = out_d; P.diag = diag_d;
+  CU(h, grf_force_opt_launch(P, h->sms, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+int go1mpc_grf_force_distribution_batch(go1mpc_t* h, int B, int gait_mode, double y_coefficient, const double* com_des_d,
+                                        const double* leg_des_d, const double* F_force_des_d, const double* rfoot_des_d,
+                                        const double* lfoot_des_d, double* F_leg_ref_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !com_des_d || !leg_des_d || !F_force_des_d || !rfoot_des_d || !lfoot_des_d || !F_leg_ref_d)
+    return fail(h, GO1MPC_E_INVALID, "grf_force_distribution_batch: bad argument");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  GrfDistParams P;
+  P.B = B; P.mode = gait_mode; P.y_coefficient = y_coefficient;
+  P.com = com_des_d; P.leg = leg_des_d; P.F = F_force_des_d; P.rfoot = rfoot_des_d; P.lfoot = lfoot_des_d; P.F_leg_ref = F_leg_ref_d;
+  CU(h, grf_force_distribution_launch(P, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
 // ------------------------------------------------------------------ pipelined host entries
 int go1mpc_body_mpc_step_batch_host_async(go1mpc_t* h, int nh, int B, const double* in, double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;

@@ -99,6 +99,24 @@ struct ServoKParams {
 cudaError_t servo_kin_launch(ServoKParams P, cudaStream_t st);
 cudaError_t leg_ik_launch(LegKParams P, cudaStream_t st);
 
+// ---- GRF distribution of the servo loop (grf_qp.cu) ----
+constexpr int GRF_IN_DOUBLES = 48, GRF_OUT_DOUBLES = 16, GRF_DIAG_INTS = 32;
+struct GrfKParams {
+  int B, cap, warp_doubles;
+  double qp_alpha, qp_beta, qp_gama, fz_max, mu;
+  const double* in;     // [B][48]: base_p 3 | leg_p 12 (FR FL RR RL) | FT 6 | F_leg_guess 12 | grf_prev 12 | mode | right_support | pad
+  double* out;          // [B][16]: grf 12 | cost | qp_solution | pad 2
+  int* diag;            // [B][32] or null: status nactive iters[4] qp_solution 0 | active[24]
+};
+struct GrfDistParams {
+  int B, mode;
+  double y_coefficient;
+  const double *com, *leg, *F, *rfoot, *lfoot;   // SoA [3][B], [12][B], [6][B], [3][B], [3][B]
+  double* F_leg_ref;                             // SoA [12][B] (FR, FL, RR, RL xyz)
+};
+cudaError_t grf_force_opt_launch(GrfKParams P, int sms, cudaStream_t st);
+cudaError_t grf_force_distribution_launch(GrfDistParams P, cudaStream_t st);
+
 // register-resident DFMA loop: flops executed are returned through *flops
 cudaError_t dfma_peak_launch(int grid, int block, int iters, double* sink, cudaStream_t st);
 

@@ -155,6 +155,22 @@ def gen_step(nl):
     print("step_ref.npz replay", T, "pushes", N, "finite pushes", int(np.isfinite(pout).all(axis=1).sum()))
 
 
+def gen_grf(dl):
+    """Dynamiccclass::force_distribution + force_opt on 240 seeded cases (tests/test_grf.py: grf_inputs)."""
+    from tests.test_grf import grf_inputs
+    dl.ref_dyn_new.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(dl.ref_dyn_new())
+    d = grf_inputs(240, seed=6); N = 240
+    Fg = np.zeros((N, 12)); grf = d["prev"].copy(); ok = np.zeros(N, np.int32)
+    for b in range(N):
+        dl.ref_dyn_force_distribution(h, P(d["base"][b].copy()), P(d["legs"][b].copy()), P(d["F6"][b].copy()), int(d["mode"][b]),
+                                      ctypes.c_double(0.9), P(d["rf"][b].copy()), P(d["lf"][b].copy()), P(Fg[b]))
+        ok[b] = dl.ref_dyn_force_opt(h, P(d["base"][b].copy()), P(d["legs"][b].copy()), P(d["FT"][b].copy()), P(Fg[b]),
+                                     int(d["mode"][b]), int(d["rs"][b]), ctypes.c_double(0.9), P(grf[b]))
+    np.savez_compressed(os.path.join(HERE, "grf_ref.npz"), Fg=Fg, grf=grf, ok=ok, **d)
+    print("grf_ref.npz", N)
+
+
 if __name__ == "__main__":
     ref, rt, nlp = ref_path("libref.so"), ref_path("libref_rt.so"), ref_path("libref_nlp.so")
     if not ref or not rt or not nlp:
@@ -169,3 +185,5 @@ if __name__ == "__main__":
         gen_kin(lib)
     if not only or "step" in only:
         gen_step(ctypes.CDLL(nlp))
+    if not only or "grf" in only:
+        gen_grf(ctypes.CDLL(ref_path("libref_dyn.so")))
