@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--nh", type=int, default=10, help="body-MPC horizon")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the device-resident leg deals its steps over")
     ap.add_argument("--sweep", action="store_true", help="also print per-batch-size throughput (stderr)")
     return ap.parse_args()
 
@@ -60,7 +61,7 @@ def workload_config(a, n_gpus):
             "qp_shapes": [[2 * a.nh, 0, 12 * a.nh], [4, 1, 24]], "seed": "0xB2000002+rank",
             "parallelism": f"batch-sharded x{n_gpus}, no collective",
             "l2": "inputs rotate through distinct batches totalling > 2x L2 (no flush needed)",
-            "streams": "device-resident leg: steps dealt round-robin over 4 CUDA streams (independent robot batches in flight)"}
+            "streams": f"device-resident leg: body ticks round-robin over 2 CUDA streams, planner ticks over {max(3, a.streams) - 2} (independent robot batches in flight)"}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -319,7 +320,11 @@ def run_b200(a):
     # NSTREAM), join once; the timed region is fork -> join.  One 4096-robot batch fills 1/64 of the
     # GPU's warp slots in the SQP kernel and 1.7 waves in the body kernel, so batches in flight on
     # several streams are what keeps the SMs busy at this batch size.
-    NSTREAM = 4
+    # body ticks go round-robin over 2 streams (each launch is ~1.7 waves of the whole GPU: a second
+    # stream fills the tail of the first), planner ticks over the remaining a.streams - 2 (each launch
+    # is 128 warps for ~0.19 ms: several must be in flight to hide that latency)
+    NSTREAM = max(3, a.streams)
+    NB = 2
     lanes = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NSTREAM - 1)]
     lane_ptr = [None] + [x.cuda_stream for x in lanes[1:]]
     joins = [torch.cuda.Event() for _ in range(NSTREAM)]
@@ -328,8 +333,8 @@ def run_b200(a):
         for x in lanes[1:]:
             x.wait_event(ev[0])
         for i in range(K):
-            launch_sqp(i, lane_ptr[i % NSTREAM])
-            launch_body(i, lane_ptr[i % NSTREAM])
+            launch_sqp(i, lane_ptr[NB + i % (NSTREAM - NB)])
+            launch_body(i, lane_ptr[i % NB])
         for k in range(1, NSTREAM):
             joins[k].record(lanes[k])
             stream.wait_event(joins[k])

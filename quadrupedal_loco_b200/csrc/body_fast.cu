@@ -53,22 +53,6 @@ __device__ __forceinline__ void warp_sum3(double& a, double& b, double& c) {
   }
 }
 
-// Arg-min over the warp of (value, index) pairs, lowest index among equal values, with three
-// integer warp reductions (REDUX) instead of a 5-step shuffle butterfly: doubles are mapped to
-// order-preserving unsigned 64-bit keys and reduced high word first.
-__device__ __forceinline__ void warp_argmin_redux(double& v, int& idx) {
-  unsigned long long k = (unsigned long long)__double_as_longlong(v);
-  k ^= (k >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull;
-  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
-  const unsigned mhi = __reduce_min_sync(FULL_MASK, hi);
-  const unsigned mlo = __reduce_min_sync(FULL_MASK, hi == mhi ? lo : 0xffffffffu);
-  const bool win = (hi == mhi) && (lo == mlo);
-  idx = (int)__reduce_min_sync(FULL_MASK, win ? (unsigned)idx : 0xffffffffu);
-  unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
-  m ^= (m >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull;
-  v = __longlong_as_double((long long)m);
-}
-
 template <int NH>
 struct FastDims {
   static constexpr int N = 2 * NH;

@@ -14,10 +14,9 @@
 //   * lanes own rows of J for z = J2 d and for the Givens sweeps, and columns of
 //     J for d = J' n+ (J is stored with an odd leading dimension so both access
 //     patterns are shared-memory bank-conflict free);
-//   * the serial hypot chain of add_constraint (n-q-1 dependent sqrt/div
-//     groups) is replaced by per-lane suffix sums of d^2, so all rotation
-//     parameters are produced in parallel and only the 2-FMA row update stays
-//     sequential -- same rotations, rounding differs in the last bits;
+//   * the chain of n-q-1 Givens rotations of add_constraint is replaced by one
+//     Householder reflection built from the z already computed in step 2a (an
+//     equivalent orthogonal update of the null-space basis, one parallel pass);
 //   * the working-set membership vectors iai/iaexcl are per-lane bit masks in
 //     registers (constraint c lives in lane c&31, bit c>>5);
 //   * n+ is produced by a policy object, so a front-end with structured
@@ -53,6 +52,21 @@ __device__ __forceinline__ void warp_argmin(double& v, int& idx) {
   }
   v = __shfl_sync(FULL_MASK, v, 0);
   idx = __shfl_sync(FULL_MASK, idx, 0);
+}
+
+// The same arg-min with three integer warp reductions (REDUX): doubles are mapped to
+// order-preserving unsigned 64-bit keys and reduced high word first.
+__device__ __forceinline__ void warp_argmin_redux(double& v, int& idx) {
+  unsigned long long k = (unsigned long long)__double_as_longlong(v);
+  k ^= (k >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull;
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mhi = __reduce_min_sync(FULL_MASK, hi);
+  const unsigned mlo = __reduce_min_sync(FULL_MASK, hi == mhi ? lo : 0xffffffffu);
+  const bool win = (hi == mhi) && (lo == mlo);
+  idx = (int)__reduce_min_sync(FULL_MASK, win ? (unsigned)idx : 0xffffffffu);
+  unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+  m ^= (m >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull;
+  v = __longlong_as_double((long long)m);
 }
 
 // EiQuadProg.hpp:100-118
@@ -130,60 +144,37 @@ __device__ __forceinline__ void gi_update_r(const GiWs& w, int iq, int lane) {
   }
 }
 
-// EiQuadProg.cpp:30-93.  d is consumed; on return d[iq_old] = +-|d[iq_old:]|, d[j>iq_old] = 0.
+// EiQuadProg.cpp:30-93.  The reference zeroes d[iq+1:] with a chain of n-iq-1 Givens rotations of J's
+// trailing columns; any orthogonal map sending d2 = d[iq:] to a multiple of e_0 yields an equivalent
+// null-space basis, so ONE Householder reflection H = I - tau v v', v = d2 + sigma e_0,
+// sigma = sign(d_iq)|d2| is used: J2 <- J2 - tau (J2 v) v' with J2 v = z + sigma J(:,iq), where
+// z = J2 d2 is still in w.z from step 2a -- a single dependency-free pass, rows per lane.
+// On return d[iq_old] = -sigma, d[j > iq_old] = 0, R(:, iq_old) = d[0..iq_old].
 __device__ inline bool gi_add_constraint(const GiWs& w, int& iq, double& R_norm, int lane) {
   const int n = w.n, ld = w.ld;
-  // rotation j acts on columns (j-1, j), j = n-1 .. iq+1.  Lane-parallel parameters:
-  // S_j = sum_{k>=j} d_k^2 accumulated from the bottom, exactly the order in which
-  // the reference's hypot chain grows.
-  double new_diag = 0.0;
-  bool have_diag = false;
-  for (int j = iq + 1 + lane; j < n; j += 32) {
-    double S = 0.0;
-    for (int k = n - 1; k >= j; k--) S = fma(w.d[k], w.d[k], S);
-    double dj = w.d[j], dm = w.d[j - 1];
-    double hj = sqrt(S);
-    double h = sqrt(fma(dm, dm, S));
-    double ssr = (j == n - 1) ? dj : (dj < 0.0 ? -hj : hj);
-    double cc = 1.0, ss = 0.0, xny = 0.0, skip = 1.0;
-    if (h != 0.0) {
-      skip = 0.0;
-      ss = ssr / h;
-      cc = dm / h;
-      if (cc < 0.0) { cc = -cc; ss = -ss; }
-      xny = ss / (1.0 + cc);
-    }
-    double* rp = w.rot + 4 * j;
-    rp[0] = cc; rp[1] = ss; rp[2] = xny; rp[3] = skip;
-    if (j == iq + 1) { have_diag = true; new_diag = (h != 0.0) ? (dm < 0.0 ? -h : h) : dm; }
-  }
+  double dd = 0.0;
+  for (int j = iq + lane; j < n; j += 32) dd = fma(w.d[j], w.d[j], dd);
+  dd = warp_sum(dd);
+  const double nrm = sqrt(dd);
+  const double diq = w.d[iq];
+  const double sigma = (diq < 0.0) ? -nrm : nrm;
   __syncwarp();
-  // the lane that handled j = iq+1 (lane 0, if any rotation exists) owns the new d[iq]
-  if (iq + 1 < n) {
-    if (have_diag) w.d[iq] = new_diag;
-    for (int j = iq + 1 + lane; j < n; j += 32) w.d[j] = 0.0;
-  }
-  // sequential sweep over columns, lanes own rows
-  for (int k = lane; k < n; k += 32) {
-    double carry = w.J[(n - 1) * ld + k];
-    for (int j = n - 1; j >= iq + 1; j--) {
-      const double* rp = w.rot + 4 * j;
-      double t1 = w.J[(j - 1) * ld + k];
-      if (rp[3] != 0.0) {             // h == 0: the reference leaves both columns untouched
-        w.J[j * ld + k] = carry;
-        carry = t1;
-      } else {
-        double a = fma(carry, rp[1], t1 * rp[0]);
-        w.J[j * ld + k] = fma(rp[2], t1 + a, -carry);
-        carry = a;
-      }
+  if (nrm != 0.0) {
+    const double tau = 1.0 / (nrm * (nrm + fabs(diq)));
+    const double viq = diq + sigma;
+    for (int k = lane; k < n; k += 32) {
+      const double sw = tau * fma(sigma, w.J[iq * ld + k], w.z[k]);
+      w.J[iq * ld + k] = fma(-sw, viq, w.J[iq * ld + k]);
+      for (int j = iq + 1; j < n; j++) w.J[j * ld + k] = fma(-sw, w.d[j], w.J[j * ld + k]);
     }
-    w.J[iq * ld + k] = carry;
+    __syncwarp();
+    if (lane == 0) w.d[iq] = -sigma;
+    for (int j = iq + 1 + lane; j < n; j += 32) w.d[j] = 0.0;
   }
   __syncwarp();
   iq++;
   for (int t = lane; t < iq; t += 32) w.R[(iq - 1) * ld + t] = w.d[t];
-  double dq = w.d[iq - 1];
+  const double dq = w.d[iq - 1];
   __syncwarp();
   if (fabs(dq) <= EPS_D * R_norm) return false;  // degenerate
   R_norm = fmax(R_norm, fabs(dq));
@@ -365,7 +356,7 @@ __device__ inline void gi_loop(const GiWs& w, Pol& pol, double c1, double c2, in
           double sv = w.s[c];
           if (sv < bv && !((inA >> t) & 1u) && !((excl >> t) & 1u)) { bv = sv; bi = c; }
         }
-        warp_argmin(bv, bi);
+        warp_argmin_redux(bv, bi);
         if (bv < ss) { ss = bv; ip = bi; }
         if (ss >= 0.0) break;
         pol.load_np(w, ip, lane, klo, khi);
@@ -386,7 +377,7 @@ __device__ inline void gi_loop(const GiWs& w, Pol& pol, double c1, double c2, in
         double rk = w.r[k];
         if (rk > 0.0) { double tmp = w.u[k] / rk; if (tmp < t1) { t1 = tmp; kmin = k; } }
       }
-      warp_argmin(t1, kmin);
+      warp_argmin_redux(t1, kmin);
       l = (kmin != 0x7fffffff && t1 < inf) ? w.A[kmin] : 0;
       double zz = 0.0, zn = 0.0;
       for (int k = lane; k < n; k += 32) { zz = fma(w.z[k], w.z[k], zz); zn = fma(w.z[k], w.np[k], zn); }
