@@ -14,11 +14,15 @@
 //
 // Layout: structure of arrays, element-major / batch-minor -- field f of instance b is at
 // [f * B + b] -- so a warp's 32 instances read and write 256 contiguous bytes per field.
-// Compiled with -fmad=false: same operation order as the CPU oracle, no FMA contraction.
+// Compiled with -fmad=false: same operation order as the CPU oracle, no FMA contraction (measured:
+// contraction would make the thread-per-planner tick 10-20 % faster and keep the QP parity at 1e-9,
+// but the step period it writes back then differs from the host's by an ulp, which the badly
+// conditioned swing-foot fit downstream amplifies to 1e-6 -- fidelity wins).
 #include <cuda_runtime.h>
 #include "gi_thread.cuh"
 #include "gi_warp.cuh"
 #include "kernels.h"
+#include "powi.cuh"
 
 namespace go1 {
 
@@ -29,24 +33,6 @@ constexpr int S_TS = 0, S_TX = 27, S_FX = 54, S_FY = 81, S_FZ = 108, S_LXX = 135
 // input fields
 constexpr int I_EST = 0, I_RF = 6, I_LF = 8, I_CZ = 10, I_CAZ = 13, I_ZSC = 16, I_CVZ = 19;
 }  // namespace
-
-// t^k for k = 0..6, correctly rounded (double-double running product, one final rounding): the
-// time-polynomial systems below are badly conditioned, so a 1-2 ulp difference in a power (CUDA's
-// pow vs the host libm's, which is correctly rounded for these arguments) would show up as 1e-7 in
-// the fitted accelerations.
-__device__ __forceinline__ double powi(double t, int k) {
-  if (k == 0) return 1.0;
-  double hi = t, lo = 0.0;
-  for (int q = 1; q < k; q++) {
-    const double p = hi * t;
-    double e = fma(hi, t, -p);
-    e = fma(lo, t, e);
-    const double s = p + e;
-    lo = e - (s - p);
-    hi = s;
-  }
-  return hi + lo;
-}
 
 // inverse by Gauss-Jordan with partial (row) pivoting, first maximal |pivot| wins; row-major 7 x 7
 // (the elimination order of the CPU oracle: the time-polynomial matrix is badly conditioned, so
@@ -68,7 +54,7 @@ __device__ void gj_inverse7(double* a, double* r) {
     for (int i = 0; i < n; i++) {
       if (i == k) continue;
       const double f = a[i * n + k];
-      for (int j = 0; j < n; j++) { a[i * n + j] -= f * a[k * n + j]; r[i * n + j] -= f * r[k * n + j]; }
+      for (int j = 0; j < n; j++) { a[i * n + j] = __dsub_rn(a[i * n + j], __dmul_rn(f, a[k * n + j])); r[i * n + j] = __dsub_rn(r[i * n + j], __dmul_rn(f, r[k * n + j])); }
     }
   }
 }
@@ -92,14 +78,14 @@ __device__ void com_height_solve(int i, int bjx1, double ts1, double tx1, double
     gj_inverse7(A, Ainv);
     const double plan[7] = {0, 0, f0 + hcom, (f0 + f1) / 2 + hcom, f1 + hcom, 0, 0};
     double co[7];
-    for (int r = 0; r < 7; r++) { double acc = 0.0; for (int k = 0; k < 7; k++) acc += Ainv[7 * r + k] * plan[k]; co[r] = acc; }
+    for (int r = 0; r < 7; r++) { double acc = 0.0; for (int k = 0; k < 7; k++) acc = __dadd_rn(acc, __dmul_rn(Ainv[7 * r + k], plan[k])); co[r] = acc; }
     for (int jxx = 1; jxx <= 3; jxx++) {
       const double t = (i + jxx - round(tx1 / dt)) * dt;
       const double p[7] = {powi(t, 6), powi(t, 5), powi(t, 4), powi(t, 3), powi(t, 2), powi(t, 1), 1};
       const double v[7] = {6 * powi(t, 5), 5 * powi(t, 4), 4 * powi(t, 3), 3 * powi(t, 2), 2 * powi(t, 1), 1, 0};
       const double a[7] = {30 * powi(t, 4), 20 * powi(t, 3), 12 * powi(t, 2), 6 * powi(t, 1), 2, 0, 0};
       double z = 0.0, vz = 0.0, az = 0.0;
-      for (int k = 0; k < 7; k++) { z += p[k] * co[k]; vz += v[k] * co[k]; az += a[k] * co[k]; }
+      for (int k = 0; k < 7; k++) { z = __dadd_rn(z, __dmul_rn(p[k], co[k])); vz = __dadd_rn(vz, __dmul_rn(v[k], co[k])); az = __dadd_rn(az, __dmul_rn(a[k], co[k])); }
       comz[jxx - 1] = z; comvz[jxx - 1] = vz; comaz[jxx - 1] = az;
     }
   } else {
@@ -130,7 +116,7 @@ __device__ void com_height_solve_warp(int i, int bjx1, double ts1, double tx1, d
     gj_inverse7_warp(M, lane);
     const double plan[7] = {0, 0, f0 + hcom, (f0 + f1) / 2 + hcom, f1 + hcom, 0, 0};
     double* co = M + 98;
-    if (lane < 7) { double acc = 0.0; for (int k = 0; k < 7; k++) acc += M[14 * lane + 7 + k] * plan[k]; co[lane] = acc; }
+    if (lane < 7) { double acc = 0.0; for (int k = 0; k < 7; k++) acc = __dadd_rn(acc, __dmul_rn(M[14 * lane + 7 + k], plan[k])); co[lane] = acc; }
     __syncwarp();
     double z = 0.0, vz = 0.0, az = 0.0;
     if (lane < 3) {
@@ -139,7 +125,7 @@ __device__ void com_height_solve_warp(int i, int bjx1, double ts1, double tx1, d
       const double p[7] = {powi(t, 6), powi(t, 5), powi(t, 4), powi(t, 3), powi(t, 2), powi(t, 1), 1};
       const double v[7] = {6 * powi(t, 5), 5 * powi(t, 4), 4 * powi(t, 3), 3 * powi(t, 2), 2 * powi(t, 1), 1, 0};
       const double a[7] = {30 * powi(t, 4), 20 * powi(t, 3), 12 * powi(t, 2), 6 * powi(t, 1), 2, 0, 0};
-      for (int k = 0; k < 7; k++) { z += p[k] * co[k]; vz += v[k] * co[k]; az += a[k] * co[k]; }
+      for (int k = 0; k < 7; k++) { z = __dadd_rn(z, __dmul_rn(p[k], co[k])); vz = __dadd_rn(vz, __dmul_rn(v[k], co[k])); az = __dadd_rn(az, __dmul_rn(a[k], co[k])); }
     }
     for (int q = 0; q < 3; q++) {
       comz[q] = __shfl_sync(FULL_MASK, z, q); comvz[q] = __shfl_sync(FULL_MASK, vz, q); comaz[q] = __shfl_sync(FULL_MASK, az, q);
@@ -203,7 +189,7 @@ __device__ void gj_inverse7_warp(double* M, int lane) {
     if (lane < W) {
       const double pk = M[k * W + lane] / d;
       M[k * W + lane] = pk;
-      for (int i = 0; i < n; i++) if (i != k) M[i * W + lane] -= f[i] * pk;
+      for (int i = 0; i < n; i++) if (i != k) M[i * W + lane] = __dsub_rn(M[i * W + lane], __dmul_rn(f[i], pk));
     }
     __syncwarp();
   }
@@ -533,129 +519,6 @@ __global__ void __launch_bounds__(128) step_timing_kernel(StepKParams P) {
 #undef ST
 #undef STW
 #undef INP
-}
-
-// ---------------------------------------------------------------------------------------------
-// Swing-foot trajectory of the step planner: NLPClass::Foot_trajectory_solve_mod2
-// (NLPClass_sqp.cpp:2039-2358) with solve_AAA_inv2 (:3633-3645); run after the step-timing tick
-// of the same index.  Thread per instance, SoA.  The reference's whole-walk foot arrays shrink
-// to a 32-double window (layout: include/go1mpc.h).  Stop-walking is not on the device.
-__device__ void gj_inverse4(double* a, double* r) {
-  constexpr int n = 4;
-  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) r[i * n + j] = (i == j) ? 1.0 : 0.0;
-  for (int k = 0; k < n; k++) {
-    int piv = k;
-    double best = fabs(a[k * n + k]);
-    for (int i = k + 1; i < n; i++) if (fabs(a[i * n + k]) > best) { best = fabs(a[i * n + k]); piv = i; }
-    if (piv != k)
-      for (int j = 0; j < n; j++) {
-        double t = a[k * n + j]; a[k * n + j] = a[piv * n + j]; a[piv * n + j] = t;
-        t = r[k * n + j]; r[k * n + j] = r[piv * n + j]; r[piv * n + j] = t;
-      }
-    const double d = a[k * n + k];
-    for (int j = 0; j < n; j++) { a[k * n + j] = a[k * n + j] / d; r[k * n + j] = r[k * n + j] / d; }
-    for (int i = 0; i < n; i++) {
-      if (i == k) continue;
-      const double f = a[i * n + k];
-      for (int j = 0; j < n; j++) { a[i * n + j] -= f * a[k * n + j]; r[i * n + j] -= f * r[k * n + j]; }
-    }
-  }
-}
-
-__global__ void __launch_bounds__(128) foot_traj_kernel(FootKParams P) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= P.B) return;
-  const size_t B = (size_t)P.B;
-  const double* S = P.state + b;
-  double* F = P.foot + b;
-#define ST(f) S[(size_t)(f) * B]
-#define FS(f) F[(size_t)(f) * B]
-  const double dt = P.dt, sw0 = P.stepwidth0;
-  const int j = P.tick[b];
-  const int bjx1 = (int)ST(S_BJX1);
-  const int bjxx = (int)P.out38[(size_t)27 * B + b];
-  double pm1[6], pj[6], pm2[6], pm3[6], frz[6];
-  for (int k = 0; k < 6; k++) { pm1[k] = FS(k); pj[k] = FS(6 + k); pm2[k] = FS(12 + k); pm3[k] = FS(18 + k); frz[k] = FS(24 + k); }
-  double frz_s = FS(30), ry_lr = FS(31);
-  double cur[6], nxt[6], vel[6] = {0, 0, 0, 0, 0, 0}, acc[6] = {0, 0, 0, 0, 0, 0};
-  bool wrote_next[6] = {false, false, false, false, false, false};
-  for (int k = 0; k < 6; k++) { cur[k] = pj[k]; nxt[k] = 0.0; }
-  int right_support;
-  // _footxyz_real: the step tables with (1,0) overwritten by -stepwidth(0) (:2050)
-  auto fxr = [&](int r, int k) -> double {
-    k = k < 0 ? 0 : (k > NS - 1 ? NS - 1 : k);
-    return r == 0 ? ST(S_FX + k) : (r == 1 ? (k == 0 ? -sw0 : ST(S_FY + k)) : ST(S_FZ + k));
-  };
-  if (bjx1 >= 2 && bjx1 <= NS) {
-    const double tx1 = ST(S_TX + bjx1 - 1), ts1 = ST(S_TS + bjx1 - 1);
-    const int s = (int)round(tx1 / dt);
-    if ((double)s != frz_s) {
-      const int back = j - (s - 2);
-      for (int k = 0; k < 6; k++) frz[k] = (back <= 1) ? pm1[k] : (back == 2 ? pm2[k] : pm3[k]);
-      frz_s = (double)s;
-    }
-    const bool left_support = (bjx1 % 2 == 0);
-    const int so = left_support ? 3 : 0, wo = left_support ? 0 : 3;
-    right_support = left_support ? 0 : 1;
-    for (int k = 0; k < 3; k++) { cur[so + k] = frz[so + k]; nxt[so + k] = frz[so + k]; wrote_next[so + k] = true; }
-    if ((j + 1 - s) * dt < 0.2 * ts1) {
-      right_support = 2;
-      for (int k = 0; k < 3; k++) { cur[wo + k] = frz[wo + k]; nxt[wo + k] = frz[wo + k]; wrote_next[wo + k] = true; }
-    } else {
-      const double t_des = (j + 1 - s + 1) * dt;
-      const double td1 = 0.2 * ts1;
-      const double tp[3] = {t_des - dt, (td1 + ts1) / 2 + 0.0001, ts1};
-      if (fabs(t_des - ts1) <= (+0.0005)) {
-        for (int k = 0; k < 3; k++) { cur[wo + k] = fxr(k, bjxx); nxt[wo + k] = fxr(k, bjxx); wrote_next[wo + k] = true; }
-      } else {
-        double A[16], Ai[16];
-        for (int r = 0; r < 3; r++) { A[4 * r] = powi(tp[r], 3); A[4 * r + 1] = powi(tp[r], 2); A[4 * r + 2] = powi(tp[r], 1); A[4 * r + 3] = 1; }
-        A[12] = 3 * powi(tp[2], 2); A[13] = 2 * powi(tp[2], 1); A[14] = powi(tp[2], 0); A[15] = 0;
-        gj_inverse4(A, Ai);
-        const double tap[4] = {powi(t_des, 3), powi(t_des, 2), powi(t_des, 1), 1};
-        const double tav[4] = {3 * powi(t_des, 2), 2 * powi(t_des, 1), 1, 0};
-        const double taa[4] = {6 * powi(t_des, 1), 2, 0, 0};
-        if ((j + 1 - s) * dt < td1 + dt) ry_lr = (fxr(1, bjxx) + fxr(1, bjxx - 2)) / 2;
-        for (int k = 0; k < 3; k++) {
-          double plan[4];
-          plan[0] = pm1[wo + k];
-          if (k == 0) plan[1] = (fxr(0, bjxx - 2) + fxr(0, bjxx)) / 2;
-          else if (k == 1) plan[1] = ry_lr;
-          else plan[1] = fmax(fxr(2, bjxx - 2), fxr(2, bjxx)) + ((bjx1 - 1 >= NS - 2) ? 0.0 : P.lift_height);
-          plan[2] = fxr(k, bjxx);
-          plan[3] = 0;
-          double co[4];
-          for (int r = 0; r < 4; r++) { double a_ = 0.0; for (int q = 0; q < 4; q++) a_ += Ai[4 * r + q] * plan[q]; co[r] = a_; }
-          double p_ = 0.0, v_ = 0.0, a2 = 0.0;
-          for (int q = 0; q < 4; q++) { p_ += tap[q] * co[q]; v_ += tav[q] * co[q]; a2 += taa[q] * co[q]; }
-          cur[wo + k] = p_; vel[wo + k] = v_; acc[wo + k] = a2;
-          nxt[wo + k] = cur[wo + k] + dt * vel[wo + k];
-          wrote_next[wo + k] = true;
-        }
-      }
-    }
-  } else {
-    right_support = 2;
-    cur[1] = -sw0;
-    cur[4] = sw0;
-  }
-  double* O = P.out18 + b;
-  for (int k = 0; k < 6; k++) { O[(size_t)k * B] = cur[k]; O[(size_t)(6 + k) * B] = vel[k]; O[(size_t)(12 + k) * B] = acc[k]; }
-  if (P.right_support) P.right_support[b] = right_support;
-  const double init[6] = {0, -sw0, 0, 0, sw0, 0};
-  for (int k = 0; k < 6; k++) {
-    FS(18 + k) = pm2[k]; FS(12 + k) = pm1[k]; FS(k) = cur[k];
-    FS(6 + k) = wrote_next[k] ? nxt[k] : init[k];
-    FS(24 + k) = frz[k];
-  }
-  FS(30) = frz_s; FS(31) = ry_lr;
-#undef ST
-#undef FS
-}
-
-cudaError_t foot_traj_launch(FootKParams P, cudaStream_t st) {
-  foot_traj_kernel<<<(P.B + 127) / 128, 128, 0, st>>>(P);
-  return cudaGetLastError();
 }
 
 cudaError_t step_timing_launch(StepKParams P, bool warp_mode, cudaStream_t st) {

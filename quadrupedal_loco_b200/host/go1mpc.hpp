@@ -182,7 +182,10 @@ class StepTimingMPC {
   void Initialize() {
     state.assign(GO1MPC_STEP_STATE_DOUBLES, 0.0);
     go1mpc_step_default_state(ctx_->get(), sl_, sw_, sh_, 0.7, state.data());
-    _periond_i = _k_yu = _bjxx = _bjx1 = 0;
+    foot_state.assign(GO1MPC_FOOT_STATE_DOUBLES, 0.0);
+    go1mpc_foot_default_state(ctx_->get(), foot_state.data());
+    last_out38_.assign(GO1MPC_STEP_OUT_DOUBLES, 0.0);
+    _periond_i = _k_yu = _bjxx = _bjx1 = 0; right_support = 2;
   }
   Vec<38> step_timing_opti_loop(int i, const Vec<18>& estimated_state, const Vec<3>& _Rfoot_location_feedback,
                                 const Vec<3>& _Lfoot_location_feedback, double /*lamda*/, bool /*_stopwalking*/) {
@@ -196,13 +199,27 @@ class StepTimingMPC {
     _periond_i = diag[0]; _k_yu = diag[1]; _bjxx = diag[2]; _bjx1 = diag[3];
     for (int q = 0; q < 5; q++) qp_status[q] = diag[5 + 11 * q];
     Vec<38> r;
-    for (int k = 0; k < 38; k++) r(k) = out[k];
+    for (int k = 0; k < 38; k++) { r(k) = out[k]; last_out38_[k] = out[k]; }
+    return r;
+  }
+  // NLPClass::Foot_trajectory_solve_mod2 (NLP/src/NLP/NLPClass_sqp.cpp:2039-2358): call it right after
+  // step_timing_opti_loop with the same index, as NLPRTControlClass::rt_nlp_gait does.
+  Vec<18> Foot_trajectory_solve_mod2(int j_index, bool _stopwalking) {
+    if (_stopwalking) throw std::runtime_error("Foot_trajectory_solve_mod2: the stop-walking branch is not provided");
+    double out[GO1MPC_FOOT_OUT_DOUBLES];
+    int rc = go1mpc_foot_trajectory_batch_host(ctx_->get(), 1, &j_index, state.data(), last_out38_.data(), foot_state.data(), out, &right_support);
+    if (rc != GO1MPC_OK) throw std::runtime_error(std::string("Foot_trajectory_solve_mod2: ") + go1mpc_last_error(ctx_->get()));
+    Vec<18> r;
+    for (int k = 0; k < 18; k++) r(k) = out[k];
     return r;
   }
   std::vector<double> state;          // the 202-double planner state (layout: go1mpc.h)
+  std::vector<double> foot_state;     // the 32-double swing-foot window
+  int right_support = 2;
   int _periond_i, _k_yu, _bjxx, _bjx1, qp_status[5];
  private:
   double sw_ = 0.2535, sl_ = 0.075, sh_ = 0.0;
+  std::vector<double> last_out38_;
   std::shared_ptr<Context> ctx_;
 };
 

@@ -52,12 +52,17 @@ int main() {
   StepTimingMPC nlp;
   nlp.FootStepInputs(0.2535, 0.075, 0.0); nlp.Initialize();
   Vec<18> est; Vec<3> rfb, lfb; rfb(1) = -0.12675; lfb(1) = 0.12675;
-  double o38[120 * 38];
+  double o38[120 * 38], o18[120 * 18];
+  int rs[120];
   for (int i = 1; i <= 120; i++) {
     Vec<38> o = nlp.step_timing_opti_loop(i, est, rfb, lfb, 0.0, false);
     for (int k = 0; k < 38; k++) o38[(i - 1) * 38 + k] = o(k);
+    Vec<18> f = nlp.Foot_trajectory_solve_mod2(i, false);
+    for (int k = 0; k < 18; k++) o18[(i - 1) * 18 + k] = f(k);
+    rs[i - 1] = nlp.right_support;
   }
-  arr("step_out38", o38, 120 * 38);
+  arr("step_out38", o38, 120 * 38); arr("foot_out18", o18, 120 * 18);
+  printf("\"right_support\": ["); for (int i = 0; i < 120; i++) printf("%s%d", i ? ", " : "", rs[i]); printf("],\n");
 
   // --- Kinematicclass: FK_g -> IK_g round trip, Jacobian side channel
   LegKinematics kin;

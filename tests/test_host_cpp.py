@@ -62,6 +62,9 @@ def test_host_classes_reproduce_oracle(oracle):
     ref = g["replay_out"][1:121]
     assert np.abs(got - ref).max() / max(1, np.abs(ref).max()) < 1e-9
     assert np.array_equal(got[:, 27], ref[:, 27]) and np.array_equal(got[:, 34], ref[:, 34])
+    assert list(d["right_support"]) == list(g["replay_right_support"][1:121])
+    foot = np.array(d["foot_out18"]).reshape(120, 18)
+    assert np.abs(foot[:, :6] - g["replay_foot"][1:121, :6]).max() < 2e-6     # closed loop: see test_foot_trajectory_replay...
     # kinematics
     pos, J = oracle.leg_fk(np.array([[0.1, 0.8, -1.5]]), [1], np.array([[0, 0, 0.31]]), np.array([[0.05, -0.04, 0.1]]))
     np.testing.assert_allclose(d["fk_pos"], pos[0], atol=1e-13)
