@@ -470,7 +470,11 @@ def run_b200(a):
             "kernels_ms": {"body_fast_kernel": kern_ms, "step_timing_kernel": float(np.mean(sqp_ms)),
                            "step_both_overlapped": float(np.mean(lat_ms))},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": None,
+                         "frac": achieved_tf / peak_tf if peak_tf else None,
+                         "traffic": 4855552 if (nh == 10 and B == 4096) else None,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one body_fast_kernel launch, ncu --set full, "
+                                           "profiles/r01_summary.md (4.86 MB read, 0 written: the 1.9 MB of outputs stay in L2); "
+                                           "algorithmic input 4.78 MB",
                          "kernel": "body_fast_kernel (dominant: body-inclination MPC tick)", "kernel_ms": kern_ms,
                          "flops_per_launch": fl, "flops_per_solve": fl / B,
                          "flops_def": "algorithmic flops of the dense reference algorithm along each problem's path "
