@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--streams", type=int, default=8, help="CUDA streams the device-resident leg deals its steps over")
+    ap.add_argument("--body-streams", type=int, default=2, help="of those, streams the body-MPC ticks are dealt over")
     ap.add_argument("--sweep", action="store_true", help="also print per-batch-size throughput (stderr)")
     return ap.parse_args()
 
@@ -323,8 +324,8 @@ def run_b200(a):
     # body ticks go round-robin over 2 streams (each launch is ~1.7 waves of the whole GPU: a second
     # stream fills the tail of the first), planner ticks over the remaining a.streams - 2 (each launch
     # is 128 warps for ~0.19 ms: several must be in flight to hide that latency)
-    NSTREAM = max(3, a.streams)
-    NB = 2
+    NB = max(1, a.body_streams)
+    NSTREAM = max(NB + 1, a.streams)
     lanes = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NSTREAM - 1)]
     lane_ptr = [None] + [x.cuda_stream for x in lanes[1:]]
     joins = [torch.cuda.Event() for _ in range(NSTREAM)]

@@ -194,6 +194,12 @@ int go1mpc_body_diag_stride(int nh);
 int go1mpc_body_mpc_step_batch(go1mpc_t *h, int nh, int B,
                                const double *in_d, double *out_d, int *diag_d,
                                void *stream);
+/* Diagnostic: number of instances the roll/pitch-split kernel handed to the combined-solve kernel
+ * (infeasible / degenerate / non-converged halves) since the handle was created.  Synchronises the device. */
+int go1mpc_body_handover_total(go1mpc_t *h, long long *total);
+/* Diagnostic: warps of the body solve kernel that left through its defensive iteration guard (0 unless
+ * there is a bug).  Synchronises the device. */
+int go1mpc_body_guard_trips(go1mpc_t *h, long long *total);
 int go1mpc_body_mpc_step_batch_host(go1mpc_t *h, int nh, int B,
                                     const double *in, double *out, int *diag);
 /* Pipelined host entries: enqueue H2D copy, kernel and D2H copy on one of the handle's eight

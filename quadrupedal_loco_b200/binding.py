@@ -16,7 +16,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_stream", "go1mpc_sm_count", "go1mpc_copy_device_async",
     "go1mpc_qp_solve_batch", "go1mpc_qp_solve_batch_host",
     "go1mpc_body_in_stride", "go1mpc_body_out_stride", "go1mpc_body_diag_stride",
-    "go1mpc_body_mpc_step_batch", "go1mpc_body_mpc_step_batch_host",
+    "go1mpc_body_mpc_step_batch", "go1mpc_body_mpc_step_batch_host", "go1mpc_body_handover_total", "go1mpc_body_guard_trips",
     "go1mpc_body_model", "go1mpc_body_default_tx", "go1mpc_measure_dfma_peak",
     "go1mpc_step_timing_step_batch", "go1mpc_step_timing_step_batch_host", "go1mpc_step_default_state",
     "go1mpc_body_mpc_step_batch_host_async", "go1mpc_step_timing_step_batch_host_async",
@@ -99,6 +99,8 @@ def load_library():
     lib.go1mpc_body_mpc_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     lib.go1mpc_body_mpc_step_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     lib.go1mpc_body_model.argtypes = [vp, ctypes.c_int] + [vp] * 6
+    lib.go1mpc_body_handover_total.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
+    lib.go1mpc_body_guard_trips.argtypes = [vp, ctypes.POINTER(ctypes.c_longlong)]
     lib.go1mpc_body_default_tx.argtypes = [vp, vp]
     lib.go1mpc_measure_dfma_peak.argtypes = [vp, ctypes.c_int, c_double_p]
     lib.go1mpc_step_timing_step_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp]
@@ -237,6 +239,17 @@ class Go1Mpc:
         """Host-buffer entry: H2D, launch, D2H and a stream sync inside the call."""
         self._check(self.lib.go1mpc_body_mpc_step_batch_host(self.h, nh, B, _ptr(in_h), _ptr(out_h), _ptr(diag_h)),
                     "body_mpc_step_batch_host")
+
+    def body_handover_total(self):
+        """Instances the roll/pitch-split kernel handed to the combined-solve kernel so far (synchronises)."""
+        t = ctypes.c_longlong(0)
+        self._check(self.lib.go1mpc_body_handover_total(self.h, ctypes.byref(t)), "body_handover_total")
+        return int(t.value)
+
+    def body_guard_trips(self):
+        t = ctypes.c_longlong(0)
+        self._check(self.lib.go1mpc_body_guard_trips(self.h, ctypes.byref(t)), "body_guard_trips")
+        return int(t.value)
 
     def body_mpc_step_host_async(self, nh, B, in_h, out_h, diag_h=None):
         """Pipelined: returns after enqueueing H2D + kernel + D2H; call synchronize() before reading out_h."""

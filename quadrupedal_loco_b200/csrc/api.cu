@@ -22,6 +22,7 @@ struct BodyModel {
   int nh = 0, tab_doubles = 0;
   std::vector<double> pps, pvs, ppu, pvu, ppu2, pvu2;   // host copies (column-major)
   double* tab_d = nullptr;
+  std::vector<double> tab_h;       // host copy of the device table (kernels that take it as a launch parameter)
   int nstepx = 0, nsum_mpc = 0, gate = 0;
   double tx0[GO1MPC_FOOTSTEPS];
 };
@@ -56,6 +57,14 @@ struct go1mpc {
   std::map<const void*, cudaEvent_t> last_writer;
   int* sched_d = nullptr;          // ring of {next, done} counter pairs for body_fast launches
   unsigned sched_next = 0;
+  int* flist_d = nullptr;          // ring of hand-over lists of body_split launches: {count, ids[kFlistCap]} each
+  unsigned flist_next = 0;
+  int body_mode = 2;               // GO1MPC_BODY_MODE: 0 "fast" combined kernel only, 1 "split" halves side by side in
+                                   // one warp, 2 "tri" (default) setup / 4-lanes-per-half solve / merge launches
+  // body_tri workspace, one per stream the entry point is called with (calls on one stream are ordered, so the
+  // buffers are free again when the next call's first kernel starts); grown on demand
+  struct TriWs { char* p = nullptr; int capB = 0; size_t off[5] = {0, 0, 0, 0, 0}; size_t qctl_off = 0; };
+  std::map<cudaStream_t, TriWs> tri_ws;
   bool force_generic = false;      // GO1MPC_FORCE_GENERIC=1: always use the run-time-sized kernel
   int step_mode = 0;               // 0 auto, 1 thread per planner, 2 warp per planner (GO1MPC_STEP_MODE)
   int step_warp_below = 1024;      // auto: warp per planner below this batch size (measured: 82 vs 124 us at B = 256,
@@ -63,6 +72,7 @@ struct go1mpc {
                                    // replicated per warp, so it only pays while the GPU is mostly empty)
 };
 static const int kSchedRing = 64;
+static const int kFlistCap = 8190;   // ints per hand-over list; beyond it the combined kernel redoes the whole batch
 
 namespace {
 
@@ -162,6 +172,7 @@ int build_body_model(go1mpc* h, int nh, BodyModel& M) {
   mm(s2, M.pps.data(), m2, nh, nh, 2);          // (beta  Ppu') Pps
   memcpy(pps, M.pps.data(), sizeof(double) * 2 * nh);
 
+  M.tab_h = tab;
   CU(h, cudaMalloc(&M.tab_d, sizeof(double) * td));
   CU(h, cudaMemcpyAsync(M.tab_d, tab.data(), sizeof(double) * td, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
@@ -251,6 +262,14 @@ int go1mpc_create(const Go1MpcConfig* cfg, int device, go1mpc_t** out) {
   }
   for (auto& L : h->lanes)
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { go1mpc_destroy(h); return GO1MPC_E_CUDA; }
+  if (cudaMalloc(&h->flist_d, sizeof(int) * (size_t)(kFlistCap + 2) * kSchedRing) != cudaSuccess ||
+      cudaMemset(h->flist_d, 0, sizeof(int) * (size_t)(kFlistCap + 2) * kSchedRing) != cudaSuccess) {
+    go1mpc_destroy(h);
+    return GO1MPC_E_CUDA;
+  }
+  const char* bm = getenv("GO1MPC_BODY_MODE");
+  if (bm && !strcmp(bm, "fast")) h->body_mode = 0;
+  else if (bm && !strcmp(bm, "split")) h->body_mode = 1;
   const char* fg = getenv("GO1MPC_FORCE_GENERIC");
   h->force_generic = fg && fg[0] == '1';
   const char* sm = getenv("GO1MPC_STEP_MODE");
@@ -266,6 +285,8 @@ void go1mpc_destroy(go1mpc_t* h) {
   for (auto& kv : h->body_models) if (kv.second.tab_d) cudaFree(kv.second.tab_d);
   for (DevBuf& b : h->stage) if (b.p) cudaFree(b.p);
   if (h->sched_d) cudaFree(h->sched_d);
+  if (h->flist_d) cudaFree(h->flist_d);
+  for (auto& kv : h->tri_ws) if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->last_writer) cudaEventDestroy(kv.second);
   for (auto& L : h->lanes) {
     for (DevBuf& b : L.stage) if (b.p) cudaFree(b.p);
@@ -387,9 +408,39 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
     P.cap_scale = h->cfg.qp_iter_cap_scale; P.gate = M->gate; P.nstepx = M->nstepx; P.nsum_mpc = M->nsum_mpc;
     P.in = in_d; P.out = out_d; P.diag = diag_d; P.tab = M->tab_d;
     P.sched = h->sched_d + 2 * (h->sched_next++ % kSchedRing);
+    P.flist = nullptr; P.flist_count = nullptr; P.flist_cap = 0;
     P.dt_mpc = c.dt_mpc; P.j_ini = c.j_ini; P.mass = c.mass; P.g = c.g; P.gama = c.gama_zmp;
     P.theta_lim = c.theta_lim; P.torque_lim = c.torque_lim;
     for (int k = 0; k < 4; k++) P.lamda[k] = c.lamda[k];
+    if (body_tri_supported(nh) && h->body_mode == 2) {
+      go1mpc::TriWs& W = h->tri_ws[st];
+      if (W.capB < B) {
+        if (W.p) { CU(h, cudaStreamSynchronize(st)); cudaFree(W.p); W.p = nullptr; W.capB = 0; }
+        const size_t bytes = body_tri_workspace_bytes(nh, B, W.off);
+        W.qctl_off = bytes;
+        CU(h, cudaMalloc((void**)&W.p, bytes + 16));
+        CU(h, cudaMemsetAsync(W.p + W.qctl_off, 0, 16, st));
+        W.capB = B;
+      }
+      P.tri_jb = (double*)(W.p + W.off[0]); P.tri_hs = (double*)(W.p + W.off[1]); P.tri_res = (double*)(W.p + W.off[2]);
+      P.tri_queue = (int*)(W.p + W.off[3]); P.tri_qctl = (int*)(W.p + W.qctl_off); P.tri_meta = (int*)(W.p + W.off[4]);
+      int* fl = h->flist_d + (size_t)(kFlistCap + 2) * (h->flist_next++ % kSchedRing);
+      P.flist_count = fl; P.flist = fl + 2; P.flist_cap = kFlistCap;
+      CU(h, body_tri_launch(P, M->tab_h.data(), h->sms, st));
+      CU(h, body_fast_launch(P, h->sms, st));   // list mode: what the merge kernel handed over (normally nothing)
+      h->launches += 4;
+      return GO1MPC_OK;
+    }
+    if (body_split_supported(nh) && h->body_mode == 1) {
+      // halves side by side; what it cannot reproduce goes through the combined kernel right behind it
+      int* fl = h->flist_d + (size_t)(kFlistCap + 2) * (h->flist_next++ % kSchedRing);
+      P.flist_count = fl; P.flist = fl + 2; P.flist_cap = kFlistCap;
+      CU(h, body_split_launch(P, h->sms, st));
+      P.sched = h->sched_d + 2 * (h->sched_next++ % kSchedRing);
+      CU(h, body_fast_launch(P, h->sms, st));
+      h->launches += 2;
+      return GO1MPC_OK;
+    }
     CU(h, body_fast_launch(P, h->sms, st));
     h->launches++;
     return GO1MPC_OK;
@@ -409,11 +460,44 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
   P.tab_doubles = M->tab_doubles; P.warp_doubles = wd;
   P.cap_scale = h->cfg.qp_iter_cap_scale; P.gate = M->gate; P.nstepx = M->nstepx; P.nsum_mpc = M->nsum_mpc;
   P.in = in_d; P.out = out_d; P.diag = diag_d; P.tab = M->tab_d; P.sched = nullptr;
+  P.flist = nullptr; P.flist_count = nullptr; P.flist_cap = 0;
   P.dt_mpc = c.dt_mpc; P.j_ini = c.j_ini; P.mass = c.mass; P.g = c.g; P.gama = c.gama_zmp;
   P.theta_lim = c.theta_lim; P.torque_lim = c.torque_lim;
   for (int k = 0; k < 4; k++) P.lamda[k] = c.lamda[k];
   CU(h, body_mpc_launch(P, wpc, grid, smem, st));
   h->launches++;
+  return GO1MPC_OK;
+}
+
+// instances the split kernel handed to the combined kernel since the handle was created (synchronises)
+int go1mpc_body_handover_total(go1mpc_t* h, long long* total) {
+  if (!h || !total) return GO1MPC_E_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaDeviceSynchronize());
+  long long t = 0;
+  for (int k = 0; k < kSchedRing; k++) {
+    int v = 0;
+    CU(h, cudaMemcpy(&v, h->flist_d + (size_t)(kFlistCap + 2) * k + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    t += v;
+  }
+  *total = t;
+  return GO1MPC_OK;
+}
+
+// health counter of the three-launch body path: warps of the solve kernel that left through the defensive
+// iteration guard (always 0 unless there is a bug); synchronises
+int go1mpc_body_guard_trips(go1mpc_t* h, long long* total) {
+  if (!h || !total) return GO1MPC_E_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaDeviceSynchronize());
+  long long t = 0;
+  for (auto& kv : h->tri_ws) {
+    if (!kv.second.p) continue;
+    int v = 0;
+    CU(h, cudaMemcpy(&v, kv.second.p + kv.second.qctl_off + 8, sizeof(int), cudaMemcpyDeviceToHost));
+    t += v;
+  }
+  *total = t;
   return GO1MPC_OK;
 }
 

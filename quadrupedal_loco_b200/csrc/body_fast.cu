@@ -114,9 +114,20 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
   const double j_ini = P.j_ini, tq = P.torque_lim / P.j_ini;
   const double inf = CUDART_INF;
 
+  // list mode: the instances body_split_kernel handed over (all of them if its list overflowed)
+  int nB = P.B;
+  bool listed = false;
+  if (P.flist) {
+    const int cnt = *reinterpret_cast<volatile const int*>(P.flist_count);
+    if (cnt <= P.flist_cap) { nB = cnt; listed = true; }
+  }
+
   for (;;) {
     int b = 0;
-    if (lane == 0) b = atomicAdd(P.sched, 1);
+    if (lane == 0) {
+      b = atomicAdd(P.sched, 1);
+      if (listed && b < nB) b = P.flist[b]; else if (listed) b = 0x7fffffff;
+    }
     b = __shfl_sync(FULL_MASK, b, 0);
     if (b >= P.B) break;
 
@@ -632,7 +643,11 @@ __global__ void __launch_bounds__(WPC * 32, (NH <= 10 ? GO1_FAST_WARPS : 12) / W
     tma_store_wait_all();
     // last warp out resets the instance counter for the next launch
     const int done = atomicAdd(P.sched + 1, 1);
-    if (done == (int)(gridDim.x * WPC) - 1) { P.sched[0] = 0; P.sched[1] = 0; __threadfence(); }
+    if (done == (int)(gridDim.x * WPC) - 1) {
+      P.sched[0] = 0; P.sched[1] = 0;
+      if (P.flist) { P.flist_count[1] += P.flist_count[0]; P.flist_count[0] = 0; }   // [1]: running total, read by go1mpc_body_handover_total
+      __threadfence();
+    }
   }
 }
 
@@ -658,6 +673,7 @@ static cudaError_t fast_launch_nh(const BodyKParams& P, int sms, cudaStream_t st
   }
   int grid = (P.B + WPC - 1) / WPC;
   if (grid > sms * occ_cache) grid = sms * occ_cache;
+  if (P.flist && grid > sms) grid = sms;     // list mode: the list is short (normally empty)
   if (grid_out) *grid_out = grid;
   body_fast_kernel<NH, WPC><<<grid, WPC * 32, smem, st>>>(P);
   return cudaGetLastError();

@@ -14,7 +14,17 @@ struct BodyKParams {
   double* out;
   int* diag;
   const double* tab;
-  int* sched;          // body_fast only: {next instance, warps finished}, zero between launches
+  int* sched;          // body_fast / body_split: {next instance, warps finished}, zero between launches
+  // body_split appends the instances it hands to the combined kernel to flist (count in *flist_count);
+  // body_fast with flist != null runs in list mode: it processes flist[0 .. *flist_count) -- or all B
+  // instances when the count exceeded flist_cap -- and zeroes the count when its last warp leaves
+  int* flist;
+  int* flist_count;
+  int flist_cap;
+  // body_tri workspace (per stream): J per instance, state / result records per half, queue of active halves
+  double *tri_jb, *tri_hs, *tri_res;
+  int *tri_queue, *tri_qctl;      // qctl: {queued, fetched, guard trips}
+  int* tri_meta;                  // per instance: 1 = finished by the setup kernel
   double dt_mpc, j_ini, mass, g, gama, theta_lim, torque_lim;
   double lamda[4];
 };
@@ -24,6 +34,13 @@ cudaError_t body_mpc_occupancy(int wpc, size_t smem, int* blocks_per_sm);
 // compile-time-horizon kernel (body_fast.cu); in/out strides and the table size must be the ABI's
 bool body_fast_supported(int nh);
 cudaError_t body_fast_launch(BodyKParams P, int sms, cudaStream_t st);
+// roll / pitch halves side by side (body_split.cu); instances it cannot reproduce go to flist
+// three launches, register-resident solver state (body_tri.cu)
+bool body_tri_supported(int nh);
+size_t body_tri_workspace_bytes(int nh, int B, size_t off[5]);   // offsets: J | half state | half result | queue | meta
+cudaError_t body_tri_launch(BodyKParams P, const double* tab_host, int sms, cudaStream_t st);
+bool body_split_supported(int nh);
+cudaError_t body_split_launch(BodyKParams P, int sms, cudaStream_t st);
 
 struct DenseKParams {
   int n, p, m, B, cap;
