@@ -63,7 +63,7 @@ struct go1mpc {
                                    // one warp, 2 "tri" (default) setup / 4-lanes-per-half solve / merge launches
   // body_tri workspace, one per stream the entry point is called with (calls on one stream are ordered, so the
   // buffers are free again when the next call's first kernel starts); grown on demand
-  struct TriWs { char* p = nullptr; int capB = 0; size_t off[5] = {0, 0, 0, 0, 0}; size_t qctl_off = 0; };
+  struct TriWs { char* p = nullptr; int capB = 0; size_t off[6] = {0, 0, 0, 0, 0, 0}; size_t qctl_off = 0; };
   std::map<cudaStream_t, TriWs> tri_ws;
   bool force_generic = false;      // GO1MPC_FORCE_GENERIC=1: always use the run-time-sized kernel
   int step_mode = 0;               // 0 auto, 1 thread per planner, 2 warp per planner (GO1MPC_STEP_MODE)
@@ -423,7 +423,7 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
         W.capB = B;
       }
       P.tri_jb = (double*)(W.p + W.off[0]); P.tri_hs = (double*)(W.p + W.off[1]); P.tri_res = (double*)(W.p + W.off[2]);
-      P.tri_queue = (int*)(W.p + W.off[3]); P.tri_qctl = (int*)(W.p + W.qctl_off); P.tri_meta = (int*)(W.p + W.off[4]);
+      P.tri_queue = (int*)(W.p + W.off[3]); P.tri_qctl = (int*)(W.p + W.qctl_off); P.tri_meta = (int*)(W.p + W.off[4]); P.tri_fr = (double*)(W.p + W.off[5]);
       int* fl = h->flist_d + (size_t)(kFlistCap + 2) * (h->flist_next++ % kSchedRing);
       P.flist_count = fl; P.flist = fl + 2; P.flist_cap = kFlistCap;
       CU(h, body_tri_launch(P, M->tab_h.data(), h->sms, st));

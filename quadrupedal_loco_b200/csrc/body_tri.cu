@@ -44,6 +44,8 @@ struct TriDims {
   static constexpr int TAB = (3 * NH * NH + 6 * NH + 1) & ~1;
   static constexpr int JB = NH * NH;                          // per instance: J row-major (entries c >= i valid)
   static constexpr int HS = (2 * NH + 2 + 1) & ~1;            // per half: x0 | pk | tol | f0
+  static constexpr int FR = 24;                               // per instance, setup -> merge: theta 4 | measured 4 | zmp x 3 | zmp y 3 |
+                                                              // com acc z 3 | i | bjx1 | bjx2 | tol | pad
   static constexpr int OMAX = 16, PMAX = 24;
   static constexpr int RES_D = NH + 4 + OMAX;                 // x | f psi_end R_norm dq_min | ssv
   static constexpr int RES_I = 4 + OMAX + PMAX;               // nout npass end_tol flag | ipv | plog
@@ -64,7 +66,7 @@ __device__ __forceinline__ int tri_index(const double* tx, double t) {
 }
 
 template <int NH>
-__device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const double* rec, int i, const double* xr, const double* xp,
+__device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const double* fr, const double* xr, const double* xp,
                                            double f_value, int iqc, int it_outer, int it_add, int it_drop, int it_l2a,
                                            unsigned flops, const int* Ac);
 template <int NH>
@@ -121,7 +123,19 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
   if (b < P.B && !live) { tri_gated<NH>(P, b, rec); P.tri_meta[b] = 1; }
   if (live) {
     const double* refs = rec + 36 + N;
-    const int bjx1 = tri_index(rec, (i + 1) * dt);
+    const int bjx1 = tri_index(rec, (i + 1) * dt), bjx2 = tri_index(rec, (i + NH) * dt);
+    double* xpark = const_cast<double*>(rec) + 36;      // 2 NH doubles of shared memory owned by this thread
+    double* fr = const_cast<double*>(rec);              // the step table is consumed: its slots carry the hand-over record
+    {
+      double t8[8];
+#pragma unroll
+      for (int k = 0; k < 8; k++) t8[k] = rec[28 + k];
+#pragma unroll
+      for (int k = 0; k < 8; k++) fr[k] = t8[k];
+#pragma unroll
+      for (int k = 0; k < 3; k++) { fr[8 + k] = refs[k]; fr[11 + k] = refs[NH + k]; fr[14 + k] = refs[8 * NH + k]; }
+      fr[17] = (double)i; fr[18] = (double)bjx1; fr[19] = (double)bjx2;
+    }
     const int t_yu = (i + 1) % P.nstepx;
     const bool left = (bjx1 < 2) || (bjx1 % 2 == 0);
     const bool sw = (bjx1 >= 2) && !((t_yu + NH - 1) < P.nstepx);
@@ -163,13 +177,13 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
 
     // ---- J = L^-T, column by column, straight to the instance's J buffer (row-major, entries c >= i) ----
     double* jb = P.tri_jb + (size_t)b * D::JB;
-    jb[NH] = tol;                              // entry (1,0) is never read as J: carries tol to the merge kernel
+    fr[20] = tol;
 #pragma unroll
     for (int c = 0; c < NH; c++) {
       double y[NH];
 #pragma unroll
       for (int ii = NH - 1; ii >= 0; ii--) {
-        if (ii > c) { y[ii] = 0.0; if (!(ii == 1 && c == 0)) jb[ii * NH + c] = 0.0; continue; }   // (1,0) carries tol
+        if (ii > c) { y[ii] = 0.0; jb[ii * NH + c] = 0.0; continue; }
         double t = 0.0;
 #pragma unroll
         for (int k = ii + 1; k <= c; k++) t = fma(L[k][ii], y[k], t);
@@ -181,7 +195,7 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
     // ---- both halves: gradient (cpp:427-526), x0 = -H^-1 g0 by two triangular solves, first slack scan ----
 #pragma unroll 1
     for (int h = 0; h < 2; h++) {
-      const double my0 = rec[28 + 2 * h], my1 = rec[29 + 2 * h];
+      const double my0 = fr[2 * h], my1 = fr[1 + 2 * h];
       const double* bref = refs + (2 + h) * NH;
       double w[NH], pk[NH];
       double f0 = 0.0;
@@ -220,6 +234,7 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
 #pragma unroll
       for (int k = 0; k < NH; k++) {
         w[k] = -w[k];                      // x0
+        xpark[h * NH + k] = w[k];
         nan = nan || (w[k] != w[k]);
         f0 = fma(g0[k], w[k], f0);
       }
@@ -259,14 +274,18 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
         // SUM of both exceeds the tolerance is not reproducible here)
         const bool unsure = fabs(psi0 + psi) > tol && ((tol0 && psi0 != 0.0) || (!over && psi != 0.0));
         if (!unsure) {
-          const double* r0 = P.tri_res + (size_t)(2 * b) * D::RES;     // own stores of this thread
-          tri_finish<NH>(P, b, rec, i, r0, r0 + D::RES, f00 + f0, 0, 1, 0, 0, 0,
+          tri_finish<NH>(P, b, fr, xpark, xpark + NH, f00 + f0, 0, 1, 0, 0, 0,
                          (unsigned)gi_flops_setup(N, 0) + 2u * N * M, nullptr);
           done = true;
         }
       }
     }
     P.tri_meta[b] = done ? 1 : 0;
+    if (!done) {
+      double* frg = P.tri_fr + (size_t)b * D::FR;
+#pragma unroll
+      for (int k = 0; k < 21; k++) frg[k] = fr[k];
+    }
   }
   // ---- queue the active halves (warp-aggregated) ----
   const unsigned m0 = __ballot_sync(FULL_MASK, act0), m1b = __ballot_sync(FULL_MASK, act1);
@@ -379,7 +398,6 @@ __global__ void __launch_bounds__(WPC * 32, GO1_TRI_WARPS / WPC) tri_solve_kerne
             x[m] = valid[m] ? hs[row[m]] : 0.0;
             pk[m] = hs[NH + row[m]];
           }
-          if (gl == 1) Jr[0][0] = 0.0;          // entry (1,0) of the buffer carries tol, not J
           tol = hs[2 * NH]; f_value = hs[2 * NH + 1];
           res = P.tri_res + (size_t)cur * D::RES;
           resi = res_ints(res, D::RES_D);
@@ -416,17 +434,20 @@ __global__ void __launch_bounds__(WPC * 32, GO1_TRI_WARPS / WPC) tri_solve_kerne
         const unsigned bits = valid[m] ? (inA >> (4 * m)) : 0xfu;
         sl[m][0] = (thmax - pk[m]) - v; sl[m][1] = v + (thmax + pk[m]);
         sl[m][2] = fma(-j_ini, x[m], tq); sl[m][3] = fma(j_ini, x[m], tq);
-        double p4 = (fmin(0.0, sl[m][0]) + fmin(0.0, sl[m][1])) + (fmin(0.0, sl[m][2]) + fmin(0.0, sl[m][3]));
+        // min(0, s) as a select: fmin() carries IEEE NaN handling that costs 8 instructions a piece (NaN in x is
+        // screened by the merge kernel); up and low slack of one angle cannot both be negative, nor both torque slacks
+        const double pa = sl[m][0] < sl[m][1] ? sl[m][0] : sl[m][1], pt = sl[m][2] < sl[m][3] ? sl[m][2] : sl[m][3];
+        const double p4 = (pa < 0.0 ? pa : 0.0) + (pt < 0.0 ? pt : 0.0);
         psi += valid[m] ? p4 : 0.0;
 #pragma unroll
         for (int s4 = 0; s4 < 4; s4++) {
           if (bits & (1u << s4)) sl[m][s4] = inf;          // in the working set (or a padding row): not eligible
-          bv = fmin(bv, sl[m][s4]);
+          bv = sl[m][s4] < bv ? sl[m][s4] : bv;
         }
       }
       psi = q4sum(psi);
-      bv = fmin(bv, __shfl_xor_sync(FULL_MASK, bv, 2));
-      bv = fmin(bv, __shfl_xor_sync(FULL_MASK, bv, 1));
+      { const double o2 = __shfl_xor_sync(FULL_MASK, bv, 2); bv = o2 < bv ? o2 : bv; }
+      { const double o1 = __shfl_xor_sync(FULL_MASK, bv, 1); bv = o1 < bv ? o1 : bv; }
       int bi = 0x7fffffff;
 #pragma unroll
       for (int m = RW - 1; m >= 0; m--) {
@@ -490,8 +511,9 @@ __global__ void __launch_bounds__(WPC * 32, GO1_TRI_WARPS / WPC) tri_solve_kerne
 #pragma unroll
       for (int m = 0; m < RW; m++) z[m] = fma(Jr[m][j], dj, z[m]);
       dd = fma(dj, dj, dd);
-      if (j == iq) diq = d[j];
+      xs[j] = d[j];                                        // every lane of the group stores the same value
     }
+    diq = xs[iq];                                          // slot NH exists (V > NH): iq = NH reads a stale, unused value
     double zz = 0.0, zn = 0.0;
 #pragma unroll
     for (int m = 0; m < RW; m++) { zz = fma(z[m], z[m], zz); zn = fma(z[m], np_[m], zn); }
@@ -674,7 +696,7 @@ __global__ void __launch_bounds__(WPC * 32, GO1_TRI_WARPS / WPC) tri_solve_kerne
 // kernel: first-control clamp (cpp:567-625), roll-out (cpp:629-655), output record, diagnostics.
 // xr / xp: the NH accelerations of the roll / pitch half.
 template <int NH>
-__device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const double* rec, int i, const double* xr, const double* xp,
+__device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const double* fr, const double* xr, const double* xp,
                                            double f_value, int iqc, int it_outer, int it_add, int it_drop, int it_l2a,
                                            unsigned flops, const int* Ac) {
   using D = TriDims<NH>;
@@ -683,8 +705,7 @@ __device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const do
   const double dt = P.dt_mpc, b0 = dt * dt / 2, b1 = dt;
   const double thmax = P.theta_lim, thmin = -P.theta_lim;
   const double j_ini = P.j_ini;
-  const double thx0 = rec[28], thx1 = rec[29], thy0 = rec[30], thy1 = rec[31];
-  const double* refs = rec + 36 + N;
+  const double thx0 = fr[0], thx1 = fr[1], thy0 = fr[2], thy1 = fr[3];
   double xa[3], ya[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) { xa[k] = xr[k]; ya[k] = xp[k]; }
@@ -702,7 +723,7 @@ __device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const do
     const double a0 = ax ? ya[0] : xa[0], a1 = ax ? ya[1] : xa[1], a2 = ax ? ya[2] : xa[2];
     const double p0 = ax ? thy0 : thx0, v0 = ax ? thy1 : thx1;
     const double lam_p = P.lamda[2 * ax], lam_v = P.lamda[2 * ax + 1];
-    const double bs_p = rec[32 + 2 * ax], bs_v = rec[33 + 2 * ax];
+    const double bs_p = fr[4 + 2 * ax], bs_v = fr[5 + 2 * ax];
     double pkk = (p0 + dt * v0) + b0 * a0, vk = v0 + b1 * a0;
     outg[14 + 2 * ax] = lam_p * bs_p + (1 - lam_p) * pkk;
     outg[15 + 2 * ax] = lam_v * bs_v + (1 - lam_v) * vk;
@@ -716,10 +737,10 @@ __device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const do
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     // cpp:651-652 ZMP consistent with the planned angular acceleration (steps 0..2)
-    const double den = P.mass * (P.g + refs[8 * NH + k]);
+    const double den = P.mass * (P.g + fr[14 + k]);
     const int o = (k == 0) ? 4 : (k == 1 ? 8 : 12);
-    outg[o] = refs[k] - j_ini * ya[k] / den;
-    outg[o + 1] = refs[NH + k] + j_ini * xa[k] / den;
+    outg[o] = fr[8 + k] - j_ini * ya[k] / den;
+    outg[o + 1] = fr[11 + k] + j_ini * xa[k] / den;
   }
   outg[18] = xa[0]; outg[18 + NH] = ya[0];
 #pragma unroll
@@ -730,7 +751,7 @@ __device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const do
     int* dg = P.diag + (size_t)b * P.diag_stride;
     dg[0] = ST_OK; dg[1] = iqc;
     dg[2] = it_outer; dg[3] = it_add; dg[4] = it_drop; dg[5] = 0;
-    dg[6] = tri_index(rec, (i + 1) * dt); dg[7] = tri_index(rec, (i + NH) * dt); dg[8] = it_l2a; dg[9] = (int)flops;
+    dg[6] = (int)fr[18]; dg[7] = (int)fr[19]; dg[8] = it_l2a; dg[9] = (int)flops;
     for (int k = 0; k < N; k++) dg[10 + k] = (k < iqc) ? Ac[k] : -1;
   }
 }
@@ -759,33 +780,37 @@ constexpr int TRI_MERGE_THREADS = 64;
 template <int NH>
 __global__ void __launch_bounds__(TRI_MERGE_THREADS) tri_merge_kernel(BodyKParams P) {
   using D = TriDims<NH>;
-  constexpr int N = D::N, M = D::M, RSTR = D::RES + 1;     // odd stride: conflict-free per-thread records
+  constexpr int N = D::N, M = D::M, RSTR = D::RES + 2;     // 432-byte rows: 16-byte aligned for TMA, 12 banks apart
+  constexpr int FSTR = D::FR + 2;
+  static_assert((D::RES * sizeof(double)) % 16 == 0 && (D::FR * sizeof(double)) % 16 == 0, "records move as TMA bulk copies");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sres = reinterpret_cast<double*>(smem_raw);
+  double* sres = reinterpret_cast<double*>(smem_raw);      // roll records [thread], pitch records [thread], hand-over records
+  double* sfr = sres + (size_t)2 * TRI_MERGE_THREADS * RSTR;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sfr + (size_t)TRI_MERGE_THREADS * FSTR);
   const int tid = threadIdx.x;
   const int b0 = blockIdx.x * TRI_MERGE_THREADS;
   const int b = b0 + tid;
   if (b == 0) { P.tri_qctl[0] = 0; P.tri_qctl[1] = 0; }    // queue counters for the next call on this stream
   const bool mine = b < P.B && P.tri_meta[b < P.B ? b : 0] == 0;   // 1: finished by the setup kernel
-  if (!__syncthreads_or(mine)) return;
-  // stage the result records of this block's halves: coalesced copy, then every thread reads its own pair
-  {
-    const int nrec = 2 * min(TRI_MERGE_THREADS, P.B - b0);
-    const double* src = P.tri_res + (size_t)2 * b0 * D::RES;
-    for (int e = tid; e < nrec * D::RES; e += TRI_MERGE_THREADS) {
-      const int rr = e / D::RES, cc = e - rr * D::RES;
-      sres[rr * RSTR + cc] = src[e];
-    }
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  const int nmine = __syncthreads_count(mine);
+  if (nmine == 0) return;
+  // every thread fetches its own records (2 x 416 + 192 bytes) with TMA onto one mbarrier: no other global load
+  if (tid == 0) mbar_expect_tx(bar, (uint32_t)(nmine * (2 * D::RES + D::FR) * sizeof(double)));
+  if (mine) {
+    const double* src = P.tri_res + (size_t)2 * b * D::RES;
+    tma_load_1d(sres + (size_t)tid * RSTR, src, (uint32_t)(D::RES * sizeof(double)), bar);
+    tma_load_1d(sres + (size_t)(TRI_MERGE_THREADS + tid) * RSTR, src + D::RES, (uint32_t)(D::RES * sizeof(double)), bar);
+    tma_load_1d(sfr + (size_t)tid * FSTR, P.tri_fr + (size_t)b * D::FR, (uint32_t)(D::FR * sizeof(double)), bar);
   }
-  __syncthreads();
   if (!mine) return;
-  const double* rec = P.in + (size_t)b * D::IN;
-  int i = (int)rec[27] - P.gate;
-  const double* rx = sres + (size_t)(2 * tid) * RSTR;
-  const double* ry = rx + RSTR;
-  const int* ix = reinterpret_cast<const int*>(rx + D::RES_D);     // RSTR odd: int view of ry starts at an odd int offset,
-  const int* iy = reinterpret_cast<const int*>(ry + D::RES_D);     // still 4-byte aligned
-  const double tol = P.tri_jb[(size_t)b * D::JB + NH];   // left by the setup kernel in J's unused (1,0) slot
+  mbar_wait(bar, 0);
+  const double* fr = sfr + (size_t)tid * FSTR;
+  const double* rx = sres + (size_t)tid * RSTR;
+  const double* ry = sres + (size_t)(TRI_MERGE_THREADS + tid) * RSTR;
+  const int* ix = reinterpret_cast<const int*>(rx + D::RES_D);
+  const int* iy = reinterpret_cast<const int*>(ry + D::RES_D);
+  const double tol = fr[20];
   bool flag = ix[3] || iy[3];
   const double psi_x = rx[NH + 1], psi_y = ry[NH + 1];
   if (fabs(psi_x + psi_y) > tol && ((ix[2] && psi_x != 0.0) || (iy[2] && psi_y != 0.0))) flag = true;
@@ -837,11 +862,11 @@ __global__ void __launch_bounds__(TRI_MERGE_THREADS) tri_merge_kernel(BodyKParam
     if (slot < P.flist_cap) P.flist[slot] = b;
     return;
   }
-  tri_finish<NH>(P, b, rec, i, rx, ry, rx[NH] + ry[NH], iqc, it_outer, it_add, it_drop, it_l2a, flops, Ac);
+  tri_finish<NH>(P, b, fr, rx, ry, rx[NH] + ry[NH], iqc, it_outer, it_add, it_drop, it_l2a, flops, Ac);
 }
 
 // ======================================================================================= host side
-size_t body_tri_workspace_bytes(int nh, int B, size_t off[5]) {
+size_t body_tri_workspace_bytes(int nh, int B, size_t off[6]) {
   if (nh != 10) return 0;
   using D = TriDims<10>;
   size_t o = 0;
@@ -850,6 +875,7 @@ size_t body_tri_workspace_bytes(int nh, int B, size_t off[5]) {
   off[2] = o; o += (size_t)2 * B * D::RES * sizeof(double);
   off[3] = o; o += ((size_t)2 * B * sizeof(int) + 15) & ~(size_t)15;
   off[4] = o; o += ((size_t)B * sizeof(int) + 15) & ~(size_t)15;
+  off[5] = o; o += (size_t)B * D::FR * sizeof(double);
   return o;
 }
 
@@ -888,7 +914,7 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
   tri_solve_kernel<NH, WPC><<<grid, WPC * 32, smem, st>>>(P);
   if (stages < 3) return cudaGetLastError();
   {
-    const size_t msmem = (size_t)2 * TRI_MERGE_THREADS * (D::RES + 1) * sizeof(double);
+    const size_t msmem = (size_t)TRI_MERGE_THREADS * (2 * (D::RES + 2) + D::FR + 2) * sizeof(double) + 16;
     static bool attr = false;
     if (!attr) {
       cudaError_t e = cudaFuncSetAttribute(tri_merge_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);

@@ -25,6 +25,7 @@ struct BodyKParams {
   double *tri_jb, *tri_hs, *tri_res;
   int *tri_queue, *tri_qctl;      // qctl: {queued, fetched, guard trips}
   int* tri_meta;                  // per instance: 1 = finished by the setup kernel
+  double* tri_fr;                 // per instance: what the merge kernel needs of the input record
   double dt_mpc, j_ini, mass, g, gama, theta_lim, torque_lim;
   double lamda[4];
 };
@@ -37,7 +38,7 @@ cudaError_t body_fast_launch(BodyKParams P, int sms, cudaStream_t st);
 // roll / pitch halves side by side (body_split.cu); instances it cannot reproduce go to flist
 // three launches, register-resident solver state (body_tri.cu)
 bool body_tri_supported(int nh);
-size_t body_tri_workspace_bytes(int nh, int B, size_t off[5]);   // offsets: J | half state | half result | queue | meta
+size_t body_tri_workspace_bytes(int nh, int B, size_t off[6]);   // offsets: J | half state | half result | queue | meta | hand-over
 cudaError_t body_tri_launch(BodyKParams P, const double* tab_host, int sms, cudaStream_t st);
 bool body_split_supported(int nh);
 cudaError_t body_split_launch(BodyKParams P, int sms, cudaStream_t st);
