@@ -48,8 +48,8 @@ def parse():
     ap.add_argument("--nh", type=int, default=10, help="body-MPC horizon")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=8, help="CUDA streams the device-resident leg deals its steps over")
-    ap.add_argument("--body-streams", type=int, default=2, help="of those, streams the body-MPC ticks are dealt over")
+    ap.add_argument("--streams", type=int, default=16, help="CUDA streams the device-resident leg deals its steps over")
+    ap.add_argument("--body-streams", type=int, default=6, help="of those, streams the body-MPC ticks are dealt over")
     ap.add_argument("--sweep", action="store_true", help="also print per-batch-size throughput (stderr)")
     return ap.parse_args()
 
@@ -62,7 +62,8 @@ def workload_config(a, n_gpus):
             "qp_shapes": [[2 * a.nh, 0, 12 * a.nh], [4, 1, 24]], "seed": "0xB2000002+rank",
             "parallelism": f"batch-sharded x{n_gpus}, no collective",
             "l2": "inputs rotate through distinct batches totalling > 2x L2 (no flush needed)",
-            "streams": f"device-resident leg: body ticks round-robin over 2 CUDA streams, planner ticks over {max(3, a.streams) - 2} (independent robot batches in flight)"}
+            "streams": f"device-resident leg: body ticks round-robin over {max(1, a.body_streams)} CUDA streams, planner ticks over "
+                       f"{max(max(1, a.body_streams) + 1, a.streams) - max(1, a.body_streams)} (independent robot batches in flight)"}
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -203,6 +204,10 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm
+# DRAM bytes (read + write) of the kernels of one three-launch body-MPC call, per batch size, from ncu --set full
+TRAFFIC_TRI = {}
+
+
 def run_b200(a):
     import torch
     import quadrupedal_loco_b200 as q
@@ -314,21 +319,29 @@ def run_b200(a):
     clocks = ClockSampler(local)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     barrier()
-    clocks.start()
-    l0 = mpc.launch_count
     # the two ticks of a robot are independent and so are the steps (distinct robot batches): fork once,
     # deal the steps round-robin over NSTREAM streams (step i: SQP tick then body tick on stream i mod
     # NSTREAM), join once; the timed region is fork -> join.  One 4096-robot batch fills 1/64 of the
     # GPU's warp slots in the SQP kernel and 1.7 waves in the body kernel, so batches in flight on
     # several streams are what keeps the SMs busy at this batch size.
-    # body ticks go round-robin over 2 streams (each launch is ~1.7 waves of the whole GPU: a second
-    # stream fills the tail of the first), planner ticks over the remaining a.streams - 2 (each launch
-    # is 128 warps for ~0.19 ms: several must be in flight to hide that latency)
+    # body ticks go round-robin over NB streams (one call is three dependent launches -- setup, solve, merge --
+    # that each fill only part of the GPU at this batch size: calls in flight on several streams overlap them),
+    # planner ticks over the remaining a.streams - NB (each launch is 128 warps for ~0.19 ms: several must be
+    # in flight to hide that latency)
     NB = max(1, a.body_streams)
     NSTREAM = max(NB + 1, a.streams)
     lanes = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NSTREAM - 1)]
     lane_ptr = [None] + [x.cuda_stream for x in lanes[1:]]
     joins = [torch.cuda.Event() for _ in range(NSTREAM)]
+    # first use of a stream allocates the body path's per-stream workspace: keep that out of the timed region
+    for k in range(NB):
+        launch_body(k, lane_ptr[k])
+    for k in range(NB, NSTREAM):
+        launch_sqp(k, lane_ptr[k])
+    torch.cuda.synchronize()
+    barrier()
+    clocks.start()
+    l0 = mpc.launch_count
     with torch.cuda.stream(stream):
         ev[0].record(stream)
         for x in lanes[1:]:
@@ -362,7 +375,31 @@ def run_b200(a):
     lat_ms = timed(step)
     body_ms = timed(launch_body)
     sqp_ms = timed(launch_sqp)
+
+    # each tick alone under the timed region's stream layout: k_ov calls dealt over the same streams, one
+    # fork, one join -- the average duration of a call when independent batches are in flight, which is what
+    # the roofline of the body tick is computed from (a lone call leaves most of the GPU idle at this batch size)
+    k_ov = min(K, 600)
+
+    def overlapped(fn, first, count):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for x in lanes[1:]:
+                x.wait_event(e0)
+            for i in range(k_ov):
+                fn(i, lane_ptr[first + i % count])
+            for k in range(1, NSTREAM):
+                joins[k].record(lanes[k])
+                stream.wait_event(joins[k])
+            e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) / k_ov
+    body_ov_ms = overlapped(launch_body, 0, NB)
+    sqp_ov_ms = overlapped(launch_sqp, NB, NSTREAM - NB)
     clk = clocks.stop()
+    handed_over = mpc.body_handover_total(); guard_trips = mpc.body_guard_trips()
+    body_mode = os.environ.get("GO1MPC_BODY_MODE", "auto")
 
     t = torch.tensor([total_ms, solves_timed], dtype=torch.float64, device=dev)
     if dist:
@@ -451,7 +488,8 @@ def run_b200(a):
                       "recorded before the first enqueue and after the last synchronize)"}
 
     if rank == 0:
-        kern_ms = float(np.mean(body_ms))
+        kern_ms = float(body_ov_ms)
+        kern_alone_ms = float(np.mean(body_ms))
         fl = float(np.mean(flops_per_batch[np.arange(k_lat) % nrot]))
         achieved_tf = fl / (kern_ms * 1e-3) / 1e12
         peak_tf = dfma_gflops / 1e3
@@ -460,6 +498,12 @@ def run_b200(a):
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]; hbm_src = "measured"
         except Exception:
             hbm_peak = 6650.0; hbm_src = "fallback"
+        tri = body_mode in ("auto", "tri") and nh == 10 and (body_mode == "tri" or B >= 2048)
+        body_kernel = ("body-inclination MPC tick = tri_setup_kernel + tri_solve_kernel + tri_merge_kernel (+ the list-mode "
+                       "body_fast_kernel launch, empty on this workload)") if tri else "body_fast_kernel (body-inclination MPC tick)"
+        # DRAM bytes of one call's kernels, ncu --set full at this batch size (profiles/r01_summary.md)
+        traffic = TRAFFIC_TRI.get(B) if tri else ({4096: 4855552}.get(B) if nh == 10 else None)
+        sqp_fl = float(np.mean(sqp_flops_per_batch))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, nrot),
             "ms_per_step": total_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -467,30 +511,39 @@ def run_b200(a):
             "solves_per_step_per_gpu": solves_per_step, "robot_ticks_per_s": world * B * K / (total_ms_max * 1e-3),
             "latency_ms": {"p50": float(np.percentile(lat_ms, 50)), "p99": float(np.percentile(lat_ms, 99)),
                            "max": float(lat_ms.max()),
-                           "what": f"one {B}-robot batch through both ticks (2 launches on 2 streams), CUDA events, {k_lat} samples"},
-            "kernels_ms": {"body_fast_kernel": kern_ms, "step_timing_kernel": float(np.mean(sqp_ms)),
-                           "step_both_overlapped": float(np.mean(lat_ms))},
+                           "what": f"one {B}-robot batch through both ticks (planner launch beside the body launches, 2 streams), "
+                                   f"CUDA events, {k_lat} samples"},
+            "kernels_ms": {"body_tick_alone": kern_alone_ms, "body_tick_overlapped": kern_ms,
+                           "step_timing_kernel_alone": float(np.mean(sqp_ms)), "step_timing_kernel_overlapped": float(sqp_ov_ms),
+                           "step_both_alone": float(np.mean(lat_ms))},
+            "body_path": {"mode": body_mode, "three_launch": bool(tri), "handed_to_combined_kernel": int(handed_over),
+                          "guard_trips": int(guard_trips)},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None,
-                         "traffic": 4855552 if (nh == 10 and B == 4096) else None,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one body_fast_kernel launch, ncu --set full, "
-                                           "profiles/r01_summary.md (4.86 MB read, 0 written: the 1.9 MB of outputs stay in L2); "
-                                           "algorithmic input 4.78 MB",
-                         "kernel": "body_fast_kernel (dominant: body-inclination MPC tick)", "kernel_ms": kern_ms,
+                         "traffic": traffic,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum summed over the kernels of one body-MPC call, "
+                                           "ncu --set full (profiles/r01_summary.md); algorithmic I/O is bytes_per_launch below, the rest "
+                                           "is the setup -> solve -> merge hand-over (J per instance, state / result records per half)",
+                         "kernel": body_kernel, "kernel_ms": kern_ms, "kernel_ms_alone": kern_alone_ms,
+                         "kernel_ms_def": f"average duration of a call with independent {B}-robot batches in flight on {NB} streams "
+                                          f"({k_ov} calls between one fork and one join, CUDA events on the launching stream), i.e. under "
+                                          "the timed region's schedule; kernel_ms_alone is a lone call (most of the GPU idle at this batch size)",
+                         "frac_alone": fl / (kern_alone_ms * 1e-3) / 1e12 / peak_tf if peak_tf else None,
                          "flops_per_launch": fl, "flops_per_solve": fl / B,
                          "flops_def": "algorithmic flops of the dense reference algorithm along each problem's path "
-                                      "(SURVEY.md 8d formula, counted per problem in-kernel)",
+                                      "(SURVEY.md 8d formula, n = 20, m = 120, counted per problem on the device); the kernels exploit "
+                                      "G = blockdiag(H, H) and execute fewer",
                          "peak_source": "measured live on this GPU: register-resident DFMA loop (go1mpc_measure_dfma_peak); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "hbm": {"achieved": io_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "peak_source": f"{hbm_src} (MEASURED_PEAKS.json)", "bytes_per_launch": io_bytes},
                          "other_kernels": {"step_timing_kernel": {
-                             "kernel_ms": float(np.mean(sqp_ms)), "flops_per_launch": float(np.mean(sqp_flops_per_batch)),
-                             "achieved": float(np.mean(sqp_flops_per_batch)) / (float(np.mean(sqp_ms)) * 1e-3) / 1e12,
-                             "frac": float(np.mean(sqp_flops_per_batch)) / (float(np.mean(sqp_ms)) * 1e-3) / 1e12 / peak_tf if peak_tf else None,
-                             "note": "thread-per-planner scalar kernel: longest launch of the step when run alone (128 warps, "
-                                     "latency-bound), but 1.4 % of the step's warp-slot time; body_fast_kernel holds 94 % of the "
-                                     "step's algorithmic flops"}}},
+                             "kernel_ms": float(sqp_ov_ms), "kernel_ms_alone": float(np.mean(sqp_ms)), "flops_per_launch": sqp_fl,
+                             "achieved": sqp_fl / (float(sqp_ov_ms) * 1e-3) / 1e12,
+                             "frac": sqp_fl / (float(sqp_ov_ms) * 1e-3) / 1e12 / peak_tf if peak_tf else None,
+                             "note": "thread-per-planner scalar kernel (3 QPs of 4 variables + front-end per tick): local-memory and "
+                                     "latency bound (profiles/r01_summary.md); the body tick holds 94 % of the step's algorithmic flops, "
+                                     "this kernel most of its time -- the next kernel to restructure"}}},
             "solver": {"body_mean_outer": float(mean_iters[0]), "body_mean_add": float(mean_iters[1]),
                        "body_mean_drop": float(mean_iters[2]), "body_mean_degen": float(mean_iters[3]),
                        "body_mean_l2a": float(mean_l2a), "sqp_solves_per_robot": float(np.mean(sqp_solves)) / B,

@@ -175,24 +175,35 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
     c2 = 2 * c2;
     const double tol = M * EPS_D * c1 * c2 * 100.0;
 
-    // ---- J = L^-T, column by column, straight to the instance's J buffer (row-major, entries c >= i) ----
-    double* jb = P.tri_jb + (size_t)b * D::JB;
+    // ---- X = L^-1 in place, row by row (row i needs the original row i of L and the finished rows above);
+    //      J = L^-T = X' goes to the instance's J buffer row-major, zeros below the diagonal, 16-byte stores ----
     fr[20] = tol;
 #pragma unroll
-    for (int c = 0; c < NH; c++) {
-      double y[NH];
+    for (int i2 = 0; i2 < NH; i2++) {
+      double t[NH];
 #pragma unroll
-      for (int ii = NH - 1; ii >= 0; ii--) {
-        if (ii > c) { y[ii] = 0.0; jb[ii * NH + c] = 0.0; continue; }
-        double t = 0.0;
+      for (int j = 0; j < i2; j++) {
+        double a = L[i2][j] * L[j][j];                   // k = j term: X(j,j) already holds 1 / L(j,j)
 #pragma unroll
-        for (int k = ii + 1; k <= c; k++) t = fma(L[k][ii], y[k], t);
-        y[ii] = (ii == c) ? linv[ii] : -t * linv[ii];
-        jb[ii * NH + c] = y[ii];
+        for (int k = j + 1; k < i2; k++) a = fma(L[i2][k], L[k][j], a);
+        t[j] = a;
       }
+#pragma unroll
+      for (int j = 0; j < i2; j++) L[i2][j] = -linv[i2] * t[j];
+      L[i2][i2] = linv[i2];
+    }
+    {
+      double2* jb2 = reinterpret_cast<double2*>(P.tri_jb + (size_t)b * D::JB);
+#pragma unroll
+      for (int r = 0; r < NH; r++)
+#pragma unroll
+        for (int c2i = 0; c2i < NH / 2; c2i++) {
+          const int ca = 2 * c2i, cb = 2 * c2i + 1;      // J(r,c) = X(c,r) for c >= r
+          jb2[(r * NH) / 2 + c2i] = make_double2(ca >= r ? L[ca][r] : 0.0, cb >= r ? L[cb][r] : 0.0);
+        }
     }
 
-    // ---- both halves: gradient (cpp:427-526), x0 = -H^-1 g0 by two triangular solves, first slack scan ----
+    // ---- both halves: gradient (cpp:427-526), unconstrained minimiser, first slack scan ----
 #pragma unroll 1
     for (int h = 0; h < 2; h++) {
       const double my0 = fr[2 * h], my1 = fr[1 + 2 * h];
@@ -215,19 +226,23 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
         g0[k] = ((t1 + t2) - t3) + (P.gama * (h ? -pth[k] : pth[k])) * det;
         w[k] = g0[k];
       }
-      // L w = g0 (column oriented), L' x = w (row oriented)
+      // x0 = -J (J' g0) with J' = X: two triangular products, no division
+      {
+        double d0[NH];
 #pragma unroll
-      for (int k = 0; k < NH; k++) {
-        w[k] *= linv[k];
+        for (int c = 0; c < NH; c++) {
+          double a = L[c][0] * w[0];
 #pragma unroll
-        for (int r = k + 1; r < NH; r++) w[r] = fma(-w[k], L[r][k], w[r]);
-      }
+          for (int r = 1; r <= c; r++) a = fma(L[c][r], w[r], a);
+          d0[c] = a;
+        }
 #pragma unroll
-      for (int k = NH - 1; k >= 0; k--) {
-        double t = w[k];
+        for (int r = 0; r < NH; r++) {
+          double a = L[r][r] * d0[r];
 #pragma unroll
-        for (int r = k + 1; r < NH; r++) t = fma(-L[r][k], w[r], t);
-        w[k] = t * linv[k];
+          for (int c = r + 1; c < NH; c++) a = fma(L[c][r], d0[c], a);
+          w[r] = a;
+        }
       }
       double psi = 0.0, smin = 0.0;
       bool nan = false;
@@ -253,16 +268,17 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
       const bool active = !bad && !nan && over && (smin < 0.0);
       const size_t hid = 2 * (size_t)b + h;
       if (active) {
-        double* hs = P.tri_hs + hid * D::HS;
+        double2* hs2 = reinterpret_cast<double2*>(P.tri_hs + hid * D::HS);
 #pragma unroll
-        for (int k = 0; k < NH; k++) { hs[k] = w[k]; hs[NH + k] = pk[k]; }
-        hs[2 * NH] = tol; hs[2 * NH + 1] = f0;
+        for (int k = 0; k < NH / 2; k++) { hs2[k] = make_double2(w[2 * k], w[2 * k + 1]); hs2[NH / 2 + k] = make_double2(pk[2 * k], pk[2 * k + 1]); }
+        hs2[NH] = make_double2(tol, f0);
       } else {
         double* rs_ = P.tri_res + hid * D::RES;
         int* ri = res_ints(rs_, D::RES_D);
+        double2* rs2 = reinterpret_cast<double2*>(rs_);
 #pragma unroll
-        for (int k = 0; k < NH; k++) rs_[k] = w[k];
-        rs_[NH] = f0; rs_[NH + 1] = psi; rs_[NH + 2] = 1.0; rs_[NH + 3] = CUDART_INF;
+        for (int k = 0; k < NH / 2; k++) rs2[k] = make_double2(w[2 * k], w[2 * k + 1]);
+        rs2[NH / 2] = make_double2(f0, psi); rs2[NH / 2 + 1] = make_double2(1.0, CUDART_INF);
         ri[0] = 0; ri[1] = 0; ri[2] = over ? 0 : 1; ri[3] = (bad || nan || psi != psi) ? 1 : 0;
       }
       if (h == 0) act0 = active; else act1 = active;
@@ -282,9 +298,9 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
     }
     P.tri_meta[b] = done ? 1 : 0;
     if (!done) {
-      double* frg = P.tri_fr + (size_t)b * D::FR;
+      double2* frg = reinterpret_cast<double2*>(P.tri_fr + (size_t)b * D::FR);
 #pragma unroll
-      for (int k = 0; k < 21; k++) frg[k] = fr[k];
+      for (int k = 0; k < 11; k++) frg[k] = make_double2(fr[2 * k], fr[2 * k + 1]);
     }
   }
   // ---- queue the active halves (warp-aggregated) ----
@@ -701,11 +717,13 @@ __device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const do
                                            unsigned flops, const int* Ac) {
   using D = TriDims<NH>;
   constexpr int N = D::N;
-  double* outg = P.out + (size_t)b * D::OUT;
+  static_assert(D::OUT % 2 == 0 && N % 2 == 0, "the output record is stored 16 bytes at a time");
   const double dt = P.dt_mpc, b0 = dt * dt / 2, b1 = dt;
   const double thmax = P.theta_lim, thmin = -P.theta_lim;
   const double j_ini = P.j_ini;
   const double thx0 = fr[0], thx1 = fr[1], thy0 = fr[2], thy1 = fr[3];
+  double o[18];              // head of the output record, built in registers (one thread writes a whole record:
+                             // 16-byte stores halve the number of uncoalesced store instructions)
   double xa[3], ya[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) { xa[k] = xr[k]; ya[k] = xp[k]; }
@@ -725,34 +743,49 @@ __device__ __forceinline__ void tri_finish(const BodyKParams& P, int b, const do
     const double lam_p = P.lamda[2 * ax], lam_v = P.lamda[2 * ax + 1];
     const double bs_p = fr[4 + 2 * ax], bs_v = fr[5 + 2 * ax];
     double pkk = (p0 + dt * v0) + b0 * a0, vk = v0 + b1 * a0;
-    outg[14 + 2 * ax] = lam_p * bs_p + (1 - lam_p) * pkk;
-    outg[15 + 2 * ax] = lam_v * bs_v + (1 - lam_v) * vk;
-    outg[0 + ax] = pkk;
+    o[14 + 2 * ax] = lam_p * bs_p + (1 - lam_p) * pkk;
+    o[15 + 2 * ax] = lam_v * bs_v + (1 - lam_v) * vk;
+    o[0 + ax] = pkk;
     double pn = (pkk + dt * vk) + b0 * a1; vk = vk + b1 * a1; pkk = pn;
-    outg[6 + ax] = pkk;
+    o[6 + ax] = pkk;
     pn = (pkk + dt * vk) + b0 * a2; pkk = pn;
-    outg[10 + ax] = pkk;
-    outg[2 + ax] = j_ini * a0;
+    o[10 + ax] = pkk;
+    o[2 + ax] = j_ini * a0;
   }
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     // cpp:651-652 ZMP consistent with the planned angular acceleration (steps 0..2)
     const double den = P.mass * (P.g + fr[14 + k]);
-    const int o = (k == 0) ? 4 : (k == 1 ? 8 : 12);
-    outg[o] = fr[8 + k] - j_ini * ya[k] / den;
-    outg[o + 1] = fr[11 + k] + j_ini * xa[k] / den;
+    const int oo = (k == 0) ? 4 : (k == 1 ? 8 : 12);
+    o[oo] = fr[8 + k] - j_ini * ya[k] / den;
+    o[oo + 1] = fr[11 + k] + j_ini * xa[k] / den;
   }
-  outg[18] = xa[0]; outg[18 + NH] = ya[0];
+  double2* og = reinterpret_cast<double2*>(P.out + (size_t)b * D::OUT);
 #pragma unroll
-  for (int k = 1; k < NH; k++) { outg[18 + k] = xr[k]; outg[18 + NH + k] = xp[k]; }
-  outg[18 + N] = f_value;
-  if (D::OUT > 19 + N) outg[19 + N] = 0.0;
+  for (int k = 0; k < 9; k++) og[k] = make_double2(o[2 * k], o[2 * k + 1]);
+  og[9] = make_double2(xa[0], xr[1]);
+#pragma unroll
+  for (int k = 1; k < NH / 2; k++) og[9 + k] = make_double2(xr[2 * k], xr[2 * k + 1]);
+  og[9 + NH / 2] = make_double2(ya[0], xp[1]);
+#pragma unroll
+  for (int k = 1; k < NH / 2; k++) og[9 + NH / 2 + k] = make_double2(xp[2 * k], xp[2 * k + 1]);
+  og[9 + NH] = make_double2(f_value, 0.0);
   if (P.diag) {
+    int dgv[10 + N];
+    dgv[0] = ST_OK; dgv[1] = iqc;
+    dgv[2] = it_outer; dgv[3] = it_add; dgv[4] = it_drop; dgv[5] = 0;
+    dgv[6] = (int)fr[18]; dgv[7] = (int)fr[19]; dgv[8] = it_l2a; dgv[9] = (int)flops;
+#pragma unroll
+    for (int k = 0; k < N; k++) dgv[10 + k] = (Ac != nullptr && k < iqc) ? Ac[k] : -1;
     int* dg = P.diag + (size_t)b * P.diag_stride;
-    dg[0] = ST_OK; dg[1] = iqc;
-    dg[2] = it_outer; dg[3] = it_add; dg[4] = it_drop; dg[5] = 0;
-    dg[6] = (int)fr[18]; dg[7] = (int)fr[19]; dg[8] = it_l2a; dg[9] = (int)flops;
-    for (int k = 0; k < N; k++) dg[10 + k] = (k < iqc) ? Ac[k] : -1;
+    if ((P.diag_stride & 1) == 0 && ((uintptr_t)P.diag & 7) == 0) {
+      int2* dg2 = reinterpret_cast<int2*>(dg);
+#pragma unroll
+      for (int k = 0; k < (10 + N) / 2; k++) dg2[k] = make_int2(dgv[2 * k], dgv[2 * k + 1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 10 + N; k++) dg[k] = dgv[k];
+    }
   }
 }
 
