@@ -21,8 +21,10 @@ for l in sass.splitlines():
         amap[int(a.group(1), 16)] = (line, a.group(2))
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-# first kernel block only
-start = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+# the block of the kernel whose name contains the first word of <kernel-mangled-substring> (else the first block)
+key = re.split(r"_kernel|IL", kern)[0]
+kstart = next((i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and key in r[1]), 0)
+start = next(i for i in range(kstart, len(rows)) if rows[i] and rows[i][0] == "Address")
 h = rows[start]; ix = {n: i for i, n in enumerate(h)}
 agg = collections.defaultdict(lambda: [0, 0, 0]); base = None
 stall_cols = [c for c in h if c.startswith("stall_") and "Not Issued" not in c]
