@@ -346,9 +346,11 @@ def run_b200(a):
         ev[0].record(stream)
         for x in lanes[1:]:
             x.wait_event(ev[0])
+        t_host = time.perf_counter()
         for i in range(K):
             launch_sqp(i, lane_ptr[NB + i % (NSTREAM - NB)])
             launch_body(i, lane_ptr[i % NB])
+        t_host = time.perf_counter() - t_host
         for k in range(1, NSTREAM):
             joins[k].record(lanes[k])
             stream.wait_event(joins[k])
@@ -516,6 +518,7 @@ def run_b200(a):
             "kernels_ms": {"body_tick_alone": kern_alone_ms, "body_tick_overlapped": kern_ms,
                            "step_timing_kernel_alone": float(np.mean(sqp_ms)), "step_timing_kernel_overlapped": float(sqp_ov_ms),
                            "step_both_alone": float(np.mean(lat_ms))},
+            "host_enqueue_ms_per_step": 1e3 * t_host / K,
             "body_path": {"mode": body_mode, "three_launch": bool(tri), "handed_to_combined_kernel": int(handed_over),
                           "guard_trips": int(guard_trips)},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",

@@ -534,8 +534,12 @@ cudaError_t step_timing_launch(StepKParams P, bool warp_mode, cudaStream_t st) {
     const int grid = (P.B + wpc - 1) / wpc;
     step_timing_kernel<true><<<grid, block, (size_t)wpc * STEP_WARP_DOUBLES * sizeof(double), st>>>(P);
   } else {
-    const int grid = (P.B + block - 1) / block;
-    step_timing_kernel<false><<<grid, block, 0, st>>>(P);
+#ifndef GO1_STEP_BLOCK
+#define GO1_STEP_BLOCK 128
+#endif
+    const int tb = GO1_STEP_BLOCK;
+    const int grid = (P.B + tb - 1) / tb;
+    step_timing_kernel<false><<<grid, tb, 0, st>>>(P);
   }
   return cudaGetLastError();
 }
