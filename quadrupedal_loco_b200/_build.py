@@ -10,7 +10,7 @@ SOURCES = ["api.cu", "body_mpc.cu", "body_fast.cu", "body_split.cu", "body_tri.c
 # per-source extra flags: the thread-per-instance kernels keep the oracle's operation order and
 # must not contract a*b+c into FMA
 EXTRA = {"step_timing.cu": ["-fmad=false"], "foot_traj.cu": ["-fmad=false"], "leg_kin.cu": ["-fmad=false"]}
-HEADERS = ["gi_warp.cuh", "gi_thread.cuh", "tma.cuh", "powi.cuh", "kernels.h", os.path.join("..", "..", "include", "go1mpc.h")]
+HEADERS = ["gi_warp.cuh", "gi_thread.cuh", "gi_thread4.cuh", "tma.cuh", "powi.cuh", "kernels.h", os.path.join("..", "..", "include", "go1mpc.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

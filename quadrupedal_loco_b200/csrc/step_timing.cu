@@ -20,6 +20,7 @@
 // conditioned swing-foot fit downstream amplifies to 1e-6 -- fidelity wins).
 #include <cuda_runtime.h>
 #include "gi_thread.cuh"
+#include "gi_thread4.cuh"
 #include "gi_warp.cuh"
 #include "kernels.h"
 #include "powi.cuh"
@@ -361,7 +362,11 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
       for (int k = 0; k < 4; k++) X[k] = v[k];
       int st, q_iq, q_out, q_add, q_drop, q_degen, qA[5];
       if (!WARP) {
-        GiThread<4, 1, 24> qp;
+#ifdef GO1_STEP_GENERIC_QP
+        GiThread<4, 1, 24> qp;     // run-time indexed state in local memory (A/B against GiThread4)
+#else
+        GiThread4 qp;              // the same solve with its state in registers
+#endif
         st = qp.solve(G, g0, CE, ce0, CI, bb, X, P.cap);
         q_iq = qp.iq; q_out = qp.it_outer; q_add = qp.it_add; q_drop = qp.it_drop; q_degen = qp.it_degen;
         for (int k = 0; k < 5; k++) qA[k] = qp.A[k];
