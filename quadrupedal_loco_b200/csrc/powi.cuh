@@ -22,5 +22,22 @@ __device__ __forceinline__ double powi(double t, int k) {
   return hi + lo;
 }
 
+// pw[k] = powi(t, k) for k = 0..6 from ONE running product: powi's chain for t^k passes through the states of
+// t^2 .. t^(k-1), so rounding every intermediate state gives bit-identical values at a sixth of the multiplications
+__device__ __forceinline__ void powi_all(double t, double pw[7]) {
+  pw[0] = 1.0;
+  double hi = t, lo = 0.0;
+  pw[1] = hi + lo;
+#pragma unroll
+  for (int q = 1; q < 6; q++) {
+    const double p = hi * t;
+    double e = fma(hi, t, -p);
+    e = fma(lo, t, e);
+    const double s = p + e;
+    lo = e - (s - p);
+    hi = s;
+    pw[q + 1] = hi + lo;
+  }
+}
 
 }  // namespace go1

@@ -60,6 +60,47 @@ __device__ void gj_inverse7(double* a, double* r) {
   }
 }
 
+// The same elimination, fully unrolled with the matrix in registers, for the three columns of the inverse
+// CoM_height_solve uses (its right-hand side `plan` is zero outside entries 2..4): rinv[i*3 + c] = A^-1(i, 2 + c).
+// Pivot search, row swaps (as predicated register swaps), normalisation and elimination are the reference's,
+// entry for entry; columns of `a` left of the pivot are exact zeros below the diagonal and are skipped.
+__device__ __forceinline__ void gj_inverse7_cols234(double (&a)[49], double (&rinv)[21]) {
+  constexpr int n = 7;
+#pragma unroll
+  for (int i = 0; i < n; i++)
+#pragma unroll
+    for (int c = 0; c < 3; c++) rinv[i * 3 + c] = (i == 2 + c) ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 0; k < n; k++) {
+    int piv = k;
+    double best = fabs(a[k * n + k]);
+#pragma unroll
+    for (int i = k + 1; i < n; i++) if (fabs(a[i * n + k]) > best) { best = fabs(a[i * n + k]); piv = i; }
+#pragma unroll
+    for (int i = k + 1; i < n; i++)
+      if (piv == i) {
+#pragma unroll
+        for (int j = k; j < n; j++) { const double t = a[k * n + j]; a[k * n + j] = a[i * n + j]; a[i * n + j] = t; }
+#pragma unroll
+        for (int c = 0; c < 3; c++) { const double t = rinv[k * 3 + c]; rinv[k * 3 + c] = rinv[i * 3 + c]; rinv[i * 3 + c] = t; }
+      }
+    const double d = a[k * n + k];
+#pragma unroll
+    for (int j = k; j < n; j++) a[k * n + j] = a[k * n + j] / d;
+#pragma unroll
+    for (int c = 0; c < 3; c++) rinv[k * 3 + c] = rinv[k * 3 + c] / d;
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+      if (i == k) continue;
+      const double f = a[i * n + k];
+#pragma unroll
+      for (int j = k; j < n; j++) a[i * n + j] = __dsub_rn(a[i * n + j], __dmul_rn(f, a[k * n + j]));
+#pragma unroll
+      for (int c = 0; c < 3; c++) rinv[i * 3 + c] = __dsub_rn(rinv[i * 3 + c], __dmul_rn(f, rinv[k * 3 + c]));
+    }
+  }
+}
+
 // NLPClass::CoM_height_solve (NLPClass_sqp.cpp:2361-2473) for the samples i, i+1, i+2:
 // 6th-order polynomial through (value, velocity, acceleration) at the step's start and end and
 // the value at mid-step.  ts1 / tx1 / f0 / f1: _ts(bjx1-1), _tx(bjx1-1), footz(bjx1-2), footz(bjx1-1).
@@ -67,6 +108,7 @@ __device__ void com_height_solve(int i, int bjx1, double ts1, double tx1, double
                                  double comz[3], double comvz[3], double comaz[3]) {
   if (bjx1 >= 2) {
     const double tp[3] = {0.0001, ts1 / 2 + 0.0001, ts1 + 0.0001};
+#ifdef GO1_STEP_GJ_GENERIC
     double A[49], Ainv[49];
     const int rowt[7] = {0, 0, 0, 1, 2, 2, 2}, kind[7] = {1, 2, 0, 0, 0, 1, 2};
     for (int r = 0; r < 7; r++) {
@@ -89,6 +131,47 @@ __device__ void com_height_solve(int i, int bjx1, double ts1, double tx1, double
       for (int k = 0; k < 7; k++) { z = __dadd_rn(z, __dmul_rn(p[k], co[k])); vz = __dadd_rn(vz, __dmul_rn(v[k], co[k])); az = __dadd_rn(az, __dmul_rn(a[k], co[k])); }
       comz[jxx - 1] = z; comvz[jxx - 1] = vz; comaz[jxx - 1] = az;
     }
+#else
+    // matrix in registers, the powers of each time from one running product (powi_all), the three columns of the
+    // inverse that meet non-zero entries of `plan`
+    double A[49], Rinv[21];
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      double pw[7];
+      powi_all(tp[g], pw);
+      // rows: g = 0 -> velocity, acceleration, position at the start; g = 1 -> position at mid-step;
+      //       g = 2 -> position, velocity, acceleration at the end   (NLPClass_sqp.cpp:2376-2412)
+      const int r_pos = (g == 0) ? 2 : (g == 1 ? 3 : 4), r_vel = (g == 0) ? 0 : 5, r_acc = (g == 0) ? 1 : 6;
+      { double* a = A + 7 * r_pos; a[0] = pw[6]; a[1] = pw[5]; a[2] = pw[4]; a[3] = pw[3]; a[4] = pw[2]; a[5] = pw[1]; a[6] = 1; }
+      if (g != 1) {
+        { double* a = A + 7 * r_vel; a[0] = 6 * pw[5]; a[1] = 5 * pw[4]; a[2] = 4 * pw[3]; a[3] = 3 * pw[2]; a[4] = 2 * pw[1]; a[5] = 1; a[6] = 0; }
+        { double* a = A + 7 * r_acc; a[0] = 30 * pw[4]; a[1] = 20 * pw[3]; a[2] = 12 * pw[2]; a[3] = 6 * pw[1]; a[4] = 2; a[5] = 0; a[6] = 0; }
+      }
+    }
+    gj_inverse7_cols234(A, Rinv);
+    const double plan3[3] = {f0 + hcom, (f0 + f1) / 2 + hcom, f1 + hcom};
+    double co[7];
+#pragma unroll
+    for (int r = 0; r < 7; r++) {
+      double acc = 0.0;      // the reference's sum over k = 0..6 adds exact zeros for k = 0, 1, 5, 6
+#pragma unroll
+      for (int c = 0; c < 3; c++) acc = __dadd_rn(acc, __dmul_rn(Rinv[3 * r + c], plan3[c]));
+      co[r] = acc;
+    }
+#pragma unroll
+    for (int jxx = 1; jxx <= 3; jxx++) {
+      const double t = (i + jxx - round(tx1 / dt)) * dt;
+      double pw[7];
+      powi_all(t, pw);
+      const double p[7] = {pw[6], pw[5], pw[4], pw[3], pw[2], pw[1], 1};
+      const double v[7] = {6 * pw[5], 5 * pw[4], 4 * pw[3], 3 * pw[2], 2 * pw[1], 1, 0};
+      const double a[7] = {30 * pw[4], 20 * pw[3], 12 * pw[2], 6 * pw[1], 2, 0, 0};
+      double z = 0.0, vz = 0.0, az = 0.0;
+#pragma unroll
+      for (int k = 0; k < 7; k++) { z = __dadd_rn(z, __dmul_rn(p[k], co[k])); vz = __dadd_rn(vz, __dmul_rn(v[k], co[k])); az = __dadd_rn(az, __dmul_rn(a[k], co[k])); }
+      comz[jxx - 1] = z; comvz[jxx - 1] = vz; comaz[jxx - 1] = az;
+    }
+#endif
   } else {
     for (int q = 0; q < 3; q++) { comz[q] = hcom; comvz[q] = 0; comaz[q] = 0; }
   }
