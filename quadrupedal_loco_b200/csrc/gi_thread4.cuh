@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include "powi.cuh"
 
 namespace go1 {
 
@@ -31,10 +32,10 @@ struct GiThread4 {
   int it_outer, it_add, it_drop, it_degen, iq;
   double f_value;
 
-  __device__ static double hyp(double a, double b) {
+  __device__ __noinline__ static double hyp(double a, double b) {
     double a1 = fabs(a), b1 = fabs(b), t;
-    if (a1 > b1) { t = b1 / a1; return a1 * sqrt(1.0 + t * t); }
-    if (b1 > a1) { t = a1 / b1; return b1 * sqrt(1.0 + t * t); }
+    if (a1 > b1) { t = div_z(b1, a1); return a1 * sqrt(1.0 + t * t); }
+    if (b1 > a1) { t = div_z(a1, b1); return b1 * sqrt(1.0 + t * t); }
     return a1 * sqrt(2.0);
   }
   __device__ __forceinline__ static double dot4(const double* a, const double* b) {
@@ -67,7 +68,7 @@ struct GiThread4 {
 #pragma unroll
     for (int i = 3; i >= 0; i--)
       if (i < iq) {
-        r[i] = r[i] / R[i * 4 + i];
+        r[i] = div_z(r[i], R[i * 4 + i]);
         const double ri = r[i];
 #pragma unroll
         for (int t = 0; t < i; t++) r[t] -= ri * R[i * 4 + t];
@@ -82,9 +83,9 @@ struct GiThread4 {
         const double h = hyp(cc, ss);
         if (h != 0.0) {
           d[j] = 0.0;
-          ss = ss / h; cc = cc / h;
+          ss = div_z(ss, h); cc = div_z(cc, h);
           if (cc < 0.0) { cc = -cc; ss = -ss; d[j - 1] = -h; } else d[j - 1] = h;
-          const double xny = ss / (1.0 + cc);
+          const double xny = div_z(ss, 1.0 + cc);
 #pragma unroll
           for (int k = 0; k < 4; k++) {
             const double t1 = J[(j - 1) * 4 + k], t2 = J[j * 4 + k];
@@ -136,10 +137,10 @@ struct GiThread4 {
         double cc = R[j * 4 + j], ss = R[j * 4 + j + 1];
         const double h = hyp(cc, ss);
         if (h != 0.0) {
-          cc = cc / h; ss = ss / h;
+          cc = div_z(cc, h); ss = div_z(ss, h);
           R[j * 4 + j + 1] = 0.0;
           if (cc < 0.0) { R[j * 4 + j] = -h; cc = -cc; ss = -ss; } else R[j * 4 + j] = h;
-          const double xny = ss / (1.0 + cc);
+          const double xny = div_z(ss, 1.0 + cc);
 #pragma unroll
           for (int k = j + 1; k < 4; k++)
             if (k < iq) {
@@ -211,7 +212,7 @@ struct GiThread4 {
         for (int j = 0; j < k; j++) t += L[j * 4 + i] * L[j * 4 + k];
         double v = L[k * 4 + i];
         if (k > 0) v -= t;
-        L[k * 4 + i] = v / xx;
+        L[k * 4 + i] = div_z(v, xx);
       }
     }
 #pragma unroll
@@ -229,7 +230,7 @@ struct GiThread4 {
         for (int k = i + 1; k < 4; k++) t += L[i * 4 + k] * J[c * 4 + k];
         double rhs = (i == c) ? 1.0 : 0.0;
         if (i < 3) rhs -= t;
-        J[c * 4 + i] = rhs / L[i * 4 + i];
+        J[c * 4 + i] = div_z(rhs, L[i * 4 + i]);
       }
     double c2 = 0.0;
 #pragma unroll
@@ -239,7 +240,7 @@ struct GiThread4 {
     for (int i = 0; i < 4; i++) y[i] = g0[i];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-      y[i] = y[i] / L[i * 4 + i];
+      y[i] = div_z(y[i], L[i * 4 + i]);
       const double yi = y[i];
 #pragma unroll
       for (int k = i + 1; k < 4; k++) y[k] -= yi * L[i * 4 + k];
@@ -251,7 +252,7 @@ struct GiThread4 {
       for (int k = i + 1; k < 4; k++) t += L[i * 4 + k] * y[k];
       double rhs = y[i];
       if (i < 3) rhs -= t;
-      y[i] = rhs / L[i * 4 + i];
+      y[i] = div_z(rhs, L[i * 4 + i]);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) x[i] = -y[i];
@@ -307,7 +308,7 @@ struct GiThread4 {
       double t1 = inf, t2;
 #pragma unroll
       for (int k = P; k < 4; k++)
-        if (k < iq && r[k] > 0.0) { const double tmp = u[k] / r[k]; if (tmp < t1) { t1 = tmp; l = A[k]; } }
+        if (k < iq && r[k] > 0.0) { const double tmp = div_z(u[k], r[k]); if (tmp < t1) { t1 = tmp; l = A[k]; } }
       if (fabs(dot4(z, z)) > EPS) t2 = -s_ip / dot4(z, np); else t2 = inf;
       const double t = fmin(t1, t2);
       if (t >= inf) { status = 2; f_value = inf; break; }

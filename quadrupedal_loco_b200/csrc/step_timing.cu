@@ -86,9 +86,9 @@ __device__ __forceinline__ void gj_inverse7_cols234(double (&a)[49], double (&ri
       }
     const double d = a[k * n + k];
 #pragma unroll
-    for (int j = k; j < n; j++) a[k * n + j] = a[k * n + j] / d;
+    for (int j = k; j < n; j++) a[k * n + j] = div_z(a[k * n + j], d);
 #pragma unroll
-    for (int c = 0; c < 3; c++) rinv[k * 3 + c] = rinv[k * 3 + c] / d;
+    for (int c = 0; c < 3; c++) rinv[k * 3 + c] = div_z(rinv[k * 3 + c], d);
 #pragma unroll
     for (int i = 0; i < n; i++) {
       if (i == k) continue;
