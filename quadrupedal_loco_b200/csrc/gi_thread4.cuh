@@ -22,6 +22,23 @@
 
 namespace go1 {
 
+// Inequality rows as dense arrays (CI 4 x 24 column-major, ci0): the generic way to hand them to GiThread4.
+struct GiRowsArray {
+  const double* CI;
+  const double* ci0;
+  __device__ __forceinline__ double slack(int i, const double* x) const {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc += CI[i * 4 + k] * x[k];
+    return acc + ci0[i];
+  }
+  __device__ __forceinline__ void column(int i, double* np) const {
+#pragma unroll
+    for (int k = 0; k < 4; k++) np[k] = CI[i * 4 + k];
+  }
+  __device__ __forceinline__ double rhs(int i) const { return ci0[i]; }
+};
+
 struct GiThread4 {
   static constexpr int N = 4, P = 1, M = 24;
   static constexpr double EPS = 2.220446049250313e-16;
@@ -164,18 +181,18 @@ struct GiThread4 {
   // Steps 1 and 2 in one pass over the 24 constraints (cpp:282-342).  first = true: step 1 (psi, reset of ss / ip)
   // followed by step 2; first = false: the step-2 re-scan after a degenerate add (ss keeps its value, cpp:461).
   // Returns psi; ss / ip / s_ip / np are updated when a better candidate is found.
-  __device__ __forceinline__ double scan(const double* CI, const double* ci0, const double* x, bool first,
+  template <class Rows>
+  __device__ __forceinline__ double scan(const Rows& rows, const double* x, bool first,
                                          double& ss, int& ip, double& s_ip) {
     double psi = 0.0;
     if (first) { ss = 0.0; ip = 0; }
 #pragma unroll
     for (int i = 0; i < M; i++) {
-      const double sum = dot4(CI + i * 4, x) + ci0[i];
+      const double sum = rows.slack(i, x);      // i is a compile-time constant after unrolling
       psi += fmin(0.0, sum);
       if (sum < ss && !((inA >> i) & 1u) && !((excl >> i) & 1u)) {
         ss = sum; ip = i; s_ip = sum;
-#pragma unroll
-        for (int k = 0; k < 4; k++) np[k] = CI[i * 4 + k];
+        rows.column(i, np);
       }
     }
     // nothing found: ss / ip keep their values, as in the reference's scan
@@ -185,6 +202,14 @@ struct GiThread4 {
   // G, CE (4 x 1), CI (4 x 24) column-major.  x: in/out.  Returns the status code of go1mpc.h.
   __device__ int solve(const double* G, const double* g0, const double* CE, const double* ce0,
                        const double* CI, const double* ci0, double* x, int cap) {
+    GiRowsArray rows{CI, ci0};
+    return solve_rows(G, g0, CE, ce0, rows, x, cap);
+  }
+  // the same with the inequality rows behind a policy: slack(i, x) = CI(:, i)' x + ci0(i) summed in dot-product order,
+  // column(i, np) = CI(:, i), rhs(i) = ci0(i); i is a compile-time constant wherever the solver calls them
+  template <class Rows>
+  __device__ int solve_rows(const double* G, const double* g0, const double* CE, const double* ce0,
+                            const Rows& rows, double* x, int cap) {
     const double inf = CUDART_INF;
     double L[16], y[4];
     it_outer = it_add = it_drop = it_degen = 0; iq = 0; inA = 0u; excl = 0u;
@@ -286,7 +311,7 @@ struct GiThread4 {
 #pragma unroll
         for (int i = P; i < 4; i++) if (i < iq) inA |= 1u << A[i];
         excl = 0u;
-        const double psi = scan(CI, ci0, x, true, ss, ip, s_ip);
+        const double psi = scan(rows, x, true, ss, ip, s_ip);
         if (fabs(psi) <= M * EPS * c1 * c2 * 100.0) break;
 #pragma unroll
         for (int i = 0; i < 4; i++) if (i < iq) { u_old[i] = u[i]; A_old[i] = A[i]; }
@@ -294,7 +319,7 @@ struct GiThread4 {
         for (int k = 0; k < 4; k++) x_old[k] = x[k];
         phase = PH_L2;
       } else if (phase == PH_L2) {
-        (void)scan(CI, ci0, x, false, ss, ip, s_ip);
+        (void)scan(rows, x, false, ss, ip, s_ip);
       }
       if (phase == PH_L2) {
         if (ss >= 0.0) break;
@@ -361,7 +386,7 @@ struct GiThread4 {
         s_ip = dot4(np, x);
         double cv = 0.0;
 #pragma unroll
-        for (int i = 0; i < M; i++) if (i == ip) cv = ci0[i];
+        for (int i = 0; i < M; i++) if (i == ip) cv = rows.rhs(i);
         s_ip = s_ip + cv;
       }
     }

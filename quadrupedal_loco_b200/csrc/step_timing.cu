@@ -279,6 +279,43 @@ __device__ void gj_inverse7_warp(double* M, int lane) {
   }
 }
 
+// The 24 inequality rows of the step-timing QP (NLPClass_sqp.cpp:1193-1455) without their dense 4 x 24 matrix:
+// rows 0-11 have ONE non-zero coefficient (-+1 on tr1, tr2, Lx, Ly; rows 8-11 are empty while k_yu = 0), rows 12-23
+// three (on Lx or Ly, tr1, tr2).  slack() adds the non-zero products in the dot product's order -- the skipped terms
+// are exact zeros, so the sums are the dense ones -- and column() returns the dense column (structural zeros are the
+// -0.0 the reference's `0.0 * (-1)` leaves).  All indices are compile-time constants where GiThread4 calls these.
+struct StepRows {
+  double a0[12], a2[12], a3[12];   // rows 12..23: CI(i0, r), CI(2, r), CI(3, r)
+  double bb[24];
+  bool vel_rows;                   // k_yu != 0: rows 8..11 populated
+  __device__ __forceinline__ static int var_of(int i) { return (i < 2) ? 2 : (i < 4) ? 3 : ((i & 2) ? 1 : 0); }   // rows 0..11
+  __device__ __forceinline__ static int i0_of(int i) { return ((i - 12) & 2) ? 1 : 0; }                            // rows 12..23
+  __device__ __forceinline__ double slack(int i, const double* x) const {
+    if (i < 12) {
+      if (i >= 8 && !vel_rows) return 0.0 + bb[i];
+      const double cf = (i & 1) ? 1.0 : -1.0;          // CI = val * (-1), val = +1 on even rows
+      return cf * x[var_of(i)] + bb[i];
+    }
+    const int r = i - 12;
+    double acc = a0[r] * x[i0_of(i)];
+    acc += a2[r] * x[2];
+    acc += a3[r] * x[3];
+    return acc + bb[i];
+  }
+  __device__ __forceinline__ void column(int i, double* np) const {
+#pragma unroll
+    for (int k = 0; k < 4; k++) np[k] = -0.0;
+    if (i < 12) {
+      if (i >= 8 && !vel_rows) return;
+      np[var_of(i)] = (i & 1) ? 1.0 : -1.0;
+    } else {
+      const int r = i - 12;
+      np[i0_of(i)] = a0[r]; np[2] = a2[r]; np[3] = a3[r];
+    }
+  }
+  __device__ __forceinline__ double rhs(int i) const { return bb[i]; }
+};
+
 // WARP = false: one THREAD per planner (throughput mode, large batches).
 // WARP = true : one WARP per planner (latency mode): the scalar front-end runs warp-uniformly, the
 //               QP is solved by the warp-cooperative core (gi_warp.cuh) with one lane per constraint,
@@ -307,19 +344,21 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
   const StepCfgDev& c = P.cfg;
   const double dt = c.dt, Wn = c.Wn;
   const int i = P.tick[b];
-  double ts[NS], tx[NS];
-  for (int k = 0; k < NS; k++) { ts[k] = ST(S_TS + k); tx[k] = ST(S_TX + k); }
-
-  // :702-704 Indexfind((i+1) dt, xyz0 = -1)
-  int j = 0;
-  while (j < NS && (i + 1) * dt > tx[j] + 0.0001) j++;
+  // The step tables _ts / _tx (27 entries each) are not copied into per-thread arrays (run-time indexed, i.e. local
+  // memory, and searched by dependent loads): the searches run over the state's columns as independent coalesced
+  // loads, the few entries a tick needs are fetched by index.
+  // :702-704 Indexfind((i+1) dt, xyz0 = -1): first entry the time has not passed
+  int j = NS;
+#pragma unroll
+  for (int k = NS - 1; k >= 0; k--) { const double txk = ST(S_TX + k); if (!((i + 1) * dt > txk + 0.0001)) j = k; }
   int p = (j - 1) + 1;
   const bool valid = (p >= 1 && p <= NS);
   if (!valid) p = 1;   // table overrun (UB in the reference): flagged in diag, nothing is written
   const double px = ST(S_FX + p - 1), py = ST(S_FY + p - 1);
-  const int ki = (int)round(tx[p - 1] / dt);
+  const double tx_p1 = ST(S_TX + p - 1), ts_p1 = ST(S_TS + p - 1), ts_1 = ST(S_TS + 1);
+  const int ki = (int)round(tx_p1 / dt);
   const int k_yu = i - ki;
-  const double Tk = ts[p - 1] - k_yu * dt;
+  const double Tk = ts_p1 - k_yu * dt;
   const double Lxx_refx = ST(S_LXX + p - 1), Lyy_refy = ST(S_LYY + p - 1);
   const double tr1_ref = cosh(Wn * Tk), tr2_ref = sinh(Wn * Tk);
   double v[4];
@@ -364,7 +403,7 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
 
   // lateral reachability (:1216-1246)
   double footy_max, footy_min;
-  const bool wide = (i >= (round(2 * ts[1] / dt)) + 1);
+  const bool wide = (i >= (round(2 * ts_1 / dt)) + 1);
   const double HW = c.half_hip_width, FW = c.foot_width;
   if (p % 2 == 0) { footy_min = -(2 * HW + 0.03); footy_max = wide ? -(FW + 0.01) : -(HW - 0.03); }
   else { footy_max = 2 * HW + 0.03; footy_min = wide ? FW + 0.01 : HW - 0.03; }
@@ -403,7 +442,9 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
       for (int k = 0; k < 4; k++) CE[k] = trx12[k] * (-1);
     }
     double CI[96], bb[24];   // CI(:, r) = -A(r, :)
+#pragma unroll
     for (int k = 0; k < 96; k++) CI[k] = 0.0 * (-1);
+#pragma unroll
     for (int k = 0; k < 24; k++) bb[k] = 0.0;
 #define AROW(r, k, val) CI[(r) * 4 + (k)] = (val) * (-1)
     AROW(0, 2, 1.0);  bb[0] = -(v[2]) + tr1_max;
@@ -440,17 +481,28 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
     }
 #undef ROW3
 #undef AROW
-    if (Tk >= 0.1 * ts[p - 1]) {
+    if (Tk >= 0.1 * ts_p1) {
       double X[4];
       for (int k = 0; k < 4; k++) X[k] = v[k];
       int st, q_iq, q_out, q_add, q_drop, q_degen, qA[5];
       if (!WARP) {
 #ifdef GO1_STEP_GENERIC_QP
         GiThread<4, 1, 24> qp;     // run-time indexed state in local memory (A/B against GiThread4)
-#else
-        GiThread4 qp;              // the same solve with its state in registers
-#endif
         st = qp.solve(G, g0, CE, ce0, CI, bb, X, P.cap);
+#else
+        GiThread4 qp;              // the same solve with its state in registers, the rows behind StepRows
+        StepRows rows;
+        rows.vel_rows = (k_yu != 0);
+#pragma unroll
+        for (int r = 0; r < 24; r++) rows.bb[r] = bb[r];
+#pragma unroll
+        for (int r = 0; r < 12; r++) {
+          rows.a0[r] = CI[(12 + r) * 4 + StepRows::i0_of(12 + r)];
+          rows.a2[r] = CI[(12 + r) * 4 + 2];
+          rows.a3[r] = CI[(12 + r) * 4 + 3];
+        }
+        st = qp.solve_rows(G, g0, CE, ce0, rows, X, P.cap);
+#endif
         q_iq = qp.iq; q_out = qp.it_outer; q_add = qp.it_add; q_drop = qp.it_drop; q_degen = qp.it_degen;
         for (int k = 0; k < 5; k++) qA[k] = qp.A[k];
       } else {
@@ -513,9 +565,43 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
   const double ts_new = k_yu * dt + log(v[2] + v[3]) / Wn;
   const double isx = comx_f - px, esx = v[0] * 0.5, visx = (esx - isx * v[2]) / (1 / Wn * v[3]);
   const double isy = comy_f - py, esy = v[1] * 0.5, visy = (esy - isy * v[2]) / (1 / Wn * v[3]);
-  ts[p - 1] = ts_new;
-  for (int jxx = p + 1; jxx <= NS; jxx++) tx[jxx - 1] = tx[jxx - 2] + ts[jxx - 2];
   const double fx_next = px + v[0], fy_next = py + v[1];
+  if (SO != S) {   // out-of-place: carry the untouched fields over (before any field of the new state is stored)
+#pragma unroll 1
+    for (int f0 = 0; f0 < STEP_STATE_DOUBLES; f0 += 32) {
+      double tmp[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) if (f0 + k < STEP_STATE_DOUBLES) tmp[k] = ST(f0 + k);
+#pragma unroll
+      for (int k = 0; k < 32; k++) if (f0 + k < STEP_STATE_DOUBLES) STW(f0 + k) = tmp[k];
+    }
+  }
+  // _ts(p-1) = ts_new and the running sum _tx(k) = _tx(k-1) + _ts(k-1) for k >= p (:906-909), in the reference's order;
+  // in the same pass: the two index searches against the UPDATED table (:1031-1041), the entry CoM_height_solve
+  // reads, and the store of the new _tx entries (every load of column k precedes its store: in-place safe)
+  const int bp = (int)ST(S_BJX1);
+  const int b1 = bp >= 1 && bp <= NS ? bp : 1, b2 = bp >= 2 && bp <= NS + 1 ? bp : 2;
+  const double ts_b1 = (b1 == p) ? ts_new : ST(S_TS + b1 - 1);
+  double tx_b1 = ST(S_TX + b1 - 1);
+  int jA = NS, jB = NS;
+  {
+    double cur = tx_p1;
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      double txk;
+      if (k >= 1 && k >= p) {
+        const double tsk = (k == p) ? ts_new : ST(S_TS + (k >= 1 ? k - 1 : 0));
+        cur = cur + tsk;
+        txk = cur;
+        if (valid) STW(S_TX + k) = txk;
+      } else {
+        txk = ST(S_TX + k);
+      }
+      if (k == b1 - 1) tx_b1 = txk;
+      if (jA == NS && !(i * dt >= txk)) jA = k;
+      if (jB == NS && !((i + 1) * dt >= txk)) jB = k;
+    }
+  }
 
   // vertical CoM samples (:936): after the write-back of ts / tx, with the _bjx1 the previous tick left
   double hz_z[3], hz_vz[3], hz_az[3];
@@ -523,10 +609,8 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
     for (int q = 0; q < 3; q++) { hz_z[q] = INP(I_CZ + q); hz_az[q] = INP(I_CAZ + q); hz_vz[q] = 0.0; }
     hz_vz[0] = INP(I_CVZ);
   } else {
-    const int bp = (int)ST(S_BJX1);
-    const int b1 = bp >= 1 && bp <= NS ? bp : 1, b2 = bp >= 2 && bp <= NS + 1 ? bp : 2;
-    if (!WARP) com_height_solve(i, bp <= NS ? bp : 0, ts[b1 - 1], tx[b1 - 1], ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az);
-    else com_height_solve_warp(i, bp <= NS ? bp : 0, ts[b1 - 1], tx[b1 - 1], ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az, wsm, lane);
+    if (!WARP) com_height_solve(i, bp <= NS ? bp : 0, ts_b1, tx_b1, ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az);
+    else com_height_solve_warp(i, bp <= NS ? bp : 0, ts_b1, tx_b1, ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az, wsm, lane);
   }
   // LIPM roll-out of samples i, i+1, i+2 (:938-955)
   double comx[3], comy[3], comvx[3], comvy[3], comax[3], comay[3], zmpx[3], zmpy[3], dcmx[3], dcmy[3];
@@ -552,32 +636,18 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
   const double lx = c.lamda[0], lvx = c.lamda[1], ly = c.lamda[2], lvy = c.lamda[3];
 
   // integer step indices against the UPDATED table (:1031-1041)
-  j = 0; while (j < NS && i * dt >= tx[j]) j++;
-  const int bjxx = (j - 1) + 1;
-  j = 0; while (j < NS && (i + 1) * dt >= tx[j]) j++;
-  const int bjx1 = (j - 1) + 1;
+  const int bjxx = jA, bjx1 = jB;
   // foot tables at the two entries the outputs read, taken BEFORE any write (in-place safe)
   const int bq0 = bjxx < NS ? bjxx : NS - 1, bq1 = bjxx + 1 < NS ? bjxx + 1 : NS - 1;
   const bool upd = valid && p < NS;
   const double fx0 = (upd && bq0 == p) ? fx_next : ST(S_FX + bq0), fx1 = (upd && bq1 == p) ? fx_next : ST(S_FX + bq1);
   const double fy0 = (upd && bq0 == p) ? fy_next : ST(S_FY + bq0), fy1 = (upd && bq1 == p) ? fy_next : ST(S_FY + bq1);
   const double fz0 = ST(S_FZ + bq0), fz1 = ST(S_FZ + bq1);
-  if (SO != S) {   // out-of-place: carry the untouched fields over, 32 loads in flight at a time
-#pragma unroll 1
-    for (int f0 = 0; f0 < STEP_STATE_DOUBLES; f0 += 32) {
-      double tmp[32];
-#pragma unroll
-      for (int k = 0; k < 32; k++) if (f0 + k < STEP_STATE_DOUBLES) tmp[k] = ST(f0 + k);
-#pragma unroll
-      for (int k = 0; k < 32; k++) if (f0 + k < STEP_STATE_DOUBLES) STW(f0 + k) = tmp[k];
-    }
-  }
   if (valid) {
     for (int k = 0; k < 4; k++) STW(S_VARI + k) = v[k];
     STW(S_LXX + p - 1) = v[0];
     STW(S_LYY + p - 1) = v[1];
     STW(S_TS + p - 1) = ts_new;
-    for (int jxx = p + 1; jxx <= NS; jxx++) STW(S_TX + jxx - 1) = tx[jxx - 1];
     if (p < NS) { STW(S_FX + p) = fx_next; STW(S_FY + p) = fy_next; }
     STW(S_END + 0) = Wn * isx * v[3] + visx * v[2];
     STW(S_END + 1) = Wn * isy * v[3] + visy * v[2];
