@@ -332,6 +332,45 @@ int go1mpc_servo_kin_tick_batch(go1mpc_t *h, int B, int gait_mode, double y_offs
                                 double *q_d, double *jac_d, double *foot_des_d, int *iters_d, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Fused control tick for B robots: ONE call enqueues, on one stream and with every
+ * intermediate resident on the device,
+ *   1. the step-location / step-timing SQP tick   (= go1mpc_step_timing_step_batch, state updated in place)
+ *   2. the planner's swing-foot trajectory        (= go1mpc_foot_trajectory_batch on the new state / out38)
+ *   3. the body-inclination MPC tick               (= go1mpc_body_mpc_step_batch)
+ *   4. the servo kinematics tick                   (= go1mpc_servo_kin_tick_batch) with the body pose taken from the
+ *      ticks above: position = planner CoM (out38 rows 0..2), roll / pitch = body-MPC angles (out record [0], [1]),
+ *      yaw 0; virtual right / left foot = swing-foot positions (out18 rows 0..2 / 3..5)
+ * i.e. NLPClass::step_timing_opti_loop + Foot_trajectory_solve_mod2 -> PRMPCClass::body_theta_mpc -> the leg mapping
+ * and four Inverse_kinematics_g of GO1/servo_control/servo.cpp:935-1051 without a host round trip.  Results are
+ * bit-identical to calling the four entry points in that order.  All pointers are device pointers with the layouts
+ * of the individual entry points; servo_theta_d [3][B] is scratch the call fills (roll, pitch, yaw).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+  int n_sqp;                    /* 1: planner */
+  const int *tick_d;
+  double *step_state_d;         /*    [202][B], in place */
+  const double *step_in_d;      /*    [20][B] */
+  double *out38_d;              /*    [38][B] */
+  int *step_diag_d;             /*    [60][B] or NULL */
+  double *foot_d;               /* 2: [32][B] in/out */
+  double *out18_d;              /*    [18][B] */
+  int *right_support_d;         /*    [B] or NULL */
+  int nh;                       /* 3: body MPC */
+  const double *body_in_d;      /*    [B][go1mpc_body_in_stride(nh)] */
+  double *body_out_d;           /*    [B][go1mpc_body_out_stride(nh)] in/out */
+  int *body_diag_d;             /*    [B][go1mpc_body_diag_stride(nh)] or NULL */
+  int gait_mode;                /* 4: servo kinematics (101 pace, 102 trot, 103 gallop) */
+  double y_offset;
+  const double *homing_d;       /*    [12][B] */
+  double *q_d;                  /*    [12][B] in/out */
+  double *jac_d;                /*    [36][B] or NULL */
+  double *foot_des_d;           /*    [12][B] or NULL */
+  int *ik_iters_d;              /*    [4][B] or NULL */
+  double *servo_theta_d;        /*    [3][B] scratch (filled by the call) */
+} Go1FusedTick;
+int go1mpc_fused_tick_batch(go1mpc_t *h, int B, const Go1FusedTick *t, void *stream);
+
+/* ---------------------------------------------------------------------------
  * Ground-reaction-force distribution of go1_servo's 1 kHz loop for B robots.  Replaces
  * Dynamiccclass (GO1/whole_body_dynamics/dynmics_compute.cpp):
  *   go1mpc_grf_force_distribution_batch -> force_distribution :141-261 (gait_mode 101 / 102)

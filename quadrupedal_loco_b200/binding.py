@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_step_timing_step_batch", "go1mpc_step_timing_step_batch_host", "go1mpc_step_default_state",
     "go1mpc_body_mpc_step_batch_host_async", "go1mpc_step_timing_step_batch_host_async",
     "go1mpc_foot_trajectory_batch", "go1mpc_foot_trajectory_batch_host", "go1mpc_foot_default_state",
-    "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch",
+    "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch", "go1mpc_fused_tick_batch",
     "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
@@ -115,6 +115,7 @@ def load_library():
     lib.go1mpc_grf_force_opt_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
     lib.go1mpc_grf_force_distribution_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 7
     lib.go1mpc_servo_kin_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 10
+    lib.go1mpc_fused_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.POINTER(FusedTick), vp]
     lib.go1mpc_leg_ik_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
     lib.go1mpc_leg_fk_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
     lib.go1mpc_leg_ik_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 8
@@ -151,6 +152,17 @@ def pack_body_inputs(nh, tick, tx, theta, bodyangle_state, x_warm, refs):
     rec[:, 36:36 + 2 * nh] = x_warm
     rec[:, 36 + 2 * nh:36 + 11 * nh] = np.asarray(refs).reshape(B, 9 * nh)
     return rec
+
+
+class FusedTick(ctypes.Structure):
+    """Go1FusedTick of include/go1mpc.h (device pointers)."""
+    _fields_ = [("n_sqp", ctypes.c_int), ("tick_d", ctypes.c_void_p), ("step_state_d", ctypes.c_void_p),
+                ("step_in_d", ctypes.c_void_p), ("out38_d", ctypes.c_void_p), ("step_diag_d", ctypes.c_void_p),
+                ("foot_d", ctypes.c_void_p), ("out18_d", ctypes.c_void_p), ("right_support_d", ctypes.c_void_p),
+                ("nh", ctypes.c_int), ("body_in_d", ctypes.c_void_p), ("body_out_d", ctypes.c_void_p),
+                ("body_diag_d", ctypes.c_void_p), ("gait_mode", ctypes.c_int), ("y_offset", ctypes.c_double),
+                ("homing_d", ctypes.c_void_p), ("q_d", ctypes.c_void_p), ("jac_d", ctypes.c_void_p),
+                ("foot_des_d", ctypes.c_void_p), ("ik_iters_d", ctypes.c_void_p), ("servo_theta_d", ctypes.c_void_p)]
 
 
 def _ptr(a):
@@ -334,6 +346,18 @@ class Go1Mpc:
         self._check(self.lib.go1mpc_servo_kin_tick_batch(self.h, B, gait_mode, y_offset, _ptr(com), _ptr(theta), _ptr(rfoot),
                                                          _ptr(lfoot), _ptr(homing), _ptr(q), _ptr(jac), _ptr(foot_des),
                                                          _ptr(iters), stream), "servo_kin_tick_batch")
+
+    def fused_tick(self, B, n_sqp, tick, step_state, step_in, out38, foot, out18, nh, body_in, body_out, gait_mode, y_offset,
+                   homing, q, servo_theta, step_diag=None, right_support=None, body_diag=None, jac=None, foot_des=None,
+                   ik_iters=None, stream=None):
+        """go1mpc_fused_tick_batch: planner tick -> swing foot -> body MPC -> servo IK in one call (device buffers)."""
+        def a(x):
+            v = _ptr(x)
+            return v if isinstance(v, int) or v is None else ctypes.cast(v, ctypes.c_void_p).value
+        t = FusedTick(n_sqp, a(tick), a(step_state), a(step_in), a(out38), a(step_diag), a(foot), a(out18), a(right_support),
+                      nh, a(body_in), a(body_out), a(body_diag), gait_mode, y_offset, a(homing), a(q), a(jac), a(foot_des),
+                      a(ik_iters), a(servo_theta))
+        self._check(self.lib.go1mpc_fused_tick_batch(self.h, B, ctypes.byref(t), stream), "fused_tick_batch")
 
     def grf_force_opt(self, B, in_d, out_d, diag_d=None, stream=None):
         """Device records: in [B,48], out [B,16], diag [B,32] ints."""

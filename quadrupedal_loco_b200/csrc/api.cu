@@ -843,6 +843,25 @@ int go1mpc_servo_kin_tick_batch(go1mpc_t* h, int B, int gait_mode, double y_offs
   h->launches++;
   return GO1MPC_OK;
 }
+// ------------------------------------------------------------------ fused tick (planner -> swing foot -> body MPC -> servo IK)
+int go1mpc_fused_tick_batch(go1mpc_t* h, int B, const Go1FusedTick* t, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (!t || B < 0) return fail(h, GO1MPC_E_INVALID, "fused_tick_batch: bad argument");
+  if (!t->servo_theta_d || !t->out38_d || !t->out18_d || !t->body_out_d) return fail(h, GO1MPC_E_INVALID, "fused_tick_batch: bad argument");
+  if (B == 0) return GO1MPC_OK;
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  int rc;
+  if ((rc = go1mpc_step_timing_step_batch(h, t->n_sqp, B, t->tick_d, t->step_state_d, t->step_state_d, t->step_in_d, t->out38_d,
+                                          t->step_diag_d, st))) return rc;
+  if ((rc = go1mpc_foot_trajectory_batch(h, B, t->tick_d, t->step_state_d, t->out38_d, t->foot_d, t->out18_d, t->right_support_d, st))) return rc;
+  if ((rc = go1mpc_body_mpc_step_batch(h, t->nh, B, t->body_in_d, t->body_out_d, t->body_diag_d, st))) return rc;
+  CU(h, body_theta_gather_launch(B, t->body_out_d, go1mpc_body_out_stride(t->nh), t->servo_theta_d, st));
+  h->launches++;
+  // SoA: the CoM position is rows 0..2 of out38, the right / left foot positions rows 0..2 / 3..5 of out18
+  return go1mpc_servo_kin_tick_batch(h, B, t->gait_mode, t->y_offset, t->out38_d, t->servo_theta_d, t->out18_d,
+                                     t->out18_d + (size_t)3 * B, t->homing_d, t->q_d, t->jac_d, t->foot_des_d, t->ik_iters_d, st);
+}
+
 namespace {
 // shared host staging for the two leg entries: ins[k] (bytes) up, outs[k] down
 int leg_host(go1mpc* h, int B, bool ik, const double* a3, const double* b3, const int* leg, const double* bp, const double* br,

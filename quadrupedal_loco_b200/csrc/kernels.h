@@ -116,6 +116,7 @@ struct ServoKParams {
 };
 cudaError_t servo_kin_launch(ServoKParams P, cudaStream_t st);
 cudaError_t leg_ik_launch(LegKParams P, cudaStream_t st);
+cudaError_t body_theta_gather_launch(int B, const double* body_out, int stride, double* theta, cudaStream_t st);
 
 // ---- GRF distribution of the servo loop (grf_qp.cu) ----
 constexpr int GRF_IN_DOUBLES = 48, GRF_OUT_DOUBLES = 16, GRF_DIAG_INTS = 32;

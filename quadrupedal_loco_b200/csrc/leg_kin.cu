@@ -183,4 +183,19 @@ cudaError_t leg_ik_launch(LegKParams P, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+// Fused tick glue: body orientation for the servo stage from the body-MPC output records (AoS, stride doubles):
+// roll = out[0], pitch = out[1] (the Vec14's next-step angles, PRMPCClass.cpp:696-712), yaw = 0.  -> theta [3][B] SoA.
+__global__ void __launch_bounds__(256) body_theta_gather_kernel(int B, const double* body_out, int stride, double* theta) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* o = body_out + (size_t)b * stride;
+  theta[b] = o[0];
+  theta[(size_t)B + b] = o[1];
+  theta[2 * (size_t)B + b] = 0.0;
+}
+cudaError_t body_theta_gather_launch(int B, const double* body_out, int stride, double* theta, cudaStream_t st) {
+  body_theta_gather_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, body_out, stride, theta);
+  return cudaGetLastError();
+}
+
 }  // namespace go1
