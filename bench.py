@@ -48,8 +48,8 @@ def parse():
     ap.add_argument("--nh", type=int, default=10, help="body-MPC horizon")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--streams", type=int, default=16, help="CUDA streams the device-resident leg deals its steps over")
-    ap.add_argument("--body-streams", type=int, default=6, help="of those, streams the body-MPC ticks are dealt over")
+    ap.add_argument("--streams", type=int, default=20, help="CUDA streams the device-resident leg deals its steps over")
+    ap.add_argument("--body-streams", type=int, default=8, help="of those, streams the body-MPC ticks are dealt over")
     ap.add_argument("--sweep", action="store_true", help="also print per-batch-size throughput (stderr)")
     return ap.parse_args()
 
@@ -331,25 +331,40 @@ def run_b200(a):
     NB = max(1, a.body_streams)
     NSTREAM = max(NB + 1, a.streams)
     lanes = [stream] + [torch.cuda.Stream(device=dev) for _ in range(NSTREAM - 1)]
-    lane_ptr = [None] + [x.cuda_stream for x in lanes[1:]]
+    lane_ptr = [x.cuda_stream for x in lanes]
     joins = [torch.cuda.Event() for _ in range(NSTREAM)]
+    mpc_b = q.Go1Mpc(local)          # the body feeder thread's handle
+    hb = mpc_b.h
     # first use of a stream allocates the body path's per-stream workspace: keep that out of the timed region
     for k in range(NB):
         launch_body(k, lane_ptr[k])
+        rc = lib.go1mpc_body_mpc_step_batch(hb, nh, B, P_in[k % nrot], P_out[k % nrot], P_dg[k % nrot], lane_ptr[k])
+        assert rc == 0, rc
     for k in range(NB, NSTREAM):
         launch_sqp(k, lane_ptr[k])
     torch.cuda.synchronize()
     barrier()
     clocks.start()
-    l0 = mpc.launch_count
+    l0 = mpc.launch_count; l0b = mpc_b.launch_count
+    # two host threads enqueue (ctypes releases the GIL inside the C calls): one deals the planner ticks, the other --
+    # through a second handle, handles being thread-compatible, not thread-safe -- the body ticks (4 launches per
+    # call).  One thread alone needs ~40 us per step for the 6 launches + 1 copy, close to what the GPU needs.
+    def feed_planner():
+        for i in range(K):
+            launch_sqp(i, lane_ptr[NB + i % (NSTREAM - NB)])
+
+    def feed_body():
+        for i in range(K):
+            r = i % nrot
+            rc = lib.go1mpc_body_mpc_step_batch(hb, nh, B, P_in[r], P_out[r], P_dg[r], lane_ptr[i % NB])
+            assert rc == 0, rc
     with torch.cuda.stream(stream):
         ev[0].record(stream)
         for x in lanes[1:]:
             x.wait_event(ev[0])
         t_host = time.perf_counter()
-        for i in range(K):
-            launch_sqp(i, lane_ptr[NB + i % (NSTREAM - NB)])
-            launch_body(i, lane_ptr[i % NB])
+        ta = threading.Thread(target=feed_planner); tb = threading.Thread(target=feed_body)
+        ta.start(); tb.start(); ta.join(); tb.join()
         t_host = time.perf_counter() - t_host
         for k in range(1, NSTREAM):
             joins[k].record(lanes[k])
@@ -357,7 +372,7 @@ def run_b200(a):
         ev[K].record(stream)
     torch.cuda.synchronize()
     barrier()
-    launches = mpc.launch_count - l0
+    launches = (mpc.launch_count - l0) + (mpc_b.launch_count - l0b)
     total_ms = ev[0].elapsed_time(ev[K])
     solves_timed = float(sum(B + sqp_solves[i % nrot] for i in range(K)))
 
@@ -400,7 +415,8 @@ def run_b200(a):
     body_ov_ms = overlapped(launch_body, 0, NB)
     sqp_ov_ms = overlapped(launch_sqp, NB, NSTREAM - NB)
     clk = clocks.stop()
-    handed_over = mpc.body_handover_total(); guard_trips = mpc.body_guard_trips()
+    handed_over = mpc.body_handover_total() + mpc_b.body_handover_total(); guard_trips = mpc.body_guard_trips() + mpc_b.body_guard_trips()
+    mpc_b.close()
     body_mode = os.environ.get("GO1MPC_BODY_MODE", "auto")
 
     t = torch.tensor([total_ms, solves_timed], dtype=torch.float64, device=dev)

@@ -420,6 +420,12 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
     P.theta_lim = c.theta_lim; P.torque_lim = c.torque_lim;
     for (int k = 0; k < 4; k++) P.lamda[k] = c.lamda[k];
     if (body_tri_supported(nh) && (h->body_mode == 2 || (h->body_mode == 3 && B >= h->body_tri_min))) {
+      if (h->tri_ws.size() >= 64 && h->tri_ws.find(st) == h->tri_ws.end()) {
+        // a caller that keeps creating streams: drop the workspaces of the old ones (their work is done after the sync)
+        CU(h, cudaDeviceSynchronize());
+        for (auto& kv : h->tri_ws) if (kv.second.p) cudaFree(kv.second.p);
+        h->tri_ws.clear();
+      }
       go1mpc::TriWs& W = h->tri_ws[st];
       if (W.capB < B) {
         if (W.p) { CU(h, cudaStreamSynchronize(st)); cudaFree(W.p); W.p = nullptr; W.capB = 0; }
