@@ -350,10 +350,12 @@ def run_b200(a):
     # through a second handle, handles being thread-compatible, not thread-safe -- the body ticks (4 launches per
     # call).  One thread alone needs ~40 us per step for the 6 launches + 1 copy, close to what the GPU needs.
     def feed_planner():
+        torch.cuda.set_device(local)         # CUDA's current device is per host thread
         for i in range(K):
             launch_sqp(i, lane_ptr[NB + i % (NSTREAM - NB)])
 
     def feed_body():
+        torch.cuda.set_device(local)
         for i in range(K):
             r = i % nrot
             rc = lib.go1mpc_body_mpc_step_batch(hb, nh, B, P_in[r], P_out[r], P_dg[r], lane_ptr[i % NB])

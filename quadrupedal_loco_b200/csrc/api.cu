@@ -312,11 +312,13 @@ int go1mpc_sm_count(const go1mpc_t* h) { return h ? h->sms : 0; }
 // so checkpointing or restoring a batch is a memcpy
 int go1mpc_copy_device_async(go1mpc_t* h, void* dst_d, const void* src_d, size_t bytes, void* stream) {
   if (!h || !dst_d || !src_d) return GO1MPC_E_INVALID;
+  CU(h, cudaSetDevice(h->device));     // a host thread other than the creating one starts on device 0
   CU(h, cudaMemcpyAsync(dst_d, src_d, bytes, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : h->stream));
   return GO1MPC_OK;
 }
 int go1mpc_synchronize(go1mpc_t* h) {
   if (!h) return GO1MPC_E_INVALID;
+  CU(h, cudaSetDevice(h->device));
   CU(h, cudaStreamSynchronize(h->stream));
   for (auto& L : h->lanes) CU(h, cudaStreamSynchronize(L.stream));
   return GO1MPC_OK;
@@ -861,6 +863,7 @@ int go1mpc_fused_tick_batch(go1mpc_t* h, int B, const Go1FusedTick* t, void* str
                                           t->step_diag_d, st))) return rc;
   if ((rc = go1mpc_foot_trajectory_batch(h, B, t->tick_d, t->step_state_d, t->out38_d, t->foot_d, t->out18_d, t->right_support_d, st))) return rc;
   if ((rc = go1mpc_body_mpc_step_batch(h, t->nh, B, t->body_in_d, t->body_out_d, t->body_diag_d, st))) return rc;
+  CU(h, cudaSetDevice(h->device));
   CU(h, body_theta_gather_launch(B, t->body_out_d, go1mpc_body_out_stride(t->nh), t->servo_theta_d, st));
   h->launches++;
   // SoA: the CoM position is rows 0..2 of out38, the right / left foot positions rows 0..2 / 3..5 of out18
