@@ -356,6 +356,12 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
   if (!valid) p = 1;   // table overrun (UB in the reference): flagged in diag, nothing is written
   const double px = ST(S_FX + p - 1), py = ST(S_FY + p - 1);
   const double tx_p1 = ST(S_TX + p - 1), ts_p1 = ST(S_TS + p - 1), ts_1 = ST(S_TS + 1);
+  // what the write-back and CoM_height_solve read of the pre-tick tables, fetched now: two dependent global loads
+  // (the period the previous tick left, then its table entries) would otherwise sit exposed behind the SQP loop
+  const int bp = (int)ST(S_BJX1);
+  const int b1 = bp >= 1 && bp <= NS ? bp : 1, b2 = bp >= 2 && bp <= NS + 1 ? bp : 2;
+  const double ts_b1_old = ST(S_TS + b1 - 1), tx_b1_old = ST(S_TX + b1 - 1);
+  const double fz_b2 = ST(S_FZ + b2 - 2), fz_b1 = ST(S_FZ + b1 - 1);
   const int ki = (int)round(tx_p1 / dt);
   const int k_yu = i - ki;
   const double Tk = ts_p1 - k_yu * dt;
@@ -579,10 +585,8 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
   // _ts(p-1) = ts_new and the running sum _tx(k) = _tx(k-1) + _ts(k-1) for k >= p (:906-909), in the reference's order;
   // in the same pass: the two index searches against the UPDATED table (:1031-1041), the entry CoM_height_solve
   // reads, and the store of the new _tx entries (every load of column k precedes its store: in-place safe)
-  const int bp = (int)ST(S_BJX1);
-  const int b1 = bp >= 1 && bp <= NS ? bp : 1, b2 = bp >= 2 && bp <= NS + 1 ? bp : 2;
-  const double ts_b1 = (b1 == p) ? ts_new : ST(S_TS + b1 - 1);
-  double tx_b1 = ST(S_TX + b1 - 1);
+  const double ts_b1 = (b1 == p) ? ts_new : ts_b1_old;
+  double tx_b1 = tx_b1_old;
   int jA = NS, jB = NS;
   {
     double cur = tx_p1;
@@ -609,8 +613,8 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
     for (int q = 0; q < 3; q++) { hz_z[q] = INP(I_CZ + q); hz_az[q] = INP(I_CAZ + q); hz_vz[q] = 0.0; }
     hz_vz[0] = INP(I_CVZ);
   } else {
-    if (!WARP) com_height_solve(i, bp <= NS ? bp : 0, ts_b1, tx_b1, ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az);
-    else com_height_solve_warp(i, bp <= NS ? bp : 0, ts_b1, tx_b1, ST(S_FZ + b2 - 2), ST(S_FZ + b1 - 1), c.hcom, dt, hz_z, hz_vz, hz_az, wsm, lane);
+    if (!WARP) com_height_solve(i, bp <= NS ? bp : 0, ts_b1, tx_b1, fz_b2, fz_b1, c.hcom, dt, hz_z, hz_vz, hz_az);
+    else com_height_solve_warp(i, bp <= NS ? bp : 0, ts_b1, tx_b1, fz_b2, fz_b1, c.hcom, dt, hz_z, hz_vz, hz_az, wsm, lane);
   }
   // LIPM roll-out of samples i, i+1, i+2 (:938-955)
   double comx[3], comy[3], comvx[3], comvy[3], comax[3], comay[3], zmpx[3], zmpy[3], dcmx[3], dcmy[3];
