@@ -35,6 +35,11 @@ constexpr int S_TS = 0, S_TX = 27, S_FX = 54, S_FY = 81, S_FZ = 108, S_LXX = 135
 constexpr int I_EST = 0, I_RF = 6, I_LF = 8, I_CZ = 10, I_CAZ = 13, I_ZSC = 16, I_CVZ = 19;
 }  // namespace
 
+// libm calls of the tick's front-end, out of line: eight inlined cosh / sinh expansions are ~1 k SASS instructions of a
+// kernel that stalls on instruction fetch; the routines (and therefore the results) are the same
+static __device__ __noinline__ double cosh_nl(double x) { return cosh(x); }
+static __device__ __noinline__ double sinh_nl(double x) { return sinh(x); }
+
 // inverse by Gauss-Jordan with partial (row) pivoting, first maximal |pivot| wins; row-major 7 x 7
 // (the elimination order of the CPU oracle: the time-polynomial matrix is badly conditioned, so
 // the order is part of the contract -- SURVEY.md Appendix B)
@@ -366,14 +371,14 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
   const int k_yu = i - ki;
   const double Tk = ts_p1 - k_yu * dt;
   const double Lxx_refx = ST(S_LXX + p - 1), Lyy_refy = ST(S_LYY + p - 1);
-  const double tr1_ref = cosh(Wn * Tk), tr2_ref = sinh(Wn * Tk);
+  const double tr1_ref = cosh_nl(Wn * Tk), tr2_ref = sinh_nl(Wn * Tk);
   double v[4];
   if (i == 1) { v[0] = Lxx_refx; v[1] = Lyy_refy; v[2] = tr1_ref; v[3] = tr2_ref; }
   else { for (int k = 0; k < 4; k++) v[k] = ST(S_VARI + k); }
   double tr1_min, tr2_min;
-  if ((c.t_min - k_yu * dt) >= 0.001) { tr1_min = cosh(Wn * (c.t_min - k_yu * dt)); tr2_min = sinh(Wn * (c.t_min - k_yu * dt)); }
-  else { tr1_min = cosh(Wn * (0.001)); tr2_min = sinh(Wn * (0.001)); }
-  const double tr1_max = cosh(Wn * (c.t_max - k_yu * dt)), tr2_max = sinh(Wn * (c.t_max - k_yu * dt));
+  if ((c.t_min - k_yu * dt) >= 0.001) { tr1_min = cosh_nl(Wn * (c.t_min - k_yu * dt)); tr2_min = sinh_nl(Wn * (c.t_min - k_yu * dt)); }
+  else { tr1_min = cosh_nl(Wn * (0.001)); tr2_min = sinh_nl(Wn * (0.001)); }
+  const double tr1_max = cosh_nl(Wn * (c.t_max - k_yu * dt)), tr2_max = sinh_nl(Wn * (c.t_max - k_yu * dt));
 
   const double comx_f = ST(S_FEED + 0), comvx_f = ST(S_FEED + 1), comy_f = ST(S_FEED + 3), comvy_f = ST(S_FEED + 4);
   double endx = ST(S_END + 0), endy = ST(S_END + 1);
