@@ -120,3 +120,32 @@ def test_modes_agree_with_each_other_at_full_size(oracle):
             x0, x1 = res["fast"][0], res[mode][0]
             err = np.abs(x1 - x0) / np.maximum(1.0, np.abs(x0).max(axis=1, keepdims=True))
             assert err.max() < 1e-12, (mode, B, err.max())
+
+
+def test_tri_handover_list_overflow():
+    """More hand-overs than the list holds (8190): the combined kernel then redoes the whole batch.  3x perturbation,
+    40000 instances, ~55 % non-converged: the three-launch path must still equal the combined-solve kernel."""
+    nh, B = 10, 40000
+    d = synth.body_mpc_inputs(B, nh, seed=108, scale=3.0)
+    res = {}
+    for mode in ("fast", "tri"):
+        os.environ["GO1MPC_BODY_MODE"] = mode
+        h = q.Go1Mpc(0)
+        try:
+            h0 = h.body_handover_total()
+            res[mode] = run_gpu(h, nh, d, device=True)
+            res[mode + "_handed"] = h.body_handover_total() - h0
+            assert h.body_guard_trips() == 0
+        finally:
+            h.close()
+            os.environ.pop("GO1MPC_BODY_MODE", None)
+    assert res["tri_handed"] > 8190, res["tri_handed"]
+    da, db = res["fast"][1], res["tri"][1]
+    conv = da[:, 0] == 0
+    assert conv.sum() > B // 4
+    np.testing.assert_array_equal(da[:, 0], db[:, 0])
+    np.testing.assert_array_equal(da[conv], db[conv])
+    xa, xb = res["fast"][0], res["tri"][0]
+    err = np.abs(xa - xb) / np.maximum(1.0, np.abs(xa).max(axis=1, keepdims=True))
+    err = np.where(np.isfinite(err), err, 0.0)
+    assert err.max() < 1e-9
