@@ -534,19 +534,23 @@ __global__ void __launch_bounds__(WPC * 32, GO1_TRI_WARPS / WPC) tri_solve_kerne
 #pragma unroll
     for (int m = 0; m < RW; m++) { zz = fma(z[m], z[m], zz); zn = fma(z[m], np_[m], zn); }
     zz = q4sum(zz); zn = q4sum(zn);
-    // r = R^-1 d[0:iq): every lane of the group solves redundantly (d is replicated, R in shared memory)
-    double r[NH];
+    // d[0:iq) would be the new column of R if this pass ends in an add: stored now (column iq is not read before it
+    // is added), so that r = R^-1 d[0:iq) can overwrite it in place -- 20 registers less (168 -> 12 warps/SM is the
+    // solve kernel's occupancy limit).  Every lane of the group solves redundantly (d is replicated).
+    if (gl == 0 && iq < NH) {
 #pragma unroll
-    for (int j = 0; j < NH; j++) r[j] = d[j];
+      for (int tt = 0; tt < NH; tt++) if (tt < iq) Rp[iq * (iq + 3) / 2 + tt] = d[tt];
+    }
 #pragma unroll
     for (int c = NH - 1; c >= 0; c--) {
       if (c < iq) {
-        const double rc = r[c] * rinvs[c];
-        r[c] = rc;
+        const double rc = d[c] * rinvs[c];
+        d[c] = rc;
 #pragma unroll
-        for (int t = 0; t < c; t++) r[t] = fma(-rc, Rp[c * (c + 3) / 2 + t], r[t]);
+        for (int t = 0; t < c; t++) d[t] = fma(-rc, Rp[c * (c + 3) / 2 + t], d[t]);
       }
     }
+    double (&r)[NH] = d;      // entries below iq now hold r, entries from iq on are still d2
     // ratio test (cpp:360-367): arg-min of u_k / r_k over r_k > 0 by cross-multiplication (strict '<', first
     // slot wins, as the reference's scan), no division
     double ub = 0.0, rb = -1.0; int kb = -1;
@@ -592,23 +596,21 @@ __global__ void __launch_bounds__(WPC * 32, GO1_TRI_WARPS / WPC) tri_solve_kerne
       // ---- add_constraint (cpp:30-93) as ONE Householder reflection H = I - tau v v', v = d2 + sigma e_iq ----
       const double sigma = (diq < 0.0) ? -nrm : nrm;
       if (nrm != 0.0) {
-        double v[NH];
+        // v overwrites d in place (entries below iq -- r, no longer needed -- become 0)
 #pragma unroll
-        for (int j = 0; j < NH; j++) v[j] = (j > iq) ? d[j] : ((j == iq) ? diq + sigma : 0.0);
+        for (int j = 0; j < NH; j++) d[j] = (j > iq) ? d[j] : ((j == iq) ? diq + sigma : 0.0);
 #pragma unroll
         for (int m = 0; m < RW; m++) {
           double w = 0.0;
 #pragma unroll
-          for (int j = 0; j < NH; j++) w = fma(Jr[m][j], v[j], w);
+          for (int j = 0; j < NH; j++) w = fma(Jr[m][j], d[j], w);
           const double sw2 = tau * w;
 #pragma unroll
-          for (int j = 0; j < NH; j++) Jr[m][j] = fma(-sw2, v[j], Jr[m][j]);
+          for (int j = 0; j < NH; j++) Jr[m][j] = fma(-sw2, d[j], Jr[m][j]);
         }
       }
       const double dq = (nrm != 0.0) ? -sigma : diq;           // new R(iq,iq)
       if (gl == 0) {
-#pragma unroll
-        for (int tt = 0; tt < NH; tt++) if (tt < iq) Rp[iq * (iq + 3) / 2 + tt] = d[tt];
         Rp[iq * (iq + 3) / 2 + iq] = dq;
         rinvs[iq] = (nrm != 0.0) ? ((diq < 0.0) ? inrm : -inrm) : 1.0 / dq;
         resi[4 + D::OMAX + npass] = ip;
