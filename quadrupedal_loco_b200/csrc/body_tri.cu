@@ -332,7 +332,7 @@ template <int NH, int WPC>
 __global__ void __launch_bounds__(WPC * 32, GO1_TRI_WARPS / WPC) tri_solve_kernel(BodyKParams P) {
   using D = TriDims<NH>;
   constexpr int RW = (NH + 3) / 4;          // rows of J per lane
-  static_assert(RW == 3, "written for 9 <= NH <= 12");
+  static_assert(RW >= 1 && RW <= 3 && NH % 2 == 0, "4 lanes per half, up to 3 rows of J per lane, rows moved 16 bytes at a time");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -901,9 +901,10 @@ __global__ void __launch_bounds__(TRI_MERGE_THREADS) tri_merge_kernel(BodyKParam
 }
 
 // ======================================================================================= host side
+bool body_tri_supported(int nh);
 size_t body_tri_workspace_bytes(int nh, int B, size_t off[6]) {
-  if (nh != 10) return 0;
-  using D = TriDims<10>;
+  if (!body_tri_supported(nh)) return 0;
+  using D = TriDims<10>;        // sized for the largest supported horizon: a stream's workspace serves every horizon
   size_t o = 0;
   off[0] = o; o += (size_t)B * D::JB * sizeof(double);
   off[1] = o; o += (size_t)2 * B * D::HS * sizeof(double);
@@ -914,7 +915,7 @@ size_t body_tri_workspace_bytes(int nh, int B, size_t off[6]) {
   return o;
 }
 
-bool body_tri_supported(int nh) { return nh == 10; }
+bool body_tri_supported(int nh) { return nh == 10 || nh == 4; }
 
 template <int NH>
 static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, int sms, cudaStream_t st) {
@@ -963,6 +964,7 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
 
 cudaError_t body_tri_launch(BodyKParams P, const double* tab_host, int sms, cudaStream_t st) {
   switch (P.nh) {
+    case 4: return tri_launch_nh<4>(P, tab_host, sms, st);       // the reference's own horizon (PRMPCClass.h:34)
     case 10: return tri_launch_nh<10>(P, tab_host, sms, st);
     default: return cudaErrorInvalidValue;
   }

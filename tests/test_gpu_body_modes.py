@@ -149,3 +149,24 @@ def test_tri_handover_list_overflow():
     err = np.abs(xa - xb) / np.maximum(1.0, np.abs(xa).max(axis=1, keepdims=True))
     err = np.where(np.isfinite(err), err, 0.0)
     assert err.max() < 1e-9
+
+
+@pytest.mark.parametrize("B,scale", [(1, 1.0), (257, 1.0), (3000, 1.0), (3000, 2.0)])
+def test_tri_at_the_reference_horizon(oracle, B, scale):
+    """nh = 4 (PRMPCClass.h:34, the horizon the reference ships) through the three-launch path."""
+    nh = 4
+    os.environ["GO1MPC_BODY_MODE"] = "tri"
+    h = q.Go1Mpc(0)
+    try:
+        d = synth.body_mpc_inputs(B, nh, seed=synth.SEED_CFG2 + B, scale=scale)
+        l0 = h.launch_count
+        out, diag = run_gpu(h, nh, d, device=True)
+        assert h.launch_count - l0 == 4          # setup, solve, merge, list-mode combined kernel
+        r = run_oracle(oracle, nh, d)
+        assert_body_parity(out, diag, r, nh, f"tri nh=4 B={B} scale={scale}")
+        assert h.body_guard_trips() == 0
+        if B >= 257:
+            assert (r["nactive"] > 0).any()
+    finally:
+        h.close()
+        os.environ.pop("GO1MPC_BODY_MODE", None)
