@@ -205,7 +205,7 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- GPU arm
 # DRAM bytes (read + write) of the kernels of one three-launch body-MPC call, per batch size, from ncu --set full
-TRAFFIC_TRI = {4096: 11812608, 65536: 231043072}   # profiles/r01_tri_kernels.md
+TRAFFIC_TRI = {4096: 32007936, 65536: 230868736}   # profiles/r01_tri_kernels.md (4096: 11.8 - 32.0 MB, depends on what L2 still holds)
 
 
 def run_b200(a):
