@@ -189,7 +189,8 @@ struct GiThread4 {
 #pragma unroll
     for (int i = 0; i < M; i++) {
       const double sum = rows.slack(i, x);      // i is a compile-time constant after unrolling
-      psi += fmin(0.0, sum);
+      psi += (sum < 0.0) ? sum : 0.0;           // = fmin(0.0, sum) for every input that matters: NaN gives 0 either way, and the
+                                                // sign of a zero cannot change psi; fmin's IEEE handling costs 5 instructions more per row
       if (sum < ss && !((inA >> i) & 1u) && !((excl >> i) & 1u)) {
         ss = sum; ip = i; s_ip = sum;
         rows.column(i, np);
