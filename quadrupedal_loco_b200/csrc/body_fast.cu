@@ -663,7 +663,10 @@ static cudaError_t fast_launch_nh(const BodyKParams& P, int sms, cudaStream_t st
   using D = FastDims<NH>;
   if (P.in_stride != D::IN || P.out_stride != D::OUT || P.tab_doubles != D::TAB) return cudaErrorInvalidValue;
   const size_t smem = fast_smem<NH>(WPC);
-  static int occ_cache = 0;
+  int dev_ = 0;            // function attributes and occupancy are per device
+  cudaGetDevice(&dev_);
+  static int occ_cache_[64] = {};
+  int& occ_cache = occ_cache_[dev_ & 63];
   if (occ_cache == 0) {
     cudaError_t e = cudaFuncSetAttribute(body_fast_kernel<NH, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

@@ -924,7 +924,12 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
   if (P.in_stride != D::IN || P.out_stride != D::OUT || P.tab_doubles != D::TAB) return cudaErrorInvalidValue;
   const int blocks = (P.B + TRI_SETUP_THREADS - 1) / TRI_SETUP_THREADS;
   const size_t ssmem = (size_t)TRI_SETUP_THREADS * D::IN * sizeof(double) + 16;
-  static bool sattr = false;
+  // function attributes (opt-in dynamic shared memory) and occupancy are per device: one slot per device ordinal
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  dev_ &= 63;
+  static bool sattr_[64] = {};
+  bool& sattr = sattr_[dev_];
   if (!sattr) {
     cudaError_t e = cudaFuncSetAttribute(tri_setup_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
     if (e != cudaSuccess) return e;
@@ -937,7 +942,8 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
   tri_setup_kernel<NH><<<blocks, TRI_SETUP_THREADS, ssmem, st>>>(P, T);
   if (stages < 2) return cudaGetLastError();
   const size_t smem = (size_t)(((NH * NH + 1) & ~1) + WPC * 8 * D::GSP) * sizeof(double);
-  static int occ = 0;
+  static int occ_[64] = {};
+  int& occ = occ_[dev_];
   if (occ == 0) {
     cudaError_t e = cudaFuncSetAttribute(tri_solve_kernel<NH, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -951,7 +957,8 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
   if (stages < 3) return cudaGetLastError();
   {
     const size_t msmem = (size_t)TRI_MERGE_THREADS * (2 * (D::RES + 2) + D::FR + 2) * sizeof(double) + 16;
-    static bool attr = false;
+    static bool attr_[64] = {};
+    bool& attr = attr_[dev_];
     if (!attr) {
       cudaError_t e = cudaFuncSetAttribute(tri_merge_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
       if (e != cudaSuccess) return e;

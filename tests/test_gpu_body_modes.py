@@ -170,3 +170,24 @@ def test_tri_at_the_reference_horizon(oracle, B, scale):
     finally:
         h.close()
         os.environ.pop("GO1MPC_BODY_MODE", None)
+
+
+def test_two_devices_in_one_process(oracle):
+    """Handles on two GPUs of one process: the kernels' opt-in shared-memory attributes and occupancy caches are per
+    device.  Skipped on a single-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    nh, B = 10, 2500
+    d = synth.body_mpc_inputs(B, nh, seed=77)
+    r = run_oracle(oracle, nh, d)
+    for dev in (0, 1):
+        for mode in ("tri", "fast"):
+            os.environ["GO1MPC_BODY_MODE"] = mode
+            h = q.Go1Mpc(dev)
+            try:
+                out, diag = run_gpu(h, nh, d)      # host entry: the handle's own device
+                assert_body_parity(out, diag, r, nh, f"device {dev} {mode}")
+            finally:
+                h.close()
+                os.environ.pop("GO1MPC_BODY_MODE", None)
