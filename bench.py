@@ -518,11 +518,11 @@ def run_b200(a):
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]; hbm_src = "measured"
         except Exception:
             hbm_peak = 6650.0; hbm_src = "fallback"
-        tri = body_mode in ("auto", "tri") and nh == 10 and (body_mode == "tri" or B >= 2048)
+        tri = body_mode in ("auto", "tri") and nh in (4, 10) and (body_mode == "tri" or B >= 2048)
         body_kernel = ("body-inclination MPC tick = tri_setup_kernel + tri_solve_kernel + tri_merge_kernel (+ the list-mode "
                        "body_fast_kernel launch, empty on this workload)") if tri else "body_fast_kernel (body-inclination MPC tick)"
         # DRAM bytes of one call's kernels, ncu --set full at this batch size (profiles/r01_summary.md)
-        traffic = TRAFFIC_TRI.get(B) if tri else ({4096: 4855552}.get(B) if nh == 10 else None)
+        traffic = (TRAFFIC_TRI.get(B) if nh == 10 else None) if tri else ({4096: 4855552}.get(B) if nh == 10 else None)
         sqp_fl = float(np.mean(sqp_flops_per_batch))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(W, nrot),
