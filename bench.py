@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--nh", type=int, default=10, help="body-MPC horizon")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-records", choices=("resident", "full"), default="resident",
+                    help="body records of the e2e leg: 'resident' keeps tx and the previous output record on the device "
+                         "(go1mpc_body_mpc_step_batch_resident_host_async), 'full' uploads whole records every tick")
     ap.add_argument("--streams", type=int, default=20, help="CUDA streams the device-resident leg deals its steps over")
     ap.add_argument("--body-streams", type=int, default=8, help="of those, streams the body-MPC ticks are dealt over")
     ap.add_argument("--sweep", action="store_true", help="also print per-batch-size throughput (stderr)")
@@ -447,6 +450,20 @@ def run_b200(a):
         H_dg = [diag_np[r].ctypes.data for r in range(nrot)]; H_tk = [tk_np[r].ctypes.data for r in range(nrot)]
         H_si = [si_np[r].ctypes.data for r in range(nrot)]; H_so = [so_np[r].ctypes.data for r in range(nrot)]
         H_sd = [sd_np[r].ctypes.data for r in range(nrot)]
+        resident = a.e2e_records == "resident"
+        if resident:
+            # what stays in HBM between ticks: tx [B][28] and the output records (warm start x, stale out14)
+            tk_s = q.body_tick_in_stride(nh)
+            tx_np, xw_np, tick_np = q.split_body_record(nh, in_np.reshape(nrot * B, in_s))
+            R_tx = torch.from_numpy(tx_np).to(dev).view(nrot, B, 28)
+            R_out = torch.zeros(nrot, B, out_s, dtype=torch.float64, device=dev)
+            R_out[:, :, 18:18 + 2 * nh] = torch.from_numpy(xw_np).to(dev).view(nrot, B, 2 * nh)
+            ti_h = torch.from_numpy(tick_np).view(nrot, B, tk_s).pin_memory()
+            to_h = torch.zeros(nrot, B, q.BODY_TICK_OUT, dtype=torch.float64).pin_memory()
+            ti_np, to_np = ti_h.numpy(), to_h.numpy()
+            P_rtx = [R_tx[r].data_ptr() for r in range(nrot)]; P_rout = [R_out[r].data_ptr() for r in range(nrot)]
+            H_ti = [ti_np[r].ctypes.data for r in range(nrot)]; H_to = [to_np[r].ctypes.data for r in range(nrot)]
+            torch.cuda.synchronize()
 
         # one handle per host thread (handles are thread-compatible, not thread-safe): thread A feeds the
         # planner ticks, thread B the body ticks; ctypes releases the GIL inside the C calls, so the two
@@ -466,7 +483,10 @@ def run_b200(a):
         def feed_body(n):
             for i in range(n):
                 r = i % nrot
-                rc = lib2.go1mpc_body_mpc_step_batch_host_async(hh2, nh, B, H_in[r], H_out[r], H_dg[r])
+                if resident:
+                    rc = lib2.go1mpc_body_mpc_step_batch_resident_host_async(hh2, nh, B, P_rtx[r], P_rout[r], H_ti[r], H_to[r], H_dg[r])
+                else:
+                    rc = lib2.go1mpc_body_mpc_step_batch_host_async(hh2, nh, B, H_in[r], H_out[r], H_dg[r])
                 assert rc == 0, rc
                 if r == nrot - 1:
                     mpc2.synchronize()
@@ -498,12 +518,18 @@ def run_b200(a):
             te_ms, se_all = float(te[0].item()), se
         assert (diag_np[:min(Ke, nrot), :, 0] == 0).all()
         assert np.array_equal(diag_np[0], diag_all[0]) and np.array_equal(sd_np[0], sdiag[0]), "e2e results differ from the device-resident leg"
+        if resident:
+            want = out_d[0].cpu().numpy()
+            assert np.array_equal(to_np[0][:, :18], want[:, :18]) and np.array_equal(to_np[0][:, 18], want[:, 18 + 2 * nh]), \
+                "e2e body results differ from the device-resident leg"
+        body_up, body_down = (tk_s, q.BODY_TICK_OUT) if resident else (in_s, out_s)
         e2e = {"value": se_all / (te_ms * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": B * (in_s * 8 + q.STEP_IN * 8 + 4),
-               "d2h_bytes_per_step": B * (out_s * 8 + dg_s * 4 + q.STEP_OUT * 8 + q.STEP_DIAG * 4),
+               "h2d_bytes_per_step": B * (body_up * 8 + q.STEP_IN * 8 + 4),
+               "d2h_bytes_per_step": B * (body_down * 8 + dg_s * 4 + q.STEP_OUT * 8 + q.STEP_DIAG * 4),
+               "body_records": a.e2e_records,
                "steps": Ke, "ms_per_step": te_ms / Ke, "wall_ms_per_step": 1e3 * t_wall / Ke, "launches": e2e_launches,
-               "api": "go1mpc_step_timing_step_batch_host_async + go1mpc_body_mpc_step_batch_host_async (pinned host buffers; "
-                      "H2D, kernel, D2H per call on 8 internal lanes; planner state resident on the device; two handles fed by two "
+               "api": "go1mpc_step_timing_step_batch_host_async + " + ("go1mpc_body_mpc_step_batch_resident_host_async" if resident else "go1mpc_body_mpc_step_batch_host_async") + " (pinned host buffers; "
+                      "H2D, kernel, D2H per call on 8 internal lanes; planner state" + (", body step table and previous body output record" if resident else "") + " resident on the device; two handles fed by two "
                       "host threads; go1mpc_synchronize before a host slot is reused and at the end; timed with CUDA events "
                       "recorded before the first enqueue and after the last synchronize)"}
 

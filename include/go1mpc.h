@@ -214,6 +214,22 @@ int go1mpc_body_mpc_step_batch_host_async(go1mpc_t *h, int nh, int B,
 int go1mpc_step_timing_step_batch_host_async(go1mpc_t *h, int n_sqp, int B, const int *tick,
                                              const double *state_d, double *state_out_d,
                                              const double *in, double *out, int *diag);
+/* Pipelined body tick with the slow part of the record RESIDENT ON THE DEVICE, as the planner state is:
+ * what PRMPCClass::body_theta_mpc takes per call (RT/FastMPC/PRMPCClass.cpp:379-395) moves, what the class
+ * keeps as members (_tx :174-178, _V_ini :258-261, the stale results a gated tick returns) stays in HBM.
+ *   tx_d     device [B][28] doubles: tx[27] + 1 pad (the caller rewrites a row when the planner re-times a step)
+ *   out_d    device [B][go1mpc_body_out_stride(nh)], in/out: the output records of go1mpc_body_mpc_step_batch;
+ *            the tick reads its warm start x (and, when gated, its out14) from here and writes its results back
+ *   tick_in  host [B][go1mpc_body_tick_in_stride(nh)]: tick | theta(4) | bodyangle_state(4) | 9 rows of nh
+ *            (= record doubles [27,36) and [36+2nh, 36+11nh) of the full format; + pad to an even count)
+ *   tick_out host [B][GO1MPC_BODY_TICK_OUT]: out14 | theta(4) | cost | 0
+ *   diag     host [B][go1mpc_body_diag_stride(nh)] or NULL
+ * Results are bit-identical to the full-record entries.  Calls on the same out_d are ordered. */
+#define GO1MPC_BODY_TICK_OUT 20
+int go1mpc_body_tick_in_stride(int nh);
+int go1mpc_body_mpc_step_batch_resident_host_async(go1mpc_t *h, int nh, int B,
+                                                   const double *tx_d, double *out_d,
+                                                   const double *tick_in, double *tick_out, int *diag);
 
 /* Model matrices the handle condenses with, for inspection/tests (host
  * buffers, column-major): pps,pvs nh x 2; ppu,pvu,ppu_2,pvu_2 nh x nh.

@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgo1mpc.so")
-SOURCES = ["api.cu", "body_mpc.cu", "body_fast.cu", "body_split.cu", "body_tri.cu", "qp_dense.cu", "step_timing.cu", "foot_traj.cu", "leg_kin.cu", "grf_qp.cu"]
+SOURCES = ["api.cu", "body_mpc.cu", "body_fast.cu", "body_split.cu", "body_tri.cu", "body_resident.cu", "qp_dense.cu", "step_timing.cu", "foot_traj.cu", "leg_kin.cu", "grf_qp.cu"]
 # per-source extra flags: the thread-per-instance kernels keep the oracle's operation order and
 # must not contract a*b+c into FMA
 EXTRA = {"step_timing.cu": ["-fmad=false"], "foot_traj.cu": ["-fmad=false"], "leg_kin.cu": ["-fmad=false"]}

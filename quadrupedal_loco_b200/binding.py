@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_body_model", "go1mpc_body_default_tx", "go1mpc_measure_dfma_peak",
     "go1mpc_step_timing_step_batch", "go1mpc_step_timing_step_batch_host", "go1mpc_step_default_state",
     "go1mpc_body_mpc_step_batch_host_async", "go1mpc_step_timing_step_batch_host_async",
+    "go1mpc_body_tick_in_stride", "go1mpc_body_mpc_step_batch_resident_host_async",
     "go1mpc_foot_trajectory_batch", "go1mpc_foot_trajectory_batch_host", "go1mpc_foot_default_state",
     "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch", "go1mpc_fused_tick_batch",
     "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
@@ -108,6 +109,8 @@ def load_library():
     lib.go1mpc_step_default_state.argtypes = [vp] + [ctypes.c_double] * 4 + [vp]
     lib.go1mpc_body_mpc_step_batch_host_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]
     lib.go1mpc_step_timing_step_batch_host_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    lib.go1mpc_body_tick_in_stride.argtypes = [ctypes.c_int]
+    lib.go1mpc_body_mpc_step_batch_resident_host_async.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp]
     lib.go1mpc_foot_trajectory_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
     lib.go1mpc_foot_trajectory_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
     lib.go1mpc_foot_default_state.argtypes = [vp, vp]
@@ -135,6 +138,24 @@ def body_out_stride(nh):
 
 def body_diag_stride(nh):
     return BODY_DIAG_ACTIVE + 2 * nh
+
+
+BODY_TICK_OUT = 20     # GO1MPC_BODY_TICK_OUT: out14 | theta(4) | cost | 0
+
+
+def body_tick_in_stride(nh):
+    return (9 + 9 * nh + 1) & ~1
+
+
+def split_body_record(nh, rec):
+    """Full input records -> (tx [B,28], x_warm [B,2nh], tick records [B, body_tick_in_stride]) of the
+    device-resident entry go1mpc_body_mpc_step_batch_resident_host_async."""
+    B = rec.shape[0]
+    tx = np.zeros((B, 28)); tx[:, :27] = rec[:, :27]
+    tick = np.zeros((B, body_tick_in_stride(nh)))
+    tick[:, :9] = rec[:, 27:36]
+    tick[:, 9:9 + 9 * nh] = rec[:, 36 + 2 * nh:36 + 11 * nh]
+    return tx, rec[:, 36:36 + 2 * nh].copy(), tick
 
 
 def pack_body_inputs(nh, tick, tx, theta, bodyangle_state, x_warm, refs):
@@ -267,6 +288,13 @@ class Go1Mpc:
         """Pipelined: returns after enqueueing H2D + kernel + D2H; call synchronize() before reading out_h."""
         self._check(self.lib.go1mpc_body_mpc_step_batch_host_async(self.h, nh, B, _ptr(in_h), _ptr(out_h), _ptr(diag_h)),
                     "body_mpc_step_batch_host_async")
+
+    def body_mpc_step_resident_host_async(self, nh, B, tx_d, out_d, tick_in_h, tick_out_h, diag_h=None):
+        """Pipelined, tx [B][28] and the output records [B][out_stride] resident on the device; only the
+        per-tick record (body_tick_in_stride doubles) goes up and BODY_TICK_OUT doubles (+ diag) come down."""
+        self._check(self.lib.go1mpc_body_mpc_step_batch_resident_host_async(self.h, nh, B, _ptr(tx_d), _ptr(out_d), _ptr(tick_in_h),
+                                                                            _ptr(tick_out_h), _ptr(diag_h)),
+                    "body_mpc_step_batch_resident_host_async")
 
     def step_timing_step_host_async(self, n_sqp, B, tick_h, state_d, in_h, out_h, diag_h=None, state_out_d=None):
         """Pipelined; the planner state stays on the device (state_d: device buffer, updated in place

@@ -48,7 +48,7 @@ struct go1mpc {
   // hundred microseconds at batch 4096, while the PCIe link needs a new batch every ~100 us): consecutive calls go to consecutive lanes
   // (own stream, own staging), so the H2D copy of one batch overlaps the kernel of the previous
   // one and the D2H copy of the one before that
-  struct Lane { cudaStream_t stream = nullptr; DevBuf stage[8]; };
+  struct Lane { cudaStream_t stream = nullptr; DevBuf stage[12]; };
   static const int kLanes = 8;
   Lane lanes[8];
   unsigned lane_next = 0;
@@ -768,6 +768,49 @@ int go1mpc_body_mpc_step_batch_host_async(go1mpc_t* h, int nh, int B, const doub
   rc = go1mpc_body_mpc_step_batch(h, nh, B, (const double*)din, (double*)dout, (int*)ddiag, L.stream);
   if (rc) return rc;
   CU(h, cudaMemcpyAsync(out, dout, ob, cudaMemcpyDeviceToHost, L.stream));
+  if (diag) CU(h, cudaMemcpyAsync(diag, ddiag, db, cudaMemcpyDeviceToHost, L.stream));
+  return GO1MPC_OK;
+}
+
+// Same tick with tx and the previous output record resident on the device (body_resident.cu): per instance
+// 9+9nh doubles go up and 20 doubles (+ diagnostics) come down.
+int go1mpc_body_tick_in_stride(int nh) { return (9 + 9 * nh + 1) & ~1; }
+int go1mpc_body_mpc_step_batch_resident_host_async(go1mpc_t* h, int nh, int B, const double* tx_d, double* out_d,
+                                                   const double* tick_in, double* tick_out, int* diag) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!tx_d || !out_d || !tick_in || !tick_out) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch_resident_host_async: bad argument");
+  if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "body_mpc_step_batch_resident_host_async: 3 <= nh <= 40");
+  CU(h, cudaSetDevice(h->device));
+  const int is = go1mpc_body_in_stride(nh), os = go1mpc_body_out_stride(nh), ts = go1mpc_body_tick_in_stride(nh);
+  const size_t ib = (size_t)B * is * sizeof(double), tb = (size_t)B * ts * sizeof(double);
+  const size_t tob = (size_t)B * GO1MPC_BODY_TICK_OUT * sizeof(double);
+  const size_t db = (size_t)B * go1mpc_body_diag_stride(nh) * sizeof(int);
+  go1mpc::Lane& L = h->lanes[h->lane_next++ % go1mpc::kLanes];
+  void *drec, *dtick, *dto, *ddiag = nullptr;
+  int rc;
+  if ((rc = stage_buf2(h, L.stage[0], ib, &drec))) return rc;
+  if ((rc = stage_buf2(h, L.stage[8], tb, &dtick))) return rc;
+  if ((rc = stage_buf2(h, L.stage[9], tob, &dto))) return rc;
+  if (diag && (rc = stage_buf2(h, L.stage[2], db, &ddiag))) return rc;
+  CU(h, cudaMemcpyAsync(dtick, tick_in, tb, cudaMemcpyHostToDevice, L.stream));
+  // consecutive ticks of the same instances sit on different lanes: order them through the resident records
+  {
+    auto it = h->last_writer.find((const void*)out_d);
+    if (it != h->last_writer.end()) CU(h, cudaStreamWaitEvent(L.stream, it->second, 0));
+  }
+  CU(h, body_record_expand_launch(B, nh, is, ts, os, tx_d, (const double*)dtick, out_d, (double*)drec, h->sms, L.stream));
+  h->launches++;
+  rc = go1mpc_body_mpc_step_batch(h, nh, B, (const double*)drec, out_d, (int*)ddiag, L.stream);
+  if (rc) return rc;
+  CU(h, body_record_pack_launch(B, nh, os, out_d, (double*)dto, h->sms, L.stream));
+  h->launches++;
+  {
+    cudaEvent_t& ev = h->last_writer[(const void*)out_d];
+    if (!ev) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU(h, cudaEventRecord(ev, L.stream));
+  }
+  CU(h, cudaMemcpyAsync(tick_out, dto, tob, cudaMemcpyDeviceToHost, L.stream));
   if (diag) CU(h, cudaMemcpyAsync(diag, ddiag, db, cudaMemcpyDeviceToHost, L.stream));
   return GO1MPC_OK;
 }

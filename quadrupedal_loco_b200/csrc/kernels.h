@@ -117,6 +117,10 @@ struct ServoKParams {
 cudaError_t servo_kin_launch(ServoKParams P, cudaStream_t st);
 cudaError_t leg_ik_launch(LegKParams P, cudaStream_t st);
 cudaError_t body_theta_gather_launch(int B, const double* body_out, int stride, double* theta, cudaStream_t st);
+// device-resident body records (body_resident.cu)
+cudaError_t body_record_expand_launch(int B, int nh, int in_stride, int tick_stride, int out_stride, const double* tx,
+                                      const double* tick_in, const double* out_res, double* rec, int sms, cudaStream_t st);
+cudaError_t body_record_pack_launch(int B, int nh, int out_stride, const double* out_res, double* tick_out, int sms, cudaStream_t st);
 
 // ---- GRF distribution of the servo loop (grf_qp.cu) ----
 constexpr int GRF_IN_DOUBLES = 48, GRF_OUT_DOUBLES = 16, GRF_DIAG_INTS = 32;

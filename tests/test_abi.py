@@ -29,6 +29,22 @@ def test_version_and_strides():
         assert lib.go1mpc_body_out_stride(nh) == q.body_out_stride(nh)
         assert lib.go1mpc_body_diag_stride(nh) == q.body_diag_stride(nh)
         assert q.body_in_stride(nh) % 2 == 0 and q.body_out_stride(nh) % 2 == 0   # TMA: 16-byte records
+        assert lib.go1mpc_body_tick_in_stride(nh) == q.body_tick_in_stride(nh)
+
+
+def test_split_body_record_is_a_partition_of_the_full_record():
+    """Resident entry: tx | tick record | warm start together hold every double of the full record."""
+    import numpy as np
+    nh, B = 10, 5
+    rec = np.arange(B * q.body_in_stride(nh), dtype=np.float64).reshape(B, -1) + 1.0
+    rec[:, 36 + 11 * nh:] = 0.0
+    tx, xw, tick = q.split_body_record(nh, rec)
+    assert tx.shape == (B, 28) and tick.shape == (B, q.body_tick_in_stride(nh)) and xw.shape == (B, 2 * nh)
+    back = np.zeros_like(rec)
+    back[:, :27] = tx[:, :27]; back[:, 27:36] = tick[:, :9]
+    back[:, 36:36 + 2 * nh] = xw; back[:, 36 + 2 * nh:36 + 11 * nh] = tick[:, 9:9 + 9 * nh]
+    np.testing.assert_array_equal(back, rec)
+    assert (tx[:, 27] == 0).all() and (tick[:, 9 + 9 * nh:] == 0).all()
 
 
 def test_no_device_is_an_error_not_a_fallback():

@@ -205,3 +205,47 @@ def test_body_pipelined_host_entry_matches_sync(mpc):
     for k in range(NB):
         np.testing.assert_array_equal(outs[k].numpy(), want[k][0], err_msg=f"batch {k}")
         np.testing.assert_array_equal(diags[k].numpy(), want[k][1])
+
+
+def test_body_resident_entry_matches_full_records(mpc):
+    """go1mpc_body_mpc_step_batch_resident_host_async: tx and the previous output record stay on the device,
+    9+9nh doubles go up and 20 come down per instance; three consecutive ticks of the same instances (the
+    second with gated ticks, the third warm-started from the resident x) equal the full-record host entry
+    bit for bit, through calls that land on different lanes."""
+    import torch
+    nh, B, NT = 10, 1500, 3
+    os_, ds_ = q.body_out_stride(nh), q.body_diag_stride(nh)
+    d0 = synth.body_mpc_inputs(B, nh, seed=300)
+    out_ref = np.zeros((B, os_)); out_ref[:, :14] = 7.0
+    out_ref[:, 18:18 + 2 * nh] = d0["x_warm"]
+    tx_d = None
+    out_d = torch.from_numpy(out_ref.copy()).cuda()
+    ticks, touts, diags, want = [], [], [], []
+    for k in range(NT):
+        d = synth.body_mpc_inputs(B, nh, seed=300 + k)
+        if k == 1:
+            d["tick"][::4] = 50          # gated ticks return the resident (stale) out14
+        # reference chain: full records whose warm start is the previous tick's x
+        rec = q.pack_body_inputs(nh, d["tick"], d0["tx"], d["theta"], d["bstate"], out_ref[:, 18:18 + 2 * nh], d["refs"])
+        dg = np.zeros((B, ds_), np.int32)
+        mpc.body_mpc_step_host(nh, B, rec, out_ref, dg)
+        want.append((out_ref.copy(), dg))
+        tx, _, tick = q.split_body_record(nh, rec)
+        if tx_d is None:
+            tx_d = torch.from_numpy(tx).cuda()
+        ticks.append(torch.from_numpy(tick).pin_memory())
+        touts.append(torch.full((B, q.BODY_TICK_OUT), -1.0, dtype=torch.float64).pin_memory())
+        diags.append(torch.zeros((B, ds_), dtype=torch.int32).pin_memory())
+    assert q.body_tick_in_stride(nh) == mpc.lib.go1mpc_body_tick_in_stride(nh) == 100
+    torch.cuda.synchronize()
+    for k in range(NT):
+        mpc.body_mpc_step_resident_host_async(nh, B, tx_d, out_d, ticks[k].numpy(), touts[k].numpy(), diags[k].numpy())
+    mpc.synchronize()
+    for k in range(NT):
+        o, dg = want[k]
+        t = touts[k].numpy()
+        np.testing.assert_array_equal(t[:, :18], o[:, :18], err_msg=f"tick {k}")
+        np.testing.assert_array_equal(t[:, 18], o[:, 18 + 2 * nh])
+        assert (t[:, 19] == 0).all()
+        np.testing.assert_array_equal(diags[k].numpy(), dg)
+    np.testing.assert_array_equal(out_d.cpu().numpy(), want[-1][0])
