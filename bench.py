@@ -507,6 +507,27 @@ def run_b200(a):
         e1.synchronize()
         barrier()
         e2e_launches = int(mpc.launch_count + mpc2.launch_count - l1)
+        # host-to-host latency of ONE batch through the same entries: enqueue both ticks, wait for both handles
+        # (wall clock on the calling thread: H2D + kernels + D2H + the driver calls; nothing else in flight)
+        lat_e2e = []
+        for i in range(8 + 100):
+            r = i % nrot
+            t0 = time.perf_counter()
+            feed_sqp_one = lib.go1mpc_step_timing_step_batch_host_async(hh, 3, B, H_tk[r], P_st[r], P_sto[r], H_si[r], H_so[r], H_sd[r])
+            if resident:
+                rc = lib2.go1mpc_body_mpc_step_batch_resident_host_async(hh2, nh, B, P_rtx[r], P_rout[r], H_ti[r], H_to[r], H_dg[r])
+            else:
+                rc = lib2.go1mpc_body_mpc_step_batch_host_async(hh2, nh, B, H_in[r], H_out[r], H_dg[r])
+            assert rc == 0 and feed_sqp_one == 0
+            mpc.synchronize(); mpc2.synchronize()
+            if i >= 8:
+                lat_e2e.append(1e3 * (time.perf_counter() - t0))
+        lat_t = torch.tensor([np.percentile(lat_e2e, 50), np.percentile(lat_e2e, 99), max(lat_e2e)], dtype=torch.float64, device=dev)
+        if dist:
+            dist.all_reduce(lat_t, op=dist.ReduceOp.MAX)
+        lat_e2e_ms = {"p50": float(lat_t[0].item()), "p99": float(lat_t[1].item()), "max": float(lat_t[2].item()),
+                      "what": "one %d-robot batch host to host through the same two entries (enqueue both ticks, synchronize both handles), "
+                              "wall clock on the calling thread, 100 samples, max over ranks" % B}
         mpc2.close()
         se = float(sum(B + sqp_solves[i % nrot] for i in range(Ke)))
         te = torch.tensor([e0.elapsed_time(e1), se], dtype=torch.float64, device=dev)
@@ -526,7 +547,7 @@ def run_b200(a):
         e2e = {"value": se_all / (te_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": B * (body_up * 8 + q.STEP_IN * 8 + 4),
                "d2h_bytes_per_step": B * (body_down * 8 + dg_s * 4 + q.STEP_OUT * 8 + q.STEP_DIAG * 4),
-               "body_records": a.e2e_records,
+               "body_records": a.e2e_records, "latency_ms": lat_e2e_ms,
                "steps": Ke, "ms_per_step": te_ms / Ke, "wall_ms_per_step": 1e3 * t_wall / Ke, "launches": e2e_launches,
                "api": "go1mpc_step_timing_step_batch_host_async + " + ("go1mpc_body_mpc_step_batch_resident_host_async" if resident else "go1mpc_body_mpc_step_batch_host_async") + " (pinned host buffers; "
                       "H2D, kernel, D2H per call on 8 internal lanes; planner state" + (", body step table and previous body output record" if resident else "") + " resident on the device; two handles fed by two "
