@@ -408,6 +408,19 @@ int go1mpc_grf_force_distribution_batch(go1mpc_t *h, int B, int gait_mode, doubl
                                         const double *com_des_d, const double *leg_des_d, const double *F_force_des_d,
                                         const double *rfoot_des_d, const double *lfoot_des_d,
                                         double *F_leg_ref_d, void *stream);
+/* Joint torques of the four legs.  Replaces Dynamiccclass::compute_joint_torques :109-138 as go1_servo calls it once per
+ * leg (GO1/servo_control/servo.cpp:1232-1243, leg_number 0..3 = FR, FL, RR, RL):
+ *   tau = -Jaco' * w + gravity_compensate(:, leg),   w = swing_kp (p_des - p_est) + swing_kd (pv_des - pv_est) for a
+ *   swing leg (swing_kp 1, swing_kd 0.01, :37-38), the leg's column of F_leg_ref for a stance leg.
+ * SoA [f*B + b]: jac_d [36][B] (row-major 3x3 per leg, the layout go1mpc_servo_kin_tick_batch / go1mpc_leg_ik_batch
+ * write), swing_d [4][B] ints, p_des_d / p_est_d / pv_des_d / pv_est_d [12][B], tau_d [12][B].  F_leg_ref element k of
+ * robot b is read at F_leg_ref_d[k * F_elem_stride + b * F_robot_stride]: (B, 1) for the SoA output of
+ * go1mpc_grf_force_distribution_batch, (1, 16) for the out records of go1mpc_grf_force_opt_batch. */
+int go1mpc_grf_joint_torques_batch(go1mpc_t *h, int B, const double *jac_d, const int *swing_d,
+                                   const double *p_des_d, const double *p_est_d,
+                                   const double *pv_des_d, const double *pv_est_d,
+                                   const double *F_leg_ref_d, long long F_elem_stride, long long F_robot_stride,
+                                   double *tau_d, void *stream);
 
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports

@@ -40,4 +40,15 @@ int ref_dyn_force_opt(void* h, const double* base_p, const double* leg_p, const 
   return d->qp_solution ? 1 : 0;
 }
 
+// compute_joint_torques, :109-138.  Jaco row-major 3x3; F_ref = column leg_number of the member F_leg_ref.
+void ref_dyn_joint_torques(void* h, const double* Jaco, int swing, const double* p_des, const double* p_est,
+                           const double* pv_des, const double* pv_est, const double* F_ref, int leg_number, double* tau) {
+  Dynamiccclass* d = static_cast<Dynamiccclass*>(h);
+  Eigen::Matrix<double, 3, 3> J; Eigen::Matrix<double, 3, 1> a, b, c, e;
+  for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) J(r, k) = Jaco[3 * r + k];
+  for (int k = 0; k < 3; k++) { a(k) = p_des[k]; b(k) = p_est[k]; c(k) = pv_des[k]; e(k) = pv_est[k]; d->F_leg_ref(k, leg_number) = F_ref[k]; }
+  Eigen::Matrix<double, 3, 1> t = d->compute_joint_torques(J, swing != 0, a, b, c, e, leg_number);
+  for (int k = 0; k < 3; k++) tau[k] = t(k);
+}
+
 }  // extern "C"

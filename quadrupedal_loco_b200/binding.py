@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_body_tick_in_stride", "go1mpc_body_mpc_step_batch_resident_host_async",
     "go1mpc_foot_trajectory_batch", "go1mpc_foot_trajectory_batch_host", "go1mpc_foot_default_state",
     "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch", "go1mpc_fused_tick_batch",
-    "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
+    "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_grf_joint_torques_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
 
@@ -117,6 +117,7 @@ def load_library():
     lib.go1mpc_leg_fk_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
     lib.go1mpc_grf_force_opt_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
     lib.go1mpc_grf_force_distribution_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 7
+    lib.go1mpc_grf_joint_torques_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7 + [ctypes.c_longlong, ctypes.c_longlong, vp, vp]
     lib.go1mpc_servo_kin_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 10
     lib.go1mpc_fused_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.POINTER(FusedTick), vp]
     lib.go1mpc_leg_ik_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
@@ -390,6 +391,14 @@ class Go1Mpc:
     def grf_force_opt(self, B, in_d, out_d, diag_d=None, stream=None):
         """Device records: in [B,48], out [B,16], diag [B,32] ints."""
         self._check(self.lib.go1mpc_grf_force_opt_batch(self.h, B, _ptr(in_d), _ptr(out_d), _ptr(diag_d), stream), "grf_force_opt_batch")
+
+    def grf_joint_torques(self, B, jac, swing, p_des, p_est, pv_des, pv_est, F_leg_ref, tau, F_strides=None, stream=None):
+        """Dynamiccclass::compute_joint_torques for the four legs; F_strides = (element, robot) strides of F_leg_ref in
+        doubles, default SoA (B, 1); (1, 16) reads the out records of grf_force_opt."""
+        ks, bs = F_strides if F_strides is not None else (B, 1)
+        self._check(self.lib.go1mpc_grf_joint_torques_batch(self.h, B, _ptr(jac), _ptr(swing), _ptr(p_des), _ptr(p_est), _ptr(pv_des),
+                                                            _ptr(pv_est), _ptr(F_leg_ref), ks, bs, _ptr(tau), stream),
+                    "grf_joint_torques_batch")
 
     def grf_force_distribution(self, B, gait_mode, y_coefficient, com, leg, F, rfoot, lfoot, F_leg_ref, stream=None):
         self._check(self.lib.go1mpc_grf_force_distribution_batch(self.h, B, gait_mode, y_coefficient, _ptr(com), _ptr(leg), _ptr(F),

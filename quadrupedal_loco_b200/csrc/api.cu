@@ -738,6 +738,24 @@ int go1mpc_grf_force_distribution_batch(go1mpc_t* h, int B, int gait_mode, doubl
   return GO1MPC_OK;
 }
 
+int go1mpc_grf_joint_torques_batch(go1mpc_t* h, int B, const double* jac_d, const int* swing_d, const double* p_des_d,
+                                   const double* p_est_d, const double* pv_des_d, const double* pv_est_d,
+                                   const double* F_leg_ref_d, long long F_elem_stride, long long F_robot_stride, double* tau_d,
+                                   void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !jac_d || !swing_d || !p_des_d || !p_est_d || !pv_des_d || !pv_est_d || !F_leg_ref_d || !tau_d)
+    return fail(h, GO1MPC_E_INVALID, "grf_joint_torques_batch: bad argument");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  GrfTauParams P;
+  P.B = B; P.swing_kp = 1; P.swing_kd = 0.01;   // dynmics_compute.cpp:37-38
+  P.jac = jac_d; P.swing = swing_d; P.p_des = p_des_d; P.p_est = p_est_d; P.pv_des = pv_des_d; P.pv_est = pv_est_d;
+  P.F_leg_ref = F_leg_ref_d; P.f_ks = F_elem_stride; P.f_bs = F_robot_stride; P.tau = tau_d;
+  CU(h, grf_joint_torques_launch(P, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
 // ------------------------------------------------------------------ pipelined host entries
 int go1mpc_body_mpc_step_batch_host_async(go1mpc_t* h, int nh, int B, const double* in, double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;

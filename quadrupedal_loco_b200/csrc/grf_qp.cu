@@ -215,6 +215,32 @@ __global__ void __launch_bounds__(256) grf_force_distribution_kernel(GrfDistPara
   for (int k = 0; k < 12; k++) P.F_leg_ref[k * B + b] = out[k];
 }
 
+// compute_joint_torques (:109-138), one thread per leg; SoA in/out.  tau = -Jaco' * w + gravity_compensate(:, leg) with
+// w = swing_kp (p_des - p_est) + swing_kd (pv_des - pv_est) for a swing leg, the leg's column of F_leg_ref for a stance
+// leg.  The reference's operation order, no contraction into FMA (bit-identical to the oracle).
+__global__ void __launch_bounds__(256) grf_joint_torques_kernel(GrfTauParams P) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * P.B) return;
+  const size_t B = (size_t)P.B;
+  const int leg = t / P.B;                 // leg-major over the grid: consecutive threads = consecutive robots
+  const size_t b = (size_t)(t - leg * P.B);
+  double w[3];
+  if (P.swing[leg * B + b]) {
+    for (int k = 0; k < 3; k++) {
+      const size_t i = (size_t)(3 * leg + k) * B + b;
+      w[k] = __dadd_rn(__dmul_rn(P.swing_kp, __dsub_rn(P.p_des[i], P.p_est[i])), __dmul_rn(P.swing_kd, __dsub_rn(P.pv_des[i], P.pv_est[i])));
+    }
+  } else {
+    for (int k = 0; k < 3; k++) w[k] = P.F_leg_ref[(long long)(3 * leg + k) * P.f_ks + (long long)b * P.f_bs];
+  }
+  for (int i = 0; i < 3; i++) {
+    double acc = 0.0;
+    for (int r = 0; r < 3; r++) acc = __dadd_rn(acc, __dmul_rn(-P.jac[(size_t)(9 * leg + 3 * r + i) * B + b], w[r]));
+    const double grav = (i == 0) ? ((leg & 1) ? 0.80 : -0.80) : 0.0;    // gravity_compensate, dynmics_compute.cpp:39-41
+    P.tau[(size_t)(3 * leg + i) * B + b] = __dadd_rn(acc, grav);
+  }
+}
+
 template <int WPC>
 static cudaError_t launch_opt(const GrfKParams& P0, int sms, cudaStream_t st) {
   GrfKParams P = P0;
@@ -230,6 +256,11 @@ static cudaError_t launch_opt(const GrfKParams& P0, int sms, cudaStream_t st) {
 cudaError_t grf_force_opt_launch(GrfKParams P, int sms, cudaStream_t st) { return launch_opt<4>(P, sms, st); }
 cudaError_t grf_force_distribution_launch(GrfDistParams P, cudaStream_t st) {
   grf_force_distribution_kernel<<<(P.B + 255) / 256, 256, 0, st>>>(P);
+  return cudaGetLastError();
+}
+
+cudaError_t grf_joint_torques_launch(GrfTauParams P, cudaStream_t st) {
+  grf_joint_torques_kernel<<<(4 * P.B + 255) / 256, 256, 0, st>>>(P);
   return cudaGetLastError();
 }
 

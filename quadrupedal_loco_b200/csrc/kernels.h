@@ -139,6 +139,17 @@ struct GrfDistParams {
 };
 cudaError_t grf_force_opt_launch(GrfKParams P, int sms, cudaStream_t st);
 cudaError_t grf_force_distribution_launch(GrfDistParams P, cudaStream_t st);
+struct GrfTauParams {
+  int B;
+  double swing_kp, swing_kd;
+  const double* jac;                                   // [36][B], row-major 3x3 per leg (FR, FL, RR, RL)
+  const int* swing;                                    // [4][B]
+  const double *p_des, *p_est, *pv_des, *pv_est;       // [12][B]
+  const double* F_leg_ref;                             // element k of robot b at [k * f_ks + b * f_bs]
+  long long f_ks, f_bs;
+  double* tau;                                         // [12][B]
+};
+cudaError_t grf_joint_torques_launch(GrfTauParams P, cudaStream_t st);
 
 // register-resident DFMA loop: flops executed are returned through *flops
 cudaError_t dfma_peak_launch(int grid, int block, int iters, double* sink, cudaStream_t st);

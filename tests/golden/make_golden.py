@@ -171,6 +171,21 @@ def gen_grf(dl):
     print("grf_ref.npz", N)
 
 
+def gen_grf_tau(dl):
+    """Dynamiccclass::compute_joint_torques on 400 seeded legs (tests/test_grf.py: tau_inputs)."""
+    from tests.test_grf import tau_inputs
+    dl.ref_dyn_new.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(dl.ref_dyn_new())
+    d = tau_inputs(100, seed=8); N = 100
+    tau = np.zeros((N, 4, 3))
+    for b in range(N):
+        for leg in range(4):
+            dl.ref_dyn_joint_torques(h, P(d["jac"][b, leg].copy()), int(d["swing"][b, leg]), P(d["p_des"][b, leg].copy()), P(d["p_est"][b, leg].copy()),
+                                     P(d["pv_des"][b, leg].copy()), P(d["pv_est"][b, leg].copy()), P(d["F"][b, leg].copy()), leg, P(tau[b, leg]))
+    np.savez_compressed(os.path.join(HERE, "grf_tau_ref.npz"), tau=tau, **d)
+    print("grf_tau_ref.npz", N)
+
+
 if __name__ == "__main__":
     ref, rt, nlp = ref_path("libref.so"), ref_path("libref_rt.so"), ref_path("libref_nlp.so")
     if not ref or not rt or not nlp:
@@ -187,3 +202,5 @@ if __name__ == "__main__":
         gen_step(ctypes.CDLL(nlp))
     if not only or "grf" in only:
         gen_grf(ctypes.CDLL(ref_path("libref_dyn.so")))
+    if not only or "grf_tau" in only:
+        gen_grf_tau(ctypes.CDLL(ref_path("libref_dyn.so")))

@@ -73,6 +73,81 @@ def test_oracle_grf_vs_live_reference(oracle):
     lib.ref_dyn_free(h)
 
 
+GOLD_TAU = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "grf_tau_ref.npz")
+GRAV = np.array([[-0.80, 0, 0], [0.80, 0, 0], [-0.80, 0, 0], [0.80, 0, 0]])     # gravity_compensate columns, dynmics_compute.cpp:39-41
+
+
+def tau_inputs(N, seed=8):
+    """Per robot and leg: a leg Jacobian (row-major 3x3), swing flag, desired / estimated foot position and velocity, leg force."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    d = dict(jac=rng.uniform(-0.3, 0.3, (N, 4, 9)), swing=(rng.uniform(size=(N, 4)) < 0.4).astype(np.int32),
+             p_des=rng.uniform(-0.3, 0.3, (N, 4, 3)), pv_des=rng.uniform(-1, 1, (N, 4, 3)), F=rng.uniform(-20, 80, (N, 4, 3)))
+    d["p_est"] = d["p_des"] + rng.uniform(-0.02, 0.02, (N, 4, 3)); d["pv_est"] = d["pv_des"] + rng.uniform(-0.3, 0.3, (N, 4, 3))
+    d["jac"][::7, :, 4] = 0.0          # exact zeros in the Jacobian, as hip columns have
+    return d
+
+
+def oracle_tau(oracle, d):
+    N = len(d["swing"])
+    f = oracle.lib.orc_grf_joint_torques
+    f.argtypes = [ctypes.c_void_p, ctypes.c_int] + [ctypes.c_void_p] * 6 + [ctypes.c_double, ctypes.c_double, ctypes.c_void_p]
+    f.restype = None
+    tau = np.zeros((N, 4, 3))
+    for b in range(N):
+        for leg in range(4):
+            f(P(d["jac"][b, leg].copy()), int(d["swing"][b, leg]), P(d["p_des"][b, leg].copy()), P(d["p_est"][b, leg].copy()),
+              P(d["pv_des"][b, leg].copy()), P(d["pv_est"][b, leg].copy()), P(d["F"][b, leg].copy()), P(GRAV[leg].copy()), 1.0, 0.01, P(tau[b, leg]))
+    return tau
+
+
+def test_oracle_joint_torques_vs_reference_golden(oracle):
+    """orc_grf_joint_torques against Dynamiccclass::compute_joint_torques (golden vectors of the unmodified class): bit-exact."""
+    g = np.load(GOLD_TAU)
+    d = {k: g[k] for k in ("jac", "swing", "p_des", "p_est", "pv_des", "pv_est", "F")}
+    np.testing.assert_array_equal(oracle_tau(oracle, d), g["tau"])
+    assert d["swing"].any() and not d["swing"].all()
+
+
+@pytest.mark.skipif(ref_path("libref_dyn.so") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_joint_torques_vs_live_reference(oracle):
+    lib = ctypes.CDLL(ref_path("libref_dyn.so")); lib.ref_dyn_new.restype = ctypes.c_void_p
+    if not hasattr(lib, "ref_dyn_joint_torques"):
+        pytest.skip("oracle/_ref predates ref_dyn_joint_torques")
+    h = ctypes.c_void_p(lib.ref_dyn_new())
+    d = tau_inputs(150, seed=81)
+    want = oracle_tau(oracle, d)
+    t = np.zeros(3)
+    for b in range(150):
+        for leg in range(4):
+            lib.ref_dyn_joint_torques(h, P(d["jac"][b, leg].copy()), int(d["swing"][b, leg]), P(d["p_des"][b, leg].copy()), P(d["p_est"][b, leg].copy()),
+                                      P(d["pv_des"][b, leg].copy()), P(d["pv_est"][b, leg].copy()), P(d["F"][b, leg].copy()), leg, P(t))
+            np.testing.assert_array_equal(t, want[b, leg])
+    lib.ref_dyn_free(h)
+
+
+@pytest.mark.gpu
+def test_gpu_joint_torques_vs_oracle_and_golden(mpc, oracle):
+    """go1mpc_grf_joint_torques_batch: bit-exact against the oracle and the reference's golden vectors, with F_leg_ref read
+    from the SoA layout and from force_opt-style out records."""
+    import torch
+    dev = torch.device("cuda", 0)
+    g = np.load(GOLD_TAU)
+    for src in ("golden", "synth"):
+        d = {k: g[k] for k in ("jac", "swing", "p_des", "p_est", "pv_des", "pv_est", "F")} if src == "golden" else tau_inputs(5000, seed=12)
+        N = len(d["swing"])
+        want = g["tau"] if src == "golden" else oracle_tau(oracle, d)
+        soa = lambda a: torch.from_numpy(np.array(a.reshape(N, -1).T, order="C", copy=True)).to(dev)
+        args = [soa(d[k]) for k in ("jac", "swing", "p_des", "p_est", "pv_des", "pv_est")]
+        F_soa = soa(d["F"])
+        F_rec = torch.zeros(N, 16, dtype=torch.float64, device=dev); F_rec[:, :12] = torch.from_numpy(d["F"].reshape(N, 12)).to(dev)
+        for F, strides in ((F_soa, None), (F_rec, (1, 16))):
+            tau = torch.full((12, N), np.nan, dtype=torch.float64, device=dev)
+            torch.cuda.synchronize()
+            mpc.grf_joint_torques(N, *args, F, tau, F_strides=strides)
+            mpc.synchronize()
+            np.testing.assert_array_equal(tau.cpu().numpy().T.reshape(N, 4, 3), want, err_msg=f"{src} {strides}")
+
+
 @pytest.mark.gpu
 def test_gpu_grf_vs_oracle_and_golden(mpc, oracle):
     import torch
