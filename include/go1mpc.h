@@ -422,6 +422,18 @@ int go1mpc_grf_joint_torques_batch(go1mpc_t *h, int B, const double *jac_d, cons
                                    const double *F_leg_ref_d, long long F_elem_stride, long long F_robot_stride,
                                    double *tau_d, void *stream);
 
+/* Synchronous host-buffer forms of the three entries above (same layouts, host pointers; what the C++ mirror of
+ * Dynamiccclass in host/go1mpc.hpp calls with B = 1). */
+int go1mpc_grf_force_opt_batch_host(go1mpc_t *h, int B, const double *in, double *out, int *diag);
+int go1mpc_grf_force_distribution_batch_host(go1mpc_t *h, int B, int gait_mode, double y_coefficient,
+                                             const double *com_des, const double *leg_des, const double *F_force_des,
+                                             const double *rfoot_des, const double *lfoot_des, double *F_leg_ref);
+int go1mpc_grf_joint_torques_batch_host(go1mpc_t *h, int B, const double *jac, const int *swing,
+                                        const double *p_des, const double *p_est,
+                                        const double *pv_des, const double *pv_est,
+                                        const double *F_leg_ref, long long F_elem_stride, long long F_robot_stride,
+                                        double *tau);
+
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports
  * against.  Runs ~`ms` milliseconds. */

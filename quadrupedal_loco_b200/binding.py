@@ -23,7 +23,8 @@ EXPORTED_SYMBOLS = [
     "go1mpc_body_tick_in_stride", "go1mpc_body_mpc_step_batch_resident_host_async",
     "go1mpc_foot_trajectory_batch", "go1mpc_foot_trajectory_batch_host", "go1mpc_foot_default_state",
     "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch", "go1mpc_fused_tick_batch",
-    "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_grf_joint_torques_batch", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
+    "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_grf_joint_torques_batch",
+    "go1mpc_grf_force_opt_batch_host", "go1mpc_grf_force_distribution_batch_host", "go1mpc_grf_joint_torques_batch_host", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
 
@@ -117,6 +118,9 @@ def load_library():
     lib.go1mpc_leg_fk_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
     lib.go1mpc_grf_force_opt_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
     lib.go1mpc_grf_force_distribution_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 7
+    lib.go1mpc_grf_force_opt_batch_host.argtypes = [vp, ctypes.c_int, vp, vp, vp]
+    lib.go1mpc_grf_force_distribution_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 6
+    lib.go1mpc_grf_joint_torques_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 7 + [ctypes.c_longlong, ctypes.c_longlong, vp]
     lib.go1mpc_grf_joint_torques_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7 + [ctypes.c_longlong, ctypes.c_longlong, vp, vp]
     lib.go1mpc_servo_kin_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 10
     lib.go1mpc_fused_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.POINTER(FusedTick), vp]

@@ -756,6 +756,83 @@ int go1mpc_grf_joint_torques_batch(go1mpc_t* h, int B, const double* jac_d, cons
   return GO1MPC_OK;
 }
 
+// synchronous host-buffer forms of the three GRF entries (staging on the handle's stream)
+int go1mpc_grf_force_opt_batch_host(go1mpc_t* h, int B, const double* in, double* out, int* diag) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!in || !out) return fail(h, GO1MPC_E_INVALID, "grf_force_opt_batch_host: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t ib = (size_t)B * GRF_IN_DOUBLES * sizeof(double), ob = (size_t)B * GRF_OUT_DOUBLES * sizeof(double);
+  const size_t db = (size_t)B * GRF_DIAG_INTS * sizeof(int);
+  void *di, *do_, *dd = nullptr;
+  int rc;
+  if ((rc = stage_buf(h, 0, ib, &di))) return rc;
+  if ((rc = stage_buf(h, 1, ob, &do_))) return rc;
+  if (diag && (rc = stage_buf(h, 2, db, &dd))) return rc;
+  cudaStream_t st = h->stream;
+  CU(h, cudaMemcpyAsync(di, in, ib, cudaMemcpyHostToDevice, st));
+  rc = go1mpc_grf_force_opt_batch(h, B, (const double*)di, (double*)do_, (int*)dd, st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(out, do_, ob, cudaMemcpyDeviceToHost, st));
+  if (diag) CU(h, cudaMemcpyAsync(diag, dd, db, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return GO1MPC_OK;
+}
+int go1mpc_grf_force_distribution_batch_host(go1mpc_t* h, int B, int gait_mode, double y_coefficient, const double* com_des,
+                                             const double* leg_des, const double* F_force_des, const double* rfoot_des,
+                                             const double* lfoot_des, double* F_leg_ref) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!com_des || !leg_des || !F_force_des || !rfoot_des || !lfoot_des || !F_leg_ref)
+    return fail(h, GO1MPC_E_INVALID, "grf_force_distribution_batch_host: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t d = (size_t)B * sizeof(double);
+  const double* src[5] = {com_des, leg_des, F_force_des, rfoot_des, lfoot_des};
+  const int rows[5] = {3, 12, 6, 3, 3};
+  void* dev[6];
+  int rc;
+  cudaStream_t st = h->stream;
+  for (int k = 0; k < 5; k++) {
+    if ((rc = stage_buf(h, k, rows[k] * d, &dev[k]))) return rc;
+    CU(h, cudaMemcpyAsync(dev[k], src[k], rows[k] * d, cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = stage_buf(h, 5, 12 * d, &dev[5]))) return rc;
+  rc = go1mpc_grf_force_distribution_batch(h, B, gait_mode, y_coefficient, (const double*)dev[0], (const double*)dev[1],
+                                           (const double*)dev[2], (const double*)dev[3], (const double*)dev[4], (double*)dev[5], st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(F_leg_ref, dev[5], 12 * d, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return GO1MPC_OK;
+}
+int go1mpc_grf_joint_torques_batch_host(go1mpc_t* h, int B, const double* jac, const int* swing, const double* p_des,
+                                        const double* p_est, const double* pv_des, const double* pv_est,
+                                        const double* F_leg_ref, long long F_elem_stride, long long F_robot_stride, double* tau) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!jac || !swing || !p_des || !p_est || !pv_des || !pv_est || !F_leg_ref || !tau || F_elem_stride < 0 || F_robot_stride < 0)
+    return fail(h, GO1MPC_E_INVALID, "grf_joint_torques_batch_host: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t d = (size_t)B * sizeof(double);
+  const size_t fdoubles = (size_t)(11 * F_elem_stride + (B - 1) * F_robot_stride + 1);   // extent the strides address
+  const void* src[7] = {jac, swing, p_des, p_est, pv_des, pv_est, F_leg_ref};
+  const size_t bytes[7] = {36 * d, 4 * (size_t)B * sizeof(int), 12 * d, 12 * d, 12 * d, 12 * d, fdoubles * sizeof(double)};
+  void* dev[8];
+  int rc;
+  cudaStream_t st = h->stream;
+  for (int k = 0; k < 7; k++) {
+    if ((rc = stage_buf(h, k, bytes[k], &dev[k]))) return rc;
+    CU(h, cudaMemcpyAsync(dev[k], src[k], bytes[k], cudaMemcpyHostToDevice, st));
+  }
+  if ((rc = stage_buf(h, 7, 12 * d, &dev[7]))) return rc;
+  rc = go1mpc_grf_joint_torques_batch(h, B, (const double*)dev[0], (const int*)dev[1], (const double*)dev[2], (const double*)dev[3],
+                                      (const double*)dev[4], (const double*)dev[5], (const double*)dev[6], F_elem_stride,
+                                      F_robot_stride, (double*)dev[7], st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(tau, dev[7], 12 * d, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return GO1MPC_OK;
+}
+
 // ------------------------------------------------------------------ pipelined host entries
 int go1mpc_body_mpc_step_batch_host_async(go1mpc_t* h, int nh, int B, const double* in, double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;

@@ -257,4 +257,66 @@ class LegKinematics {
   std::shared_ptr<Context> ctx_;
 };
 
+// ---------------------------------------------------------------------------------------------
+// Dynamiccclass (GO1/src/whole_body_dynamics/dynmics_compute.h:31-91): the GRF distribution of go1_servo's 1 kHz
+// loop -- force_distribution (:141-261 of the .cpp), force_opt (:265-373) and compute_joint_torques (:109-138) with
+// the members the servo reads between the calls (F_leg_ref, F_leg_guess, grf_opt, qp_solution).
+class GrfDistributor {
+ public:
+  explicit GrfDistributor(std::shared_ptr<Context> ctx = nullptr) : ctx_(ctx ? ctx : Context::shared()) {}
+  Mat<3, 4> F_leg_ref;      // columns FR, FL, RR, RL
+  Vec<12> F_leg_guess, grf_opt;
+  bool qp_solution = false;
+  double cost = 0.0;
+
+  void force_distribution(const Vec<3>& com_des, const Vec<12>& leg_des, const Vec<6>& F_force_des, int mode, double y_coefficient,
+                          const double rfoot_des[3], const double lfoot_des[3]) {
+    if (mode == 101 || mode == 102) {      // other gait modes leave F_leg_ref as it is (:154-250)
+      double out[12];
+      int rc = go1mpc_grf_force_distribution_batch_host(ctx_->get(), 1, mode, y_coefficient, com_des.v, leg_des.v, F_force_des.v,
+                                                        rfoot_des, lfoot_des, out);
+      if (rc != GO1MPC_OK) throw std::runtime_error(std::string("force_distribution: ") + go1mpc_last_error(ctx_->get()));
+      for (int c = 0; c < 4; c++) for (int r = 0; r < 3; r++) F_leg_ref(r, c) = out[3 * c + r];
+    }
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 3; r++) F_leg_guess(3 * c + r) = F_leg_ref(r, c);   // :256-259
+  }
+
+  void force_opt(const Vec<3>& base_p, const Vec<3>& FR_p, const Vec<3>& FL_p, const Vec<3>& RR_p, const Vec<3>& RL_p,
+                 const Vec<6>& FT_total_des, int mode, int right_support, double /*y_coefficient: unused by the reference too*/) {
+    double in[48] = {0}, out[16] = {0};
+    const Vec<3>* legs[4] = {&FR_p, &FL_p, &RR_p, &RL_p};
+    for (int k = 0; k < 3; k++) in[k] = base_p(k);
+    for (int l = 0; l < 4; l++) for (int k = 0; k < 3; k++) in[3 + 3 * l + k] = (*legs[l])(k);
+    for (int k = 0; k < 6; k++) in[15 + k] = FT_total_des(k);
+    for (int k = 0; k < 12; k++) { in[21 + k] = F_leg_guess(k); in[33 + k] = grf_opt(k); }
+    in[45] = mode; in[46] = right_support;
+    int rc = go1mpc_grf_force_opt_batch_host(ctx_->get(), 1, in, out, nullptr);
+    if (rc != GO1MPC_OK) throw std::runtime_error(std::string("force_opt: ") + go1mpc_last_error(ctx_->get()));
+    for (int k = 0; k < 12; k++) grf_opt(k) = out[k];
+    cost = out[12]; qp_solution = out[13] != 0.0;
+  }
+
+  Vec<3> compute_joint_torques(const Mat<3, 3>& Jaco, bool support_flag, const Vec<3>& p_des, const Vec<3>& p_est,
+                               const Vec<3>& pv_des, const Vec<3>& pv_est, int leg_number) {
+    if (leg_number < 0 || leg_number > 3) throw std::runtime_error("compute_joint_torques: leg_number 0..3");
+    double jac[36] = {0}, pd[12] = {0}, pe[12] = {0}, vd[12] = {0}, ve[12] = {0}, F[12], tau[12];
+    int swing[4] = {0, 0, 0, 0};
+    swing[leg_number] = support_flag ? 1 : 0;      // the reference's flag is TRUE for a swing leg (:119)
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) jac[9 * leg_number + 3 * r + c] = Jaco(r, c);
+    for (int k = 0; k < 3; k++) {
+      pd[3 * leg_number + k] = p_des(k); pe[3 * leg_number + k] = p_est(k);
+      vd[3 * leg_number + k] = pv_des(k); ve[3 * leg_number + k] = pv_est(k);
+    }
+    for (int c = 0; c < 4; c++) for (int r = 0; r < 3; r++) F[3 * c + r] = F_leg_ref(r, c);
+    int rc = go1mpc_grf_joint_torques_batch_host(ctx_->get(), 1, jac, swing, pd, pe, vd, ve, F, 1, 1, tau);
+    if (rc != GO1MPC_OK) throw std::runtime_error(std::string("compute_joint_torques: ") + go1mpc_last_error(ctx_->get()));
+    Vec<3> t;
+    for (int k = 0; k < 3; k++) t(k) = tau[3 * leg_number + k];
+    return t;
+  }
+
+ private:
+  std::shared_ptr<Context> ctx_;
+};
+
 }  // namespace go1host

@@ -64,6 +64,37 @@ int main() {
   arr("step_out38", o38, 120 * 38); arr("foot_out18", o18, 120 * 18);
   printf("\"right_support\": ["); for (int i = 0; i < 120; i++) printf("%s%d", i ? ", " : "", rs[i]); printf("],\n");
 
+  // --- Dynamiccclass: force_distribution -> force_opt -> compute_joint_torques as go1_servo chains them (servo.cpp:1200-1243)
+  {
+    GrfDistributor dyn;
+    Vec<3> com; com(0) = 0.01; com(1) = -0.02; com(2) = 0.31;
+    const double hom[12] = {0.1881, -0.1268, 0, 0.1881, 0.1268, 0, -0.1881, -0.1268, 0, -0.1881, 0.1268, 0};
+    Vec<12> legs; for (int k = 0; k < 12; k++) legs(k) = hom[k] + 0.01 * std::sin(1.3 * k);
+    Vec<6> F6; F6(0) = 3; F6(1) = -2; F6(2) = 60; F6(3) = -4; F6(4) = 5; F6(5) = 55;
+    Vec<6> FT; FT(0) = 5; FT(1) = -7; FT(2) = 117.6; FT(3) = 1; FT(4) = -2; FT(5) = 0.5;
+    double rf[3] = {0.01, -0.127, 0}, lf[3] = {-0.01, 0.127, 0};
+    double Fg[2 * 12], grf[2 * 12], tau[2 * 12];
+    int okk[2];
+    for (int c = 0; c < 2; c++) {
+      const int mode = 101 + c, rs = c;       // pace / trot; second call starts from the first call's grf_opt
+      dyn.force_distribution(com, legs, F6, mode, 0.9, rf, lf);
+      Vec<3> p[4]; for (int l = 0; l < 4; l++) for (int k = 0; k < 3; k++) p[l](k) = legs(3 * l + k);
+      dyn.force_opt(com, p[0], p[1], p[2], p[3], FT, mode, rs, 0.9);
+      for (int k = 0; k < 12; k++) { Fg[12 * c + k] = dyn.F_leg_guess(k); grf[12 * c + k] = dyn.grf_opt(k); }
+      okk[c] = dyn.qp_solution ? 1 : 0;
+      for (int l = 0; l < 4; l++) {
+        Mat<3, 3> J;
+        for (int r = 0; r < 3; r++) for (int k = 0; k < 3; k++) J(r, k) = 0.1 * std::cos(0.9 * (3 * r + k) + l);
+        Vec<3> pd, pe, vd, ve;
+        for (int k = 0; k < 3; k++) { pd(k) = 0.1 * k; pe(k) = 0.1 * k + 0.01; vd(k) = 0.2; ve(k) = 0.15 - 0.1 * k; }
+        Vec<3> t = dyn.compute_joint_torques(J, (l + c) % 2 == 0, pd, pe, vd, ve, l);
+        for (int k = 0; k < 3; k++) tau[12 * c + 3 * l + k] = t(k);
+      }
+    }
+    arr("grf_guess", Fg, 24); arr("grf_opt", grf, 24); arr("grf_tau", tau, 24);
+    printf("\"grf_ok\": [%d, %d],\n", okk[0], okk[1]);
+  }
+
   // --- Kinematicclass: FK_g -> IK_g round trip, Jacobian side channel
   LegKinematics kin;
   Vec<3> bp, br, q, qi; bp(2) = 0.31; br(0) = 0.05; br(1) = -0.04; br(2) = 0.1; q(0) = 0.1; q(1) = 0.8; q(2) = -1.5;

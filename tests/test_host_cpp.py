@@ -65,6 +65,25 @@ def test_host_classes_reproduce_oracle(oracle):
     assert list(d["right_support"]) == list(g["replay_right_support"][1:121])
     foot = np.array(d["foot_out18"]).reshape(120, 18)
     assert np.abs(foot[:, :6] - g["replay_foot"][1:121, :6]).max() < 2e-6     # closed loop: see test_foot_trajectory_replay...
+    # Dynamiccclass chain: closed-form split -> force QP -> torque map, twice (pace, then trot from the first grf_opt)
+    from tests.test_grf import oracle_grf, oracle_tau
+    hom = np.array([0.1881, -0.1268, 0, 0.1881, 0.1268, 0, -0.1881, -0.1268, 0, -0.1881, 0.1268, 0])
+    prev = np.zeros(12)
+    for c in range(2):
+        dd = dict(mode=np.array([101 + c], np.int32), rs=np.array([c], np.int32), base=np.array([[0.01, -0.02, 0.31]]),
+                  legs=(hom + 0.01 * np.sin(1.3 * np.arange(12)))[None, :], FT=np.array([[5, -7, 117.6, 1, -2, 0.5]]),
+                  F6=np.array([[3.0, -2, 60, -4, 5, 55]]), rf=np.array([[0.01, -0.127, 0]]), lf=np.array([[-0.01, 0.127, 0]]), prev=prev[None, :].copy())
+        o = oracle_grf(oracle, dd)
+        np.testing.assert_allclose(np.array(d["grf_guess"])[12 * c:12 * c + 12], o["Fg"][0], rtol=1e-12, atol=1e-12)
+        assert d["grf_ok"][c] == o["ok"][0] == 1
+        np.testing.assert_allclose(np.array(d["grf_opt"])[12 * c:12 * c + 12], o["grf"][0], rtol=1e-9, atol=1e-9)
+        prev = o["grf"][0]
+        kk = np.arange(9)
+        td = dict(jac=np.stack([0.1 * np.cos(0.9 * kk + l) for l in range(4)])[None], swing=np.array([[(l + c) % 2 == 0 for l in range(4)]], np.int32),
+                  p_des=np.tile(0.1 * np.arange(3), (1, 4, 1)), p_est=np.tile(0.1 * np.arange(3) + 0.01, (1, 4, 1)),
+                  pv_des=np.full((1, 4, 3), 0.2), pv_est=np.tile(0.15 - 0.1 * np.arange(3), (1, 4, 1)),
+                  F=np.array(d["grf_guess"])[12 * c:12 * c + 12].reshape(1, 4, 3))      # F_leg_ref stays the closed-form split
+        np.testing.assert_allclose(np.array(d["grf_tau"])[12 * c:12 * c + 12].reshape(4, 3), oracle_tau(oracle, td)[0], rtol=0, atol=1e-12)
     # kinematics
     pos, J = oracle.leg_fk(np.array([[0.1, 0.8, -1.5]]), [1], np.array([[0, 0, 0.31]]), np.array([[0.05, -0.04, 0.1]]))
     np.testing.assert_allclose(d["fk_pos"], pos[0], atol=1e-13)
