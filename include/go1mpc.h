@@ -356,6 +356,8 @@ int go1mpc_servo_kin_tick_batch(go1mpc_t *h, int B, int gait_mode, double y_offs
  *   4. the servo kinematics tick                   (= go1mpc_servo_kin_tick_batch) with the body pose taken from the
  *      ticks above: position = planner CoM (out38 rows 0..2), roll / pitch = body-MPC angles (out record [0], [1]),
  *      yaw 0; virtual right / left foot = swing-foot positions (out18 rows 0..2 / 3..5)
+ *   5. optionally the GRF QP and the torque map    (= go1mpc_grf_force_opt_batch, go1mpc_grf_joint_torques_batch on stage 4's
+ *      Jacobians and the QP's forces: Dynamiccclass::force_opt / compute_joint_torques, servo.cpp:1200-1243)
  * i.e. NLPClass::step_timing_opti_loop + Foot_trajectory_solve_mod2 -> PRMPCClass::body_theta_mpc -> the leg mapping
  * and four Inverse_kinematics_g of GO1/servo_control/servo.cpp:935-1051 without a host round trip.  Results are
  * bit-identical to calling the four entry points in that order.  All pointers are device pointers with the layouts
@@ -383,6 +385,12 @@ typedef struct {
   double *foot_des_d;           /*    [12][B] or NULL */
   int *ik_iters_d;              /*    [4][B] or NULL */
   double *servo_theta_d;        /*    [3][B] scratch (filled by the call) */
+  const double *grf_in_d;       /* 5: optional (NULL skips it): force QP records [B][48] of go1mpc_grf_force_opt_batch */
+  double *grf_out_d;            /*    [B][16] */
+  int *grf_diag_d;              /*    [B][32] or NULL */
+  const int *swing_d;           /*    torque map (tau_d NULL skips it): [4][B] */
+  const double *p_des_d, *p_est_d, *pv_des_d, *pv_est_d;   /* [12][B] each */
+  double *tau_d;                /*    [12][B]: -J' f + gravity term from stage 4's jac_d and the QP's forces */
 } Go1FusedTick;
 int go1mpc_fused_tick_batch(go1mpc_t *h, int B, const Go1FusedTick *t, void *stream);
 

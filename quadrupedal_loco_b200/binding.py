@@ -188,7 +188,10 @@ class FusedTick(ctypes.Structure):
                 ("nh", ctypes.c_int), ("body_in_d", ctypes.c_void_p), ("body_out_d", ctypes.c_void_p),
                 ("body_diag_d", ctypes.c_void_p), ("gait_mode", ctypes.c_int), ("y_offset", ctypes.c_double),
                 ("homing_d", ctypes.c_void_p), ("q_d", ctypes.c_void_p), ("jac_d", ctypes.c_void_p),
-                ("foot_des_d", ctypes.c_void_p), ("ik_iters_d", ctypes.c_void_p), ("servo_theta_d", ctypes.c_void_p)]
+                ("foot_des_d", ctypes.c_void_p), ("ik_iters_d", ctypes.c_void_p), ("servo_theta_d", ctypes.c_void_p),
+                ("grf_in_d", ctypes.c_void_p), ("grf_out_d", ctypes.c_void_p), ("grf_diag_d", ctypes.c_void_p),
+                ("swing_d", ctypes.c_void_p), ("p_des_d", ctypes.c_void_p), ("p_est_d", ctypes.c_void_p),
+                ("pv_des_d", ctypes.c_void_p), ("pv_est_d", ctypes.c_void_p), ("tau_d", ctypes.c_void_p)]
 
 
 def _ptr(a):
@@ -382,14 +385,17 @@ class Go1Mpc:
 
     def fused_tick(self, B, n_sqp, tick, step_state, step_in, out38, foot, out18, nh, body_in, body_out, gait_mode, y_offset,
                    homing, q, servo_theta, step_diag=None, right_support=None, body_diag=None, jac=None, foot_des=None,
-                   ik_iters=None, stream=None):
-        """go1mpc_fused_tick_batch: planner tick -> swing foot -> body MPC -> servo IK in one call (device buffers)."""
+                   ik_iters=None, stream=None, grf_in=None, grf_out=None, grf_diag=None, swing=None, p_des=None, p_est=None,
+                   pv_des=None, pv_est=None, tau=None):
+        """go1mpc_fused_tick_batch: planner tick -> swing foot -> body MPC -> servo IK (-> GRF QP -> joint torques when
+        grf_in / tau are given) in one call (device buffers)."""
         def a(x):
             v = _ptr(x)
             return v if isinstance(v, int) or v is None else ctypes.cast(v, ctypes.c_void_p).value
         t = FusedTick(n_sqp, a(tick), a(step_state), a(step_in), a(out38), a(step_diag), a(foot), a(out18), a(right_support),
                       nh, a(body_in), a(body_out), a(body_diag), gait_mode, y_offset, a(homing), a(q), a(jac), a(foot_des),
-                      a(ik_iters), a(servo_theta))
+                      a(ik_iters), a(servo_theta), a(grf_in), a(grf_out), a(grf_diag), a(swing), a(p_des), a(p_est), a(pv_des),
+                      a(pv_est), a(tau))
         self._check(self.lib.go1mpc_fused_tick_batch(self.h, B, ctypes.byref(t), stream), "fused_tick_batch")
 
     def grf_force_opt(self, B, in_d, out_d, diag_d=None, stream=None):

@@ -1005,8 +1005,16 @@ int go1mpc_fused_tick_batch(go1mpc_t* h, int B, const Go1FusedTick* t, void* str
   CU(h, body_theta_gather_launch(B, t->body_out_d, go1mpc_body_out_stride(t->nh), t->servo_theta_d, st));
   h->launches++;
   // SoA: the CoM position is rows 0..2 of out38, the right / left foot positions rows 0..2 / 3..5 of out18
-  return go1mpc_servo_kin_tick_batch(h, B, t->gait_mode, t->y_offset, t->out38_d, t->servo_theta_d, t->out18_d,
-                                     t->out18_d + (size_t)3 * B, t->homing_d, t->q_d, t->jac_d, t->foot_des_d, t->ik_iters_d, st);
+  if ((rc = go1mpc_servo_kin_tick_batch(h, B, t->gait_mode, t->y_offset, t->out38_d, t->servo_theta_d, t->out18_d,
+                                        t->out18_d + (size_t)3 * B, t->homing_d, t->q_d, t->jac_d, t->foot_des_d, t->ik_iters_d, st))) return rc;
+  // 5 (optional): force QP and torque map on the Jacobians stage 4 just wrote
+  if (!t->grf_in_d) return GO1MPC_OK;
+  if (!t->grf_out_d) return fail(h, GO1MPC_E_INVALID, "fused_tick_batch: grf_in_d without grf_out_d");
+  if ((rc = go1mpc_grf_force_opt_batch(h, B, t->grf_in_d, t->grf_out_d, t->grf_diag_d, st))) return rc;
+  if (!t->tau_d) return GO1MPC_OK;
+  if (!t->jac_d) return fail(h, GO1MPC_E_INVALID, "fused_tick_batch: tau_d needs jac_d");
+  return go1mpc_grf_joint_torques_batch(h, B, t->jac_d, t->swing_d, t->p_des_d, t->p_est_d, t->pv_des_d, t->pv_est_d, t->grf_out_d, 1,
+                                        GRF_OUT_DOUBLES, t->tau_d, st);
 }
 
 namespace {

@@ -106,3 +106,44 @@ def test_fused_tick_feet_reach_their_targets(mpc, oracle):
         conv = its[:, leg] < 15
         assert conv.mean() > 0.9
         assert np.abs(pos[conv] - fdes[conv, leg]).max() < 2e-3
+
+
+def test_fused_tick_grf_stage_equals_separate_calls(mpc):
+    """Optional stage 5: the force QP and the torque map on the Jacobians of the servo stage, bit-identical to
+    go1mpc_grf_force_opt_batch + go1mpc_grf_joint_torques_batch called after the four-stage tick."""
+    import torch
+    from tests.test_grf import grf_inputs, tau_inputs
+    B = 1500
+    I = make_inputs(mpc, B, seed=91)
+    dev = I["rec"].device
+    f64 = dict(dtype=torch.float64, device=dev); i32 = dict(dtype=torch.int32, device=dev)
+    a = run_separate(mpc, I, 102, 0.7)
+    d = grf_inputs(B, seed=92)
+    rec = np.zeros((B, 48))
+    rec[:, 0:3] = d["base"]; rec[:, 3:15] = d["legs"]; rec[:, 15:21] = d["FT"]; rec[:, 21:33] = d["prev"] * 0.5; rec[:, 33:45] = d["prev"]
+    rec[:, 45] = d["mode"]; rec[:, 46] = d["rs"]
+    t = tau_inputs(B, seed=93)
+    soa = lambda x: torch.from_numpy(np.array(x.reshape(B, -1).T, order="C", copy=True)).to(dev)
+    gin = torch.from_numpy(rec).to(dev)
+    sw, pd, pe, vd, ve = (soa(t[k]) for k in ("swing", "p_des", "p_est", "pv_des", "pv_est"))
+    gout_a = torch.zeros(B, 16, **f64); gdg_a = torch.zeros(B, 32, **i32); tau_a = torch.zeros(12, B, **f64)
+    torch.cuda.synchronize()
+    mpc.grf_force_opt(B, gin, gout_a, gdg_a)
+    mpc.grf_joint_torques(B, a["jac"], sw, pd, pe, vd, ve, gout_a, tau_a, F_strides=(1, 16))
+    mpc.synchronize()
+    # fused
+    st = I["state"].clone(); foot = I["foot"].clone(); qq = I["q"].clone()
+    out38 = torch.zeros(q.STEP_OUT, B, **f64); out18 = torch.zeros(18, B, **f64)
+    bout = torch.zeros(B, q.body_out_stride(I["nh"]), **f64); jac = torch.zeros(36, B, **f64); theta = torch.zeros(3, B, **f64)
+    gout_b = torch.zeros(B, 16, **f64); gdg_b = torch.zeros(B, 32, **i32); tau_b = torch.full((12, B), np.nan, **f64)
+    torch.cuda.synchronize()
+    mpc.fused_tick(B, 3, I["tick"], st, I["sin"], out38, foot, out18, I["nh"], I["rec"], bout, 102, 0.7, I["homing"], qq, theta, jac=jac,
+                   grf_in=gin, grf_out=gout_b, grf_diag=gdg_b, swing=sw, p_des=pd, p_est=pe, pv_des=vd, pv_est=ve, tau=tau_b)
+    mpc.synchronize()
+    same = lambda x, y: np.array_equal(x.cpu().numpy(), y.cpu().numpy(), equal_nan=True)   # an infeasible planner tick leaves NaN poses
+    assert same(jac, a["jac"]) and same(qq, a["q"])
+    assert same(gout_a, gout_b) and same(gdg_a, gdg_b)
+    assert same(tau_a, tau_b)
+    ok = torch.isfinite(jac).all(dim=0)
+    assert ok.float().mean() > 0.5 and torch.isfinite(tau_b[:, ok]).all()
+    assert (gdg_b[:, 0] == 0).float().mean() > 0.5
