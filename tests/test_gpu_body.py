@@ -249,3 +249,40 @@ def test_body_resident_entry_matches_full_records(mpc):
         assert (t[:, 19] == 0).all()
         np.testing.assert_array_equal(diags[k].numpy(), dg)
     np.testing.assert_array_equal(out_d.cpu().numpy(), want[-1][0])
+
+
+def test_body_resident_entry_edge_cases(mpc):
+    """Empty batch is a no-op, missing buffers / unsupported horizons are errors (no silent fallback), and a
+    one-robot batch equals the full-record entry."""
+    import torch
+    nh = 10
+    mpc.body_mpc_step_resident_host_async(nh, 0, None, None, None, None)           # B = 0: nothing to do
+    one = torch.zeros(1, q.body_out_stride(nh), dtype=torch.float64, device="cuda")
+    tx1 = torch.zeros(1, 28, dtype=torch.float64, device="cuda")
+    ti = torch.zeros(1, q.body_tick_in_stride(nh), dtype=torch.float64).pin_memory()
+    to = torch.zeros(1, q.BODY_TICK_OUT, dtype=torch.float64).pin_memory()
+    with pytest.raises(q.Go1MpcError):
+        mpc.body_mpc_step_resident_host_async(nh, 1, None, one, ti.numpy(), to.numpy())
+    with pytest.raises(q.Go1MpcError):
+        mpc.body_mpc_step_resident_host_async(nh, 1, tx1, one, ti.numpy(), None)
+    with pytest.raises(q.Go1MpcError):
+        mpc.body_mpc_step_resident_host_async(2, 1, tx1, one, ti.numpy(), to.numpy())
+    with pytest.raises(q.Go1MpcError):
+        mpc.body_mpc_step_resident_host_async(nh, -1, tx1, one, ti.numpy(), to.numpy())
+    # B = 1
+    d = synth.body_mpc_inputs(1, nh, seed=77)
+    rec = q.pack_body_inputs(nh, d["tick"], d["tx"], d["theta"], d["bstate"], d["x_warm"], d["refs"])
+    want = np.zeros((1, q.body_out_stride(nh))); wd = np.zeros((1, q.body_diag_stride(nh)), np.int32)
+    mpc.body_mpc_step_host(nh, 1, rec, want, wd)
+    tx, xw, tick = q.split_body_record(nh, rec)
+    out_d = torch.zeros(1, q.body_out_stride(nh), dtype=torch.float64, device="cuda")
+    out_d[:, 18:18 + 2 * nh] = torch.from_numpy(xw).cuda()
+    tx_d = torch.from_numpy(tx).cuda()
+    ti.copy_(torch.from_numpy(tick))
+    dg = torch.zeros(1, q.body_diag_stride(nh), dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+    mpc.body_mpc_step_resident_host_async(nh, 1, tx_d, out_d, ti.numpy(), to.numpy(), dg.numpy())
+    mpc.synchronize()
+    np.testing.assert_array_equal(to.numpy()[:, :18], want[:, :18])
+    np.testing.assert_array_equal(dg.numpy(), wd)
+    np.testing.assert_array_equal(out_d.cpu().numpy(), want)

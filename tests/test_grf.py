@@ -192,3 +192,20 @@ def test_gpu_grf_vs_oracle_and_golden(mpc, oracle):
         f = out[conv, :12].reshape(-1, 4, 3)
         assert (f[:, :, 2] > -1e-7).all() and (f[:, :, 2] < 160 + 1e-7).all()
         assert (np.abs(f[:, :, 0]) <= 0.25 * f[:, :, 2] + 1e-7).all() and (np.abs(f[:, :, 1]) <= 0.25 * f[:, :, 2] + 1e-7).all()
+
+
+@pytest.mark.gpu
+def test_gpu_joint_torques_edge_cases(mpc, oracle):
+    """Empty batch = no-op, missing buffers = error, one robot through the host form = the oracle."""
+    import quadrupedal_loco_b200 as q
+    assert mpc.lib.go1mpc_grf_joint_torques_batch_host(mpc.h, 0, None, None, None, None, None, None, None, 1, 1, None) == 0
+    d = tau_inputs(1, seed=3)
+    want = oracle_tau(oracle, d)
+    flat = lambda a: np.ascontiguousarray(a.reshape(1, -1).T)
+    tau = np.full((12, 1), np.nan)
+    with pytest.raises(q.Go1MpcError):
+        mpc._check(mpc.lib.go1mpc_grf_joint_torques_batch_host(mpc.h, 1, None, None, None, None, None, None, None, 1, 1, tau.ctypes.data), "null")
+    args = [flat(d[k]) for k in ("jac", "swing", "p_des", "p_est", "pv_des", "pv_est", "F")]
+    rc = mpc.lib.go1mpc_grf_joint_torques_batch_host(mpc.h, 1, *[a.ctypes.data for a in args], 1, 1, tau.ctypes.data)
+    assert rc == 0
+    np.testing.assert_array_equal(tau.T.reshape(1, 4, 3), want)
