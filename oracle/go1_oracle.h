@@ -205,6 +205,15 @@ int orc_foot_traj_tick(const orc_step_cfg *c, int j, const orc_step_state *st, i
                        double fs[ORC_FOOT_STATE], double stepwidth0, double lift_height, double out18[18]);
 
 /* ------------------------------------------------------------------------
+ * 40 Hz -> 100 Hz reference interpolation of rt_mpc_qp (ref_interp.c): PRMPCClass::solve_AAA_inv_mod1 and
+ * XGetSolution_position_mod3, RT/src/FastMPC/PRMPCClass.cpp:1170-1261,1344-1361.  inv row-major 4x4.
+ * --------------------------------------------------------------------- */
+void orc_interp_aaa_inv_mod(double dt, double inv[16]);
+void orc_interp_position_mod3(const double inv[16], int nh, int t_end_footstep, int walktime, double dt_sample,
+                              const double in1[3], const double in2[3], const double ref[3], const double ref2[3],
+                              double *out);
+
+/* ------------------------------------------------------------------------
  * Ground-reaction-force distribution of go1_servo's 1 kHz loop (Dynamiccclass,
  * GO1/src/whole_body_dynamics/dynmics_compute.cpp:55-427): closed-form split, the
  * 12-variable QP (12 equality columns of which the stance legs' are all-zero, 24

@@ -80,4 +80,17 @@ void ref_body_theta_mpc(void* h, int i, const double* state4, const double* zmp,
   *qp_solution = p->qp_solution ? 1 : 0;
 }
 
+// XGetSolution_position_mod3, PRMPCClass.cpp:1170-1261 (uses _AAA_inv_mod of solve_AAA_inv_mod1 :1344-1361, built by
+// Initialize).  out21 = the Vec21; inv16 (may be null) = _AAA_inv_mod row-major; returns _t_end_footstep.
+int ref_body_position_mod3(void* h, int walktime, double dt_sample, const double* in1, const double* in2, const double* ref,
+                           const double* ref2, double* out21, double* inv16) {
+  PRMPCClass* p = static_cast<PRMPCClass*>(h);
+  Eigen::Vector3d a, b, c, d;
+  for (int k = 0; k < 3; k++) { a(k) = in1[k]; b(k) = in2[k]; c(k) = ref[k]; d(k) = ref2[k]; }
+  Eigen::Matrix<double, 21, 1> o = p->XGetSolution_position_mod3(walktime, dt_sample, a, b, c, d);
+  for (int k = 0; k < 21; k++) out21[k] = o(k);
+  if (inv16) for (int r = 0; r < 4; r++) for (int k = 0; k < 4; k++) inv16[4 * r + k] = p->_AAA_inv_mod(r, k);
+  return (int)p->_t_end_footstep;
+}
+
 }  // extern "C"

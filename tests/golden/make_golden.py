@@ -171,6 +171,31 @@ def gen_grf(dl):
     print("grf_ref.npz", N)
 
 
+def interp_inputs(N, seed=14):
+    """Four consecutive 40 Hz samples of a 3-vector quantity per case and the 100 Hz tick they are interpolated at."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    base = rng.uniform(-0.5, 0.5, (N, 1, 3)); vel = rng.uniform(-0.02, 0.02, (N, 1, 3))
+    s = base + vel * np.arange(4).reshape(1, 4, 1) + rng.uniform(-0.002, 0.002, (N, 4, 3))
+    wt = rng.integers(0, 2000, N).astype(np.int32)          # _t_end_footstep = 1610: some cases lie beyond it
+    wt[::9] = rng.integers(0, 4, len(wt[::9]))          # the first ticks (t = 0: pow(0, 0))
+    return dict(samples=s, walktime=wt)
+
+
+def gen_interp(rtl):
+    """PRMPCClass::XGetSolution_position_mod3 (+ _AAA_inv_mod) on 300 seeded cases."""
+    rtl.ref_body_new.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(rtl.ref_body_new())
+    d = interp_inputs(300); N = 300
+    out = np.zeros((N, 21)); inv = np.zeros(16); tend = 0
+    for b in range(N):
+        s = d["samples"][b]
+        tend = rtl.ref_body_position_mod3(h, int(d["walktime"][b]), ctypes.c_double(0.01), P(s[0].copy()), P(s[1].copy()), P(s[2].copy()),
+                                          P(s[3].copy()), P(out[b]), P(inv))
+    rtl.ref_body_free(h)
+    np.savez_compressed(os.path.join(HERE, "interp_ref.npz"), out=out, inv=inv, t_end=np.array([tend]), nh=np.array([rtl.ref_body_nh()]), **d)
+    print("interp_ref.npz", N, "t_end_footstep", tend, "beyond", int((d["walktime"] > tend).sum()))
+
+
 def gen_grf_tau(dl):
     """Dynamiccclass::compute_joint_torques on 400 seeded legs (tests/test_grf.py: tau_inputs)."""
     from tests.test_grf import tau_inputs
@@ -202,5 +227,7 @@ if __name__ == "__main__":
         gen_step(ctypes.CDLL(nlp))
     if not only or "grf" in only:
         gen_grf(ctypes.CDLL(ref_path("libref_dyn.so")))
+    if not only or "interp" in only:
+        gen_interp(rtl)
     if not only or "grf_tau" in only:
         gen_grf_tau(ctypes.CDLL(ref_path("libref_dyn.so")))

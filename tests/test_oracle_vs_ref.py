@@ -177,3 +177,60 @@ def test_oracle_foot_trajectory_bit_exact_vs_reference_golden(oracle):
         np.testing.assert_array_equal(out[0], g["replay_foot"][i], err_msg=f"tick {i}")
         assert rs[0] == g["replay_right_support"][i], i
     assert set(np.unique(g["replay_right_support"][1:])) == {0, 1, 2}
+
+
+def _oracle_interp(oracle, d, nh, t_end, dt=0.025, dt_sample=0.01):
+    lib = oracle.lib
+    lib.orc_interp_aaa_inv_mod.argtypes = [ctypes.c_double, ctypes.c_void_p]; lib.orc_interp_aaa_inv_mod.restype = None
+    lib.orc_interp_position_mod3.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [ctypes.c_void_p] * 5
+    lib.orc_interp_position_mod3.restype = None
+    inv = np.zeros(16); lib.orc_interp_aaa_inv_mod(dt, P(inv))
+    N = len(d["walktime"]); out = np.full((N, 9 + 3 * (nh - 1)), np.nan)
+    for b in range(N):
+        s = d["samples"][b]
+        lib.orc_interp_position_mod3(P(inv), nh, t_end, int(d["walktime"][b]), dt_sample, P(s[0].copy()), P(s[1].copy()), P(s[2].copy()),
+                                     P(s[3].copy()), P(out[b]))
+    return inv, out
+
+
+def test_oracle_ref_interp_bit_exact_vs_reference_golden(oracle):
+    """oracle/ref_interp.c against PRMPCClass::XGetSolution_position_mod3 (golden vectors of the unmodified class at
+    its nh = 4): the 4x4 inverse and every interpolated value bit for bit, zeros beyond _t_end_footstep; at the
+    sample instants the cubic returns the samples (interpolation property, any horizon)."""
+    g = load("interp_ref.npz")
+    nh, t_end = int(g["nh"][0]), int(g["t_end"][0])
+    d = {k: g[k] for k in ("samples", "walktime")}
+    inv, out = _oracle_interp(oracle, d, nh, t_end)
+    np.testing.assert_array_equal(inv, g["inv"])
+    np.testing.assert_array_equal(out, g["out"][:, :9 + 3 * (nh - 1)])
+    assert (g["out"][:, 9 + 3 * (nh - 1):] == 0).all()
+    late = d["walktime"] > t_end
+    assert late.any() and (out[late] == 0).all() and (np.abs(out[~late]).sum(axis=1) > 0).all()
+    # the cubic passes through its four samples: walktime 0 with dt_sample = dt evaluates t = 0, dt, 2 dt
+    one = dict(samples=d["samples"][:50], walktime=np.zeros(50, np.int32))
+    _, o3 = _oracle_interp(oracle, one, 3, t_end, dt_sample=0.025)
+    s = one["samples"]
+    np.testing.assert_allclose(o3[:, 0:3], s[:, 1], atol=1e-12)
+    np.testing.assert_allclose(o3[:, 9:12], s[:, 2], atol=1e-12)
+    np.testing.assert_allclose(o3[:, 12:15], s[:, 3], atol=1e-12)
+
+
+@pytest.mark.skipif(ref_path("libref_rt.so") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_ref_interp_vs_live_reference(oracle):
+    from tests.golden.make_golden import interp_inputs
+    rtl = ctypes.CDLL(ref_path("libref_rt.so"))
+    if not hasattr(rtl, "ref_body_position_mod3"):
+        pytest.skip("oracle/_ref predates ref_body_position_mod3")
+    rtl.ref_body_new.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(rtl.ref_body_new())
+    d = interp_inputs(400, seed=141)
+    want = np.zeros((400, 21)); inv = np.zeros(16)
+    for b in range(400):
+        s = d["samples"][b]
+        t_end = rtl.ref_body_position_mod3(h, int(d["walktime"][b]), ctypes.c_double(0.01), P(s[0].copy()), P(s[1].copy()), P(s[2].copy()),
+                                           P(s[3].copy()), P(want[b]), P(inv))
+    nh = rtl.ref_body_nh()
+    rtl.ref_body_free(h)
+    oinv, out = _oracle_interp(oracle, d, nh, t_end)
+    np.testing.assert_array_equal(oinv, inv)
+    np.testing.assert_array_equal(out, want[:, :9 + 3 * (nh - 1)])
