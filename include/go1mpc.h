@@ -442,6 +442,22 @@ int go1mpc_grf_joint_torques_batch_host(go1mpc_t *h, int B, const double *jac, c
                                         const double *F_leg_ref, long long F_elem_stride, long long F_robot_stride,
                                         double *tau);
 
+/* ---------------------------------------------------------------------------
+ * 40 Hz -> 100 Hz reference interpolation for B items (one item = one 3-vector quantity of one robot).  Replaces
+ * PRMPCClass::XGetSolution_position_mod3 (RT/FastMPC/PRMPCClass.cpp:1170-1261, with _AAA_inv_mod of
+ * solve_AAA_inv_mod1 :1344-1361) as rt_mpc_qp calls it per quantity (RT/gait_fast.cpp:131-138): the cubic through
+ * four consecutive 40 Hz samples, evaluated at walktime * dt_sample + jx * dt_sample, jx = 0..nh-1.
+ *   walktime_d [B] ints; samples_d [12][B]: in1 xyz | in2 xyz | ref xyz | ref2 xyz (SoA [f*B + b])
+ *   out_d [9 + 3 (nh - 1)][B]: position, velocity, acceleration at jx = 0, then the positions at jx = 1..nh-1
+ *   (the reference's Vec21 at its nh = 4); all zero once walktime > _t_end_footstep.
+ * STATUS at the end of round 1: parity with the pinned oracle (oracle/ref_interp.c) not yet run on hardware.
+ * ------------------------------------------------------------------------ */
+int go1mpc_ref_interp_batch(go1mpc_t *h, int B, int nh, const int *walktime_d, double dt_sample,
+                            const double *samples_d, double *out_d, void *stream);
+/* Host part, needs no device: _AAA_inv_mod (row-major 4x4) and _t_end_footstep (:179) for a configuration
+ * (NULL = defaults); either output may be NULL. */
+int go1mpc_ref_interp_model(const Go1MpcConfig *cfg, double *inv16, int *t_end_footstep);
+
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports
  * against.  Runs ~`ms` milliseconds. */

@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_body_tick_in_stride", "go1mpc_body_mpc_step_batch_resident_host_async",
     "go1mpc_foot_trajectory_batch", "go1mpc_foot_trajectory_batch_host", "go1mpc_foot_default_state",
     "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch", "go1mpc_fused_tick_batch",
-    "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_grf_joint_torques_batch",
+    "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_grf_joint_torques_batch", "go1mpc_ref_interp_batch", "go1mpc_ref_interp_model",
     "go1mpc_grf_force_opt_batch_host", "go1mpc_grf_force_distribution_batch_host", "go1mpc_grf_joint_torques_batch_host", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
@@ -118,6 +118,8 @@ def load_library():
     lib.go1mpc_leg_fk_batch.argtypes = [vp, ctypes.c_int] + [vp] * 7
     lib.go1mpc_grf_force_opt_batch.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp]
     lib.go1mpc_grf_force_distribution_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 7
+    lib.go1mpc_ref_interp_model.argtypes = [vp, vp, vp]
+    lib.go1mpc_ref_interp_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, ctypes.c_double, vp, vp, vp]
     lib.go1mpc_grf_force_opt_batch_host.argtypes = [vp, ctypes.c_int, vp, vp, vp]
     lib.go1mpc_grf_force_distribution_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 6
     lib.go1mpc_grf_joint_torques_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 7 + [ctypes.c_longlong, ctypes.c_longlong, vp]
@@ -409,6 +411,11 @@ class Go1Mpc:
         self._check(self.lib.go1mpc_grf_joint_torques_batch(self.h, B, _ptr(jac), _ptr(swing), _ptr(p_des), _ptr(p_est), _ptr(pv_des),
                                                             _ptr(pv_est), _ptr(F_leg_ref), ks, bs, _ptr(tau), stream),
                     "grf_joint_torques_batch")
+
+    def ref_interp(self, B, nh, walktime, dt_sample, samples, out, stream=None):
+        """PRMPCClass::XGetSolution_position_mod3 for B items: walktime [B] ints, samples [12,B], out [9+3(nh-1),B] (device)."""
+        self._check(self.lib.go1mpc_ref_interp_batch(self.h, B, nh, _ptr(walktime), dt_sample, _ptr(samples), _ptr(out), stream),
+                    "ref_interp_batch")
 
     def grf_force_distribution(self, B, gait_mode, y_coefficient, com, leg, F, rfoot, lfoot, F_leg_ref, stream=None):
         self._check(self.lib.go1mpc_grf_force_distribution_batch(self.h, B, gait_mode, y_coefficient, _ptr(com), _ptr(leg), _ptr(F),

@@ -833,6 +833,69 @@ int go1mpc_grf_joint_torques_batch_host(go1mpc_t* h, int B, const double* jac, c
   return GO1MPC_OK;
 }
 
+// ------------------------------------------------------------------ 40 Hz -> 100 Hz reference interpolation
+namespace {
+// _AAA_inv_mod of PRMPCClass::solve_AAA_inv_mod1 (PRMPCClass.cpp:1344-1361): inverse of the rows (t^3, t^2, t, 1) at
+// t = -dt, 0, dt, 2 dt by row-pivoted Gauss-Jordan (first maximal pivot wins), row-major.
+void build_aaa_inv_mod(double dt, double inv[16]) {
+  const double t[4] = {-dt, 0.0, dt, 2 * dt};
+  double a[4][4], r[4][4];
+  for (int i = 0; i < 4; i++) {
+    a[i][0] = pow(t[i], 3); a[i][1] = pow(t[i], 2); a[i][2] = pow(t[i], 1); a[i][3] = 1.0;
+    for (int j = 0; j < 4; j++) r[i][j] = (i == j) ? 1.0 : 0.0;
+  }
+  for (int k = 0; k < 4; k++) {
+    int piv = k;
+    double best = fabs(a[k][k]);
+    for (int i = k + 1; i < 4; i++) if (fabs(a[i][k]) > best) { best = fabs(a[i][k]); piv = i; }
+    if (piv != k) for (int j = 0; j < 4; j++) { std::swap(a[k][j], a[piv][j]); std::swap(r[k][j], r[piv][j]); }
+    const double d = a[k][k];
+    for (int j = 0; j < 4; j++) { a[k][j] = a[k][j] / d; r[k][j] = r[k][j] / d; }
+    for (int i = 0; i < 4; i++) {
+      if (i == k) continue;
+      const double f = a[i][k];
+      for (int j = 0; j < 4; j++) {
+        const double pa = f * a[k][j], pr = f * r[k][j];     // separate statements: no contraction into FMA
+        a[i][j] = a[i][j] - pa; r[i][j] = r[i][j] - pr;
+      }
+    }
+  }
+  memcpy(inv, r, sizeof r);
+}
+}  // namespace
+
+// host part of the interpolation (no device needed): _AAA_inv_mod (row-major) and _t_end_footstep for a configuration
+int go1mpc_ref_interp_model(const Go1MpcConfig* cfg, double* inv16, int* t_end_footstep) {
+  if (!inv16 && !t_end_footstep) return GO1MPC_E_INVALID;
+  Go1MpcConfig def;
+  if (!cfg) { go1mpc_config_default(&def); cfg = &def; }
+  const Go1BodyMpcConfig& c = cfg->body;
+  if (inv16) build_aaa_inv_mod(c.dt_slow, inv16);
+  if (t_end_footstep) {
+    // _tx and _t_end_footstep of PRMPCClass::Initialize (:174-179)
+    double tx = 0.0;
+    for (int i = 1; i < GO1MPC_FOOTSTEPS; i++) { tx = tx + c.tstep; tx = round(tx / c.dt_slow) * c.dt_slow - 0.00001; }
+    *t_end_footstep = (int)round((tx - 3 * c.tstep) / c.dt_mpc);
+  }
+  return GO1MPC_OK;
+}
+
+int go1mpc_ref_interp_batch(go1mpc_t* h, int B, int nh, const int* walktime_d, double dt_sample, const double* samples_d,
+                            double* out_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (B < 0 || !walktime_d || !samples_d || !out_d) return fail(h, GO1MPC_E_INVALID, "ref_interp_batch: bad argument");
+  if (nh < 1 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "ref_interp_batch: 1 <= nh <= 40");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  RefInterpParams P;
+  P.B = B; P.nh = nh; P.dt_sample = dt_sample;
+  go1mpc_ref_interp_model(&h->cfg, P.inv, &P.t_end_footstep);
+  P.walktime = walktime_d; P.samples = samples_d; P.out = out_d;
+  CU(h, ref_interp_launch(P, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
 // ------------------------------------------------------------------ pipelined host entries
 int go1mpc_body_mpc_step_batch_host_async(go1mpc_t* h, int nh, int B, const double* in, double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;

@@ -151,6 +151,17 @@ struct GrfTauParams {
 };
 cudaError_t grf_joint_torques_launch(GrfTauParams P, cudaStream_t st);
 
+// ---- 40 Hz -> 100 Hz reference interpolation (ref_interp.cu) ----
+struct RefInterpParams {
+  int B, nh, t_end_footstep;
+  double dt_sample;
+  double inv[16];                 // _AAA_inv_mod, row-major
+  const int* walktime;            // [B]
+  const double* samples;          // [12][B]
+  double* out;                    // [9 + 3 (nh - 1)][B]
+};
+cudaError_t ref_interp_launch(RefInterpParams P, cudaStream_t st);
+
 // register-resident DFMA loop: flops executed are returned through *flops
 cudaError_t dfma_peak_launch(int grid, int block, int iters, double* sink, cudaStream_t st);
 
