@@ -213,6 +213,13 @@ void orc_interp_position_mod3(const double inv[16], int nh, int t_end_footstep, 
                               const double in1[3], const double in2[3], const double ref[3], const double ref2[3],
                               double *out);
 
+/* Swing-foot roll / pitch reference of rt_mpc_qp (foot_rot.c): PRMPCClass::XGetSolution_Foot_rotation,
+ * RT/src/FastMPC/PRMPCClass.cpp:2255-2380.  State = the members that persist between calls. */
+typedef struct { int bjxx, bjx1; double Rr[15], Lr[15]; } orc_foot_rot_state;   /* 3x5 row-major angle members */
+void orc_foot_rot_state_init(orc_foot_rot_state *s);
+void orc_foot_rotation(const double tx[27], const double ts[27], const double td[27], const double footx[27], double footx_max,
+                       double dt_mpc, int t_end_footstep, int nh, orc_foot_rot_state *s, int walktimex, double dt_sample, double *out);
+
 /* ------------------------------------------------------------------------
  * Ground-reaction-force distribution of go1_servo's 1 kHz loop (Dynamiccclass,
  * GO1/src/whole_body_dynamics/dynmics_compute.cpp:55-427): closed-form split, the

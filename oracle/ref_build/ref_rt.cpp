@@ -93,4 +93,20 @@ int ref_body_position_mod3(void* h, int walktime, double dt_sample, const double
   return (int)p->_t_end_footstep;
 }
 
+// XGetSolution_Foot_rotation, PRMPCClass.cpp:2255-2380: tables it reads, a setter for the step lengths, the call.
+void ref_body_foot_tables(void* h, double* tx27, double* ts27, double* td27, double* footx27, double* scal4) {
+  PRMPCClass* p = static_cast<PRMPCClass*>(h);
+  for (int k = 0; k < _footstepsnumber; k++) { tx27[k] = p->_tx(k); ts27[k] = p->_ts(k); td27[k] = p->_td(k); footx27[k] = p->_footxyz_real(0, k); }
+  scal4[0] = p->_footx_max; scal4[1] = _dt_mpc; scal4[2] = p->_t_end_footstep; scal4[3] = p->_bjx1;
+}
+void ref_body_set_footx(void* h, const double* footx27) {
+  PRMPCClass* p = static_cast<PRMPCClass*>(h);
+  for (int k = 0; k < _footstepsnumber; k++) p->_footxyz_real(0, k) = footx27[k];
+}
+void ref_body_foot_rotation(void* h, int walktimex, double dt_sample, double* out30) {
+  PRMPCClass* p = static_cast<PRMPCClass*>(h);
+  Eigen::Matrix<double, 30, 1> o = p->XGetSolution_Foot_rotation(walktimex, dt_sample);
+  for (int k = 0; k < 30; k++) out30[k] = o(k);
+}
+
 }  // extern "C"

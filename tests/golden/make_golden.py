@@ -196,6 +196,33 @@ def gen_interp(rtl):
     print("interp_ref.npz", N, "t_end_footstep", tend, "beyond", int((d["walktime"] > tend).sum()))
 
 
+def foot_rot_inputs(seed=15):
+    """Step-length table with forward, backward and zero-length steps, and a tick sequence that walks the whole table,
+    runs past _t_end_footstep and jumps back (the angle members persist between calls)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    steps = rng.uniform(0.02, 0.12, 27); steps[[6, 15]] = 0.0; steps[9:12] *= -1
+    footx = np.concatenate([[0.0], np.cumsum(steps)[:-1]])
+    ticks = np.concatenate([np.arange(1, 1700, 3), [1650, 1700, 20, 500, 499, 1611, 1610]]).astype(np.int32)
+    return footx, ticks
+
+
+def gen_foot_rot(rtl):
+    """PRMPCClass::XGetSolution_Foot_rotation over one object, sequential calls (tests/test_oracle_vs_ref.py)."""
+    rtl.ref_body_new.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(rtl.ref_body_new())
+    tx = np.zeros(27); ts = np.zeros(27); td = np.zeros(27); fx0 = np.zeros(27); sc = np.zeros(4)
+    rtl.ref_body_foot_tables(h, P(tx), P(ts), P(td), P(fx0), P(sc))
+    footx, ticks = foot_rot_inputs()
+    rtl.ref_body_set_footx(h, P(footx.copy()))
+    out = np.zeros((len(ticks), 30))
+    for k, t in enumerate(ticks):
+        rtl.ref_body_foot_rotation(h, int(t), ctypes.c_double(0.01), P(out[k]))
+    nh = rtl.ref_body_nh()
+    rtl.ref_body_free(h)
+    np.savez_compressed(os.path.join(HERE, "foot_rot_ref.npz"), tx=tx, ts=ts, td=td, footx=footx, scal=sc, ticks=ticks, out=out, nh=np.array([nh]))
+    print("foot_rot_ref.npz", len(ticks), "non-zero rows", int((np.abs(out).sum(axis=1) > 0).sum()))
+
+
 def gen_grf_tau(dl):
     """Dynamiccclass::compute_joint_torques on 400 seeded legs (tests/test_grf.py: tau_inputs)."""
     from tests.test_grf import tau_inputs
@@ -227,6 +254,8 @@ if __name__ == "__main__":
         gen_step(ctypes.CDLL(nlp))
     if not only or "grf" in only:
         gen_grf(ctypes.CDLL(ref_path("libref_dyn.so")))
+    if not only or "foot_rot" in only:
+        gen_foot_rot(rtl)
     if not only or "interp" in only:
         gen_interp(rtl)
     if not only or "grf_tau" in only:

@@ -234,3 +234,56 @@ def test_oracle_ref_interp_vs_live_reference(oracle):
     oinv, out = _oracle_interp(oracle, d, nh, t_end)
     np.testing.assert_array_equal(oinv, inv)
     np.testing.assert_array_equal(out, want[:, :9 + 3 * (nh - 1)])
+
+
+class _FootRotState(ctypes.Structure):
+    _fields_ = [("bjxx", ctypes.c_int), ("bjx1", ctypes.c_int), ("Rr", ctypes.c_double * 15), ("Lr", ctypes.c_double * 15)]
+
+
+def _oracle_foot_rot(oracle, tx, ts, td, footx, scal, nh, ticks, dt_sample=0.01):
+    lib = oracle.lib
+    lib.orc_foot_rotation.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                             ctypes.c_int, ctypes.c_double, ctypes.c_void_p]
+    lib.orc_foot_rotation.restype = None
+    s = _FootRotState(); lib.orc_foot_rot_state_init(ctypes.byref(s))
+    out = np.full((len(ticks), 6 * nh), np.nan)
+    for k, t in enumerate(ticks):
+        lib.orc_foot_rotation(P(tx), P(ts), P(td), P(footx), float(scal[0]), float(scal[1]), int(scal[2]), nh, ctypes.byref(s), int(t), dt_sample, P(out[k]))
+    return out
+
+
+def test_oracle_foot_rotation_bit_exact_vs_reference_golden(oracle):
+    """oracle/foot_rot.c against PRMPCClass::XGetSolution_Foot_rotation: a 574-call sequence on one object (angle members
+    persist), forward / backward / zero-length steps, ticks beyond _t_end_footstep and jumps back -- bit for bit."""
+    g = load("foot_rot_ref.npz")
+    nh = int(g["nh"][0])
+    out = _oracle_foot_rot(oracle, g["tx"].copy(), g["ts"].copy(), g["td"].copy(), g["footx"].copy(), g["scal"], nh, g["ticks"])
+    np.testing.assert_array_equal(out, g["out"][:, :6 * nh])
+    assert (g["out"][:, 6 * nh:] == 0).all()
+    o = out.reshape(len(out), nh, 6)
+    assert (o[:, :, 0] <= 0).all() and (o[:, :, 3] >= 0).all()          # right roll bumps down, left roll up
+    assert (o[:, :, 1] <= 0).all() and (o[:, :, 4] <= 0).all() and (o[:, :, [1, 4]] < 0).any()   # pitch only toes-down
+    assert (o[:, :, [2, 5]] == 0).all()                                  # yaw is never written
+    assert np.abs(o[:, :, 0]).max() <= 0.13 + 1e-12 and np.abs(o[:, :, 3]).max() <= 0.15 + 1e-12
+
+
+@pytest.mark.skipif(ref_path("libref_rt.so") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_foot_rotation_vs_live_reference(oracle):
+    from tests.golden.make_golden import foot_rot_inputs
+    rtl = ctypes.CDLL(ref_path("libref_rt.so"))
+    if not hasattr(rtl, "ref_body_foot_rotation"):
+        pytest.skip("oracle/_ref predates ref_body_foot_rotation")
+    rtl.ref_body_new.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(rtl.ref_body_new())
+    tx = np.zeros(27); ts = np.zeros(27); td = np.zeros(27); fx0 = np.zeros(27); sc = np.zeros(4)
+    rtl.ref_body_foot_tables(h, P(tx), P(ts), P(td), P(fx0), P(sc))
+    footx, ticks = foot_rot_inputs(seed=151)
+    ticks = ticks[::2]
+    rtl.ref_body_set_footx(h, P(footx.copy()))
+    want = np.zeros((len(ticks), 30))
+    for k, t in enumerate(ticks):
+        rtl.ref_body_foot_rotation(h, int(t), ctypes.c_double(0.01), P(want[k]))
+    nh = rtl.ref_body_nh()
+    rtl.ref_body_free(h)
+    out = _oracle_foot_rot(oracle, tx, ts, td, footx, sc, nh, ticks)
+    np.testing.assert_array_equal(out, want[:, :6 * nh])
