@@ -16,8 +16,11 @@ scaling: every rank owns its own 4096 robots, no collective inside the step.
 Timing: CUDA events on the stream the kernels are launched on, W untimed steps, then exactly K
 timed steps bracketed by barrier + synchronize; max over ranks.  The steps rotate through
 enough distinct input batches that the input footprint exceeds 2x L2 (126 MB), so no step
-re-reads a cache-resident batch.  The `e2e` leg calls the host-buffer C-ABI entry (pinned
-host memory, H2D + kernel + D2H inside the timed region).
+re-reads a cache-resident batch.  The `e2e` leg calls the pipelined host-buffer C-ABI entries (pinned
+host memory, H2D + kernels + D2H inside the timed region); what the reference classes keep as members
+(planner state; body step table and previous body results) stays on the device, what their tick methods
+take as arguments moves every step (`--e2e-records full` uploads whole body records instead).  It also
+reports the host-to-host latency of one lone batch (`e2e.latency_ms`).
 """
 import argparse
 import json
