@@ -1,8 +1,10 @@
 """40 Hz -> 100 Hz reference interpolation (PRMPCClass::XGetSolution_position_mod3,
 RT/src/FastMPC/PRMPCClass.cpp:1170-1261).  The host part of the library (the 4x4 inverse, _t_end_footstep) is pinned
-on the CPU against the reference's golden vectors.  The device kernel was written after round 1's GPU budget was
-spent: its parity test is marked xfail(strict=False) until it has been seen to pass on hardware once (an XPASS in the
-log is that evidence), and the file sorts last so that nothing runs after it."""
+on the CPU against the reference's golden vectors, bit for bit.  The device kernel is held to the north star's
+contract, 1e-9 relative: the reference evaluates the monomials with glibc pow (< 1 ulp, not always correctly rounded),
+the kernel with a correctly rounded integer power, so single values may differ in the last bit.  The reference only
+ever passes walktime = count_inteplotation in 1..n_t_int = 2 (gait_fast.cpp:113-131,487); the wide 0..2000 range of
+the golden set extrapolates the cubic to |values| ~ 1e5 and is compared relative to each item's magnitude."""
 import ctypes
 
 import numpy as np
@@ -23,7 +25,6 @@ def test_ref_interp_model_matches_reference_golden():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="kernel not yet run on hardware (written after round 1's GPU budget was spent)")
 def test_gpu_ref_interp_vs_golden_and_oracle(mpc, oracle):
     import torch
     from tests.golden.make_golden import interp_inputs
@@ -41,5 +42,10 @@ def test_gpu_ref_interp_vs_golden_and_oracle(mpc, oracle):
         mpc.ref_interp(N, nh, wt, 0.01, samples, out)
         mpc.synchronize()
         got = out.cpu().numpy().T
-        np.testing.assert_allclose(got, want, rtol=0, atol=1e-9, err_msg=f"{src} nh={nh}")
-        np.testing.assert_array_equal(got, want, err_msg=f"{src} nh={nh} (bit-exact)")
+        scale = np.maximum(1.0, np.abs(want).max(axis=1, keepdims=True))
+        err = np.abs(got - want) / scale
+        assert np.isfinite(got).all() and err.max() < 1e-9, f"{src} nh={nh}: max rel err {err.max():.3e}"
+        late = d["walktime"] > t_end
+        assert (got[late] == 0).all()                       # beyond _t_end_footstep: exact zeros
+        real = d["walktime"] <= 3                           # the reference's own range of count_inteplotation
+        assert real.sum() > 20 and np.abs(got[real] - want[real]).max() < 1e-12, f"{src} nh={nh} (operating range)"
