@@ -6,7 +6,10 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgo1mpc.so")
-SOURCES = ["api.cu", "body_mpc.cu", "body_fast.cu", "body_split.cu", "body_tri.cu", "body_resident.cu", "qp_dense.cu", "step_timing.cu", "foot_traj.cu", "leg_kin.cu", "grf_qp.cu", "ref_interp.cu"]
+SOURCES = ["api.cu", "body_mpc.cu", "body_fast.cu", "body_tri.cu", "body_resident.cu", "qp_dense.cu", "step_timing.cu", "foot_traj.cu", "leg_kin.cu", "grf_qp.cu", "ref_interp.cu"]
+# A/B variants that `auto` never chooses (body_split.cu: roll / pitch halves side by side in one warp) are only compiled
+# into the library with GO1MPC_BUILD_AB=1 (then GO1MPC_BODY_MODE=split selects it)
+AB_SOURCES = ["body_split.cu"]
 # per-source extra flags: the thread-per-instance kernels keep the oracle's operation order and
 # must not contract a*b+c into FMA
 EXTRA = {"step_timing.cu": ["-fmad=false"], "foot_traj.cu": ["-fmad=false"], "leg_kin.cu": ["-fmad=false"], "ref_interp.cu": ["-fmad=false"]}
@@ -14,6 +17,9 @@ HEADERS = ["gi_warp.cuh", "gi_thread.cuh", "gi_thread4.cuh", "tma.cuh", "powi.cu
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
+    # host code builds tables that are asserted bit-identical to the reference's (build_body_model, build_aaa_inv_mod):
+    # GCC's default -ffp-contract=fast would contract a*b+c on FMA-baseline hosts (aarch64, -march=native)
+    "-Xcompiler", "-ffp-contract=off",
 ]
 
 
@@ -28,7 +34,7 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    deps = [os.path.join(CSRC, s) for s in SOURCES + AB_SOURCES + HEADERS]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
@@ -38,6 +44,10 @@ def build(force=False, verbose=False):
         return LIB
     from concurrent.futures import ThreadPoolExecutor
     extra = os.environ.get("GO1MPC_NVCC_EXTRA", "").split()
+    sources = list(SOURCES)
+    if os.environ.get("GO1MPC_BUILD_AB") == "1":
+        sources += AB_SOURCES
+        extra += ["-DGO1MPC_AB_VARIANTS"]
     # the image exports CC/CXX=/opt/gcc/bin/* whose link line picks a static libstdc++;
     # let nvcc use the PATH host compiler instead
     env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
@@ -52,8 +62,8 @@ def build(force=False, verbose=False):
             raise RuntimeError(f"nvcc failed on {src}:\n" + r.stdout + r.stderr)
         return obj, r.stderr
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        results = list(ex.map(compile_one, SOURCES))
+    with ThreadPoolExecutor(max_workers=len(sources)) as ex:
+        results = list(ex.map(compile_one, sources))
     if verbose:
         for _, err in results:
             print(err)

@@ -9,6 +9,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/go1mpc.h"
@@ -55,10 +56,12 @@ struct go1mpc {
   // device-resident buffers the pipelined calls read AND write (planner state): the last
   // enqueued writer per buffer, so that a later call on another lane is ordered after it
   std::map<const void*, cudaEvent_t> last_writer;
-  int* sched_d = nullptr;          // ring of {next, done} counter pairs for body_fast launches
-  unsigned sched_next = 0;
-  int* flist_d = nullptr;          // ring of hand-over lists of body_split launches: {count, ids[kFlistCap]} each
-  unsigned flist_next = 0;
+  // per caller stream: {next, done} scheduler counters of the persistent body kernels and the hand-over list
+  // {count, total, ids[kFlistCap]}.  Keyed by stream because launches on one stream are ordered, so a block is idle
+  // again when the next launch on that stream starts; launches on different streams never share counters.
+  struct StreamCtl { int* p = nullptr; };
+  std::map<cudaStream_t, StreamCtl> ctl;
+  std::recursive_mutex mu;         // guards the handle's host-side bookkeeping (maps, lane cursor, launch counter)
   int body_mode = 3;               // GO1MPC_BODY_MODE: 0 "fast" combined kernel only, 1 "split" halves side by side in
                                    // one warp, 2 "tri" setup / 4-lanes-per-half solve / merge launches, 3 "auto" (default):
                                    // tri from body_tri_min instances per call on (throughput: 2.6x the combined kernel at
@@ -75,7 +78,6 @@ struct go1mpc {
                                    // 107 vs 137 us at 1024, but 404 vs 190 us at 4096 -- the scalar front-end is
                                    // replicated per warp, so it only pays while the GPU is mostly empty)
 };
-static const int kSchedRing = 64;
 static const int kFlistCap = 8190;   // ints per hand-over list; beyond it the combined kernel redoes the whole batch
 
 namespace {
@@ -195,6 +197,22 @@ int get_body_model(go1mpc* h, int nh, BodyModel** out) {
   return GO1MPC_OK;
 }
 
+// scheduler counters + hand-over list of the stream `st` (allocated and zeroed on first use)
+int get_ctl(go1mpc* h, cudaStream_t st, int** out) {
+  auto it = h->ctl.find(st);
+  if (it == h->ctl.end()) {
+    if (h->ctl.size() >= 256) return fail(h, GO1MPC_E_UNSUPPORTED, "more than 256 distinct streams used with one handle");
+    int* p = nullptr;
+    const size_t bytes = sizeof(int) * (size_t)(kFlistCap + 4);
+    CU(h, cudaMalloc((void**)&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(h, e, "cudaMemset(stream control block)"); }
+    it = h->ctl.emplace(st, go1mpc::StreamCtl{p}).first;
+  }
+  *out = it->second.p;
+  return GO1MPC_OK;
+}
+
 int stage_buf2(go1mpc* h, DevBuf& b, size_t bytes, void** out);
 int stage_buf(go1mpc* h, int slot, size_t bytes, void** out) { return stage_buf2(h, h->stage[slot], bytes, out); }
 int stage_buf2(go1mpc* h, DevBuf& b, size_t bytes, void** out) {
@@ -259,21 +277,13 @@ int go1mpc_create(const Go1MpcConfig* cfg, int device, go1mpc_t** out) {
   }
   h->sms = prop.multiProcessorCount;
   h->smem_optin = prop.sharedMemPerBlockOptin;
-  if (cudaMalloc(&h->sched_d, sizeof(int) * 2 * kSchedRing) != cudaSuccess ||
-      cudaMemset(h->sched_d, 0, sizeof(int) * 2 * kSchedRing) != cudaSuccess) {
-    go1mpc_destroy(h);
-    return GO1MPC_E_CUDA;
-  }
   for (auto& L : h->lanes)
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { go1mpc_destroy(h); return GO1MPC_E_CUDA; }
-  if (cudaMalloc(&h->flist_d, sizeof(int) * (size_t)(kFlistCap + 2) * kSchedRing) != cudaSuccess ||
-      cudaMemset(h->flist_d, 0, sizeof(int) * (size_t)(kFlistCap + 2) * kSchedRing) != cudaSuccess) {
-    go1mpc_destroy(h);
-    return GO1MPC_E_CUDA;
-  }
   const char* bm = getenv("GO1MPC_BODY_MODE");
   if (bm && !strcmp(bm, "fast")) h->body_mode = 0;
+#ifdef GO1MPC_AB_VARIANTS
   else if (bm && !strcmp(bm, "split")) h->body_mode = 1;
+#endif
   else if (bm && !strcmp(bm, "tri")) h->body_mode = 2;
   const char* btm = getenv("GO1MPC_BODY_TRI_MIN");
   if (btm && atoi(btm) > 0) h->body_tri_min = atoi(btm);
@@ -291,8 +301,7 @@ void go1mpc_destroy(go1mpc_t* h) {
   cudaSetDevice(h->device);
   for (auto& kv : h->body_models) if (kv.second.tab_d) cudaFree(kv.second.tab_d);
   for (DevBuf& b : h->stage) if (b.p) cudaFree(b.p);
-  if (h->sched_d) cudaFree(h->sched_d);
-  if (h->flist_d) cudaFree(h->flist_d);
+  for (auto& kv : h->ctl) if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->tri_ws) if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->last_writer) cudaEventDestroy(kv.second);
   for (auto& L : h->lanes) {
@@ -312,12 +321,14 @@ int go1mpc_sm_count(const go1mpc_t* h) { return h ? h->sms : 0; }
 // so checkpointing or restoring a batch is a memcpy
 int go1mpc_copy_device_async(go1mpc_t* h, void* dst_d, const void* src_d, size_t bytes, void* stream) {
   if (!h || !dst_d || !src_d) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   CU(h, cudaSetDevice(h->device));     // a host thread other than the creating one starts on device 0
   CU(h, cudaMemcpyAsync(dst_d, src_d, bytes, cudaMemcpyDeviceToDevice, stream ? (cudaStream_t)stream : h->stream));
   return GO1MPC_OK;
 }
 int go1mpc_synchronize(go1mpc_t* h) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   CU(h, cudaSetDevice(h->device));
   CU(h, cudaStreamSynchronize(h->stream));
   for (auto& L : h->lanes) CU(h, cudaStreamSynchronize(L.stream));
@@ -330,6 +341,7 @@ int go1mpc_qp_solve_batch(go1mpc_t* h, int n, int p, int m, int B, const double*
                           double* x_d, double* cost_d, int* active_d, int* nactive_d, int* iters_d,
                           int* status_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (n < 1 || p < 0 || m < 0 || B < 0 || !G_d || !g0_d || !x_d || (m && (!CI_d || !ci0_d)) || (p && (!CE_d || !ce0_d)))
     return fail(h, GO1MPC_E_INVALID, "qp_solve_batch: bad argument");
   if (n > 96 || m + p > 1024 || p > n) return fail(h, GO1MPC_E_UNSUPPORTED, "qp_solve_batch: n <= 96, m + p <= 1024, p <= n");
@@ -358,6 +370,7 @@ int go1mpc_qp_solve_batch_host(go1mpc_t* h, int n, int p, int m, int B, const do
                                const double* CE, const double* ce0, const double* CI, const double* ci0,
                                double* x, double* cost, int* active, int* nactive, int* iters, int* status) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   CU(h, cudaSetDevice(h->device));
   const size_t szd = sizeof(double), szi = sizeof(int), b = (size_t)B;
@@ -399,6 +412,7 @@ int go1mpc_body_diag_stride(int nh) { return 10 + 2 * nh; }
 
 int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, double* out_d, int* diag_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !in_d || !out_d) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch: bad argument");
   if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "body_mpc_step_batch: 3 <= nh <= 40");
   if (((uintptr_t)in_d & 15) || ((uintptr_t)out_d & 15)) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch: in/out must be 16-byte aligned");
@@ -416,7 +430,9 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
     P.tab_doubles = M->tab_doubles; P.warp_doubles = 0;
     P.cap_scale = h->cfg.qp_iter_cap_scale; P.gate = M->gate; P.nstepx = M->nstepx; P.nsum_mpc = M->nsum_mpc;
     P.in = in_d; P.out = out_d; P.diag = diag_d; P.tab = M->tab_d;
-    P.sched = h->sched_d + 2 * (h->sched_next++ % kSchedRing);
+    int* ctl = nullptr;
+    if ((rc = get_ctl(h, st, &ctl))) return rc;
+    P.sched = ctl;
     P.flist = nullptr; P.flist_count = nullptr; P.flist_cap = 0;
     P.dt_mpc = c.dt_mpc; P.j_ini = c.j_ini; P.mass = c.mass; P.g = c.g; P.gama = c.gama_zmp;
     P.theta_lim = c.theta_lim; P.torque_lim = c.torque_lim;
@@ -439,23 +455,25 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
       }
       P.tri_jb = (double*)(W.p + W.off[0]); P.tri_hs = (double*)(W.p + W.off[1]); P.tri_res = (double*)(W.p + W.off[2]);
       P.tri_queue = (int*)(W.p + W.off[3]); P.tri_qctl = (int*)(W.p + W.qctl_off); P.tri_meta = (int*)(W.p + W.off[4]); P.tri_fr = (double*)(W.p + W.off[5]);
-      int* fl = h->flist_d + (size_t)(kFlistCap + 2) * (h->flist_next++ % kSchedRing);
+      int* fl = ctl + 2;
       P.flist_count = fl; P.flist = fl + 2; P.flist_cap = kFlistCap;
       CU(h, body_tri_launch(P, M->tab_h.data(), h->sms, st));
       CU(h, body_fast_launch(P, h->sms, st));   // list mode: what the merge kernel handed over (normally nothing)
       h->launches += 4;
       return GO1MPC_OK;
     }
+#ifdef GO1MPC_AB_VARIANTS
     if (body_split_supported(nh) && h->body_mode == 1) {
-      // halves side by side; what it cannot reproduce goes through the combined kernel right behind it
-      int* fl = h->flist_d + (size_t)(kFlistCap + 2) * (h->flist_next++ % kSchedRing);
+      // A/B variant (GO1MPC_BUILD_AB=1 builds): halves side by side; what it cannot reproduce goes through the
+      // combined kernel right behind it
+      int* fl = ctl + 2;
       P.flist_count = fl; P.flist = fl + 2; P.flist_cap = kFlistCap;
       CU(h, body_split_launch(P, h->sms, st));
-      P.sched = h->sched_d + 2 * (h->sched_next++ % kSchedRing);
       CU(h, body_fast_launch(P, h->sms, st));
       h->launches += 2;
       return GO1MPC_OK;
     }
+#endif
     CU(h, body_fast_launch(P, h->sms, st));
     h->launches++;
     return GO1MPC_OK;
@@ -487,12 +505,13 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
 // instances the split kernel handed to the combined kernel since the handle was created (synchronises)
 int go1mpc_body_handover_total(go1mpc_t* h, long long* total) {
   if (!h || !total) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   CU(h, cudaSetDevice(h->device));
   CU(h, cudaDeviceSynchronize());
   long long t = 0;
-  for (int k = 0; k < kSchedRing; k++) {
+  for (auto& kv : h->ctl) {
     int v = 0;
-    CU(h, cudaMemcpy(&v, h->flist_d + (size_t)(kFlistCap + 2) * k + 1, sizeof(int), cudaMemcpyDeviceToHost));
+    CU(h, cudaMemcpy(&v, kv.second.p + 3, sizeof(int), cudaMemcpyDeviceToHost));
     t += v;
   }
   *total = t;
@@ -503,6 +522,7 @@ int go1mpc_body_handover_total(go1mpc_t* h, long long* total) {
 // iteration guard (always 0 unless there is a bug); synchronises
 int go1mpc_body_guard_trips(go1mpc_t* h, long long* total) {
   if (!h || !total) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   CU(h, cudaSetDevice(h->device));
   CU(h, cudaDeviceSynchronize());
   long long t = 0;
@@ -518,6 +538,7 @@ int go1mpc_body_guard_trips(go1mpc_t* h, long long* total) {
 
 int go1mpc_body_mpc_step_batch_host(go1mpc_t* h, int nh, int B, const double* in, double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!in || !out) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch_host: bad argument");
   CU(h, cudaSetDevice(h->device));
@@ -542,6 +563,7 @@ int go1mpc_body_mpc_step_batch_host(go1mpc_t* h, int nh, int B, const double* in
 
 int go1mpc_body_model(go1mpc_t* h, int nh, double* pps, double* pvs, double* ppu, double* pvu, double* ppu_2, double* pvu_2) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (nh < 1 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "body_model: 1 <= nh <= 40");
   CU(h, cudaSetDevice(h->device));
   BodyModel* M;
@@ -558,6 +580,7 @@ int go1mpc_body_model(go1mpc_t* h, int nh, double* pps, double* pvs, double* ppu
 
 int go1mpc_body_default_tx(go1mpc_t* h, double* tx27) {
   if (!h || !tx27) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   CU(h, cudaSetDevice(h->device));
   BodyModel* M;
   int rc = get_body_model(h, 4, &M);
@@ -570,6 +593,7 @@ int go1mpc_body_default_tx(go1mpc_t* h, double* tx27) {
 int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick_d, const double* state_d, double* state_out_d,
                                   const double* in_d, double* out_d, int* diag_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !tick_d || !state_d || !state_out_d || !in_d || !out_d) return fail(h, GO1MPC_E_INVALID, "step_timing_step_batch: bad argument");
   if (n_sqp < 1 || n_sqp > STEP_MAX_SQP) return fail(h, GO1MPC_E_UNSUPPORTED, "step_timing_step_batch: 1 <= n_sqp <= 5");
   if (B == 0) return GO1MPC_OK;
@@ -604,6 +628,7 @@ int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick
 int go1mpc_step_timing_step_batch_host(go1mpc_t* h, int n_sqp, int B, const int* tick, double* state, const double* in,
                                        double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!tick || !state || !in || !out) return fail(h, GO1MPC_E_INVALID, "step_timing_step_batch_host: bad argument");
   CU(h, cudaSetDevice(h->device));
@@ -659,6 +684,7 @@ int go1mpc_step_default_state(go1mpc_t* h, double steplength, double stepwidth, 
 int go1mpc_foot_trajectory_batch(go1mpc_t* h, int B, const int* tick_d, const double* state_d, const double* out38_d,
                                  double* foot_d, double* out18_d, int* right_support_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !tick_d || !state_d || !out38_d || !foot_d || !out18_d) return fail(h, GO1MPC_E_INVALID, "foot_trajectory_batch: bad argument");
   if (B == 0) return GO1MPC_OK;
   CU(h, cudaSetDevice(h->device));
@@ -672,6 +698,7 @@ int go1mpc_foot_trajectory_batch(go1mpc_t* h, int B, const int* tick_d, const do
 int go1mpc_foot_trajectory_batch_host(go1mpc_t* h, int B, const int* tick, const double* state, const double* out38,
                                       double* foot, double* out18, int* right_support) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!tick || !state || !out38 || !foot || !out18) return fail(h, GO1MPC_E_INVALID, "foot_trajectory_batch_host: bad argument");
   CU(h, cudaSetDevice(h->device));
@@ -711,6 +738,7 @@ int go1mpc_foot_default_state(go1mpc_t* h, double* fs) {
 // ------------------------------------------------------------------ GRF distribution
 int go1mpc_grf_force_opt_batch(go1mpc_t* h, int B, const double* in_d, double* out_d, int* diag_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !in_d || !out_d) return fail(h, GO1MPC_E_INVALID, "grf_force_opt_batch: bad argument");
   if (B == 0) return GO1MPC_OK;
   CU(h, cudaSetDevice(h->device));
@@ -726,6 +754,7 @@ int go1mpc_grf_force_distribution_batch(go1mpc_t* h, int B, int gait_mode, doubl
                                         const double* leg_des_d, const double* F_force_des_d, const double* rfoot_des_d,
                                         const double* lfoot_des_d, double* F_leg_ref_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !com_des_d || !leg_des_d || !F_force_des_d || !rfoot_des_d || !lfoot_des_d || !F_leg_ref_d)
     return fail(h, GO1MPC_E_INVALID, "grf_force_distribution_batch: bad argument");
   if (B == 0) return GO1MPC_OK;
@@ -743,6 +772,7 @@ int go1mpc_grf_joint_torques_batch(go1mpc_t* h, int B, const double* jac_d, cons
                                    const double* F_leg_ref_d, long long F_elem_stride, long long F_robot_stride, double* tau_d,
                                    void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !jac_d || !swing_d || !p_des_d || !p_est_d || !pv_des_d || !pv_est_d || !F_leg_ref_d || !tau_d)
     return fail(h, GO1MPC_E_INVALID, "grf_joint_torques_batch: bad argument");
   if (B == 0) return GO1MPC_OK;
@@ -759,6 +789,7 @@ int go1mpc_grf_joint_torques_batch(go1mpc_t* h, int B, const double* jac_d, cons
 // synchronous host-buffer forms of the three GRF entries (staging on the handle's stream)
 int go1mpc_grf_force_opt_batch_host(go1mpc_t* h, int B, const double* in, double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!in || !out) return fail(h, GO1MPC_E_INVALID, "grf_force_opt_batch_host: bad argument");
   CU(h, cudaSetDevice(h->device));
@@ -782,6 +813,7 @@ int go1mpc_grf_force_distribution_batch_host(go1mpc_t* h, int B, int gait_mode, 
                                              const double* leg_des, const double* F_force_des, const double* rfoot_des,
                                              const double* lfoot_des, double* F_leg_ref) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!com_des || !leg_des || !F_force_des || !rfoot_des || !lfoot_des || !F_leg_ref)
     return fail(h, GO1MPC_E_INVALID, "grf_force_distribution_batch_host: bad argument");
@@ -808,6 +840,7 @@ int go1mpc_grf_joint_torques_batch_host(go1mpc_t* h, int B, const double* jac, c
                                         const double* p_est, const double* pv_des, const double* pv_est,
                                         const double* F_leg_ref, long long F_elem_stride, long long F_robot_stride, double* tau) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!jac || !swing || !p_des || !p_est || !pv_des || !pv_est || !F_leg_ref || !tau || F_elem_stride < 0 || F_robot_stride < 0)
     return fail(h, GO1MPC_E_INVALID, "grf_joint_torques_batch_host: bad argument");
@@ -883,6 +916,7 @@ int go1mpc_ref_interp_model(const Go1MpcConfig* cfg, double* inv16, int* t_end_f
 int go1mpc_ref_interp_batch(go1mpc_t* h, int B, int nh, const int* walktime_d, double dt_sample, const double* samples_d,
                             double* out_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !walktime_d || !samples_d || !out_d) return fail(h, GO1MPC_E_INVALID, "ref_interp_batch: bad argument");
   if (nh < 1 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "ref_interp_batch: 1 <= nh <= 40");
   if (B == 0) return GO1MPC_OK;
@@ -899,6 +933,7 @@ int go1mpc_ref_interp_batch(go1mpc_t* h, int B, int nh, const int* walktime_d, d
 // ------------------------------------------------------------------ pipelined host entries
 int go1mpc_body_mpc_step_batch_host_async(go1mpc_t* h, int nh, int B, const double* in, double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!in || !out) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch_host_async: bad argument");
   if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "body_mpc_step_batch_host_async: 3 <= nh <= 40");
@@ -936,6 +971,7 @@ int go1mpc_body_tick_in_stride(int nh) { return (9 + 9 * nh + 1) & ~1; }
 int go1mpc_body_mpc_step_batch_resident_host_async(go1mpc_t* h, int nh, int B, const double* tx_d, double* out_d,
                                                    const double* tick_in, double* tick_out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!tx_d || !out_d || !tick_in || !tick_out) return fail(h, GO1MPC_E_INVALID, "body_mpc_step_batch_resident_host_async: bad argument");
   if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "body_mpc_step_batch_resident_host_async: 3 <= nh <= 40");
@@ -976,6 +1012,7 @@ int go1mpc_body_mpc_step_batch_resident_host_async(go1mpc_t* h, int nh, int B, c
 int go1mpc_step_timing_step_batch_host_async(go1mpc_t* h, int n_sqp, int B, const int* tick, const double* state_d,
                                              double* state_out_d, const double* in, double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!tick || !state_d || !state_out_d || !in || !out) return fail(h, GO1MPC_E_INVALID, "step_timing_step_batch_host_async: bad argument");
   CU(h, cudaSetDevice(h->device));
@@ -1012,6 +1049,7 @@ int go1mpc_step_timing_step_batch_host_async(go1mpc_t* h, int n_sqp, int B, cons
 int go1mpc_leg_fk_batch(go1mpc_t* h, int B, const double* q_d, const int* leg_d, const double* body_p_d, const double* body_r_d,
                         double* pos_d, double* jac_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !q_d || !leg_d || !pos_d || ((body_p_d == nullptr) != (body_r_d == nullptr)))
     return fail(h, GO1MPC_E_INVALID, "leg_fk_batch: bad argument");
   if (B == 0) return GO1MPC_OK;
@@ -1025,6 +1063,7 @@ int go1mpc_leg_fk_batch(go1mpc_t* h, int B, const double* q_d, const int* leg_d,
 int go1mpc_leg_ik_batch(go1mpc_t* h, int B, const double* pdes_d, const double* qini_d, const int* leg_d, const double* body_p_d,
                         const double* body_r_d, double* q_d, double* jac_d, int* iters_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !pdes_d || !qini_d || !leg_d || !q_d || ((body_p_d == nullptr) != (body_r_d == nullptr)))
     return fail(h, GO1MPC_E_INVALID, "leg_ik_batch: bad argument");
   if (B == 0) return GO1MPC_OK;
@@ -1040,6 +1079,7 @@ int go1mpc_servo_kin_tick_batch(go1mpc_t* h, int B, int gait_mode, double y_offs
                                 const double* rfoot_d, const double* lfoot_d, const double* homing_d, double* q_d, double* jac_d,
                                 double* foot_des_d, int* iters_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !com_d || !theta_d || !rfoot_d || !lfoot_d || !homing_d || !q_d) return fail(h, GO1MPC_E_INVALID, "servo_kin_tick_batch: bad argument");
   if (gait_mode < 101 || gait_mode > 103) return fail(h, GO1MPC_E_UNSUPPORTED, "servo_kin_tick_batch: gait_mode 101, 102 or 103");
   if (B == 0) return GO1MPC_OK;
@@ -1055,6 +1095,7 @@ int go1mpc_servo_kin_tick_batch(go1mpc_t* h, int B, int gait_mode, double y_offs
 // ------------------------------------------------------------------ fused tick (planner -> swing foot -> body MPC -> servo IK)
 int go1mpc_fused_tick_batch(go1mpc_t* h, int B, const Go1FusedTick* t, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (!t || B < 0) return fail(h, GO1MPC_E_INVALID, "fused_tick_batch: bad argument");
   if (!t->servo_theta_d || !t->out38_d || !t->out18_d || !t->body_out_d) return fail(h, GO1MPC_E_INVALID, "fused_tick_batch: bad argument");
   if (B == 0) return GO1MPC_OK;
@@ -1112,6 +1153,7 @@ int leg_host(go1mpc* h, int B, bool ik, const double* a3, const double* b3, cons
 int go1mpc_leg_fk_batch_host(go1mpc_t* h, int B, const double* q, const int* leg, const double* body_p, const double* body_r,
                              double* pos, double* jac) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!q || !leg || !pos || ((body_p == nullptr) != (body_r == nullptr))) return fail(h, GO1MPC_E_INVALID, "leg_fk_batch_host: bad argument");
   CU(h, cudaSetDevice(h->device));
@@ -1120,6 +1162,7 @@ int go1mpc_leg_fk_batch_host(go1mpc_t* h, int B, const double* q, const int* leg
 int go1mpc_leg_ik_batch_host(go1mpc_t* h, int B, const double* pdes, const double* qini, const int* leg, const double* body_p,
                              const double* body_r, double* q, double* jac, int* iters) {
   if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
   if (!pdes || !qini || !leg || !q || ((body_p == nullptr) != (body_r == nullptr))) return fail(h, GO1MPC_E_INVALID, "leg_ik_batch_host: bad argument");
   CU(h, cudaSetDevice(h->device));
@@ -1128,6 +1171,7 @@ int go1mpc_leg_ik_batch_host(go1mpc_t* h, int B, const double* pdes, const doubl
 
 int go1mpc_measure_dfma_peak(go1mpc_t* h, int ms, double* gflops) {
   if (!h || !gflops) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
   CU(h, cudaSetDevice(h->device));
   double* sink;
   CU(h, cudaMalloc(&sink, sizeof(double)));

@@ -22,6 +22,7 @@
 // Rounding differs from the CPU oracle in the last bits; parity (1e-9 relative on x,
 // identical active set and iteration counters) is checked by tests/test_gpu_body.py.
 #include <cuda_runtime.h>
+#include <mutex>
 #include <stdint.h>
 #include "gi_warp.cuh"
 #include "tma.cuh"
@@ -665,14 +666,21 @@ static cudaError_t fast_launch_nh(const BodyKParams& P, int sms, cudaStream_t st
   const size_t smem = fast_smem<NH>(WPC);
   int dev_ = 0;            // function attributes and occupancy are per device
   cudaGetDevice(&dev_);
+  static std::mutex cache_mu;         // handles on several host threads may launch concurrently
   static int occ_cache_[64] = {};
-  int& occ_cache = occ_cache_[dev_ & 63];
-  if (occ_cache == 0) {
-    cudaError_t e = cudaFuncSetAttribute(body_fast_kernel<NH, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache, body_fast_kernel<NH, WPC>, WPC * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (occ_cache < 1) return cudaErrorLaunchOutOfResources;
+  int occ_cache;
+  {
+    std::lock_guard<std::mutex> lk(cache_mu);
+    if (occ_cache_[dev_ & 63] == 0) {
+      cudaError_t e = cudaFuncSetAttribute(body_fast_kernel<NH, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      int o = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, body_fast_kernel<NH, WPC>, WPC * 32, smem);
+      if (e != cudaSuccess) return e;
+      if (o < 1) return cudaErrorLaunchOutOfResources;
+      occ_cache_[dev_ & 63] = o;
+    }
+    occ_cache = occ_cache_[dev_ & 63];
   }
   int grid = (P.B + WPC - 1) / WPC;
   if (grid > sms * occ_cache) grid = sms * occ_cache;

@@ -30,6 +30,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "gi_warp.cuh"
 #include "tma.cuh"
 #include "kernels.h"
@@ -925,47 +926,40 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
   const int blocks = (P.B + TRI_SETUP_THREADS - 1) / TRI_SETUP_THREADS;
   const size_t ssmem = (size_t)TRI_SETUP_THREADS * D::IN * sizeof(double) + 16;
   // function attributes (opt-in dynamic shared memory) and occupancy are per device: one slot per device ordinal
+  const size_t smem = (size_t)(((NH * NH + 1) & ~1) + WPC * 8 * D::GSP) * sizeof(double);
+  const size_t msmem = (size_t)TRI_MERGE_THREADS * (2 * (D::RES + 2) + D::FR + 2) * sizeof(double) + 16;
   int dev_ = 0;
   cudaGetDevice(&dev_);
   dev_ &= 63;
-  static bool sattr_[64] = {};
-  bool& sattr = sattr_[dev_];
-  if (!sattr) {
-    cudaError_t e = cudaFuncSetAttribute(tri_setup_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
-    if (e != cudaSuccess) return e;
-    sattr = true;
+  // per-device cache of the opt-in attributes and the solve kernel's occupancy; handles on several host threads
+  // may launch concurrently, so the first use per device is serialised
+  static std::mutex cache_mu;
+  static int occ_[64] = {};
+  int occ;
+  {
+    std::lock_guard<std::mutex> lk(cache_mu);
+    if (occ_[dev_] == 0) {
+      cudaError_t e = cudaFuncSetAttribute(tri_setup_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssmem);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(tri_solve_kernel<NH, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(tri_merge_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
+      if (e != cudaSuccess) return e;
+      int o = 0;
+      e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, tri_solve_kernel<NH, WPC>, WPC * 32, smem);
+      if (e != cudaSuccess) return e;
+      if (o < 1) return cudaErrorLaunchOutOfResources;
+      occ_[dev_] = o;
+    }
+    occ = occ_[dev_];
   }
-  static int stages = -1;   // GO1MPC_TRI_STAGES=1..3: debugging aid, launch only the first kernels
-  if (stages < 0) { const char* e = getenv("GO1MPC_TRI_STAGES"); stages = e ? atoi(e) : 3; }
   TriTab<NH> T;
   memcpy(T.v, tab_host, sizeof(T.v));
   tri_setup_kernel<NH><<<blocks, TRI_SETUP_THREADS, ssmem, st>>>(P, T);
-  if (stages < 2) return cudaGetLastError();
-  const size_t smem = (size_t)(((NH * NH + 1) & ~1) + WPC * 8 * D::GSP) * sizeof(double);
-  static int occ_[64] = {};
-  int& occ = occ_[dev_];
-  if (occ == 0) {
-    cudaError_t e = cudaFuncSetAttribute(tri_solve_kernel<NH, WPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tri_solve_kernel<NH, WPC>, WPC * 32, smem);
-    if (e != cudaSuccess) return e;
-    if (occ < 1) return cudaErrorLaunchOutOfResources;
-  }
   int grid = (2 * P.B + WPC * 8 - 1) / (WPC * 8);
   if (grid > sms * occ) grid = sms * occ;
   tri_solve_kernel<NH, WPC><<<grid, WPC * 32, smem, st>>>(P);
-  if (stages < 3) return cudaGetLastError();
-  {
-    const size_t msmem = (size_t)TRI_MERGE_THREADS * (2 * (D::RES + 2) + D::FR + 2) * sizeof(double) + 16;
-    static bool attr_[64] = {};
-    bool& attr = attr_[dev_];
-    if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(tri_merge_kernel<NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem);
-      if (e != cudaSuccess) return e;
-      attr = true;
-    }
-    tri_merge_kernel<NH><<<(P.B + TRI_MERGE_THREADS - 1) / TRI_MERGE_THREADS, TRI_MERGE_THREADS, msmem, st>>>(P);
-  }
+  tri_merge_kernel<NH><<<(P.B + TRI_MERGE_THREADS - 1) / TRI_MERGE_THREADS, TRI_MERGE_THREADS, msmem, st>>>(P);
   return cudaGetLastError();
 }
 

@@ -19,7 +19,9 @@
 // but the step period it writes back then differs from the host's by an ulp, which the badly
 // conditioned swing-foot fit downstream amplifies to 1e-6 -- fidelity wins).
 #include <cuda_runtime.h>
-#include "gi_thread.cuh"
+#ifdef GO1_STEP_GENERIC_QP
+#include "gi_thread.cuh"      // A/B variant only: run-time indexed solver state (local memory)
+#endif
 #include "gi_thread4.cuh"
 #include "gi_warp.cuh"
 #include "kernels.h"

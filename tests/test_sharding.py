@@ -39,7 +39,13 @@ def _worker(rank, world, port, B, nh, ret):
                             np.ascontiguousarray(d["bstate"][lo:hi]), np.ascontiguousarray(d["refs"][lo:hi]), o14, x)
     local = torch.from_numpy(np.concatenate([o14, theta, x, r["status"][:, None].astype(float)], axis=1))
     full = sharding.gather_to_rank0(local, B)
+    # the preallocated once-per-batch gather bench.py uses must give the same rows
+    per = -(-B // world)
+    rg = sharding.ResultGather(per, local.shape[1], local.dtype, local.device)
+    rg.local.zero_(); rg.local[:hi - lo] = local
+    rg.gather()
     if rank == 0:
+        assert torch.equal(rg.rows(B), full)
         ret.put(full.numpy())
     dist.barrier()
     dist.destroy_process_group()
