@@ -450,13 +450,65 @@ int go1mpc_grf_joint_torques_batch_host(go1mpc_t *h, int B, const double *jac, c
  *   walktime_d [B] ints; samples_d [12][B]: in1 xyz | in2 xyz | ref xyz | ref2 xyz (SoA [f*B + b])
  *   out_d [9 + 3 (nh - 1)][B]: position, velocity, acceleration at jx = 0, then the positions at jx = 1..nh-1
  *   (the reference's Vec21 at its nh = 4); all zero once walktime > _t_end_footstep.
- * STATUS at the end of round 1: parity with the pinned oracle (oracle/ref_interp.c) not yet run on hardware.
+ * Parity (tests/test_zz_ref_interp.py, B200): 1e-9 relative to the pinned oracle (oracle/ref_interp.c; the reference
+ * evaluates the monomials with libm pow, the kernel with a correctly rounded integer power), 1e-12 absolute over the
+ * reference's own walktime range (count_inteplotation = 1..2, RT/gait_fast.cpp:113-131).
  * ------------------------------------------------------------------------ */
 int go1mpc_ref_interp_batch(go1mpc_t *h, int B, int nh, const int *walktime_d, double dt_sample,
                             const double *samples_d, double *out_d, void *stream);
 /* Host part, needs no device: _AAA_inv_mod (row-major 4x4) and _t_end_footstep (:179) for a configuration
  * (NULL = defaults); either output may be NULL. */
 int go1mpc_ref_interp_model(const Go1MpcConfig *cfg, double *inv16, int *t_end_footstep);
+
+/* ---------------------------------------------------------------------------
+ * One control tick for B robots with HOST inputs and COMPACT results -- the call a controller farm makes per tick:
+ * planner tick (= go1mpc_step_timing_step_batch) and body-inclination MPC tick on the device-resident records
+ * (= go1mpc_body_mpc_step_batch_resident_host_async) on ONE caller stream, then a 12-double result row per robot.
+ * What the reference classes keep as members stays in HBM (planner state, _tx, _V_ini / stale results); what their
+ * tick methods take as arguments moves up per call (tick, the 20 planner inputs, the 9+9nh body-tick doubles); what
+ * comes down is GO1MPC_COMPACT_DOUBLES per robot instead of Vec38 + Vec14 + diagnostics:
+ *   [0,3) CoM x y z (Vec38 0..2)   [3,5) body roll, pitch   [5,7) body torques (Vec14 0..3)
+ *   [7,9) next footstep x, y (Vec38 29, 31)   [9] step period (Vec38 35)
+ *   [10] status of the planner's last SQP solve (-1: none ran)   [11] body QP status
+ * compact_d is a caller-owned DEVICE buffer [B][12] (16-byte aligned; e.g. the send buffer of the once-per-batch gather
+ * to rank 0); `compact` (host, may be NULL) receives a copy.  out38 / step_diag / body_diag (host, may be NULL) receive
+ * the full results.  step_state_src_d (may be NULL): run the planner tick out of place from this pristine state.
+ * Everything is enqueued on `stream`; staging is per stream and owned by the handle.
+ * ------------------------------------------------------------------------ */
+#define GO1MPC_COMPACT_DOUBLES 12
+typedef struct {
+  int n_sqp, nh;
+  const int *tick;                /* host [B] */
+  const double *step_in;          /* host [20][B] */
+  const double *body_tick_in;     /* host [B][go1mpc_body_tick_in_stride(nh)] */
+  const double *step_state_src_d; /* device [202][B] or NULL */
+  double *step_state_d;           /* device [202][B], state after the tick */
+  const double *tx_d;             /* device [B][28] */
+  double *body_out_d;             /* device [B][go1mpc_body_out_stride(nh)], in/out */
+  double *compact_d;              /* device [B][12] */
+  double *compact;                /* host [B][12] or NULL */
+  double *out38;                  /* host [38][B] or NULL */
+  int *step_diag;                 /* host [60][B] or NULL */
+  int *body_diag;                 /* host [B][go1mpc_body_diag_stride(nh)] or NULL */
+} Go1ControlTick;
+int go1mpc_control_tick_host_async(go1mpc_t *h, int B, const Go1ControlTick *t, void *stream);
+/* The pack kernel alone (device pointers; step_diag_d / body_diag_d may be NULL). */
+int go1mpc_pack_compact_batch(go1mpc_t *h, int B, int nh, const double *out38_d, const int *step_diag_d,
+                              const double *body_out_d, const int *body_diag_d, double *compact_d, void *stream);
+
+/* ---------------------------------------------------------------------------
+ * Stream ordering and CUDA-graph capture.  Every *_batch entry only enqueues work on the stream it is given and
+ * allocates nothing once that stream has been used with the same batch size, so a sequence of ticks dealt over several
+ * streams can be captured once and replayed with one launch (launch-bound loops at small batches):
+ *   go1mpc_graph_capture_begin(h, s0); go1mpc_stream_wait(h, s1, s0); ...ticks on s0, s1...;
+ *   go1mpc_stream_wait(h, s0, s1); go1mpc_graph_capture_end(h, s0, &g); go1mpc_graph_launch(h, g, s0);
+ * go1mpc_stream_wait makes `waiter` wait for the work enqueued so far on `signaller` (NULL = the handle's stream).
+ * ------------------------------------------------------------------------ */
+int go1mpc_stream_wait(go1mpc_t *h, void *waiter, void *signaller);
+int go1mpc_graph_capture_begin(go1mpc_t *h, void *stream);
+int go1mpc_graph_capture_end(go1mpc_t *h, void *stream, void **graph_exec_out);
+int go1mpc_graph_launch(go1mpc_t *h, void *graph_exec, void *stream);
+int go1mpc_graph_destroy(go1mpc_t *h, void *graph_exec);
 
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports

@@ -24,6 +24,8 @@ EXPORTED_SYMBOLS = [
     "go1mpc_foot_trajectory_batch", "go1mpc_foot_trajectory_batch_host", "go1mpc_foot_default_state",
     "go1mpc_leg_fk_batch", "go1mpc_leg_ik_batch", "go1mpc_servo_kin_tick_batch", "go1mpc_fused_tick_batch",
     "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_grf_joint_torques_batch", "go1mpc_ref_interp_batch", "go1mpc_ref_interp_model",
+    "go1mpc_control_tick_host_async", "go1mpc_pack_compact_batch", "go1mpc_stream_wait", "go1mpc_graph_capture_begin",
+    "go1mpc_graph_capture_end", "go1mpc_graph_launch", "go1mpc_graph_destroy",
     "go1mpc_grf_force_opt_batch_host", "go1mpc_grf_force_distribution_batch_host", "go1mpc_grf_joint_torques_batch_host", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
@@ -127,6 +129,13 @@ def load_library():
     lib.go1mpc_servo_kin_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_double] + [vp] * 10
     lib.go1mpc_fused_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.POINTER(FusedTick), vp]
     lib.go1mpc_leg_ik_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
+    lib.go1mpc_control_tick_host_async.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ControlTick), vp]
+    lib.go1mpc_pack_compact_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 6
+    lib.go1mpc_stream_wait.argtypes = [vp, vp, vp]
+    lib.go1mpc_graph_capture_begin.argtypes = [vp, vp]
+    lib.go1mpc_graph_capture_end.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_void_p)]
+    lib.go1mpc_graph_launch.argtypes = [vp, vp, vp]
+    lib.go1mpc_graph_destroy.argtypes = [vp, vp]
     lib.go1mpc_leg_fk_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 6
     lib.go1mpc_leg_ik_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 8
     _LIB = lib
@@ -194,6 +203,18 @@ class FusedTick(ctypes.Structure):
                 ("grf_in_d", ctypes.c_void_p), ("grf_out_d", ctypes.c_void_p), ("grf_diag_d", ctypes.c_void_p),
                 ("swing_d", ctypes.c_void_p), ("p_des_d", ctypes.c_void_p), ("p_est_d", ctypes.c_void_p),
                 ("pv_des_d", ctypes.c_void_p), ("pv_est_d", ctypes.c_void_p), ("tau_d", ctypes.c_void_p)]
+
+
+COMPACT_DOUBLES = 12   # GO1MPC_COMPACT_DOUBLES
+
+
+class ControlTick(ctypes.Structure):
+    """Go1ControlTick of include/go1mpc.h."""
+    _fields_ = [("n_sqp", ctypes.c_int), ("nh", ctypes.c_int), ("tick", ctypes.c_void_p), ("step_in", ctypes.c_void_p),
+                ("body_tick_in", ctypes.c_void_p), ("step_state_src_d", ctypes.c_void_p), ("step_state_d", ctypes.c_void_p),
+                ("tx_d", ctypes.c_void_p), ("body_out_d", ctypes.c_void_p), ("compact_d", ctypes.c_void_p),
+                ("compact", ctypes.c_void_p), ("out38", ctypes.c_void_p), ("step_diag", ctypes.c_void_p),
+                ("body_diag", ctypes.c_void_p)]
 
 
 def _ptr(a):

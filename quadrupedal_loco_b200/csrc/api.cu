@@ -61,6 +61,12 @@ struct go1mpc {
   // again when the next launch on that stream starts; launches on different streams never share counters.
   struct StreamCtl { int* p = nullptr; };
   std::map<cudaStream_t, StreamCtl> ctl;
+  // staging of go1mpc_control_tick_host_async, one set per caller stream (grown on demand): tick | step_in | body tick
+  // records | expanded body records | out38 | planner diag | body diag
+  struct TickWs { DevBuf b[7]; };
+  std::map<cudaStream_t, TickWs> tick_ws;
+  std::vector<cudaEvent_t> ev_pool;   // go1mpc_stream_wait: events, reused round-robin
+  unsigned ev_next = 0;
   std::recursive_mutex mu;         // guards the handle's host-side bookkeeping (maps, lane cursor, launch counter)
   int body_mode = 3;               // GO1MPC_BODY_MODE: 0 "fast" combined kernel only, 1 "split" halves side by side in
                                    // one warp, 2 "tri" setup / 4-lanes-per-half solve / merge launches, 3 "auto" (default):
@@ -304,6 +310,8 @@ void go1mpc_destroy(go1mpc_t* h) {
   for (auto& kv : h->ctl) if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->tri_ws) if (kv.second.p) cudaFree(kv.second.p);
   for (auto& kv : h->last_writer) cudaEventDestroy(kv.second);
+  for (auto& kv : h->tick_ws) for (DevBuf& b : kv.second.b) if (b.p) cudaFree(b.p);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   for (auto& L : h->lanes) {
     for (DevBuf& b : L.stage) if (b.p) cudaFree(b.p);
     if (L.stream) cudaStreamDestroy(L.stream);
@@ -1167,6 +1175,111 @@ int go1mpc_leg_ik_batch_host(go1mpc_t* h, int B, const double* pdes, const doubl
   if (!pdes || !qini || !leg || !q || ((body_p == nullptr) != (body_r == nullptr))) return fail(h, GO1MPC_E_INVALID, "leg_ik_batch_host: bad argument");
   CU(h, cudaSetDevice(h->device));
   return leg_host(h, B, true, pdes, qini, leg, body_p, body_r, q, jac, iters);
+}
+
+// ------------------------------------------------------------------ control tick with host inputs and compact results
+int go1mpc_pack_compact_batch(go1mpc_t* h, int B, int nh, const double* out38_d, const int* step_diag_d, const double* body_out_d,
+                              const int* body_diag_d, double* compact_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  if (B < 0 || !out38_d || !body_out_d || !compact_d) return fail(h, GO1MPC_E_INVALID, "pack_compact_batch: bad argument");
+  if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "pack_compact_batch: 3 <= nh <= 40");
+  if (((uintptr_t)body_out_d & 15) || ((uintptr_t)compact_d & 15)) return fail(h, GO1MPC_E_INVALID, "pack_compact_batch: 16-byte alignment");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, compact_pack_launch(B, nh, go1mpc_body_out_stride(nh), go1mpc_body_diag_stride(nh), out38_d, step_diag_d, body_out_d, body_diag_d,
+                            compact_d, h->sms, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
+int go1mpc_control_tick_host_async(go1mpc_t* h, int B, const Go1ControlTick* t, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!t || !t->tick || !t->step_in || !t->body_tick_in || !t->step_state_d || !t->tx_d || !t->body_out_d || !t->compact_d)
+    return fail(h, GO1MPC_E_INVALID, "control_tick_host_async: bad argument");
+  const int nh = t->nh;
+  if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "control_tick_host_async: 3 <= nh <= 40");
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  if (h->tick_ws.size() >= 256 && h->tick_ws.find(st) == h->tick_ws.end())
+    return fail(h, GO1MPC_E_UNSUPPORTED, "more than 256 distinct streams used with one handle");
+  go1mpc::TickWs& W = h->tick_ws[st];
+  const size_t b = (size_t)B;
+  const int is = go1mpc_body_in_stride(nh), os = go1mpc_body_out_stride(nh), ts = go1mpc_body_tick_in_stride(nh), ds = go1mpc_body_diag_stride(nh);
+  const size_t bytes[7] = {b * sizeof(int), b * STEP_IN_DOUBLES * sizeof(double), b * ts * sizeof(double), b * is * sizeof(double),
+                           b * STEP_OUT_DOUBLES * sizeof(double), b * STEP_DIAG_INTS * sizeof(int), b * ds * sizeof(int)};
+  void* d[7];
+  int rc;
+  for (int k = 0; k < 7; k++) {
+    if (bytes[k] > W.b[k].cap) CU(h, cudaStreamSynchronize(st));     // growing: earlier work on this stream may still use the old buffer
+    if ((rc = stage_buf2(h, W.b[k], bytes[k], &d[k]))) return rc;
+  }
+  CU(h, cudaMemcpyAsync(d[0], t->tick, bytes[0], cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(d[1], t->step_in, bytes[1], cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(d[2], t->body_tick_in, bytes[2], cudaMemcpyHostToDevice, st));
+  // planner tick: out of place from the pristine state when the caller gives one (replays of the same tick), else in place
+  const double* src = t->step_state_src_d ? t->step_state_src_d : t->step_state_d;
+  if ((rc = go1mpc_step_timing_step_batch(h, t->n_sqp, B, (const int*)d[0], src, t->step_state_d, (const double*)d[1], (double*)d[4], (int*)d[5], st))) return rc;
+  // body tick on the resident records
+  CU(h, body_record_expand_launch(B, nh, is, ts, os, t->tx_d, (const double*)d[2], t->body_out_d, (double*)d[3], h->sms, st));
+  h->launches++;
+  if ((rc = go1mpc_body_mpc_step_batch(h, nh, B, (const double*)d[3], t->body_out_d, (int*)d[6], st))) return rc;
+  CU(h, compact_pack_launch(B, nh, os, ds, (const double*)d[4], (const int*)d[5], t->body_out_d, (const int*)d[6], t->compact_d, h->sms, st));
+  h->launches++;
+  if (t->out38) CU(h, cudaMemcpyAsync(t->out38, d[4], bytes[4], cudaMemcpyDeviceToHost, st));
+  if (t->step_diag) CU(h, cudaMemcpyAsync(t->step_diag, d[5], bytes[5], cudaMemcpyDeviceToHost, st));
+  if (t->body_diag) CU(h, cudaMemcpyAsync(t->body_diag, d[6], bytes[6], cudaMemcpyDeviceToHost, st));
+  if (t->compact) CU(h, cudaMemcpyAsync(t->compact, t->compact_d, b * GO1MPC_COMPACT_DOUBLES * sizeof(double), cudaMemcpyDeviceToHost, st));
+  return GO1MPC_OK;
+}
+
+// ------------------------------------------------------------------ stream ordering and CUDA-graph capture of tick sequences
+int go1mpc_stream_wait(go1mpc_t* h, void* waiter, void* signaller) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  CU(h, cudaSetDevice(h->device));
+  if (h->ev_pool.size() < 256) {
+    cudaEvent_t e;
+    CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    h->ev_pool.push_back(e);
+  }
+  cudaEvent_t e = h->ev_pool[h->ev_next++ % h->ev_pool.size()];
+  CU(h, cudaEventRecord(e, signaller ? (cudaStream_t)signaller : h->stream));
+  CU(h, cudaStreamWaitEvent(waiter ? (cudaStream_t)waiter : h->stream, e, 0));
+  return GO1MPC_OK;
+}
+int go1mpc_graph_capture_begin(go1mpc_t* h, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaStreamBeginCapture(stream ? (cudaStream_t)stream : h->stream, cudaStreamCaptureModeThreadLocal));
+  return GO1MPC_OK;
+}
+int go1mpc_graph_capture_end(go1mpc_t* h, void* stream, void** graph_exec_out) {
+  if (!h || !graph_exec_out) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  *graph_exec_out = nullptr;
+  cudaGraph_t g = nullptr;
+  CU(h, cudaStreamEndCapture(stream ? (cudaStream_t)stream : h->stream, &g));
+  cudaGraphExec_t ge = nullptr;
+  cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return cuda_fail(h, e, "cudaGraphInstantiate");
+  *graph_exec_out = (void*)ge;
+  return GO1MPC_OK;
+}
+int go1mpc_graph_launch(go1mpc_t* h, void* graph_exec, void* stream) {
+  if (!h || !graph_exec) return GO1MPC_E_INVALID;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, cudaGraphLaunch((cudaGraphExec_t)graph_exec, stream ? (cudaStream_t)stream : h->stream));
+  return GO1MPC_OK;
+}
+int go1mpc_graph_destroy(go1mpc_t* h, void* graph_exec) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (graph_exec) CU(h, cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+  return GO1MPC_OK;
 }
 
 int go1mpc_measure_dfma_peak(go1mpc_t* h, int ms, double* gflops) {

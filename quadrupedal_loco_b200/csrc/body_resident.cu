@@ -42,6 +42,37 @@ __global__ void __launch_bounds__(256) body_record_pack_kernel(int B, int nh, in
   }
 }
 
+// Compact per-robot result of one control tick (planner + body MPC): what a controller consumes per tick plus the
+// solver statuses, 12 doubles per robot, instance-major (one 96-byte row per robot: the unit of the once-per-batch
+// gather to rank 0 and of the device -> host read of the e2e path).
+//   0..2  CoM position x, y, z (out38 rows 0..2)      3..4  body roll / pitch (out14[0], out14[1])
+//   5..6  body torques (out14[2], out14[3])            7..8  next footstep x, y (out38 rows 29, 31)
+//   9     step period ts (out38 row 35)                10    planner: status of its last SQP solve (-1: none ran)
+//   11    body MPC: QP status
+__global__ void __launch_bounds__(256) compact_pack_kernel(int B, int nh, int out_stride, int diag_stride, const double* __restrict__ out38,
+                                                           const int* __restrict__ step_diag, const double* __restrict__ body_out,
+                                                           const int* __restrict__ body_diag, double* __restrict__ compact) {
+  const size_t Bs = (size_t)B;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < Bs; b += (size_t)gridDim.x * blockDim.x) {
+    double r[12];
+    r[0] = out38[0 * Bs + b]; r[1] = out38[1 * Bs + b]; r[2] = out38[2 * Bs + b];
+    const double2* bo = reinterpret_cast<const double2*>(body_out + b * out_stride);
+    const double2 o01 = bo[0], o23 = bo[1];
+    r[3] = o01.x; r[4] = o01.y; r[5] = o23.x; r[6] = o23.y;
+    r[7] = out38[29 * Bs + b]; r[8] = out38[31 * Bs + b]; r[9] = out38[35 * Bs + b];
+    int sst = -1;
+    if (step_diag) {
+      const int ns = step_diag[4 * Bs + b];
+      if (ns > 0) sst = step_diag[(size_t)(STEP_DIAG_HEAD + (ns - 1 < STEP_MAX_SQP ? ns - 1 : STEP_MAX_SQP - 1) * STEP_DIAG_PER) * Bs + b];
+    }
+    r[10] = (double)sst;
+    r[11] = body_diag ? (double)body_diag[b * diag_stride] : 0.0;
+    double2* c2 = reinterpret_cast<double2*>(compact + b * 12);
+#pragma unroll
+    for (int k = 0; k < 6; k++) c2[k] = make_double2(r[2 * k], r[2 * k + 1]);
+  }
+}
+
 static int copy_grid(size_t total, int sms) {
   size_t g = (total + 255) / 256;
   const size_t cap = (size_t)sms * 8;
@@ -56,6 +87,12 @@ cudaError_t body_record_expand_launch(int B, int nh, int in_stride, int tick_str
 }
 cudaError_t body_record_pack_launch(int B, int nh, int out_stride, const double* out_res, double* tick_out, int sms, cudaStream_t st) {
   body_record_pack_kernel<<<copy_grid((size_t)B * 20, sms), 256, 0, st>>>(B, nh, out_stride, out_res, tick_out);
+  return cudaGetLastError();
+}
+
+cudaError_t compact_pack_launch(int B, int nh, int out_stride, int diag_stride, const double* out38, const int* step_diag,
+                                const double* body_out, const int* body_diag, double* compact, int sms, cudaStream_t st) {
+  compact_pack_kernel<<<copy_grid((size_t)B, sms), 256, 0, st>>>(B, nh, out_stride, diag_stride, out38, step_diag, body_out, body_diag, compact);
   return cudaGetLastError();
 }
 

@@ -122,6 +122,9 @@ cudaError_t body_record_expand_launch(int B, int nh, int in_stride, int tick_str
                                       const double* tick_in, const double* out_res, double* rec, int sms, cudaStream_t st);
 cudaError_t body_record_pack_launch(int B, int nh, int out_stride, const double* out_res, double* tick_out, int sms, cudaStream_t st);
 
+cudaError_t compact_pack_launch(int B, int nh, int out_stride, int diag_stride, const double* out38, const int* step_diag,
+                                const double* body_out, const int* body_diag, double* compact, int sms, cudaStream_t st);
+
 // ---- GRF distribution of the servo loop (grf_qp.cu) ----
 constexpr int GRF_IN_DOUBLES = 48, GRF_OUT_DOUBLES = 16, GRF_DIAG_INTS = 32;
 struct GrfKParams {

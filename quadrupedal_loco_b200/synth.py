@@ -22,7 +22,7 @@ def default_tx(tstep=0.7, dt_slow=0.025, n=27):
     return tx
 
 
-def body_mpc_inputs(B, nh, seed=SEED_CFG2, scale=1.0, tick_lo=100, tick_hi=1700, ref_amp=0.25):
+def body_mpc_inputs(B, nh, seed=SEED_CFG2, scale=1.0, tick_lo=100, tick_hi=1700, ref_amp=0.25, theta_clip=None):
     """cfg2-style body-MPC batch: randomised body-angle state, tick and reference windows.
 
     Returns dict(tick [B] i32, tx [B,27], theta [B,4], bstate [B,4], x_warm [B,2nh], refs [B,9,nh]).
@@ -34,7 +34,9 @@ def body_mpc_inputs(B, nh, seed=SEED_CFG2, scale=1.0, tick_lo=100, tick_hi=1700,
     ref_amp = 0.25 rad lets about 60 % of the instances command an inclination beyond the limit
     or a move that saturates the torque bound, which is what exercises the active-set
     iteration (mean ~4 constraints added, up to 16 at nh = 10).  scale > 1.5 additionally
-    starts some instances outside the angle limit (infeasible solves, status 2).
+    starts some instances outside the angle limit (infeasible solves, status 2); theta_clip keeps the
+    initial angles inside +-theta_clip (bench.py's cfg3: 2x perturbation with the state inside the
+    reference's own +-10 deg = 0.1745 rad envelope, so every QP has a solution).
     """
     rng = np.random.Generator(np.random.Philox(seed))
     tick = rng.integers(tick_lo, tick_hi + 1, size=B).astype(np.int32)
@@ -44,6 +46,9 @@ def body_mpc_inputs(B, nh, seed=SEED_CFG2, scale=1.0, tick_lo=100, tick_hi=1700,
     theta[:, 1] = rng.uniform(-1.0, 1.0, B) * scale
     theta[:, 2] = rng.uniform(-0.12, 0.12, B) * scale
     theta[:, 3] = rng.uniform(-1.0, 1.0, B) * scale
+    if theta_clip is not None:
+        theta[:, 0] = np.clip(theta[:, 0], -theta_clip, theta_clip)
+        theta[:, 2] = np.clip(theta[:, 2], -theta_clip, theta_clip)
     bstate = theta + rng.uniform(-0.01, 0.01, (B, 4))
     x_warm = np.zeros((B, 2 * nh))
     refs = np.zeros((B, 9, nh))
@@ -97,7 +102,7 @@ def random_qp(B, n, p, m, seed=1, paired=False, dup=False, infeasible_frac=0.0):
     return dict(G=G, g0=g0, CE=CE, ce0=ce0, CI=CI, ci0=ci0)
 
 
-def step_timing_inputs(B, base_state, seed=SEED_CFG2, dt=0.025, Wn=None, amp=1.0):
+def step_timing_inputs(B, base_state, seed=SEED_CFG2, dt=0.025, Wn=None, amp=1.0, push_x=1.0, push_y=1.0, p_hi=23):
     """cfg2-style step-timing batch: every instance is a planner somewhere
     in its walk, its CoM on the nominal LIPM orbit of that step plus a random push.
 
@@ -111,6 +116,11 @@ def step_timing_inputs(B, base_state, seed=SEED_CFG2, dt=0.025, Wn=None, amp=1.0
     pushes make the reference's own formulation infeasible (its CoM-acceleration rows conflict),
     which the status codes report.  The warm start is the reference point (Lxx, Lyy, cosh(wT),
     sinh(wT)) of the previous tick; the end-of-step velocity reference is re-derived from it.
+    push_x / push_y scale the x / y pushes on top of `amp`; p_hi bounds the support period (exclusive).
+    bench.py uses p_hi = 16 (the forward-walking steps: on the backward steps 16-22 of the reference's
+    own footstep plan about 15 % of the nominal QPs are already infeasible without any push) with
+    push_x = 0.4, push_y = 0.75 -- x pushes of +-0.004 m / +-0.032 m/s at amp = 1 -- which leaves
+    > 99 % of the QPs feasible at amp = 1 (cfg2) and about 93 % at amp = 2 (cfg3).
     Returns tick [B] i32, state [B,202], inp [B,20] (instance-major; transpose for the SoA ABI).
     """
     import math
@@ -119,7 +129,7 @@ def step_timing_inputs(B, base_state, seed=SEED_CFG2, dt=0.025, Wn=None, amp=1.0
     rng = np.random.Generator(np.random.Philox(seed))
     st = np.tile(np.asarray(base_state, dtype=np.float64), (B, 1))
     ar = np.arange(B)
-    p = rng.integers(3, 23, B)
+    p = rng.integers(3, p_hi, B)
     k_yu = rng.integers(0, 25, B)
     ki = np.round(st[ar, 27 + p - 1] / dt).astype(np.int64)
     tick = (ki + k_yu).astype(np.int32)
@@ -131,10 +141,10 @@ def step_timing_inputs(B, base_state, seed=SEED_CFG2, dt=0.025, Wn=None, amp=1.0
     isx = -0.5 * st[ar, 135 + p - 2]; isy = -0.5 * st[ar, 162 + p - 2]
     visx = (0.5 * Lx - isx * np.cosh(Wn * T)) / (np.sinh(Wn * T) / Wn)
     visy = (0.5 * Ly - isy * np.cosh(Wn * T)) / (np.sinh(Wn * T) / Wn)
-    cx = fx + isx * np.cosh(Wn * t) + visx / Wn * np.sinh(Wn * t) + amp * rng.uniform(-0.01, 0.01, B)
-    cvx = Wn * isx * np.sinh(Wn * t) + visx * np.cosh(Wn * t) + amp * rng.uniform(-0.08, 0.08, B)
-    cy = fy + isy * np.cosh(Wn * t) + visy / Wn * np.sinh(Wn * t) + amp * rng.uniform(-0.006, 0.006, B)
-    cvy = Wn * isy * np.sinh(Wn * t) + visy * np.cosh(Wn * t) + amp * rng.uniform(-0.05, 0.05, B)
+    cx = fx + isx * np.cosh(Wn * t) + visx / Wn * np.sinh(Wn * t) + amp * push_x * rng.uniform(-0.01, 0.01, B)
+    cvx = Wn * isx * np.sinh(Wn * t) + visx * np.cosh(Wn * t) + amp * push_x * rng.uniform(-0.08, 0.08, B)
+    cy = fy + isy * np.cosh(Wn * t) + visy / Wn * np.sinh(Wn * t) + amp * push_y * rng.uniform(-0.006, 0.006, B)
+    cvy = Wn * isy * np.sinh(Wn * t) + visy * np.cosh(Wn * t) + amp * push_y * rng.uniform(-0.05, 0.05, B)
     st[:, 189] = cx; st[:, 190] = cvx; st[:, 191] = 0.0
     st[:, 192] = cy; st[:, 193] = cvy; st[:, 194] = 0.0
     Tk_prev = T - (k_yu - 1) * dt

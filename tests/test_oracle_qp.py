@@ -143,3 +143,35 @@ def test_iteration_cap_reports_status(oracle):
         r = oracle.qp_solve(8, 0, 48, d["G"][b], d["g0"][b], None, None, d["CI"][b], d["ci0"][b])
         assert r["status"] == 0
         assert r["nactive"] == r["iters"][1] - r["iters"][2]
+
+
+def test_native_thread_pool_matches_single_thread_drivers(oracle):
+    """oracle/mt_pool.c (the CPU arm of bench.py): a 3-thread static split of a batch gives bit for bit what the
+    single-threaded batch drivers give."""
+    import ctypes
+    from quadrupedal_loco_b200 import synth
+    from tests.oracle_lib import P
+    lib = oracle.lib
+    B, nh = 101, 10
+    d = synth.body_mpc_inputs(B, nh, seed=3)
+    bcfg = oracle.body_cfg(nh); scfg = oracle.step_cfg(3)
+    tick, st, sin = synth.step_timing_inputs(B, oracle.step_default_state(scfg), seed=3)
+    theta = d["theta"].copy(); x = d["x_warm"].copy(); o14 = np.zeros((B, 14))
+    oracle.body_step_batch(bcfg, d["tick"], d["tx"], theta, d["bstate"], d["refs"], o14, x)
+    want38, _ = oracle.step_tick_batch(scfg, tick, st.copy(), sin)
+    vp = ctypes.c_void_p
+    lib.orc_pool_create.restype = vp
+    lib.orc_pool_create.argtypes = [ctypes.c_int, vp, vp, ctypes.c_int] + [vp] * 8
+    lib.orc_pool_run.restype = ctypes.c_double; lib.orc_pool_run.argtypes = [vp, ctypes.c_int]
+    lib.orc_pool_results.argtypes = [vp, vp, vp]; lib.orc_pool_destroy.argtypes = [vp]
+    keep = [np.ascontiguousarray(d["tick"], np.int32), np.ascontiguousarray(d["tx"]), np.ascontiguousarray(d["theta"]),
+            np.ascontiguousarray(d["bstate"]), np.ascontiguousarray(d["refs"].reshape(B, 9 * nh)), np.ascontiguousarray(tick, np.int32),
+            np.ascontiguousarray(st), np.ascontiguousarray(sin)]
+    pool = lib.orc_pool_create(3, ctypes.addressof(bcfg), ctypes.addressof(scfg), B, *[P(k) for k in keep])
+    assert pool
+    assert lib.orc_pool_run(pool, 2) > 0
+    g14 = np.zeros((B, 14)); g38 = np.zeros((B, 38))
+    lib.orc_pool_results(pool, P(g14), P(g38))
+    lib.orc_pool_destroy(pool)
+    np.testing.assert_array_equal(g14, o14)
+    np.testing.assert_array_equal(g38, want38)
