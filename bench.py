@@ -288,6 +288,9 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     dist = None
     if world > 1:
+        # stdout carries exactly one JSON line: NCCL's own log lines (version banner, INFO when the caller asks for
+        # them) go to stderr; the debug LEVEL is whatever the environment sets and is never touched here
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
 
