@@ -65,6 +65,8 @@ struct go1mpc {
   // records | expanded body records | out38 | planner diag | body diag
   struct TickWs { DevBuf b[7]; };
   std::map<cudaStream_t, TickWs> tick_ws;
+  cudaStream_t side = nullptr;     // side stream of the planner tick's out-of-place state copy
+  double* trtab_d = nullptr;       // remaining-time bound table of the planner tick (host libm), built on first use
   std::vector<cudaEvent_t> ev_pool;   // go1mpc_stream_wait: events, reused round-robin
   unsigned ev_next = 0;
   std::recursive_mutex mu;         // guards the handle's host-side bookkeeping (maps, lane cursor, launch counter)
@@ -285,6 +287,12 @@ int go1mpc_create(const Go1MpcConfig* cfg, int device, go1mpc_t** out) {
   h->smem_optin = prop.sharedMemPerBlockOptin;
   for (auto& L : h->lanes)
     if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) { go1mpc_destroy(h); return GO1MPC_E_CUDA; }
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess) { go1mpc_destroy(h); return GO1MPC_E_CUDA; }
+  for (int k = 0; k < 64; k++) {        // events of go1mpc_stream_wait, created up front (none is created during a graph capture)
+    cudaEvent_t e;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { go1mpc_destroy(h); return GO1MPC_E_CUDA; }
+    h->ev_pool.push_back(e);
+  }
   const char* bm = getenv("GO1MPC_BODY_MODE");
   if (bm && !strcmp(bm, "fast")) h->body_mode = 0;
 #ifdef GO1MPC_AB_VARIANTS
@@ -312,10 +320,12 @@ void go1mpc_destroy(go1mpc_t* h) {
   for (auto& kv : h->last_writer) cudaEventDestroy(kv.second);
   for (auto& kv : h->tick_ws) for (DevBuf& b : kv.second.b) if (b.p) cudaFree(b.p);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+  if (h->trtab_d) cudaFree(h->trtab_d);
   for (auto& L : h->lanes) {
     for (DevBuf& b : L.stage) if (b.p) cudaFree(b.p);
     if (L.stream) cudaStreamDestroy(L.stream);
   }
+  if (h->side) cudaStreamDestroy(h->side);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -628,8 +638,39 @@ int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick
   bool warp_mode = B < h->step_warp_below;
   if (h->step_mode == 1) warp_mode = false;
   if (h->step_mode == 2) warp_mode = true;
-  CU(h, step_timing_launch(P, warp_mode, st));
-  h->launches++;
+  if (!h->trtab_d) {
+    // tr1_min, tr2_min, tr1_max, tr2_max of NLPClass_sqp.cpp:745-757 as functions of k_yu (the samples elapsed in the step)
+    double tab[STEP_TRTAB_ROWS * 4];
+    for (int k = 0; k < STEP_TRTAB_ROWS; k++) {
+      const double tmin = ((c.t_min - k * c.dt) >= 0.001) ? (c.t_min - k * c.dt) : 0.001;
+      tab[4 * k + 0] = cosh(c.Wn * tmin); tab[4 * k + 1] = sinh(c.Wn * tmin);
+      tab[4 * k + 2] = cosh(c.Wn * (c.t_max - k * c.dt)); tab[4 * k + 3] = sinh(c.Wn * (c.t_max - k * c.dt));
+    }
+    CU(h, cudaMalloc((void**)&h->trtab_d, sizeof tab));
+    CU(h, cudaMemcpy(h->trtab_d, tab, sizeof tab, cudaMemcpyHostToDevice));
+  }
+  P.trtab = h->trtab_d;
+  if (warp_mode) {
+    CU(h, step_timing_launch(P, st));                 // one launch, warp per planner
+    h->launches++;
+  } else {
+    // SQP kernel, CoM-height kernel, back-end kernel.  Out of place, the new state starts as a copy of the old one (the back-end
+    // updates the changed fields): that copy runs on the handle's side stream beside the compute-bound SQP kernel.
+    const bool oop = (state_out_d != state_d);
+    if (oop) {
+      int rc = go1mpc_stream_wait(h, h->side, st);
+      if (rc) return rc;
+      CU(h, cudaMemcpyAsync(state_out_d, state_d, (size_t)B * STEP_STATE_DOUBLES * sizeof(double), cudaMemcpyDeviceToDevice, h->side));
+    }
+    CU(h, step_sqp_launch(P, st));
+    CU(h, step_height_launch(P, st));
+    if (oop) {
+      int rc = go1mpc_stream_wait(h, st, h->side);
+      if (rc) return rc;
+    }
+    CU(h, step_post_launch(P, st));
+    h->launches += 3;
+  }
   return GO1MPC_OK;
 }
 
@@ -1240,11 +1281,6 @@ int go1mpc_stream_wait(go1mpc_t* h, void* waiter, void* signaller) {
   if (!h) return GO1MPC_E_INVALID;
   std::lock_guard<std::recursive_mutex> lk_(h->mu);
   CU(h, cudaSetDevice(h->device));
-  if (h->ev_pool.size() < 256) {
-    cudaEvent_t e;
-    CU(h, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    h->ev_pool.push_back(e);
-  }
   cudaEvent_t e = h->ev_pool[h->ev_next++ % h->ev_pool.size()];
   CU(h, cudaEventRecord(e, signaller ? (cudaStream_t)signaller : h->stream));
   CU(h, cudaStreamWaitEvent(waiter ? (cudaStream_t)waiter : h->stream, e, 0));

@@ -72,11 +72,17 @@ struct StepKParams {
   const double* in;     // [STEP_IN_DOUBLES][B]
   double* out;          // [STEP_OUT_DOUBLES][B]
   int* diag;            // [STEP_DIAG_INTS][B] or null
+  const double* trtab;  // [STEP_TRTAB_ROWS][4]: cosh / sinh of Wn (t_min - k dt) (floored at 0.001 s) and of Wn (t_max - k dt), k = row
   StepCfgDev cfg;
 };
+constexpr int STEP_TRTAB_ROWS = 64;
 // per-warp shared memory of the warp-cooperative mode: QP workspace (n = 4, m = 24) | 7x14 matrix + 7
 constexpr int STEP_WARP_DOUBLES = 256;
-cudaError_t step_timing_launch(StepKParams P, bool warp_mode, cudaStream_t st);
+cudaError_t step_timing_launch(StepKParams P, cudaStream_t st);   // step_timing.cu: warp per planner (small batches)
+// step_sqp.cu: thread per planner, three launches (SQP, CoM height, back-end; the back-end expects state_out to hold a copy of state)
+cudaError_t step_sqp_launch(StepKParams P, cudaStream_t st);
+cudaError_t step_height_launch(StepKParams P, cudaStream_t st);
+cudaError_t step_post_launch(StepKParams P, cudaStream_t st);
 constexpr int FOOT_STATE_DOUBLES = 32, FOOT_OUT_DOUBLES = 18;
 struct FootKParams {
   int B;

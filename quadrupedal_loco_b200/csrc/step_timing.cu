@@ -1,4 +1,5 @@
-// step_timing.cu -- step-location / step-timing SQP tick, one thread per MPC instance.
+// step_timing.cu -- step-location / step-timing SQP tick, latency mapping: one WARP per planner (batches below ~1000
+// planners, where a thread-per-planner launch leaves the GPU empty; large batches take step_sqp.cu).
 //
 // Replaces, for a batch of independent planners, one 40 Hz tick of
 //   NLPClass::step_timing_opti_loop      NLP/src/NLP/NLPClass_sqp.cpp:693-1102
@@ -19,10 +20,6 @@
 // but the step period it writes back then differs from the host's by an ulp, which the badly
 // conditioned swing-foot fit downstream amplifies to 1e-6 -- fidelity wins).
 #include <cuda_runtime.h>
-#ifdef GO1_STEP_GENERIC_QP
-#include "gi_thread.cuh"      // A/B variant only: run-time indexed solver state (local memory)
-#endif
-#include "gi_thread4.cuh"
 #include "gi_warp.cuh"
 #include "kernels.h"
 #include "powi.cuh"
@@ -41,148 +38,6 @@ constexpr int I_EST = 0, I_RF = 6, I_LF = 8, I_CZ = 10, I_CAZ = 13, I_ZSC = 16, 
 // kernel that stalls on instruction fetch; the routines (and therefore the results) are the same
 static __device__ __noinline__ double cosh_nl(double x) { return cosh(x); }
 static __device__ __noinline__ double sinh_nl(double x) { return sinh(x); }
-
-// inverse by Gauss-Jordan with partial (row) pivoting, first maximal |pivot| wins; row-major 7 x 7
-// (the elimination order of the CPU oracle: the time-polynomial matrix is badly conditioned, so
-// the order is part of the contract -- SURVEY.md Appendix B)
-__device__ void gj_inverse7(double* a, double* r) {
-  constexpr int n = 7;
-  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) r[i * n + j] = (i == j) ? 1.0 : 0.0;
-  for (int k = 0; k < n; k++) {
-    int piv = k;
-    double best = fabs(a[k * n + k]);
-    for (int i = k + 1; i < n; i++) if (fabs(a[i * n + k]) > best) { best = fabs(a[i * n + k]); piv = i; }
-    if (piv != k)
-      for (int j = 0; j < n; j++) {
-        double t = a[k * n + j]; a[k * n + j] = a[piv * n + j]; a[piv * n + j] = t;
-        t = r[k * n + j]; r[k * n + j] = r[piv * n + j]; r[piv * n + j] = t;
-      }
-    const double d = a[k * n + k];
-    for (int j = 0; j < n; j++) { a[k * n + j] = a[k * n + j] / d; r[k * n + j] = r[k * n + j] / d; }
-    for (int i = 0; i < n; i++) {
-      if (i == k) continue;
-      const double f = a[i * n + k];
-      for (int j = 0; j < n; j++) { a[i * n + j] = __dsub_rn(a[i * n + j], __dmul_rn(f, a[k * n + j])); r[i * n + j] = __dsub_rn(r[i * n + j], __dmul_rn(f, r[k * n + j])); }
-    }
-  }
-}
-
-// The same elimination, fully unrolled with the matrix in registers, for the three columns of the inverse
-// CoM_height_solve uses (its right-hand side `plan` is zero outside entries 2..4): rinv[i*3 + c] = A^-1(i, 2 + c).
-// Pivot search, row swaps (as predicated register swaps), normalisation and elimination are the reference's,
-// entry for entry; columns of `a` left of the pivot are exact zeros below the diagonal and are skipped.
-__device__ __forceinline__ void gj_inverse7_cols234(double (&a)[49], double (&rinv)[21]) {
-  constexpr int n = 7;
-#pragma unroll
-  for (int i = 0; i < n; i++)
-#pragma unroll
-    for (int c = 0; c < 3; c++) rinv[i * 3 + c] = (i == 2 + c) ? 1.0 : 0.0;
-#pragma unroll
-  for (int k = 0; k < n; k++) {
-    int piv = k;
-    double best = fabs(a[k * n + k]);
-#pragma unroll
-    for (int i = k + 1; i < n; i++) if (fabs(a[i * n + k]) > best) { best = fabs(a[i * n + k]); piv = i; }
-#pragma unroll
-    for (int i = k + 1; i < n; i++)
-      if (piv == i) {
-#pragma unroll
-        for (int j = k; j < n; j++) { const double t = a[k * n + j]; a[k * n + j] = a[i * n + j]; a[i * n + j] = t; }
-#pragma unroll
-        for (int c = 0; c < 3; c++) { const double t = rinv[k * 3 + c]; rinv[k * 3 + c] = rinv[i * 3 + c]; rinv[i * 3 + c] = t; }
-      }
-    const double d = a[k * n + k];
-#pragma unroll
-    for (int j = k; j < n; j++) a[k * n + j] = div_z(a[k * n + j], d);
-#pragma unroll
-    for (int c = 0; c < 3; c++) rinv[k * 3 + c] = div_z(rinv[k * 3 + c], d);
-#pragma unroll
-    for (int i = 0; i < n; i++) {
-      if (i == k) continue;
-      const double f = a[i * n + k];
-#pragma unroll
-      for (int j = k; j < n; j++) a[i * n + j] = __dsub_rn(a[i * n + j], __dmul_rn(f, a[k * n + j]));
-#pragma unroll
-      for (int c = 0; c < 3; c++) rinv[i * 3 + c] = __dsub_rn(rinv[i * 3 + c], __dmul_rn(f, rinv[k * 3 + c]));
-    }
-  }
-}
-
-// NLPClass::CoM_height_solve (NLPClass_sqp.cpp:2361-2473) for the samples i, i+1, i+2:
-// 6th-order polynomial through (value, velocity, acceleration) at the step's start and end and
-// the value at mid-step.  ts1 / tx1 / f0 / f1: _ts(bjx1-1), _tx(bjx1-1), footz(bjx1-2), footz(bjx1-1).
-__device__ void com_height_solve(int i, int bjx1, double ts1, double tx1, double f0, double f1, double hcom, double dt,
-                                 double comz[3], double comvz[3], double comaz[3]) {
-  if (bjx1 >= 2) {
-    const double tp[3] = {0.0001, ts1 / 2 + 0.0001, ts1 + 0.0001};
-#ifdef GO1_STEP_GJ_GENERIC
-    double A[49], Ainv[49];
-    const int rowt[7] = {0, 0, 0, 1, 2, 2, 2}, kind[7] = {1, 2, 0, 0, 0, 1, 2};
-    for (int r = 0; r < 7; r++) {
-      const double t = tp[rowt[r]];
-      double* a = A + 7 * r;
-      if (kind[r] == 0) { a[0] = powi(t, 6); a[1] = powi(t, 5); a[2] = powi(t, 4); a[3] = powi(t, 3); a[4] = powi(t, 2); a[5] = powi(t, 1); a[6] = 1; }
-      else if (kind[r] == 1) { a[0] = 6 * powi(t, 5); a[1] = 5 * powi(t, 4); a[2] = 4 * powi(t, 3); a[3] = 3 * powi(t, 2); a[4] = 2 * powi(t, 1); a[5] = 1; a[6] = 0; }
-      else { a[0] = 30 * powi(t, 4); a[1] = 20 * powi(t, 3); a[2] = 12 * powi(t, 2); a[3] = 6 * powi(t, 1); a[4] = 2; a[5] = 0; a[6] = 0; }
-    }
-    gj_inverse7(A, Ainv);
-    const double plan[7] = {0, 0, f0 + hcom, (f0 + f1) / 2 + hcom, f1 + hcom, 0, 0};
-    double co[7];
-    for (int r = 0; r < 7; r++) { double acc = 0.0; for (int k = 0; k < 7; k++) acc = __dadd_rn(acc, __dmul_rn(Ainv[7 * r + k], plan[k])); co[r] = acc; }
-    for (int jxx = 1; jxx <= 3; jxx++) {
-      const double t = (i + jxx - round(tx1 / dt)) * dt;
-      const double p[7] = {powi(t, 6), powi(t, 5), powi(t, 4), powi(t, 3), powi(t, 2), powi(t, 1), 1};
-      const double v[7] = {6 * powi(t, 5), 5 * powi(t, 4), 4 * powi(t, 3), 3 * powi(t, 2), 2 * powi(t, 1), 1, 0};
-      const double a[7] = {30 * powi(t, 4), 20 * powi(t, 3), 12 * powi(t, 2), 6 * powi(t, 1), 2, 0, 0};
-      double z = 0.0, vz = 0.0, az = 0.0;
-      for (int k = 0; k < 7; k++) { z = __dadd_rn(z, __dmul_rn(p[k], co[k])); vz = __dadd_rn(vz, __dmul_rn(v[k], co[k])); az = __dadd_rn(az, __dmul_rn(a[k], co[k])); }
-      comz[jxx - 1] = z; comvz[jxx - 1] = vz; comaz[jxx - 1] = az;
-    }
-#else
-    // matrix in registers, the powers of each time from one running product (powi_all), the three columns of the
-    // inverse that meet non-zero entries of `plan`
-    double A[49], Rinv[21];
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-      double pw[7];
-      powi_all(tp[g], pw);
-      // rows: g = 0 -> velocity, acceleration, position at the start; g = 1 -> position at mid-step;
-      //       g = 2 -> position, velocity, acceleration at the end   (NLPClass_sqp.cpp:2376-2412)
-      const int r_pos = (g == 0) ? 2 : (g == 1 ? 3 : 4), r_vel = (g == 0) ? 0 : 5, r_acc = (g == 0) ? 1 : 6;
-      { double* a = A + 7 * r_pos; a[0] = pw[6]; a[1] = pw[5]; a[2] = pw[4]; a[3] = pw[3]; a[4] = pw[2]; a[5] = pw[1]; a[6] = 1; }
-      if (g != 1) {
-        { double* a = A + 7 * r_vel; a[0] = 6 * pw[5]; a[1] = 5 * pw[4]; a[2] = 4 * pw[3]; a[3] = 3 * pw[2]; a[4] = 2 * pw[1]; a[5] = 1; a[6] = 0; }
-        { double* a = A + 7 * r_acc; a[0] = 30 * pw[4]; a[1] = 20 * pw[3]; a[2] = 12 * pw[2]; a[3] = 6 * pw[1]; a[4] = 2; a[5] = 0; a[6] = 0; }
-      }
-    }
-    gj_inverse7_cols234(A, Rinv);
-    const double plan3[3] = {f0 + hcom, (f0 + f1) / 2 + hcom, f1 + hcom};
-    double co[7];
-#pragma unroll
-    for (int r = 0; r < 7; r++) {
-      double acc = 0.0;      // the reference's sum over k = 0..6 adds exact zeros for k = 0, 1, 5, 6
-#pragma unroll
-      for (int c = 0; c < 3; c++) acc = __dadd_rn(acc, __dmul_rn(Rinv[3 * r + c], plan3[c]));
-      co[r] = acc;
-    }
-#pragma unroll
-    for (int jxx = 1; jxx <= 3; jxx++) {
-      const double t = (i + jxx - round(tx1 / dt)) * dt;
-      double pw[7];
-      powi_all(t, pw);
-      const double p[7] = {pw[6], pw[5], pw[4], pw[3], pw[2], pw[1], 1};
-      const double v[7] = {6 * pw[5], 5 * pw[4], 4 * pw[3], 3 * pw[2], 2 * pw[1], 1, 0};
-      const double a[7] = {30 * pw[4], 20 * pw[3], 12 * pw[2], 6 * pw[1], 2, 0, 0};
-      double z = 0.0, vz = 0.0, az = 0.0;
-#pragma unroll
-      for (int k = 0; k < 7; k++) { z = __dadd_rn(z, __dmul_rn(p[k], co[k])); vz = __dadd_rn(vz, __dmul_rn(v[k], co[k])); az = __dadd_rn(az, __dmul_rn(a[k], co[k])); }
-      comz[jxx - 1] = z; comvz[jxx - 1] = vz; comaz[jxx - 1] = az;
-    }
-#endif
-  } else {
-    for (int q = 0; q < 3; q++) { comz[q] = hcom; comvz[q] = 0; comaz[q] = 0; }
-  }
-}
 
 __device__ void gj_inverse7_warp(double* M, int lane);
 
@@ -285,43 +140,6 @@ __device__ void gj_inverse7_warp(double* M, int lane) {
     __syncwarp();
   }
 }
-
-// The 24 inequality rows of the step-timing QP (NLPClass_sqp.cpp:1193-1455) without their dense 4 x 24 matrix:
-// rows 0-11 have ONE non-zero coefficient (-+1 on tr1, tr2, Lx, Ly; rows 8-11 are empty while k_yu = 0), rows 12-23
-// three (on Lx or Ly, tr1, tr2).  slack() adds the non-zero products in the dot product's order -- the skipped terms
-// are exact zeros, so the sums are the dense ones -- and column() returns the dense column (structural zeros are the
-// -0.0 the reference's `0.0 * (-1)` leaves).  All indices are compile-time constants where GiThread4 calls these.
-struct StepRows {
-  double a0[12], a2[12], a3[12];   // rows 12..23: CI(i0, r), CI(2, r), CI(3, r)
-  double bb[24];
-  bool vel_rows;                   // k_yu != 0: rows 8..11 populated
-  __device__ __forceinline__ static int var_of(int i) { return (i < 2) ? 2 : (i < 4) ? 3 : ((i & 2) ? 1 : 0); }   // rows 0..11
-  __device__ __forceinline__ static int i0_of(int i) { return ((i - 12) & 2) ? 1 : 0; }                            // rows 12..23
-  __device__ __forceinline__ double slack(int i, const double* x) const {
-    if (i < 12) {
-      if (i >= 8 && !vel_rows) return 0.0 + bb[i];
-      const double cf = (i & 1) ? 1.0 : -1.0;          // CI = val * (-1), val = +1 on even rows
-      return cf * x[var_of(i)] + bb[i];
-    }
-    const int r = i - 12;
-    double acc = a0[r] * x[i0_of(i)];
-    acc += a2[r] * x[2];
-    acc += a3[r] * x[3];
-    return acc + bb[i];
-  }
-  __device__ __forceinline__ void column(int i, double* np) const {
-#pragma unroll
-    for (int k = 0; k < 4; k++) np[k] = -0.0;
-    if (i < 12) {
-      if (i >= 8 && !vel_rows) return;
-      np[var_of(i)] = (i & 1) ? 1.0 : -1.0;
-    } else {
-      const int r = i - 12;
-      np[i0_of(i)] = a0[r]; np[2] = a2[r]; np[3] = a3[r];
-    }
-  }
-  __device__ __forceinline__ double rhs(int i) const { return bb[i]; }
-};
 
 // WARP = false: one THREAD per planner (throughput mode, large batches).
 // WARP = true : one WARP per planner (latency mode): the scalar front-end runs warp-uniformly, the
@@ -498,27 +316,7 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
       double X[4];
       for (int k = 0; k < 4; k++) X[k] = v[k];
       int st, q_iq, q_out, q_add, q_drop, q_degen, qA[5];
-      if (!WARP) {
-#ifdef GO1_STEP_GENERIC_QP
-        GiThread<4, 1, 24> qp;     // run-time indexed state in local memory (A/B against GiThread4)
-        st = qp.solve(G, g0, CE, ce0, CI, bb, X, P.cap);
-#else
-        GiThread4 qp;              // the same solve with its state in registers, the rows behind StepRows
-        StepRows rows;
-        rows.vel_rows = (k_yu != 0);
-#pragma unroll
-        for (int r = 0; r < 24; r++) rows.bb[r] = bb[r];
-#pragma unroll
-        for (int r = 0; r < 12; r++) {
-          rows.a0[r] = CI[(12 + r) * 4 + StepRows::i0_of(12 + r)];
-          rows.a2[r] = CI[(12 + r) * 4 + 2];
-          rows.a3[r] = CI[(12 + r) * 4 + 3];
-        }
-        st = qp.solve_rows(G, g0, CE, ce0, rows, X, P.cap);
-#endif
-        q_iq = qp.iq; q_out = qp.it_outer; q_add = qp.it_add; q_drop = qp.it_drop; q_degen = qp.it_degen;
-        for (int k = 0; k < 5; k++) qA[k] = qp.A[k];
-      } else {
+      {
         // warp-cooperative solve (same sequence as dense_qp_kernel): lane r < 24 owns constraint r
         GiWs w;
         gi_ws_carve(w, wsm, 4, 1, 24);
@@ -620,8 +418,7 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
     for (int q = 0; q < 3; q++) { hz_z[q] = INP(I_CZ + q); hz_az[q] = INP(I_CAZ + q); hz_vz[q] = 0.0; }
     hz_vz[0] = INP(I_CVZ);
   } else {
-    if (!WARP) com_height_solve(i, bp <= NS ? bp : 0, ts_b1, tx_b1, fz_b2, fz_b1, c.hcom, dt, hz_z, hz_vz, hz_az);
-    else com_height_solve_warp(i, bp <= NS ? bp : 0, ts_b1, tx_b1, fz_b2, fz_b1, c.hcom, dt, hz_z, hz_vz, hz_az, wsm, lane);
+    com_height_solve_warp(i, bp <= NS ? bp : 0, ts_b1, tx_b1, fz_b2, fz_b1, c.hcom, dt, hz_z, hz_vz, hz_az, wsm, lane);
   }
   // LIPM roll-out of samples i, i+1, i+2 (:938-955)
   double comx[3], comy[3], comvx[3], comvy[3], comax[3], comay[3], zmpx[3], zmpy[3], dcmx[3], dcmy[3];
@@ -696,20 +493,10 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
 #undef INP
 }
 
-cudaError_t step_timing_launch(StepKParams P, bool warp_mode, cudaStream_t st) {
-  const int block = 128;
-  if (warp_mode) {
-    const int wpc = block / 32;
-    const int grid = (P.B + wpc - 1) / wpc;
-    step_timing_kernel<true><<<grid, block, (size_t)wpc * STEP_WARP_DOUBLES * sizeof(double), st>>>(P);
-  } else {
-#ifndef GO1_STEP_BLOCK
-#define GO1_STEP_BLOCK 128
-#endif
-    const int tb = GO1_STEP_BLOCK;
-    const int grid = (P.B + tb - 1) / tb;
-    step_timing_kernel<false><<<grid, tb, 0, st>>>(P);
-  }
+cudaError_t step_timing_launch(StepKParams P, cudaStream_t st) {
+  const int block = 128, wpc = block / 32;
+  const int grid = (P.B + wpc - 1) / wpc;
+  step_timing_kernel<true><<<grid, block, (size_t)wpc * STEP_WARP_DOUBLES * sizeof(double), st>>>(P);
   return cudaGetLastError();
 }
 
