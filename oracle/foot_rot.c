@@ -24,32 +24,42 @@ static int rot_indexfind(const double *tx, double goal)
 
 void orc_foot_rot_state_init(orc_foot_rot_state *s) { memset(s, 0, sizeof *s); }
 
-/* out[6 * nh]: per sample  right roll, pitch, yaw | left roll, pitch, yaw.  nh <= 5 (the reference's 3x5 members). */
-void orc_foot_rotation(const double tx[27], const double ts[27], const double td[27], const double footx[27], double footx_max,
-                       double dt_mpc, int t_end_footstep, int nh, orc_foot_rot_state *s, int walktimex, double dt_sample, double *out)
+/* General form: the angle members are 3 x ncol row-major (the reference's are 3 x 5), nh <= ncol samples. */
+void orc_foot_rotation_w(const double tx[27], const double ts[27], const double td[27], const double footx[27], double footx_max,
+                         double dt_mpc, int t_end_footstep, int nh, int ncol, int *bjxx_io, int *bjx1_io, double *Rr, double *Lr,
+                         int walktimex, double dt_sample, double *out)
 {
+    int bjxx = *bjxx_io, bjx1 = *bjx1_io;
     memset(out, 0, sizeof(double) * 6 * (size_t)nh);
     for (int walktime = walktimex; walktime < walktimex + nh; walktime++) {
         const int col = walktime - walktimex;
         if (walktime <= t_end_footstep) {
-            s->bjxx = rot_indexfind(tx, walktime * dt_mpc) + 1;
-            s->bjx1 = rot_indexfind(tx, (walktime + 1) * dt_mpc) + 1;
+            bjxx = rot_indexfind(tx, walktime * dt_mpc) + 1;
+            bjx1 = rot_indexfind(tx, (walktime + 1) * dt_mpc) + 1;
         }
-        const int k = s->bjx1 - 1;
-        if (s->bjx1 >= 2 && walktime <= t_end_footstep) {
+        const int k = bjx1 - 1;
+        if (bjx1 >= 2 && walktime <= t_end_footstep) {
             const double t_des = (walktime + 1) * dt_sample - (tx[k] + 2 * td[k] / 4);
             const double sarg = t_des + 2 * td[k] / 4;
-            const double dfx = footx[s->bjx1] - footx[s->bjx1 - 1];
-            double *A = (s->bjx1 % 2 == 0) ? s->Rr : s->Lr;          /* even: right foot swings */
-            const double amp = (s->bjx1 % 2 == 0) ? -0.065 : 0.075;
-            A[0 * 5 + col] = amp * (1 - cos(2 * M_PI / ts[k] * sarg));
+            const double dfx = footx[bjx1] - footx[bjx1 - 1];
+            double *A = (bjx1 % 2 == 0) ? Rr : Lr;          /* even: right foot swings */
+            const double amp = (bjx1 % 2 == 0) ? -0.065 : 0.075;
+            A[0 * ncol + col] = amp * (1 - cos(2 * M_PI / ts[k] * sarg));
             if (sarg >= ts[k] / 2) {
-                if (dfx > 0) A[1 * 5 + col] = 0.075 * dfx / footx_max * (cos(4 * M_PI / ts[k] * sarg) - 1);
+                if (dfx > 0) A[1 * ncol + col] = 0.075 * dfx / footx_max * (cos(4 * M_PI / ts[k] * sarg) - 1);
             } else {
-                A[1 * 5 + col] = 0;
+                A[1 * ncol + col] = 0;
             }
         }
-        out[6 * col + 0] = s->Rr[0 * 5 + col]; out[6 * col + 1] = s->Rr[1 * 5 + col]; out[6 * col + 2] = s->Rr[2 * 5 + 0];
-        out[6 * col + 3] = s->Lr[0 * 5 + col]; out[6 * col + 4] = s->Lr[1 * 5 + col]; out[6 * col + 5] = s->Lr[2 * 5 + 0];
+        out[6 * col + 0] = Rr[0 * ncol + col]; out[6 * col + 1] = Rr[1 * ncol + col]; out[6 * col + 2] = Rr[2 * ncol + 0];
+        out[6 * col + 3] = Lr[0 * ncol + col]; out[6 * col + 4] = Lr[1 * ncol + col]; out[6 * col + 5] = Lr[2 * ncol + 0];
     }
+    *bjxx_io = bjxx; *bjx1_io = bjx1;
+}
+
+/* out[6 * nh]: per sample  right roll, pitch, yaw | left roll, pitch, yaw.  nh <= 5 (the reference's 3x5 members). */
+void orc_foot_rotation(const double tx[27], const double ts[27], const double td[27], const double footx[27], double footx_max,
+                       double dt_mpc, int t_end_footstep, int nh, orc_foot_rot_state *s, int walktimex, double dt_sample, double *out)
+{
+    orc_foot_rotation_w(tx, ts, td, footx, footx_max, dt_mpc, t_end_footstep, nh, 5, &s->bjxx, &s->bjx1, s->Rr, s->Lr, walktimex, dt_sample, out);
 }

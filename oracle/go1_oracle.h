@@ -220,6 +220,39 @@ void orc_foot_rot_state_init(orc_foot_rot_state *s);
 void orc_foot_rotation(const double tx[27], const double ts[27], const double td[27], const double footx[27], double footx_max,
                        double dt_mpc, int t_end_footstep, int nh, orc_foot_rot_state *s, int walktimex, double dt_sample, double *out);
 
+void orc_foot_rotation_w(const double tx[27], const double ts[27], const double td[27], const double footx[27], double footx_max,
+                         double dt_mpc, int t_end_footstep, int nh, int ncol, int *bjxx_io, int *bjx1_io, double *Rr, double *Lr,
+                         int walktimex, double dt_sample, double *out);
+
+/* Swing-foot generator of the 100 Hz node (rt_foot.c): PRMPCClass::Foot_trajectory_solve_mod2, RT/src/FastMPC/PRMPCClass.cpp:1756-2195.
+ * State (doubles): [0,27) _ts | [27,54) [54,81) [81,108) _footxyz_real rows x y z | [108,135) _lift_height_ref | [135] _ry_left_right |
+ * [136] _bjxx | [137] _bjx1 | then six arrays of nh + 2: _Rfootx _Rfooty _Rfootz _Lfootx _Lfooty _Lfootz. */
+typedef struct { double dt, dt_mpc, tstep, tdsp_ratio, stepwidth0, lift_height; } orc_rt_foot_cfg;
+void orc_rt_foot_cfg_default(orc_rt_foot_cfg *c);
+int orc_rt_foot_state_doubles(int nh);
+void orc_rt_foot_state_default(const orc_rt_foot_cfg *c, int nh, double *s);
+void orc_rt_foot_traj(const orc_rt_foot_cfg *c, int nh, double *s, int j_indexx, int stopwalking, const double nrt[9], double *out);
+
+/* Glue of the 100 Hz node (rt_glue.c): RT/src/gait_fast.cpp:113-372 (sample bookkeeping) and :505-746 (tick).  The four
+ * PRMPCClass methods are reached through hooks, so the one restatement of the glue drives the unmodified class (golden
+ * vectors) and the oracle restatements (the checker).  Windows are signal-major [2][nh] as orc_body_theta_mpc takes them. */
+typedef struct {
+    void (*mod3)(void *ctx, int nh, int walktime, double dt_sample, const double *in1, const double *in2, const double *ref, const double *ref2, double *out);
+    void (*foot)(void *ctx, int nh, int j_index, int stop, const double *nrt9, double *out /* 6 (nh + 1) */);
+    void (*rot)(void *ctx, int nh, int walktimex, double dt_sample, double *out /* 6 nh */);
+    void (*body)(void *ctx, int nh, int i, const double *bodyangle_state, const double *zmp, const double *ang, const double *rfoot,
+                 const double *lfoot, const double *comacc_z, double *out14);
+    double (*tx_total)(void *ctx);          /* (int) _tx_total */
+} orc_rt_hooks;
+int orc_rt_node_doubles(int nh);
+void orc_rt_node_default(int nh, double *node);
+void orc_rt_node_tick(int nh, double *node, const orc_rt_hooks *hk, void *ctx, const double msg[100], int ctrl_flag,
+                      const double bodyangle_state[4], double out100[100]);
+void orc_rt_hooks_oracle(orc_rt_hooks *hk);
+int orc_rt_ctx_bytes(void);
+int orc_body_mpc_bytes(void);
+void orc_rt_ctx_init(void *ctx_mem, int nh, double *foot_state, double *rot_state, orc_body_mpc *body);
+
 /* ------------------------------------------------------------------------
  * Ground-reaction-force distribution of go1_servo's 1 kHz loop (Dynamiccclass,
  * GO1/src/whole_body_dynamics/dynmics_compute.cpp:55-427): closed-form split, the

@@ -5,8 +5,11 @@
 #define private public
 #define protected public
 #include <NLP/NLPClass.h>
+#include <NLPRTControl/NLPRTControlClass.h>
 #undef private
 #undef protected
+#include <cstdlib>
+#include <new>
 
 // KMP is dead code on this path: no-op definitions for the linker.
 kmp::kmp() {}
@@ -119,5 +122,24 @@ int ref_nlp_foot(void* h, int j, int stop, double* out18) {
   return p->right_support;
 }
 double ref_nlp_stepwidth0(void* h) { return static_cast<NLPClass*>(h)->_stepwidth(0); }
+
+// The 40 Hz node's driver, UNMODIFIED: NLPRTControlClass::WalkingReactStepping (NLPRTControl/NLPRTControlClass.cpp:191-396)
+// -> the 100-slot /MPC/Gait message.  The constructor reads the never-initialised member stepheightinput (:80): the object
+// is built in zero-filled memory so that it reads 0 (flat ground), deterministically.
+void* ref_ctl_new() {
+  void* mem = calloc(1, sizeof(NLPRTControlClass));
+  return new (mem) NLPRTControlClass();
+}
+void ref_ctl_free(void* h) { static_cast<NLPRTControlClass*>(h)->~NLPRTControlClass(); free(h); }
+void ref_ctl_step(void* h, int count, int start, const double* est18, const double* rfoot3, const double* lfoot3, double* out100) {
+  NLPRTControlClass* p = static_cast<NLPRTControlClass*>(h);
+  Eigen::Matrix<double, 18, 1> est;
+  Eigen::Vector3d rf, lf;
+  for (int k = 0; k < 18; k++) est(k) = est18[k];
+  for (int k = 0; k < 3; k++) { rf(k) = rfoot3[k]; lf(k) = lfoot3[k]; }
+  Eigen::Matrix<double, 100, 1> o = p->WalkingReactStepping(count, start != 0, est, rf, lf);
+  for (int k = 0; k < 100; k++) out100[k] = o(k);
+}
+int ref_ctl_walkdtime_max(void* h) { return static_cast<NLPRTControlClass*>(h)->_walkdtime_max; }
 
 }  // extern "C"

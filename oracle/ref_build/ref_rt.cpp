@@ -109,4 +109,54 @@ void ref_body_foot_rotation(void* h, int walktimex, double dt_sample, double* ou
   for (int k = 0; k < 30; k++) out30[k] = o(k);
 }
 
+// Foot_trajectory_solve_mod2, PRMPCClass.cpp:1756-2195: the call, and the members it leaves behind
+// (state layout of oracle/rt_foot.c at the reference's nh: ts 27 | footxyz_real 81 | lift 27 | ry | bjxx | bjx1 | six arrays of _nh + 2).
+void ref_body_foot_traj(void* h, int j_indexx, int stop, const double* nrt9, double* out30) {
+  PRMPCClass* p = static_cast<PRMPCClass*>(h);
+  Eigen::Matrix<double, 9, 1> N;
+  for (int k = 0; k < 9; k++) N(k) = nrt9[k];
+  Eigen::Matrix<double, 30, 1> o = p->Foot_trajectory_solve_mod2(j_indexx, stop != 0, N);
+  for (int k = 0; k < 30; k++) out30[k] = o(k);
+}
+void ref_body_foot_traj_state(void* h, double* s) {
+  PRMPCClass* p = static_cast<PRMPCClass*>(h);
+  int k = 0;
+  for (int j = 0; j < 27; j++) s[k++] = p->_ts(j);
+  for (int r = 0; r < 3; r++) for (int j = 0; j < 27; j++) s[k++] = p->_footxyz_real(r, j);
+  for (int j = 0; j < 27; j++) s[k++] = p->_lift_height_ref(j);
+  s[k++] = p->_ry_left_right; s[k++] = p->_bjxx; s[k++] = p->_bjx1;
+  const int W = _nh + 2;
+  for (int j = 0; j < W; j++) s[k++] = p->_Rfootx(j);
+  for (int j = 0; j < W; j++) s[k++] = p->_Rfooty(j);
+  for (int j = 0; j < W; j++) s[k++] = p->_Rfootz(j);
+  for (int j = 0; j < W; j++) s[k++] = p->_Lfootx(j);
+  for (int j = 0; j < W; j++) s[k++] = p->_Lfooty(j);
+  for (int j = 0; j < W; j++) s[k++] = p->_Lfootz(j);
+}
+
+// Hooks of oracle/rt_glue.c onto the UNMODIFIED class (ctx = the PRMPCClass object): the glue of gait_fast.cpp is restated
+// once, in C, and drives either these or the oracle restatements.  Windows are signal-major [2][nh] with nh = _nh.
+void ref_hook_mod3(void* h, int nh, int walktime, double dts, const double* a, const double* b, const double* r, const double* r2, double* out) {
+  double o21[21];
+  ref_body_position_mod3(h, walktime, dts, a, b, r, r2, o21, nullptr);
+  for (int k = 0; k < 9 + 3 * (nh - 1); k++) out[k] = o21[k];
+}
+void ref_hook_foot(void* h, int nh, int j, int stop, const double* nrt9, double* out) {
+  double o30[30];
+  ref_body_foot_traj(h, j, stop, nrt9, o30);
+  for (int k = 0; k < 6 * (nh + 1); k++) out[k] = o30[k];
+}
+void ref_hook_rot(void* h, int nh, int j, double dts, double* out) {
+  double o30[30];
+  ref_body_foot_rotation(h, j, dts, o30);
+  for (int k = 0; k < 6 * nh; k++) out[k] = o30[k];
+}
+void ref_hook_body(void* h, int nh, int i, const double* bs, const double* zmp, const double* ang, const double* rf, const double* lf,
+                   const double* acc, double* out14) {
+  int ok;
+  (void)nh;
+  ref_body_theta_mpc(h, i, bs, zmp, ang, rf, lf, acc, out14, &ok);
+}
+double ref_hook_tx_total(void* h) { return (double)(int)static_cast<PRMPCClass*>(h)->_tx_total; }
+
 }  // extern "C"

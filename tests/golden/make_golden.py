@@ -196,6 +196,92 @@ def gen_interp(rtl):
     print("interp_ref.npz", N, "t_end_footstep", tend, "beyond", int((d["walktime"] > tend).sum()))
 
 
+def rt_foot_inputs(seed=16):
+    """100 Hz call sequence of PRMPCClass::Foot_trajectory_solve_mod2: tick j = 1..1750 with the Nrtfoorpr_gen (message slots
+    86-94 = Vec38[27:36]) of the 40 Hz planner replay (step_ref.npz) that is current at that time, the planner's step
+    periods and landing positions jittered so that the swing cubics, the landing window and re-timed steps are exercised;
+    stop-walking is raised for the last 60 ticks."""
+    g = np.load(os.path.join(HERE, "step_ref.npz"))
+    rng = np.random.Generator(np.random.Philox(seed))
+    T = 1750
+    out38 = g["replay_out"]
+    nrt = np.zeros((T + 1, 9)); stop = np.zeros(T + 1, np.int32)
+    jit = rng.uniform(-0.01, 0.01, (len(out38), 9))
+    jit[:, 0] = 0; jit[:, 7] = 0; jit[:, 8] = rng.uniform(-0.05, 0.05, len(out38))
+    for j in range(1, T + 1):
+        m = min(len(out38) - 1, 1 + int(np.floor(j * 0.01 / 0.025)))
+        nrt[j] = out38[m, 27:36] + jit[m]
+    stop[T - 60:] = 1
+    return nrt, stop
+
+
+def gen_rt_foot(rtl):
+    """PRMPCClass::Foot_trajectory_solve_mod2 on one object over the 1750-call sequence (tests/test_oracle_vs_ref.py)."""
+    rtl.ref_body_new.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(rtl.ref_body_new())
+    nh = rtl.ref_body_nh()
+    nrt, stop = rt_foot_inputs()
+    T = len(nrt) - 1
+    out = np.zeros((T + 1, 30)); S = 138 + 6 * (nh + 2)
+    st = np.zeros((T + 1, S))
+    rtl.ref_body_foot_traj_state(h, P(st[0]))
+    for j in range(1, T + 1):
+        rtl.ref_body_foot_traj(h, j, int(stop[j]), P(nrt[j].copy()), P(out[j]))
+        rtl.ref_body_foot_traj_state(h, P(st[j]))
+    rtl.ref_body_free(h)
+    np.savez_compressed(os.path.join(HERE, "rt_foot_ref.npz"), nrt=nrt, stop=stop, out=out, state0=st[0], state_end=st[T],
+                        state_mid=st[T // 2], nh=np.array([nh]))
+    print("rt_foot_ref.npz", T, "moving samples", int((np.abs(np.diff(out[:, 0])) > 0).sum()))
+
+
+class RtHooks(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("mod3", "foot", "rot", "body", "tx_total")]
+
+
+def ref_rt_hooks(rtl):
+    hk = RtHooks()
+    for n in ("mod3", "foot", "rot", "body", "tx_total"):
+        setattr(hk, n, ctypes.cast(getattr(rtl, "ref_hook_" + n), ctypes.c_void_p).value)
+    return hk
+
+
+def gen_rt_node(rtl, nl, orc):
+    """cfg1 lock-step replay of the two MPC nodes from the UNMODIFIED classes: NLPRTControlClass::WalkingReactStepping at 40 Hz
+    (40 squat ticks + the 671-tick walk) publishes the 100-slot /MPC/Gait message; the 100 Hz node -- gait_fast.cpp's glue
+    (restated once in oracle/rt_glue.c) around the unmodified PRMPCClass -- consumes the latest message every 10 ms and
+    publishes /rtMPC/traj.  Slow ticks at t = 25 k ms run before the fast tick of the same instant."""
+    nl.ref_ctl_new.restype = ctypes.c_void_p
+    rtl.ref_body_new.restype = ctypes.c_void_p
+    ctl = ctypes.c_void_p(nl.ref_ctl_new()); body = ctypes.c_void_p(rtl.ref_body_new())
+    nh = rtl.ref_body_nh()
+    orc.orc_rt_node_doubles.restype = ctypes.c_int
+    node = np.zeros(orc.orc_rt_node_doubles(nh)); orc.orc_rt_node_default(nh, P(node))
+    hk = ref_rt_hooks(rtl)
+    est = np.zeros(18); rf = np.zeros(3); lf = np.zeros(3); bs = np.zeros(4)
+    n_slow = 40 + 671 + 8
+    msgs = np.zeros((n_slow + 1, 100)); outs = []; msg_of_fast = []
+    msg = np.zeros(100); count = 0
+    t_ms = 0
+    while count < n_slow or t_ms % 25:
+        if t_ms % 25 == 0:
+            count += 1
+            m = np.zeros(100)
+            nl.ref_ctl_step(ctl, count, 1, P(est), P(rf), P(lf), P(m))
+            m[98] = 0.0                                        # wall time of the tick
+            msgs[count] = m; msg = m
+        if t_ms % 10 == 0:
+            o = np.zeros(100)
+            orc.orc_rt_node_tick(nh, P(node), ctypes.byref(hk), body, P(msg.copy()), 1, P(bs), P(o))
+            outs.append(o); msg_of_fast.append(count)
+        t_ms += 5
+    nl.ref_ctl_free(ctl); rtl.ref_body_free(body)
+    outs = np.array(outs)
+    np.savez_compressed(os.path.join(HERE, "rt_node_ref.npz"), msgs=msgs, out=outs, msg_of_fast=np.array(msg_of_fast, np.int32),
+                        node_end=node, nh=np.array([nh]))
+    live = np.abs(outs[:, 72:86]).sum(axis=1) > 0
+    print("rt_node_ref.npz slow", count, "fast", len(outs), "fast ticks with a body-MPC result", int(live.sum()))
+
+
 def foot_rot_inputs(seed=15):
     """Step-length table with forward, backward and zero-length steps, and a tick sequence that walks the whole table,
     runs past _t_end_footstep and jumps back (the angle members persist between calls)."""
@@ -258,5 +344,9 @@ if __name__ == "__main__":
         gen_foot_rot(rtl)
     if not only or "interp" in only:
         gen_interp(rtl)
+    if not only or "rt_foot" in only:
+        gen_rt_foot(rtl)
+    if not only or "rt_node" in only:
+        gen_rt_node(rtl, ctypes.CDLL(nlp), ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so")))
     if not only or "grf_tau" in only:
         gen_grf_tau(ctypes.CDLL(ref_path("libref_dyn.so")))

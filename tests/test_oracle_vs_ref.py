@@ -287,3 +287,99 @@ def test_oracle_foot_rotation_vs_live_reference(oracle):
     rtl.ref_body_free(h)
     out = _oracle_foot_rot(oracle, tx, ts, td, footx, sc, nh, ticks)
     np.testing.assert_array_equal(out, want[:, :6 * nh])
+
+
+class _RtFootCfg(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_double) for n in "dt dt_mpc tstep tdsp_ratio stepwidth0 lift_height".split()]
+
+
+def oracle_rt_foot_run(oracle, nh, nrt, stop, ticks=None):
+    """oracle/rt_foot.c over a call sequence on one state; returns (out [T+1, 6 (nh+1)], state after the last call)."""
+    lib = oracle.lib
+    lib.orc_rt_foot_state_doubles.restype = ctypes.c_int
+    c = _RtFootCfg(); lib.orc_rt_foot_cfg_default(ctypes.byref(c))
+    S = lib.orc_rt_foot_state_doubles(nh)
+    s = np.zeros(S); lib.orc_rt_foot_state_default(ctypes.byref(c), nh, P(s))
+    s0 = s.copy()
+    T = len(nrt) - 1
+    out = np.zeros((T + 1, 6 * (nh + 1)))
+    for j in (range(1, T + 1) if ticks is None else ticks):
+        lib.orc_rt_foot_traj(ctypes.byref(c), nh, P(s), int(j), int(stop[j]), P(nrt[j].copy()), P(out[j]))
+    return out, s, s0
+
+
+def test_oracle_rt_foot_bit_exact_vs_reference_golden(oracle):
+    """oracle/rt_foot.c against PRMPCClass::Foot_trajectory_solve_mod2 (RT/src/FastMPC/PRMPCClass.cpp:1756-2195): the 1750-call
+    100 Hz sequence of tests/golden/rt_foot_ref.npz on one object -- every returned foot position, the initial members and the
+    members left after the last call, bit for bit."""
+    g = load("rt_foot_ref.npz")
+    nh = int(g["nh"][0])
+    out, s_end, s0 = oracle_rt_foot_run(oracle, nh, g["nrt"], g["stop"])
+    np.testing.assert_array_equal(s0, g["state0"])
+    np.testing.assert_array_equal(out[1:], g["out"][1:, :6 * (nh + 1)])
+    np.testing.assert_array_equal(s_end, g["state_end"])
+    assert (np.abs(np.diff(g["out"][:, 2])) > 0).sum() > 300          # the swing foot is lifted: cubic branch exercised
+
+
+@pytest.mark.skipif(ref_path("libref_rt.so") is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_rt_foot_vs_live_reference(oracle):
+    from tests.golden.make_golden import rt_foot_inputs
+    rtl = ctypes.CDLL(ref_path("libref_rt.so"))
+    if not hasattr(rtl, "ref_body_foot_traj"):
+        pytest.skip("oracle/_ref predates ref_body_foot_traj")
+    nrt, stop = rt_foot_inputs(seed=161)
+    rtl.ref_body_new.restype = ctypes.c_void_p
+    h = ctypes.c_void_p(rtl.ref_body_new())
+    nh = rtl.ref_body_nh()
+    T = len(nrt) - 1
+    want = np.zeros((T + 1, 30))
+    for j in range(1, T + 1):
+        rtl.ref_body_foot_traj(h, j, int(stop[j]), P(nrt[j].copy()), P(want[j]))
+    st = np.zeros(138 + 6 * (nh + 2)); rtl.ref_body_foot_traj_state(h, P(st))
+    rtl.ref_body_free(h)
+    out, s_end, _ = oracle_rt_foot_run(oracle, nh, nrt, stop)
+    np.testing.assert_array_equal(out[1:], want[1:, :6 * (nh + 1)])
+    np.testing.assert_array_equal(s_end, st)
+
+
+class _RtHooks(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("mod3", "foot", "rot", "body", "tx_total")]
+
+
+class OracleRtNode:
+    """The 100 Hz node on the oracle restatements: oracle/rt_glue.c with its orc_hook_* (rt_foot.c, foot_rot.c, ref_interp.c,
+    body_mpc.c).  One instance = one robot."""
+
+    def __init__(self, oracle, nh):
+        lib = self.lib = oracle.lib
+        self.nh = nh
+        lib.orc_rt_node_doubles.restype = ctypes.c_int; lib.orc_rt_foot_state_doubles.restype = ctypes.c_int
+        lib.orc_rt_ctx_bytes.restype = ctypes.c_int; lib.orc_body_mpc_bytes.restype = ctypes.c_int
+        self.node = np.zeros(lib.orc_rt_node_doubles(nh)); lib.orc_rt_node_default(nh, P(self.node))
+        self.foot = np.zeros(lib.orc_rt_foot_state_doubles(nh)); self.rot = np.zeros(2 + 6 * nh)
+        self.body = ctypes.create_string_buffer(lib.orc_body_mpc_bytes())
+        self.ctx = ctypes.create_string_buffer(lib.orc_rt_ctx_bytes())
+        lib.orc_rt_ctx_init(self.ctx, nh, P(self.foot), P(self.rot), self.body)
+        self.hk = _RtHooks(); lib.orc_rt_hooks_oracle(ctypes.byref(self.hk))
+
+    def tick(self, msg, ctrl=1, bs=None):
+        out = np.zeros(100)
+        bs = np.zeros(4) if bs is None else bs
+        self.lib.orc_rt_node_tick(self.nh, P(self.node), ctypes.byref(self.hk), self.ctx, P(np.ascontiguousarray(msg, dtype=float)), int(ctrl), P(bs), P(out))
+        return out
+
+
+def test_oracle_rt_node_lockstep_replay_bit_exact(oracle):
+    """cfg1 lock-step replay: the 100 Hz node on the ORACLE restatements, fed with the /MPC/Gait messages the
+    unmodified NLPRTControlClass::WalkingReactStepping published, against /rtMPC/traj of the unmodified PRMPCClass behind the
+    same glue (tests/golden/rt_node_ref.npz, 1798 fast ticks, nh = 4): all 100 slots of every tick, bit for bit."""
+    g = load("rt_node_ref.npz")
+    nh = int(g["nh"][0])
+    node = OracleRtNode(oracle, nh)
+    msgs, want, mo = g["msgs"], g["out"], g["msg_of_fast"]
+    for k in range(len(want)):
+        got = node.tick(msgs[mo[k]])
+        if not np.array_equal(got, want[k]):
+            bad = np.nonzero(got != want[k])[0]
+            raise AssertionError(f"fast tick {k}: slots {bad[:10]} differ: {got[bad[:4]]} vs {want[k][bad[:4]]}")
+    np.testing.assert_array_equal(node.node, g["node_end"])
