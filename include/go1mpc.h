@@ -510,6 +510,28 @@ int go1mpc_graph_capture_end(go1mpc_t *h, void *stream, void **graph_exec_out);
 int go1mpc_graph_launch(go1mpc_t *h, void *graph_exec, void *stream);
 int go1mpc_graph_destroy(go1mpc_t *h, void *graph_exec);
 
+/* ---------------------------------------------------------------------------
+ * The 100 Hz node of rt_mpc_qp for B robots: /MPC/Gait message in, /rtMPC/traj message out.  Replaces one pass of the
+ * main loop of RT/gait_fast.cpp:505-746 with everything it calls:
+ *   xget_position_interpolation (:113-372) + PRMPCClass::XGetSolution_position_mod3 (RT/FastMPC/PRMPCClass.cpp:1170-1261),
+ *   PRMPCClass::Foot_trajectory_solve_mod2 (:1756-2195), XGetSolution_Foot_rotation (:2255-2380), the 2 x nh reference
+ *   windows (gait_fast.cpp:568-616, with their row-0-twice quirk), PRMPCClass::body_theta_mpc, the outgoing 100 slots
+ *   (:633-729; slot 86 -- wall time -- is 0).
+ * state_d  [go1mpc_rt_node_state_doubles(nh)][B] SoA, in/out: the node's and the class's members
+ *          (go1mpc_rt_node_default_state gives one robot's initial column)
+ * msg_d    [100][B] SoA: the latest message of the 40 Hz planner per robot (slots as NLPRTControlClass.cpp:288-392)
+ * ctrl_d   [B] ints (control_gait(0) > 0) or NULL = on;  bodyangle_state_d [4][B] or NULL = 0
+ * body_in_d  [B][go1mpc_body_in_stride(nh)] workspace; body_out_d [B][go1mpc_body_out_stride(nh)] the body MPC's records
+ *          (in/out: its state lives there; zero-initialise);  body_diag_d as go1mpc_body_mpc_step_batch or NULL
+ * out100_d [100][B] SoA;  active_d [B] ints or NULL: 1 where the fast tick ran (message slot 99 > 0)
+ * Three launches on `stream`.  Parity: tests/test_gpu_rt_node.py (cfg1 lock-step replay of the unmodified classes).
+ * ------------------------------------------------------------------------ */
+int go1mpc_rt_node_state_doubles(int nh);
+int go1mpc_rt_node_default_state(go1mpc_t *h, int nh, double *state);
+int go1mpc_rt_node_tick_batch(go1mpc_t *h, int nh, int B, double *state_d, const double *msg_d, const int *ctrl_d,
+                              const double *bodyangle_state_d, double *body_in_d, double *body_out_d, int *body_diag_d,
+                              double *out100_d, int *active_d, void *stream);
+
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports
  * against.  Runs ~`ms` milliseconds. */

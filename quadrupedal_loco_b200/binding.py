@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_grf_joint_torques_batch", "go1mpc_ref_interp_batch", "go1mpc_ref_interp_model",
     "go1mpc_control_tick_host_async", "go1mpc_pack_compact_batch", "go1mpc_stream_wait", "go1mpc_graph_capture_begin",
     "go1mpc_graph_capture_end", "go1mpc_graph_launch", "go1mpc_graph_destroy",
+    "go1mpc_rt_node_state_doubles", "go1mpc_rt_node_default_state", "go1mpc_rt_node_tick_batch",
     "go1mpc_grf_force_opt_batch_host", "go1mpc_grf_force_distribution_batch_host", "go1mpc_grf_joint_torques_batch_host", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
@@ -131,6 +132,9 @@ def load_library():
     lib.go1mpc_leg_ik_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
     lib.go1mpc_control_tick_host_async.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ControlTick), vp]
     lib.go1mpc_pack_compact_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 6
+    lib.go1mpc_rt_node_state_doubles.argtypes = [ctypes.c_int]
+    lib.go1mpc_rt_node_default_state.argtypes = [vp, ctypes.c_int, vp]
+    lib.go1mpc_rt_node_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 10
     lib.go1mpc_stream_wait.argtypes = [vp, vp, vp]
     lib.go1mpc_graph_capture_begin.argtypes = [vp, vp]
     lib.go1mpc_graph_capture_end.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_void_p)]
@@ -450,6 +454,21 @@ class Go1Mpc:
     def leg_ik_host(self, B, pdes, qini, leg, body_p, body_r, q, jac=None, iters=None):
         self._check(self.lib.go1mpc_leg_ik_batch_host(self.h, B, _ptr(pdes), _ptr(qini), _ptr(leg), _ptr(body_p),
                                                       _ptr(body_r), _ptr(q), _ptr(jac), _ptr(iters)), "leg_ik_batch_host")
+
+    # --- the 100 Hz node (message in, message out) ---
+    def rt_node_state_doubles(self, nh):
+        return int(self.lib.go1mpc_rt_node_state_doubles(nh))
+
+    def rt_node_default_state(self, nh):
+        s = np.zeros(self.rt_node_state_doubles(nh))
+        self._check(self.lib.go1mpc_rt_node_default_state(self.h, nh, _ptr(s)), "rt_node_default_state")
+        return s
+
+    def rt_node_tick(self, nh, B, state_d, msg_d, body_in_d, body_out_d, out100_d, ctrl_d=None, bodyangle_state_d=None,
+                     body_diag_d=None, active_d=None, stream=None):
+        self._check(self.lib.go1mpc_rt_node_tick_batch(self.h, nh, B, _ptr(state_d), _ptr(msg_d), _ptr(ctrl_d), _ptr(bodyangle_state_d),
+                                                       _ptr(body_in_d), _ptr(body_out_d), _ptr(body_diag_d), _ptr(out100_d),
+                                                       _ptr(active_d), stream), "rt_node_tick_batch")
 
     def measure_dfma_peak(self, ms=200):
         g = ctypes.c_double(0.0)

@@ -979,6 +979,60 @@ int go1mpc_ref_interp_batch(go1mpc_t* h, int B, int nh, const int* walktime_d, d
   return GO1MPC_OK;
 }
 
+// ------------------------------------------------------------------ the 100 Hz node (message in, message out)
+int go1mpc_rt_node_state_doubles(int nh) {
+  const int ni = 9 + 3 * (nh - 1);
+  return (56 + 4 * ni + 6 * (nh + 1) + 6 * nh + 3 + 14) + (138 + 6 * (nh + 2)) + (2 + 6 * nh);
+}
+// members as the node's main() (RT/gait_fast.cpp:383-447) and PRMPCClass::Initialize / FootStepInputs (:46-55,105-139,2198-2221) leave them
+int go1mpc_rt_node_default_state(go1mpc_t* h, int nh, double* s) {
+  if (!h || !s) return GO1MPC_E_INVALID;
+  if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "rt_node_default_state: 3 <= nh <= 40");
+  const Go1BodyMpcConfig& c = h->cfg.body;
+  const int S = go1mpc_rt_node_state_doubles(nh), ni = 9 + 3 * (nh - 1), W = nh + 2;
+  memset(s, 0, sizeof(double) * S);
+  const double zc = h->cfg.step.hcom, hw = h->cfg.step.half_hip_width;
+  for (int q = 0; q < 4; q++) s[5 + 3 * q + 2] = zc;            // COM_in1, COM_in2, COMxyz_ref, COM_ref2: z = Z_C
+  s[56 + 2] = zc;                                              // rpy_mpc_body(2)
+  double* foot = s + 56 + 4 * ni;
+  for (int j = 0; j < nh + 1; j++) { foot[6 * j + 1] = -hw; foot[6 * j + 4] = hw; }
+  double* fs = s + 56 + 4 * ni + 6 * (nh + 1) + 6 * nh + 3 + 14;
+  double sw[GO1MPC_FOOTSTEPS];
+  const double lift = 0.015;                                   // PRMPCClass::Initialize :51
+  for (int i = 0; i < GO1MPC_FOOTSTEPS; i++) { sw[i] = 2 * hw; fs[i] = c.tstep; fs[108 + i] = lift; }
+  sw[0] = sw[0] / 2;
+  fs[108 + 26] = 0; fs[108 + 25] = 0; fs[108 + 24] = lift / 2; fs[108 + 23] = lift;
+  for (int i = 1; i < GO1MPC_FOOTSTEPS; i++) fs[54 + i] = fs[54 + i - 1] + (int)pow(-1, i - 1) * sw[i - 1];
+  for (int k = 0; k < W; k++) { fs[138 + 1 * W + k] = -sw[0]; fs[138 + 4 * W + k] = sw[0]; }
+  return GO1MPC_OK;
+}
+int go1mpc_rt_node_tick_batch(go1mpc_t* h, int nh, int B, double* state_d, const double* msg_d, const int* ctrl_d,
+                              const double* bodyangle_state_d, double* body_in_d, double* body_out_d, int* body_diag_d,
+                              double* out100_d, int* active_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  if (B < 0 || !state_d || !msg_d || !body_in_d || !body_out_d || !out100_d) return fail(h, GO1MPC_E_INVALID, "rt_node_tick_batch: bad argument");
+  if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "rt_node_tick_batch: 3 <= nh <= 40");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const Go1BodyMpcConfig& c = h->cfg.body;
+  RtKParams P;
+  P.B = B; P.nh = nh; P.in_stride = go1mpc_body_in_stride(nh); P.out_stride = go1mpc_body_out_stride(nh);
+  P.dt_mpc = c.dt_mpc; P.dt_slow = c.dt_slow; P.tstep = c.tstep; P.tdsp_ratio = 0.1;      // PRMPCClass::Initialize :169
+  P.stepwidth0 = h->cfg.step.half_hip_width; P.footx_max = 0.15;                              // :52,149
+  build_aaa_inv_mod(c.dt_slow, P.inv);
+  P.state = state_d; P.msg = msg_d; P.ctrl = ctrl_d; P.bodyangle_state = bodyangle_state_d;
+  P.body_in = body_in_d; P.body_out = body_out_d; P.out = out100_d; P.active = active_d;
+  CU(h, rt_pre_launch(P, st));
+  h->launches++;
+  int rc = go1mpc_body_mpc_step_batch(h, nh, B, body_in_d, body_out_d, body_diag_d, st);
+  if (rc) return rc;
+  CU(h, rt_post_launch(P, st));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
 // ------------------------------------------------------------------ pipelined host entries
 int go1mpc_body_mpc_step_batch_host_async(go1mpc_t* h, int nh, int B, const double* in, double* out, int* diag) {
   if (!h) return GO1MPC_E_INVALID;

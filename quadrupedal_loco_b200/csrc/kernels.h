@@ -171,6 +171,23 @@ struct RefInterpParams {
 };
 cudaError_t ref_interp_launch(RefInterpParams P, cudaStream_t st);
 
+// ---- the 100 Hz node around the body MPC (rt_chain.cu): state SoA [field][B], messages SoA [100][B] ----
+struct RtKParams {
+  int B, nh, in_stride, out_stride;
+  double dt_mpc, dt_slow, tstep, tdsp_ratio, stepwidth0, footx_max;
+  double inv[16];                 // _AAA_inv_mod, row-major
+  double* state;                  // [go1mpc_rt_node_state_doubles(nh)][B]
+  const double* msg;              // [100][B] /MPC/Gait
+  const int* ctrl;                // [B] control_gait(0) > 0, or null (= all on)
+  const double* bodyangle_state;  // [4][B] or null (= 0)
+  double* body_in;                // [B][in_stride] workspace: the body-MPC input records rt_pre_kernel assembles
+  double* body_out;               // [B][out_stride] the body MPC's output records = its state
+  double* out;                    // [100][B] /rtMPC/traj
+  int* active;                    // [B] or null: 1 where the fast tick ran (message slot 99 > 0)
+};
+cudaError_t rt_pre_launch(RtKParams P, cudaStream_t st);
+cudaError_t rt_post_launch(RtKParams P, cudaStream_t st);
+
 // register-resident DFMA loop: flops executed are returned through *flops
 cudaError_t dfma_peak_launch(int grid, int block, int iters, double* sink, cudaStream_t st);
 
