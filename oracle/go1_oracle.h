@@ -176,12 +176,19 @@ typedef struct {
     double x[ORC_STEP_NQP_MAX][4];  /* the QP increment of each SQP iteration      */
 } orc_step_diag;
 
+/* the part of the LIPM roll-out (:938-955) beyond sample i + 2: the reference rolls out jxx = 1.._nTdx samples per tick, and
+ * NLPClass::Zmp_distributor reads the ZMP of the later ones.  zsc: terrain height _Zsc(i + q), input (q >= 3 used). */
+#define ORC_NTD_MAX 12
+typedef struct { int ntdx; double zsc[ORC_NTD_MAX]; double zmpx[ORC_NTD_MAX], zmpy[ORC_NTD_MAX]; } orc_step_ext;
+
 void orc_step_cfg_default(orc_step_cfg *c);
 /* default tables of NLPClass::FootStepInputs/Initialize (:51-75,:160-206) */
 void orc_step_state_default(orc_step_state *s, const orc_step_cfg *c, double steplength, double stepwidth,
                             double stepheight, double tstep);
 void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const orc_step_in *in,
                           double out38[38], orc_step_diag *diag);
+void orc_step_timing_tick_ext(const orc_step_cfg *c, int i, orc_step_state *s, const orc_step_in *in,
+                              double out38[38], orc_step_diag *diag, orc_step_ext *ext);
 /* flat batch driver: states [B][202], ins [B][20], out [B][38], diag optional */
 void orc_step_timing_batch(const orc_step_cfg *c, int B, const int *tick, double *states, const double *ins,
                            double *out38, orc_step_diag *diag);
@@ -203,6 +210,29 @@ void orc_foot_state_default(double fs[ORC_FOOT_STATE], double stepwidth0);
  * out18 = the Vec18 of the reference; returns right_support (0, 1 or 2). */
 int orc_foot_traj_tick(const orc_step_cfg *c, int j, const orc_step_state *st, int bjxx,
                        double fs[ORC_FOOT_STATE], double stepwidth0, double lift_height, double out18[18]);
+
+/* ------------------------------------------------------------------------
+ * The 40 Hz planner node (nlp_node.c): NLPRTControlClass::WalkingReactStepping / rt_nlp_gait / StartWalking / StopWalking
+ * (NLP/src/NLPRTControl/NLPRTControlClass.cpp:191-596) with NLPClass::X_CoM_position_squat (NLPClass_sqp.cpp:2958-3015),
+ * Zmp_distributor / zmp_interpolation / Force_torque_calculate (:3650-3897).  The node is a flat array of
+ * orc_nlp_node_doubles() doubles: [0,202) planner state | [202,234) swing-foot window | ZMP ring | members.
+ * --------------------------------------------------------------------- */
+typedef struct {
+    orc_step_cfg step;
+    double dtx, height_offset_time, height_squat_time, height_offset, z_c, mass, rad, lift_height;
+    double steplength, stepwidth, stepheight, tstep;
+    double tx_last0;                /* _tx(last) as Initialize left it: _t_end_footstep = round((tx_last0 - 2 tstep) / dt) */
+    int nsum, walkdtime_max;
+} orc_nlp_cfg;
+void orc_nlp_cfg_default(orc_nlp_cfg *c);
+int orc_nlp_node_doubles(void);
+void orc_nlp_node_default(orc_nlp_cfg *c, double *node);        /* also fills c->nsum, walkdtime_max, tx_last0 */
+void orc_nlp_node_start(double *node);
+void orc_nlp_node_stop(double *node);
+void orc_nlp_squat(const orc_nlp_cfg *c, int walktime, double dt_sample, double zva[3]);
+double orc_nlp_lift_ref(double lift_height, int k, int zero_from);
+void orc_nlp_node_tick(const orc_nlp_cfg *c, double *node, int walkdtime, int start_mpc, const double rfoot_fb[3],
+                       const double lfoot_fb[3], double out100[100]);
 
 /* ------------------------------------------------------------------------
  * 40 Hz -> 100 Hz reference interpolation of rt_mpc_qp (ref_interp.c): PRMPCClass::solve_AAA_inv_mod1 and

@@ -140,6 +140,8 @@ void ref_ctl_step(void* h, int count, int start, const double* est18, const doub
   Eigen::Matrix<double, 100, 1> o = p->WalkingReactStepping(count, start != 0, est, rf, lf);
   for (int k = 0; k < 100; k++) out100[k] = o(k);
 }
+void ref_ctl_start(void* h) { static_cast<NLPRTControlClass*>(h)->StartWalking(); }
+void ref_ctl_stop(void* h) { static_cast<NLPRTControlClass*>(h)->StopWalking(); }
 int ref_ctl_walkdtime_max(void* h) { return static_cast<NLPRTControlClass*>(h)->_walkdtime_max; }
 
 }  // extern "C"

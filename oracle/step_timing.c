@@ -96,8 +96,8 @@ static void gj_inverse(int n, double *a, double *r)
 }
 
 /* NLPClass::CoM_height_solve :2361-2473 for the three samples the tick reads (jxx = 1..3) */
-static void com_height_solve(const orc_step_cfg *c, int i, const orc_step_state *s, int bjx1,
-                             double comz[3], double comvz[3], double comaz[3])
+static void com_height_solve(const orc_step_cfg *c, int i, const orc_step_state *s, int bjx1, int nsamp,
+                             double *comz, double *comvz, double *comaz)
 {
     if (bjx1 >= 2) {
         double tp[3] = { 0.0001, s->ts[bjx1 - 1] / 2 + 0.0001, s->ts[bjx1 - 1] + 0.0001 };
@@ -115,7 +115,7 @@ static void com_height_solve(const orc_step_cfg *c, int i, const orc_step_state 
         const double plan[7] = { 0, 0, f0 + c->hcom, (f0 + f1) / 2 + c->hcom, f1 + c->hcom, 0, 0 };
         double co[7];
         for (int r = 0; r < 7; r++) { double acc = 0.0; for (int k = 0; k < 7; k++) acc += Ainv[7 * r + k] * plan[k]; co[r] = acc; }
-        for (int jxx = 1; jxx <= 3; jxx++) {
+        for (int jxx = 1; jxx <= nsamp; jxx++) {
             const double t = (i + jxx - round(s->tx[bjx1 - 1] / c->dt)) * c->dt;
             const double p[7] = { pow(t, 6), pow(t, 5), pow(t, 4), pow(t, 3), pow(t, 2), pow(t, 1), 1 };
             const double v[7] = { 6 * pow(t, 5), 5 * pow(t, 4), 4 * pow(t, 3), 3 * pow(t, 2), 2 * pow(t, 1), 1, 0 };
@@ -125,14 +125,25 @@ static void com_height_solve(const orc_step_cfg *c, int i, const orc_step_state 
             comz[jxx - 1] = z; comvz[jxx - 1] = vz; comaz[jxx - 1] = az;
         }
     } else {
-        for (int q = 0; q < 3; q++) { comz[q] = c->hcom; comvz[q] = 0; comaz[q] = 0; }
+        /* the reference writes three samples; beyond them the arrays keep their initial values (_hcom, 0, 0) */
+        for (int q = 0; q < nsamp; q++) { comz[q] = c->hcom; comvz[q] = 0; comaz[q] = 0; }
     }
 }
 
 void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const orc_step_in *in,
                           double out38[38], orc_step_diag *dg)
 {
+    orc_step_timing_tick_ext(c, i, s, in, out38, dg, NULL);
+}
+
+void orc_step_timing_tick_ext(const orc_step_cfg *c, int i, orc_step_state *s, const orc_step_in *in,
+                              double out38[38], orc_step_diag *dg, orc_step_ext *ext)
+{
     const double dt = c->dt, Wn = c->Wn;
+    /* :933 _nTdx = round(_td(1) / _dt) + 1 with _td = 0.2 _ts as the END of the previous tick left it (:1041, :201) */
+    int ntdx = (int)round(0.2 * s->ts[1] / dt) + 1;
+    if (ntdx > ORC_NTD_MAX) ntdx = ORC_NTD_MAX;
+    if (ntdx < 3 || !ext) ntdx = 3;
     double v[4];
     if (dg) memset(dg, 0, sizeof *dg);
 
@@ -307,12 +318,13 @@ void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const
     (void)nTd_ts1;
 
     /* :936 vertical CoM samples (after the write-back of ts / tx, with the _bjx1 of the previous tick) */
-    double hz_z[3], hz_vz[3], hz_az[3];
+    double hz_z[ORC_NTD_MAX], hz_vz[ORC_NTD_MAX], hz_az[ORC_NTD_MAX];
     if (c->ext_height) {
         for (int q = 0; q < 3; q++) { hz_z[q] = in->comz[q]; hz_az[q] = in->comaz[q]; hz_vz[q] = 0.0; }
         hz_vz[0] = in->comvz0;
+        for (int q = 3; q < ntdx; q++) { hz_z[q] = in->comz[2]; hz_az[q] = in->comaz[2]; hz_vz[q] = 0.0; }   /* external heights: held */
     } else {
-        com_height_solve(c, i, s, (int)s->bjx1_prev, hz_z, hz_vz, hz_az);
+        com_height_solve(c, i, s, (int)s->bjx1_prev, ntdx, hz_z, hz_vz, hz_az);
     }
     /* :938-955 LIPM roll-out (samples i, i+1, i+2 are what the outputs read) */
     double comx[3], comy[3], comvx[3], comvy[3], comax[3], comay[3], zmpx[3], zmpy[3], dcmx[3], dcmy[3];
@@ -330,6 +342,22 @@ void orc_step_timing_tick(const orc_step_cfg *c, int i, orc_step_state *s, const
         zmpy[q] = comy[q] - hz * comay[q];
         dcmx[q] = comx[q] + comvx[q] * sqrt(hz);
         dcmy[q] = comy[q] + comvy[q] * sqrt(hz);
+    }
+    if (ext) {
+        /* the roll-out runs to jxx = _nTdx (:938); only NLPClass::Zmp_distributor ever reads samples beyond i + 2 */
+        ext->ntdx = ntdx;
+        for (int jxx = 1; jxx <= ntdx; jxx++) {
+            const int q = jxx - 1;
+            if (q < 3) { ext->zmpx[q] = zmpx[q]; ext->zmpy[q] = zmpy[q]; continue; }
+            const double w = Wn * dt * jxx;
+            const double cx = isx * cosh(w) + visx * 1 / Wn * sinh(w) + px;
+            const double cy = isy * cosh(w) + visy * 1 / Wn * sinh(w) + py;
+            const double ax = pow(Wn, 2) * isx * cosh(w) + visx * Wn * sinh(w);
+            const double ay = pow(Wn, 2) * isy * cosh(w) + visy * Wn * sinh(w);
+            const double hz = (hz_z[q] - ext->zsc[q]) / (hz_az[q] + c->ggg);
+            ext->zmpx[q] = cx - hz * ax;
+            ext->zmpy[q] = cy - hz * ay;
+        }
     }
     /* :963-972, :1017-1022 feedback blend (gains 0 as shipped) */
     double e0 = in->est[0], e3 = in->est[3];

@@ -324,6 +324,45 @@ def gen_grf_tau(dl):
     print("grf_tau_ref.npz", N)
 
 
+def nlp_node_scripts():
+    """Scripted sequences for the 40 Hz node: (name, ticks, {tick: 'stop' | 'start'}, ticks with start_mpc = 0, foot-feedback seed)."""
+    return [("walk_fb", 739, {}, (), 21),                     # cfg1 with noisy foot-location feedback, runs past the end
+            ("stop_early", 120, {45: "stop"}, (), 0),         # StopWalking while _t_int < 10: no effect on the flags
+            ("stop", 420, {200: "stop"}, (), 22),             # lift heights of the steps ahead zeroed
+            ("stop_restart", 420, {200: "stop", 300: "start"}, (), 23),   # _start_walking_again: the node freezes
+            ("idle", 200, {}, tuple(range(1, 25)) + (30, 31), 24)]       # start_mpc = 0 before / during the squat (a gap in the WALK
+                                                                          # ticks is outside the contract: the reference then
+                                                                          # reads whole-walk array entries no tick ever wrote)
+
+
+def nlp_node_feedback(seed, T):
+    rng = np.random.Generator(np.random.Philox(5000 + seed))
+    rf = np.zeros((T + 1, 3)); lf = np.zeros((T + 1, 3))
+    if seed:
+        rf[:, :2] = rng.uniform(-0.01, 0.01, (T + 1, 2)); lf[:, :2] = rng.uniform(-0.01, 0.01, (T + 1, 2))
+    return rf, lf
+
+
+def gen_nlp_node(nl):
+    """NLPRTControlClass::WalkingReactStepping / StartWalking / StopWalking of the UNMODIFIED class on scripted sequences."""
+    nl.ref_ctl_new.restype = ctypes.c_void_p
+    out = {}
+    for name, T, events, idle, seed in nlp_node_scripts():
+        ctl = ctypes.c_void_p(nl.ref_ctl_new())
+        rf, lf = nlp_node_feedback(seed, T)
+        msgs = np.zeros((T + 1, 100)); est = np.zeros(18)
+        for count in range(1, T + 1):
+            ev = events.get(count)
+            if ev == "stop": nl.ref_ctl_stop(ctl)
+            if ev == "start": nl.ref_ctl_start(ctl)
+            nl.ref_ctl_step(ctl, count, 0 if count in idle else 1, P(est), P(rf[count].copy()), P(lf[count].copy()), P(msgs[count]))
+            msgs[count, 98] = 0.0
+        nl.ref_ctl_free(ctl)
+        out[name] = msgs
+        print("nlp_node_ref.npz", name, T, "NaN slots", int(np.isnan(msgs).sum()))
+    np.savez_compressed(os.path.join(HERE, "nlp_node_ref.npz"), **out)
+
+
 if __name__ == "__main__":
     ref, rt, nlp = ref_path("libref.so"), ref_path("libref_rt.so"), ref_path("libref_nlp.so")
     if not ref or not rt or not nlp:
@@ -348,5 +387,7 @@ if __name__ == "__main__":
         gen_rt_foot(rtl)
     if not only or "rt_node" in only:
         gen_rt_node(rtl, ctypes.CDLL(nlp), ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so")))
+    if not only or "nlp_node" in only:
+        gen_nlp_node(ctypes.CDLL(nlp))
     if not only or "grf_tau" in only:
         gen_grf_tau(ctypes.CDLL(ref_path("libref_dyn.so")))

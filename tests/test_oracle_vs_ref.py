@@ -383,3 +383,88 @@ def test_oracle_rt_node_lockstep_replay_bit_exact(oracle):
             bad = np.nonzero(got != want[k])[0]
             raise AssertionError(f"fast tick {k}: slots {bad[:10]} differ: {got[bad[:4]]} vs {want[k][bad[:4]]}")
     np.testing.assert_array_equal(node.node, g["node_end"])
+
+
+class OracleNlpNode:
+    """The 40 Hz planner node on the oracle restatement (oracle/nlp_node.c)."""
+
+    def __init__(self, oracle):
+        lib = self.lib = oracle.lib
+        lib.orc_nlp_node_doubles.restype = ctypes.c_int
+        self.cfg = (ctypes.c_double * 128)()              # orc_nlp_cfg, opaque here (well under 1 KB)
+        lib.orc_nlp_cfg_default(self.cfg)
+        self.node = np.zeros(lib.orc_nlp_node_doubles())
+        lib.orc_nlp_node_default(self.cfg, P(self.node))
+
+    def start(self):
+        self.lib.orc_nlp_node_start(P(self.node))
+
+    def stop(self):
+        self.lib.orc_nlp_node_stop(P(self.node))
+
+    def tick(self, walkdtime, start_mpc, rf, lf):
+        out = np.zeros(100)
+        self.lib.orc_nlp_node_tick(self.cfg, P(self.node), int(walkdtime), int(start_mpc), P(np.ascontiguousarray(rf, dtype=float)),
+                                   P(np.ascontiguousarray(lf, dtype=float)), P(out))
+        return out
+
+
+def run_nlp_script(node, T, events, idle, rf, lf):
+    out = np.zeros((T + 1, 100))
+    for count in range(1, T + 1):
+        ev = events.get(count)
+        if ev == "stop":
+            node.stop()
+        if ev == "start":
+            node.start()
+        out[count] = node.tick(count, 0 if count in idle else 1, rf[count], lf[count])
+    return out
+
+
+def test_oracle_nlp_node_bit_exact_vs_reference_golden(oracle):
+    """NLPRTControlClass::WalkingReactStepping (+ StartWalking / StopWalking, X_CoM_position_squat, Zmp_distributor, the
+    stop-walking branch of the swing foot) of the UNMODIFIED class: every /MPC/Gait slot of every tick, bit for bit, on cfg1's
+    own message sequence (rt_node_ref.npz: 40 squat ticks, the 671-tick walk, 8 ticks beyond) and on scripted stop / restart /
+    idle sequences with noisy foot-location feedback (nlp_node_ref.npz)."""
+    from tests.golden.make_golden import nlp_node_feedback, nlp_node_scripts
+    g = load("rt_node_ref.npz")
+    msgs = g["msgs"]
+    z = np.zeros((len(msgs), 3))
+    got = run_nlp_script(OracleNlpNode(oracle), len(msgs) - 1, {}, (), z, z)
+    np.testing.assert_array_equal(got[1:], msgs[1:])
+    g2 = load("nlp_node_ref.npz")
+    for name, T, events, idle, seed in nlp_node_scripts():
+        rf, lf = nlp_node_feedback(seed, T)
+        got = run_nlp_script(OracleNlpNode(oracle), T, events, idle, rf, lf)
+        np.testing.assert_array_equal(got[1:], g2[name][1:], err_msg=name)
+    assert g2["stop"][260:, [8, 11]].max() == 0.0 and g2["walk_fb"][260:, [8, 11]].max() > 0.03      # the stop zeroed the lift heights
+
+
+def test_oracle_nlp_node_live_vs_reference(oracle):
+    """Fresh stop / start scripts against the unmodified class where oracle/_ref is present (the authoring container)."""
+    nlp = ref_path("libref_nlp.so")
+    if not nlp:
+        pytest.skip("oracle/_ref absent")
+    nl = ctypes.CDLL(nlp)
+    nl.ref_ctl_new.restype = ctypes.c_void_p
+    rng = np.random.Generator(np.random.Philox(977))
+    for trial in range(3):
+        T = 500
+        stop_at = int(rng.integers(60, 400)); start_at = stop_at + int(rng.integers(5, 80))
+        events = {stop_at: "stop"} if trial == 0 else {stop_at: "stop", start_at: "start"}
+        rf = np.zeros((T + 1, 3)); lf = np.zeros((T + 1, 3))
+        rf[:, :2] = rng.uniform(-0.02, 0.02, (T + 1, 2)); lf[:, :2] = rng.uniform(-0.02, 0.02, (T + 1, 2))
+        ctl = ctypes.c_void_p(nl.ref_ctl_new())
+        node = OracleNlpNode(oracle)
+        est = np.zeros(18)
+        for count in range(1, T + 1):
+            ev = events.get(count)
+            if ev == "stop":
+                nl.ref_ctl_stop(ctl); node.stop()
+            if ev == "start":
+                nl.ref_ctl_start(ctl); node.start()
+            m = np.zeros(100)
+            nl.ref_ctl_step(ctl, count, 1, P(est), P(rf[count].copy()), P(lf[count].copy()), P(m))
+            m[98] = 0.0
+            np.testing.assert_array_equal(node.tick(count, 1, rf[count], lf[count]), m, err_msg=f"trial {trial} tick {count}")
+        nl.ref_ctl_free(ctl)
