@@ -251,7 +251,7 @@ int go1mpc_body_default_tx(go1mpc_t *h, double *tx27);
  *
  * Layout: STRUCTURE OF ARRAYS, element-major / batch-minor: field f of instance b is
  * at [f*B + b] (one thread per instance: every access of a warp is coalesced).
- * tick_d  [B] ints         i of the reference (>= 1)
+ * tick_d  [B] ints         i of the reference (>= 1); an instance with tick < 1 is skipped (nothing read or written)
  * state_d [202][B] doubles, the planner state before the tick; state_out_d receives the
  *         state after it and may be the same buffer (in-place: only changed fields are
  *         written).  Fields:
@@ -312,8 +312,8 @@ int go1mpc_leg_ik_batch_host(go1mpc_t *h, int B, const double *pdes, const doubl
 /* ---------------------------------------------------------------------------
  * Swing-foot trajectory of the step planner for B instances; run after the step-timing tick
  * of the same index.  Replaces NLPClass::Foot_trajectory_solve_mod2 (NLP/NLP/NLPClass_sqp.cpp:
- * 2039-2358) and solve_AAA_inv2 (:3633-3645).  Stop-walking (_stopwalking, ticks beyond
- * _t_end_footstep) is not covered.  SoA layout [f*B + b].
+ * 2039-2358) and solve_AAA_inv2 (:3633-3645); the stop-walking branch is go1mpc_foot_trajectory_stop_batch.
+ * SoA layout [f*B + b].  Instances with tick < 1 are skipped.
  * state_d [202][B]  planner state AFTER go1mpc_step_timing_step_batch;  out38_d [38][B] its output
  * foot_d  [32][B] in/out, the window of the reference's whole-walk foot arrays:
  *           [0,6) R xyz, L xyz at tick j-1   [6,12) what the arrays hold at j   [12,18) at j-2
@@ -330,6 +330,14 @@ int go1mpc_foot_trajectory_batch(go1mpc_t *h, int B, const int *tick_d, const do
 int go1mpc_foot_trajectory_batch_host(go1mpc_t *h, int B, const int *tick, const double *state,
                                       const double *out38, double *foot, double *out18, int *right_support);
 int go1mpc_foot_default_state(go1mpc_t *h, double *foot32);
+/* The same with the stop-walking branch (:2043-2048): lift0_d [B] doubles, in/out -- the first step index whose lift height is
+ * zeroed (initially GO1MPC_FOOTSTEPS = none); stop_d [B] doubles or NULL -- the caller's _stopwalking flag (non-zero = set).
+ * A tick beyond _t_end_footstep (go1mpc_nlp_t_end_footstep) acts like a stop, as in the reference. */
+int go1mpc_foot_trajectory_stop_batch(go1mpc_t *h, int B, const int *tick_d, const double *state_d, const double *out38_d,
+                                      double *foot_d, double *out18_d, int *right_support_d, double *lift0_d,
+                                      const double *stop_d, void *stream);
+int go1mpc_foot_trajectory_stop_batch_host(go1mpc_t *h, int B, const int *tick, const double *state, const double *out38,
+                                           double *foot, double *out18, int *right_support, double *lift0, const double *stop);
 
 /* ---------------------------------------------------------------------------
  * Servo kinematics tick for B robots (cfg5's fused leg IK / Jacobian stage).  Replaces the
@@ -511,6 +519,38 @@ int go1mpc_graph_launch(go1mpc_t *h, void *graph_exec, void *stream);
 int go1mpc_graph_destroy(go1mpc_t *h, void *graph_exec);
 
 /* ---------------------------------------------------------------------------
+ * The 40 Hz planner node of mosek_nlp_kmp for B robots: one call of NLPRTControlClass::WalkingReactStepping per robot,
+ * /MPC/Gait message out.  Replaces NLP/NLPRTControl/NLPRTControlClass.cpp:191-396 (squat / walk / over / idle branches and the
+ * 100-slot message layout :288-392), StartWalking / StopWalking :400-432, rt_nlp_gait :436-596 with everything it calls:
+ *   NLPClass::X_CoM_position_squat (NLP/NLP/NLPClass_sqp.cpp:2958-3015), step_timing_opti_loop + CoM_height_solve,
+ *   Foot_trajectory_solve_mod2 with its stop-walking branch, Zmp_distributor / zmp_interpolation / Force_torque_calculate
+ *   (:3650-3897).
+ * state_d     [go1mpc_nlp_node_state_doubles()][B] SoA, in/out: rows [0,202) the planner state, [202,234) the swing-foot
+ *             window, then the ZMP ring and the node's members (go1mpc_nlp_node_default_state gives one robot's column)
+ * walkdtime_d [B] ints: the caller's tick counter (the reference's walkdtime, 1, 2, 3 ...; the walk's ticks must be consecutive)
+ * start_d     [B] ints or NULL (= 1): start_mpc;   cmd_d [B] ints or NULL: 1 = StopWalking(), 2 = StartWalking() before the tick
+ * rfoot_fb_d / lfoot_fb_d  [3][B] or NULL (= 0): measured foot locations.  The reference ignores its estimated-state argument
+ *             (rt_nlp_gait passes the all-zero member _estimated_state, :446), so there is none here.
+ * msg_d       [100][B] SoA: the message (slot 98 = 0)
+ * Six launches on `stream`.  Parity: tests/test_gpu_nlp_node.py (cfg1 and stop / restart scripts of the unmodified class).
+ * ------------------------------------------------------------------------ */
+/* rows of the node state a host may read or set between ticks (exact integers / flags stored as doubles) */
+#define GO1MPC_NLP_ROW_STOP 365          /* _stop_walking */
+#define GO1MPC_NLP_ROW_START_AGAIN 366   /* _start_walking_again */
+#define GO1MPC_NLP_ROW_T_INT 367         /* _t_int: planner tick of the last walking call */
+#define GO1MPC_NLP_ROW_MPC_STOP 368      /* mpc_stop */
+#define GO1MPC_NLP_ROW_RIGHT_SUPPORT 369 /* right_support */
+int go1mpc_nlp_node_state_doubles(void);
+int go1mpc_nlp_node_default_state(go1mpc_t *h, double *state);
+int go1mpc_nlp_walkdtime_max(const go1mpc_t *h);         /* _walkdtime_max: ticks of the walk (672) */
+int go1mpc_nlp_t_end_footstep(const go1mpc_t *h);        /* _t_end_footstep */
+int go1mpc_nlp_node_tick_batch(go1mpc_t *h, int B, double *state_d, const int *walkdtime_d, const int *start_d, const int *cmd_d,
+                               const double *rfoot_fb_d, const double *lfoot_fb_d, double *msg_d, void *stream);
+/* host buffers of the same SoA shapes (synchronous: copies up, tick, copies down) */
+int go1mpc_nlp_node_tick_batch_host(go1mpc_t *h, int B, double *state, const int *walkdtime, const int *start, const int *cmd,
+                                    const double *rfoot_fb, const double *lfoot_fb, double *msg);
+
+/* ---------------------------------------------------------------------------
  * The 100 Hz node of rt_mpc_qp for B robots: /MPC/Gait message in, /rtMPC/traj message out.  Replaces one pass of the
  * main loop of RT/gait_fast.cpp:505-746 with everything it calls:
  *   xget_position_interpolation (:113-372) + PRMPCClass::XGetSolution_position_mod3 (RT/FastMPC/PRMPCClass.cpp:1170-1261),
@@ -531,6 +571,9 @@ int go1mpc_rt_node_default_state(go1mpc_t *h, int nh, double *state);
 int go1mpc_rt_node_tick_batch(go1mpc_t *h, int nh, int B, double *state_d, const double *msg_d, const int *ctrl_d,
                               const double *bodyangle_state_d, double *body_in_d, double *body_out_d, int *body_diag_d,
                               double *out100_d, int *active_d, void *stream);
+/* host buffers (synchronous); body_out [B][go1mpc_body_out_stride(nh)] is the body MPC's state, in/out */
+int go1mpc_rt_node_tick_batch_host(go1mpc_t *h, int nh, int B, double *state, const double *msg, const int *ctrl,
+                                   const double *bodyangle_state, double *body_out, double *out100);
 
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports

@@ -27,6 +27,8 @@ EXPORTED_SYMBOLS = [
     "go1mpc_control_tick_host_async", "go1mpc_pack_compact_batch", "go1mpc_stream_wait", "go1mpc_graph_capture_begin",
     "go1mpc_graph_capture_end", "go1mpc_graph_launch", "go1mpc_graph_destroy",
     "go1mpc_rt_node_state_doubles", "go1mpc_rt_node_default_state", "go1mpc_rt_node_tick_batch",
+    "go1mpc_nlp_node_state_doubles", "go1mpc_nlp_node_default_state", "go1mpc_nlp_walkdtime_max", "go1mpc_nlp_t_end_footstep",
+    "go1mpc_nlp_node_tick_batch", "go1mpc_foot_trajectory_stop_batch", "go1mpc_nlp_node_tick_batch_host", "go1mpc_rt_node_tick_batch_host", "go1mpc_foot_trajectory_stop_batch_host",
     "go1mpc_grf_force_opt_batch_host", "go1mpc_grf_force_distribution_batch_host", "go1mpc_grf_joint_torques_batch_host", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
 ]
 
@@ -135,6 +137,15 @@ def load_library():
     lib.go1mpc_rt_node_state_doubles.argtypes = [ctypes.c_int]
     lib.go1mpc_rt_node_default_state.argtypes = [vp, ctypes.c_int, vp]
     lib.go1mpc_rt_node_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 10
+    lib.go1mpc_nlp_node_state_doubles.argtypes = []
+    lib.go1mpc_nlp_node_default_state.argtypes = [vp, vp]
+    lib.go1mpc_nlp_walkdtime_max.argtypes = [vp]
+    lib.go1mpc_nlp_t_end_footstep.argtypes = [vp]
+    lib.go1mpc_nlp_node_tick_batch.argtypes = [vp, ctypes.c_int] + [vp] * 8
+    lib.go1mpc_foot_trajectory_stop_batch.argtypes = [vp, ctypes.c_int] + [vp] * 9
+    lib.go1mpc_foot_trajectory_stop_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 9
+    lib.go1mpc_nlp_node_tick_batch_host.argtypes = [vp, ctypes.c_int] + [vp] * 7
+    lib.go1mpc_rt_node_tick_batch_host.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 6
     lib.go1mpc_stream_wait.argtypes = [vp, vp, vp]
     lib.go1mpc_graph_capture_begin.argtypes = [vp, vp]
     lib.go1mpc_graph_capture_end.argtypes = [vp, vp, ctypes.POINTER(ctypes.c_void_p)]
@@ -469,6 +480,22 @@ class Go1Mpc:
         self._check(self.lib.go1mpc_rt_node_tick_batch(self.h, nh, B, _ptr(state_d), _ptr(msg_d), _ptr(ctrl_d), _ptr(bodyangle_state_d),
                                                        _ptr(body_in_d), _ptr(body_out_d), _ptr(body_diag_d), _ptr(out100_d),
                                                        _ptr(active_d), stream), "rt_node_tick_batch")
+
+    # --- the 40 Hz planner node (message out) ---
+    def nlp_node_state_doubles(self):
+        return int(self.lib.go1mpc_nlp_node_state_doubles())
+
+    def nlp_node_default_state(self):
+        s = np.zeros(self.nlp_node_state_doubles())
+        self._check(self.lib.go1mpc_nlp_node_default_state(self.h, _ptr(s)), "nlp_node_default_state")
+        return s
+
+    def nlp_walkdtime_max(self):
+        return int(self.lib.go1mpc_nlp_walkdtime_max(self.h))
+
+    def nlp_node_tick(self, B, state_d, walkdtime_d, msg_d, start_d=None, cmd_d=None, rfoot_fb_d=None, lfoot_fb_d=None, stream=None):
+        self._check(self.lib.go1mpc_nlp_node_tick_batch(self.h, B, _ptr(state_d), _ptr(walkdtime_d), _ptr(start_d), _ptr(cmd_d),
+                                                        _ptr(rfoot_fb_d), _ptr(lfoot_fb_d), _ptr(msg_d), stream), "nlp_node_tick_batch")
 
     def measure_dfma_peak(self, ms=200):
         g = ctypes.c_double(0.0)

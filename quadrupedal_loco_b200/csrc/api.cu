@@ -66,6 +66,9 @@ struct go1mpc {
   struct TickWs { DevBuf b[7]; };
   std::map<cudaStream_t, TickWs> tick_ws;
   cudaStream_t side = nullptr;     // side stream of the planner tick's out-of-place state copy
+  double* squat_d = nullptr;       // X_CoM_position_squat table of the planner node (host libm), built on first use
+  struct NlpWs { DevBuf b[7]; };   // workspace of go1mpc_nlp_node_tick_batch, one per caller stream
+  std::map<cudaStream_t, NlpWs> nlp_ws;
   double* trtab_d = nullptr;       // remaining-time bound table of the planner tick (host libm), built on first use
   std::vector<cudaEvent_t> ev_pool;   // go1mpc_stream_wait: events, reused round-robin
   unsigned ev_next = 0;
@@ -299,6 +302,7 @@ int go1mpc_create(const Go1MpcConfig* cfg, int device, go1mpc_t** out) {
   else if (bm && !strcmp(bm, "split")) h->body_mode = 1;
 #endif
   else if (bm && !strcmp(bm, "tri")) h->body_mode = 2;
+  else if (bm && !strcmp(bm, "duo")) h->body_mode = 4;      // the any-horizon interleaved-halves kernel also at nh = 4 / 10 (A/B)
   const char* btm = getenv("GO1MPC_BODY_TRI_MIN");
   if (btm && atoi(btm) > 0) h->body_tri_min = atoi(btm);
   const char* fg = getenv("GO1MPC_FORCE_GENERIC");
@@ -321,6 +325,8 @@ void go1mpc_destroy(go1mpc_t* h) {
   for (auto& kv : h->tick_ws) for (DevBuf& b : kv.second.b) if (b.p) cudaFree(b.p);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->trtab_d) cudaFree(h->trtab_d);
+  if (h->squat_d) cudaFree(h->squat_d);
+  for (auto& kv : h->nlp_ws) for (DevBuf& b : kv.second.b) if (b.p) cudaFree(b.p);
   for (auto& L : h->lanes) {
     for (DevBuf& b : L.stage) if (b.p) cudaFree(b.p);
     if (L.stream) cudaStreamDestroy(L.stream);
@@ -441,7 +447,7 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
   int rc = get_body_model(h, nh, &M);
   if (rc) return rc;
   const int is = go1mpc_body_in_stride(nh), os = go1mpc_body_out_stride(nh);
-  if (body_fast_supported(nh) && !h->force_generic) {
+  if (body_fast_supported(nh) && !h->force_generic && h->body_mode != 4) {
     const Go1BodyMpcConfig& c = h->cfg.body;
     BodyKParams P;
     P.nh = nh; P.B = B; P.in_stride = is; P.out_stride = os; P.diag_stride = go1mpc_body_diag_stride(nh);
@@ -496,6 +502,9 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
     h->launches++;
     return GO1MPC_OK;
   }
+  // every other horizon: the interleaved-halves kernel (body_duo.cu) with the dense kernel in list mode right behind it for
+  // the instances it hands over (normally none); GO1MPC_FORCE_GENERIC=1 keeps the dense kernel alone
+  const bool duo = !h->force_generic;
   int wpc = 4, wd = 0;
   size_t smem = body_smem_bytes(nh, wpc, is, os, M->tab_doubles, &wd);
   while (wpc > 1 && smem > h->smem_optin / 2) { wpc >>= 1; smem = body_smem_bytes(nh, wpc, is, os, M->tab_doubles, &wd); }
@@ -515,6 +524,18 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
   P.dt_mpc = c.dt_mpc; P.j_ini = c.j_ini; P.mass = c.mass; P.g = c.g; P.gama = c.gama_zmp;
   P.theta_lim = c.theta_lim; P.torque_lim = c.torque_lim;
   for (int k = 0; k < 4; k++) P.lamda[k] = c.lamda[k];
+  if (duo) {
+    int* ctl = nullptr;
+    if ((rc = get_ctl(h, st, &ctl))) return rc;
+    int* fl = ctl + 2;
+    P.flist_count = fl; P.flist = fl + 2; P.flist_cap = kFlistCap;
+    CU(h, body_duo_launch(P, h->sms, h->smem_optin, st));
+    P.warp_doubles = wd;
+    CU(h, body_mpc_launch(P, wpc, grid, smem, st));           // list mode
+    CU(h, cudaMemsetAsync(fl, 0, sizeof(int), st));
+    h->launches += 2;
+    return GO1MPC_OK;
+  }
   CU(h, body_mpc_launch(P, wpc, grid, smem, st));
   h->launches++;
   return GO1MPC_OK;
@@ -608,8 +629,18 @@ int go1mpc_body_default_tx(go1mpc_t* h, double* tx27) {
 }
 
 // ------------------------------------------------------------------ step timing
+namespace {
+int step_tick_enqueue(go1mpc_t* h, int n_sqp, int B, const int* tick_d, const double* state_d, double* state_out_d,
+                      const double* in_d, double* out_d, int* diag_d, void* stream, double* hz_co_d, double* lipm_d);
+}
 int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick_d, const double* state_d, double* state_out_d,
                                   const double* in_d, double* out_d, int* diag_d, void* stream) {
+  return step_tick_enqueue(h, n_sqp, B, tick_d, state_d, state_out_d, in_d, out_d, diag_d, stream, nullptr, nullptr);
+}
+namespace {
+// hz_co_d / lipm_d: optional hand-over rows for the planner node (nlp_chain.cu); they force the three-launch mapping
+int step_tick_enqueue(go1mpc_t* h, int n_sqp, int B, const int* tick_d, const double* state_d, double* state_out_d,
+                      const double* in_d, double* out_d, int* diag_d, void* stream, double* hz_co_d, double* lipm_d) {
   if (!h) return GO1MPC_E_INVALID;
   std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !tick_d || !state_d || !state_out_d || !in_d || !out_d) return fail(h, GO1MPC_E_INVALID, "step_timing_step_batch: bad argument");
@@ -621,6 +652,7 @@ int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick
   StepKParams P;
   P.B = B; P.n_sqp = n_sqp; P.cap = h->cfg.qp_iter_cap_scale * (4 + 24 + 1) + 50;
   P.tick = tick_d; P.state = state_d; P.state_out = state_out_d; P.in = in_d; P.out = out_d; P.diag = diag_d;
+  P.hz_co = hz_co_d; P.lipm = lipm_d;
   StepCfgDev& d = P.cfg;
   d.dt = c.dt; d.Wn = c.Wn; d.ggg = c.ggg; d.t_min = c.t_min; d.t_max = c.t_max;
   d.footx_max = c.footx_max; d.footx_min = c.footx_min;
@@ -638,6 +670,7 @@ int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick
   bool warp_mode = B < h->step_warp_below;
   if (h->step_mode == 1) warp_mode = false;
   if (h->step_mode == 2) warp_mode = true;
+  if (hz_co_d || lipm_d) warp_mode = false;
   if (!h->trtab_d) {
     // tr1_min, tr2_min, tr1_max, tr2_max of NLPClass_sqp.cpp:745-757 as functions of k_yu (the samples elapsed in the step)
     double tab[STEP_TRTAB_ROWS * 4];
@@ -673,6 +706,7 @@ int go1mpc_step_timing_step_batch(go1mpc_t* h, int n_sqp, int B, const int* tick
   }
   return GO1MPC_OK;
 }
+}  // namespace
 
 int go1mpc_step_timing_step_batch_host(go1mpc_t* h, int n_sqp, int B, const int* tick, double* state, const double* in,
                                        double* out, int* diag) {
@@ -730,8 +764,24 @@ int go1mpc_step_default_state(go1mpc_t* h, double steplength, double stepwidth, 
 }
 
 // ------------------------------------------------------------------ swing-foot trajectory
+namespace {
+int foot_enqueue(go1mpc_t* h, int B, const int* tick_d, const double* state_d, const double* out38_d, double* foot_d, double* out18_d,
+                 int* right_support_d, void* stream, double* lift0_d, const double* stop_d, int t_end);
+}
 int go1mpc_foot_trajectory_batch(go1mpc_t* h, int B, const int* tick_d, const double* state_d, const double* out38_d,
                                  double* foot_d, double* out18_d, int* right_support_d, void* stream) {
+  return foot_enqueue(h, B, tick_d, state_d, out38_d, foot_d, out18_d, right_support_d, stream, nullptr, nullptr, 0);
+}
+int go1mpc_foot_trajectory_stop_batch(go1mpc_t* h, int B, const int* tick_d, const double* state_d, const double* out38_d,
+                                      double* foot_d, double* out18_d, int* right_support_d, double* lift0_d,
+                                      const double* stop_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (!lift0_d) return fail(h, GO1MPC_E_INVALID, "foot_trajectory_stop_batch: bad argument");
+  return foot_enqueue(h, B, tick_d, state_d, out38_d, foot_d, out18_d, right_support_d, stream, lift0_d, stop_d, go1mpc_nlp_t_end_footstep(h));
+}
+namespace {
+int foot_enqueue(go1mpc_t* h, int B, const int* tick_d, const double* state_d, const double* out38_d, double* foot_d, double* out18_d,
+                 int* right_support_d, void* stream, double* lift0_d, const double* stop_d, int t_end) {
   if (!h) return GO1MPC_E_INVALID;
   std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !tick_d || !state_d || !out38_d || !foot_d || !out18_d) return fail(h, GO1MPC_E_INVALID, "foot_trajectory_batch: bad argument");
@@ -740,12 +790,18 @@ int go1mpc_foot_trajectory_batch(go1mpc_t* h, int B, const int* tick_d, const do
   FootKParams P;
   P.B = B; P.tick = tick_d; P.state = state_d; P.out38 = out38_d; P.foot = foot_d; P.out18 = out18_d; P.right_support = right_support_d;
   P.dt = h->cfg.step.dt; P.stepwidth0 = h->cfg.step.stepwidth0; P.lift_height = h->cfg.step.lift_height;
+  P.lift0 = lift0_d; P.stop = stop_d; P.t_end = t_end;
   CU(h, foot_traj_launch(P, stream ? (cudaStream_t)stream : h->stream));
   h->launches++;
   return GO1MPC_OK;
 }
+}  // namespace
 int go1mpc_foot_trajectory_batch_host(go1mpc_t* h, int B, const int* tick, const double* state, const double* out38,
                                       double* foot, double* out18, int* right_support) {
+  return go1mpc_foot_trajectory_stop_batch_host(h, B, tick, state, out38, foot, out18, right_support, nullptr, nullptr);
+}
+int go1mpc_foot_trajectory_stop_batch_host(go1mpc_t* h, int B, const int* tick, const double* state, const double* out38,
+                                           double* foot, double* out18, int* right_support, double* lift0, const double* stop) {
   if (!h) return GO1MPC_E_INVALID;
   std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
@@ -761,16 +817,24 @@ int go1mpc_foot_trajectory_batch_host(go1mpc_t* h, int B, const int* tick, const
   if ((rc = stage_buf(h, 5, fb, &df))) return rc;
   if ((rc = stage_buf(h, 6, o18, &d18))) return rc;
   if (right_support && (rc = stage_buf(h, 7, tb, &drs))) return rc;
+  void *dl0 = nullptr, *dstop = nullptr;
+  const size_t lb = b * sizeof(double);
+  if (lift0 && (rc = stage_buf(h, 8, lb, &dl0))) return rc;
+  if (lift0 && stop && (rc = stage_buf(h, 9, lb, &dstop))) return rc;
   cudaStream_t st = h->stream;
   CU(h, cudaMemcpyAsync(dt_, tick, tb, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(ds, state, sb, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(do_, out38, ob, cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(df, foot, fb, cudaMemcpyHostToDevice, st));
-  rc = go1mpc_foot_trajectory_batch(h, B, (const int*)dt_, (const double*)ds, (const double*)do_, (double*)df, (double*)d18, (int*)drs, st);
+  if (lift0) CU(h, cudaMemcpyAsync(dl0, lift0, lb, cudaMemcpyHostToDevice, st));
+  if (dstop) CU(h, cudaMemcpyAsync(dstop, stop, lb, cudaMemcpyHostToDevice, st));
+  rc = foot_enqueue(h, B, (const int*)dt_, (const double*)ds, (const double*)do_, (double*)df, (double*)d18, (int*)drs, st,
+                    (double*)dl0, (const double*)dstop, lift0 ? go1mpc_nlp_t_end_footstep(h) : 0);
   if (rc) return rc;
   CU(h, cudaMemcpyAsync(foot, df, fb, cudaMemcpyDeviceToHost, st));
   CU(h, cudaMemcpyAsync(out18, d18, o18, cudaMemcpyDeviceToHost, st));
   if (right_support) CU(h, cudaMemcpyAsync(right_support, drs, tb, cudaMemcpyDeviceToHost, st));
+  if (lift0) CU(h, cudaMemcpyAsync(lift0, dl0, lb, cudaMemcpyDeviceToHost, st));
   CU(h, cudaStreamSynchronize(st));
   return GO1MPC_OK;
 }
@@ -979,6 +1043,181 @@ int go1mpc_ref_interp_batch(go1mpc_t* h, int B, int nh, const int* walktime_d, d
   return GO1MPC_OK;
 }
 
+// ------------------------------------------------------------------ the 40 Hz planner node (message out)
+namespace {
+// reference constants of NLPRTControlClass / NLPClass (NLPRTControlClass.h:16-18, NLPClass.h:35-38, NLPClass_sqp.cpp:262)
+constexpr double kNlpDtx = 0.025, kNlpHeightOffsetTime = 1.0, kNlpSquatTime = 1.0, kNlpHeightOffset = 0.0, kNlpMass = 12.0, kNlpRad = 0.1;
+constexpr double kNlpStepLength = 0.075, kNlpStepHeight = 0.0, kNlpTstep = 0.7;
+constexpr int kNlpRing = 234, kNlpZhi = 362, kNlpLift0 = 363, kNlpStop = 365, kNlpRsup = 369, kNlpPel = 371, kNlpLf = 380, kNlpRf = 383, kNlpComx = 466;
+
+// the default step table's last entry (_tx(last) of Initialize): _t_end_footstep and _walkdtime_max derive from it
+void nlp_limits(const go1mpc* h, int* t_end, int* walkdtime_max) {
+  const double dt = h->cfg.step.dt;
+  double tx = 0.0;
+  for (int j = 1; j < GO1MPC_FOOTSTEPS; j++) { tx = tx + kNlpTstep; tx = round(tx / dt) * dt - 0.000001; }
+  if (t_end) *t_end = (int)round((tx - 2 * kNlpTstep) / dt);                                  // NLPClass_sqp.cpp:593
+  const int nsum = (GO1MPC_FOOTSTEPS - 1) * (int)round(kNlpTstep / dt);                        // NLPClass.h:35-36
+  const int omit = 2 * (int)round(kNlpTstep / dt);                                             // :311
+  if (walkdtime_max) *walkdtime_max = (int)((nsum - omit - 1) * floor(dt / kNlpDtx)) + 1;      // :3026-3032, NLPRTControlClass.cpp:93
+}
+
+// NLPClass::X_CoM_position_squat (NLPClass_sqp.cpp:2958-3015, solve_AAA_inv_x :3585-3628) for walktime = 0 .. n-1: the squat
+// does not depend on the robot, so the node reads a table built once by the host libm (the reference's own pow / divisions)
+void build_squat_table(double z_c, int n, double* tab /* [3][n] */) {
+  const double tp[3] = {0.00001, kNlpSquatTime / 2 + 0.0001, kNlpSquatTime + 0.0001};
+  double A[49], R[49];
+  const int rowt[7] = {0, 0, 0, 1, 2, 2, 2}, kind[7] = {1, 2, 0, 0, 0, 1, 2};
+  for (int r = 0; r < 7; r++) {
+    const double t = tp[rowt[r]];
+    double* a = A + 7 * r;
+    if (kind[r] == 0) { a[0] = pow(t, 6); a[1] = pow(t, 5); a[2] = pow(t, 4); a[3] = pow(t, 3); a[4] = pow(t, 2); a[5] = pow(t, 1); a[6] = 1; }
+    else if (kind[r] == 1) { a[0] = 6 * pow(t, 5); a[1] = 5 * pow(t, 4); a[2] = 4 * pow(t, 3); a[3] = 3 * pow(t, 2); a[4] = 2 * pow(t, 1); a[5] = 1; a[6] = 0; }
+    else { a[0] = 30 * pow(t, 4); a[1] = 20 * pow(t, 3); a[2] = 12 * pow(t, 2); a[3] = 6 * pow(t, 1); a[4] = 2; a[5] = 0; a[6] = 0; }
+  }
+  for (int i = 0; i < 7; i++) for (int j = 0; j < 7; j++) R[i * 7 + j] = (i == j) ? 1.0 : 0.0;
+  for (int k = 0; k < 7; k++) {       // row-pivoted Gauss-Jordan, first maximal pivot wins
+    int piv = k;
+    double best = fabs(A[k * 7 + k]);
+    for (int i = k + 1; i < 7; i++) if (fabs(A[i * 7 + k]) > best) { best = fabs(A[i * 7 + k]); piv = i; }
+    if (piv != k) for (int j = 0; j < 7; j++) { std::swap(A[k * 7 + j], A[piv * 7 + j]); std::swap(R[k * 7 + j], R[piv * 7 + j]); }
+    const double d = A[k * 7 + k];
+    for (int j = 0; j < 7; j++) { A[k * 7 + j] = A[k * 7 + j] / d; R[k * 7 + j] = R[k * 7 + j] / d; }
+    for (int i = 0; i < 7; i++) {
+      if (i == k) continue;
+      const double f = A[i * 7 + k];
+      for (int j = 0; j < 7; j++) {
+        const double pa = f * A[k * 7 + j], pr = f * R[k * 7 + j];
+        A[i * 7 + j] = A[i * 7 + j] - pa; R[i * 7 + j] = R[i * 7 + j] - pr;
+      }
+    }
+  }
+  const double plan[7] = {0, 0, z_c, z_c - kNlpHeightOffset / 2, z_c - kNlpHeightOffset, 0, 0};
+  double co[7];
+  for (int r = 0; r < 7; r++) { double acc = 0.0; for (int k = 0; k < 7; k++) { const double pr = R[7 * r + k] * plan[k]; acc = acc + pr; } co[r] = acc; }
+  for (int w = 0; w < n; w++) {
+    const double t = w * kNlpDtx;
+    double z = 0.0, vz = 0.0, az = 0.0;
+    if (t <= kNlpSquatTime) {
+      const double p[7] = {pow(t, 6), pow(t, 5), pow(t, 4), pow(t, 3), pow(t, 2), pow(t, 1), 1};
+      const double v[7] = {6 * pow(t, 5), 5 * pow(t, 4), 4 * pow(t, 3), 3 * pow(t, 2), 2 * pow(t, 1), 1, 0};
+      const double a[7] = {30 * pow(t, 4), 20 * pow(t, 3), 12 * pow(t, 2), 6 * pow(t, 1), 2, 0, 0};
+      for (int k = 0; k < 7; k++) {
+        const double a1 = p[k] * co[k], a2 = v[k] * co[k], a3 = a[k] * co[k];
+        z = z + a1; vz = vz + a2; az = az + a3;
+      }
+    } else {
+      z = z_c - kNlpHeightOffset;
+    }
+    tab[w] = z; tab[n + w] = vz; tab[2 * n + w] = az;
+  }
+}
+constexpr int kSquatN = 48;
+}  // namespace
+
+int go1mpc_nlp_node_state_doubles(void) { return NLP_NODE_DOUBLES; }
+int go1mpc_nlp_t_end_footstep(const go1mpc_t* h) { int t = 0; if (h) nlp_limits(h, &t, nullptr); return t; }
+int go1mpc_nlp_walkdtime_max(const go1mpc_t* h) { int w = 0; if (h) nlp_limits(h, nullptr, &w); return w; }
+// members as NLPRTControlClass() (NLPRTControlClass.cpp:25-189) and NLPClass::Initialize leave them
+int go1mpc_nlp_node_default_state(go1mpc_t* h, double* s) {
+  if (!h || !s) return GO1MPC_E_INVALID;
+  memset(s, 0, sizeof(double) * NLP_NODE_DOUBLES);
+  const double hw = h->cfg.step.half_hip_width, z_c = h->cfg.step.hcom + kNlpHeightOffset;
+  int rc = go1mpc_step_default_state(h, kNlpStepLength, 2 * hw, kNlpStepHeight, kNlpTstep, s);
+  if (rc) return rc;
+  if ((rc = go1mpc_foot_default_state(h, s + STEP_STATE_DOUBLES))) return rc;
+  s[kNlpZhi] = -1.0; s[kNlpLift0] = GO1MPC_FOOTSTEPS; s[kNlpRsup] = 2.0;
+  s[kNlpPel + 2] = z_c; s[kNlpLf + 1] = hw; s[kNlpRf + 1] = -hw;
+  s[kNlpComx + 2] = z_c - kNlpHeightOffset;
+  return GO1MPC_OK;
+}
+
+int go1mpc_nlp_node_tick_batch(go1mpc_t* h, int B, double* state_d, const int* walkdtime_d, const int* start_d, const int* cmd_d,
+                               const double* rfoot_fb_d, const double* lfoot_fb_d, double* msg_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  if (B < 0 || !state_d || !walkdtime_d || !msg_d) return fail(h, GO1MPC_E_INVALID, "nlp_node_tick_batch: bad argument");
+  if (h->cfg.step.ext_height) return fail(h, GO1MPC_E_UNSUPPORTED, "nlp_node_tick_batch: cfg.step.ext_height must be 0 (the node owns CoM_height_solve)");
+  if (B == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  const Go1StepMpcConfig& c = h->cfg.step;
+  if (!h->squat_d) {
+    double tab[3 * kSquatN];
+    build_squat_table(c.hcom + kNlpHeightOffset, kSquatN, tab);
+    CU(h, cudaMalloc((void**)&h->squat_d, sizeof tab));
+    CU(h, cudaMemcpy(h->squat_d, tab, sizeof tab, cudaMemcpyHostToDevice));
+  }
+  // per-stream workspace: tick | in | out38 | out18 | right_support | hz_co | lipm
+  go1mpc::NlpWs& W = h->nlp_ws[st];
+  const size_t need[7] = {(size_t)B * sizeof(int), (size_t)B * STEP_IN_DOUBLES * sizeof(double), (size_t)B * STEP_OUT_DOUBLES * sizeof(double),
+                          (size_t)B * FOOT_OUT_DOUBLES * sizeof(double), (size_t)B * sizeof(int), (size_t)B * 8 * sizeof(double),
+                          (size_t)B * 6 * sizeof(double)};
+  for (int k = 0; k < 7; k++)
+    if (W.b[k].cap < need[k]) {
+      CU(h, cudaStreamSynchronize(st));
+      if (W.b[k].p) CU(h, cudaFree(W.b[k].p));
+      W.b[k].p = nullptr; W.b[k].cap = 0;
+      CU(h, cudaMalloc(&W.b[k].p, need[k]));
+      W.b[k].cap = need[k];
+    }
+  NlpKParams P;
+  P.B = B;
+  nlp_limits(h, &P.t_end, &P.walkdtime_max);
+  P.dt = c.dt; P.dtx = kNlpDtx; P.height_offset_time = kNlpHeightOffsetTime; P.half_hip_width = c.half_hip_width;
+  P.stepwidth0 = c.stepwidth0; P.mass = kNlpMass; P.rad = kNlpRad; P.ggg = c.ggg; P.z_c = c.hcom + kNlpHeightOffset;
+  P.height_offset = kNlpHeightOffset; P.Wn = c.Wn;
+  for (int q = 0; q < NLP_NTD_MAX; q++) { const double w = c.Wn * c.dt * (q + 1); P.sh_w[q] = sinh(w); P.ch_w[q] = cosh(w); }
+  P.squat = h->squat_d; P.squat_n = kSquatN;
+  P.node = state_d; P.walkdtime = walkdtime_d; P.start = start_d; P.cmd = cmd_d; P.rfoot_fb = rfoot_fb_d; P.lfoot_fb = lfoot_fb_d;
+  P.tick = (int*)W.b[0].p; P.in = (double*)W.b[1].p; P.out38 = (double*)W.b[2].p; P.out18 = (double*)W.b[3].p;
+  P.right_support = (int*)W.b[4].p; P.hz_co = (double*)W.b[5].p; P.lipm = (double*)W.b[6].p; P.msg = msg_d;
+  CU(h, nlp_pre_launch(P, st));
+  h->launches++;
+  // the planner state is rows [0, 202) of the node, the swing-foot window rows [202, 234): same SoA stride B
+  int rc = step_tick_enqueue(h, 3, B, P.tick, state_d, state_d, P.in, P.out38, nullptr, st, P.hz_co, P.lipm);
+  if (rc) return rc;
+  rc = foot_enqueue(h, B, P.tick, state_d, P.out38, state_d + (size_t)STEP_STATE_DOUBLES * B, P.out18, P.right_support, st,
+                    state_d + (size_t)kNlpLift0 * B, state_d + (size_t)kNlpStop * B, P.t_end);
+  if (rc) return rc;
+  CU(h, nlp_post_launch(P, st));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
+// host form: SoA host buffers of the same shapes; state and msg are copied up, the tick runs, state and msg come down
+int go1mpc_nlp_node_tick_batch_host(go1mpc_t* h, int B, double* state, const int* walkdtime, const int* start, const int* cmd,
+                                    const double* rfoot_fb, const double* lfoot_fb, double* msg) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!state || !walkdtime || !msg) return fail(h, GO1MPC_E_INVALID, "nlp_node_tick_batch_host: bad argument");
+  CU(h, cudaSetDevice(h->device));
+  const size_t b = (size_t)B, ib = b * sizeof(int), sb = b * NLP_NODE_DOUBLES * sizeof(double), fb = b * 3 * sizeof(double), mb = b * 100 * sizeof(double);
+  void *ds, *dw, *dst_ = nullptr, *dc = nullptr, *drf = nullptr, *dlf = nullptr, *dm;
+  int rc;
+  if ((rc = stage_buf(h, 0, sb, &ds))) return rc;
+  if ((rc = stage_buf(h, 1, ib, &dw))) return rc;
+  if (start && (rc = stage_buf(h, 2, ib, &dst_))) return rc;
+  if (cmd && (rc = stage_buf(h, 3, ib, &dc))) return rc;
+  if (rfoot_fb && (rc = stage_buf(h, 4, fb, &drf))) return rc;
+  if (lfoot_fb && (rc = stage_buf(h, 5, fb, &dlf))) return rc;
+  if ((rc = stage_buf(h, 6, mb, &dm))) return rc;
+  cudaStream_t st = h->stream;
+  CU(h, cudaMemcpyAsync(ds, state, sb, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(dw, walkdtime, ib, cudaMemcpyHostToDevice, st));
+  if (start) CU(h, cudaMemcpyAsync(dst_, start, ib, cudaMemcpyHostToDevice, st));
+  if (cmd) CU(h, cudaMemcpyAsync(dc, cmd, ib, cudaMemcpyHostToDevice, st));
+  if (rfoot_fb) CU(h, cudaMemcpyAsync(drf, rfoot_fb, fb, cudaMemcpyHostToDevice, st));
+  if (lfoot_fb) CU(h, cudaMemcpyAsync(dlf, lfoot_fb, fb, cudaMemcpyHostToDevice, st));
+  rc = go1mpc_nlp_node_tick_batch(h, B, (double*)ds, (const int*)dw, (const int*)dst_, (const int*)dc, (const double*)drf,
+                                  (const double*)dlf, (double*)dm, st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(state, ds, sb, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaMemcpyAsync(msg, dm, mb, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
+  return GO1MPC_OK;
+}
+
 // ------------------------------------------------------------------ the 100 Hz node (message in, message out)
 int go1mpc_rt_node_state_doubles(int nh) {
   const int ni = 9 + 3 * (nh - 1);
@@ -1030,6 +1269,43 @@ int go1mpc_rt_node_tick_batch(go1mpc_t* h, int nh, int B, double* state_d, const
   if (rc) return rc;
   CU(h, rt_post_launch(P, st));
   h->launches++;
+  return GO1MPC_OK;
+}
+
+// host form of the 100 Hz node: state / msg / body_out (the body MPC's state) are host SoA / record buffers
+int go1mpc_rt_node_tick_batch_host(go1mpc_t* h, int nh, int B, double* state, const double* msg, const int* ctrl,
+                                   const double* bodyangle_state, double* body_out, double* out100) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  if (B <= 0) return B == 0 ? GO1MPC_OK : GO1MPC_E_INVALID;
+  if (!state || !msg || !body_out || !out100) return fail(h, GO1MPC_E_INVALID, "rt_node_tick_batch_host: bad argument");
+  if (nh < 3 || nh > GO1MPC_BODY_NH_MAX) return fail(h, GO1MPC_E_UNSUPPORTED, "rt_node_tick_batch_host: 3 <= nh <= 40");
+  CU(h, cudaSetDevice(h->device));
+  const size_t b = (size_t)B, sb = b * go1mpc_rt_node_state_doubles(nh) * sizeof(double), mb = b * 100 * sizeof(double);
+  const size_t ib = b * sizeof(int), ab = b * 4 * sizeof(double), bib = b * go1mpc_body_in_stride(nh) * sizeof(double);
+  const size_t bob = b * go1mpc_body_out_stride(nh) * sizeof(double);
+  void *ds, *dm, *dc = nullptr, *da = nullptr, *dbi, *dbo, *dout;
+  int rc;
+  if ((rc = stage_buf(h, 0, sb, &ds))) return rc;
+  if ((rc = stage_buf(h, 1, mb, &dm))) return rc;
+  if (ctrl && (rc = stage_buf(h, 2, ib, &dc))) return rc;
+  if (bodyangle_state && (rc = stage_buf(h, 3, ab, &da))) return rc;
+  if ((rc = stage_buf(h, 4, bib, &dbi))) return rc;
+  if ((rc = stage_buf(h, 5, bob, &dbo))) return rc;
+  if ((rc = stage_buf(h, 6, mb, &dout))) return rc;
+  cudaStream_t st = h->stream;
+  CU(h, cudaMemcpyAsync(ds, state, sb, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(dm, msg, mb, cudaMemcpyHostToDevice, st));
+  if (ctrl) CU(h, cudaMemcpyAsync(dc, ctrl, ib, cudaMemcpyHostToDevice, st));
+  if (bodyangle_state) CU(h, cudaMemcpyAsync(da, bodyangle_state, ab, cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(dbo, body_out, bob, cudaMemcpyHostToDevice, st));
+  rc = go1mpc_rt_node_tick_batch(h, nh, B, (double*)ds, (const double*)dm, (const int*)dc, (const double*)da, (double*)dbi,
+                                 (double*)dbo, nullptr, (double*)dout, nullptr, st);
+  if (rc) return rc;
+  CU(h, cudaMemcpyAsync(state, ds, sb, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaMemcpyAsync(body_out, dbo, bob, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaMemcpyAsync(out100, dout, mb, cudaMemcpyDeviceToHost, st));
+  CU(h, cudaStreamSynchronize(st));
   return GO1MPC_OK;
 }
 

@@ -128,7 +128,17 @@ __global__ void __launch_bounds__(WPC * 32) body_mpc_kernel(BodyKParams P) {
   const double b0 = dt * dt / 2, b1 = dt;  // _b = [dt^2/2, dt]; pow(dt,2) == dt*dt exactly
   const double thmax = P.theta_lim, thmin = -P.theta_lim;
 
-  for (int b = blockIdx.x * WPC + warp; b < P.B; b += gridDim.x * WPC) {
+  // list mode (P.flist != null): the instances body_duo.cu handed over -- or all B when the list overflowed
+  int total = P.B;
+  bool listed = false;
+  if (P.flist) {
+    const int cnt = *P.flist_count;
+    listed = cnt <= P.flist_cap;
+    total = listed ? cnt : P.B;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && cnt > 0) atomicAdd(P.flist_count + 1, cnt);    // hand-over statistic
+  }
+  for (int bi = blockIdx.x * WPC + warp; bi < total; bi += gridDim.x * WPC) {
+    const int b = listed ? P.flist[bi] : bi;
     // ---- stage the input record (TMA bulk copy, async proxy) ----
     if (lane == 0) {
       mbar_expect_tx(my_bar, (uint32_t)(P.in_stride * sizeof(double)));

@@ -19,7 +19,7 @@ constexpr int S_TS = 0, S_TX = 27, S_FX = 54, S_FY = 81, S_FZ = 108, S_BJX1 = 20
 // Swing-foot trajectory of the step planner: NLPClass::Foot_trajectory_solve_mod2
 // (NLPClass_sqp.cpp:2039-2358) with solve_AAA_inv2 (:3633-3645); run after the step-timing tick
 // of the same index.  Thread per instance, SoA.  The reference's whole-walk foot arrays shrink
-// to a 32-double window (layout: include/go1mpc.h).  Stop-walking is not on the device.
+// to a 32-double window (layout: include/go1mpc.h).  Stop-walking: FootKParams::lift0 / stop.
 __device__ void gj_inverse4(double* a, double* r) {
   constexpr int n = 4;
   for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) r[i * n + j] = (i == j) ? 1.0 : 0.0;
@@ -52,7 +52,18 @@ __global__ void __launch_bounds__(128) foot_traj_kernel(FootKParams P) {
 #define FS(f) F[(size_t)(f) * B]
   const double dt = P.dt, sw0 = P.stepwidth0;
   const int j = P.tick[b];
+  if (j < 1) return;          // no tick for this planner
   const int bjx1 = (int)ST(S_BJX1);
+  // _lift_height_ref(bjx1 - 1): FootStepInputs :71-75 (last two steps 0, the one before half) and the stop-walking
+  // branch :2043-2048, which zeroes the steps ahead of the current one for good
+  int lift0 = NS;
+  if (P.lift0) {
+    lift0 = (int)P.lift0[b];
+    const bool stop = (P.stop && P.stop[b] != 0.0) || j > P.t_end;
+    if (stop && bjx1 + 1 < lift0) { lift0 = bjx1 + 1; P.lift0[b] = (double)lift0; }
+  }
+  const int ks = bjx1 - 1;
+  const double lift_h = (ks >= lift0 || ks >= NS - 2) ? 0.0 : (ks == NS - 3 ? P.lift_height / 2 : P.lift_height);
   const int bjxx = (int)P.out38[(size_t)27 * B + b];
   double pm1[6], pj[6], pm2[6], pm3[6], frz[6];
   for (int k = 0; k < 6; k++) { pm1[k] = FS(k); pj[k] = FS(6 + k); pm2[k] = FS(12 + k); pm3[k] = FS(18 + k); frz[k] = FS(24 + k); }
@@ -101,7 +112,7 @@ __global__ void __launch_bounds__(128) foot_traj_kernel(FootKParams P) {
           plan[0] = pm1[wo + k];
           if (k == 0) plan[1] = (fxr(0, bjxx - 2) + fxr(0, bjxx)) / 2;
           else if (k == 1) plan[1] = ry_lr;
-          else plan[1] = fmax(fxr(2, bjxx - 2), fxr(2, bjxx)) + ((bjx1 - 1 >= NS - 2) ? 0.0 : P.lift_height);
+          else plan[1] = fmax(fxr(2, bjxx - 2), fxr(2, bjxx)) + lift_h;
           plan[2] = fxr(k, bjxx);
           plan[3] = 0;
           double co[4];

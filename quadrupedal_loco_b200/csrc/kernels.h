@@ -32,6 +32,9 @@ struct BodyKParams {
 size_t body_smem_bytes(int nh, int wpc, int in_stride, int out_stride, int tab_doubles, int* warp_doubles);
 cudaError_t body_mpc_launch(BodyKParams P, int wpc, int grid, size_t smem, cudaStream_t st);
 cudaError_t body_mpc_occupancy(int wpc, size_t smem, int* blocks_per_sm);
+// any horizon, roll / pitch halves interleaved in one warp (body_duo.cu); rare corners go to flist for body_mpc_launch
+size_t body_duo_smem_bytes(int nh, int wpc, int in_stride, int out_stride, int* warp_doubles);
+cudaError_t body_duo_launch(BodyKParams P, int sms, size_t smem_optin, cudaStream_t st);
 // compile-time-horizon kernel (body_fast.cu); in/out strides and the table size must be the ABI's
 bool body_fast_supported(int nh);
 cudaError_t body_fast_launch(BodyKParams P, int sms, cudaStream_t st);
@@ -72,6 +75,9 @@ struct StepKParams {
   const double* in;     // [STEP_IN_DOUBLES][B]
   double* out;          // [STEP_OUT_DOUBLES][B]
   int* diag;            // [STEP_DIAG_INTS][B] or null
+  double* hz_co;        // [8][B] or null: the CoM-height polynomial of the tick (7 coefficients, highest power first) and the
+                        //   sample index its time starts at -- for callers that evaluate samples beyond i + 2 (nlp_chain.cu)
+  double* lipm;         // [6][B] or null: isx, visx, isy, visy, px, py of the LIPM roll-out (:896-901)
   const double* trtab;  // [STEP_TRTAB_ROWS][4]: cosh / sinh of Wn (t_min - k dt) (floored at 0.001 s) and of Wn (t_max - k dt), k = row
   StepCfgDev cfg;
 };
@@ -93,6 +99,11 @@ struct FootKParams {
   double* out18;         // [18][B]
   int* right_support;    // [B] or null
   double dt, stepwidth0, lift_height;
+  // stop-walking branch (:2043-2048), optional: lift0 [B] in/out = first step index whose lift height is zeroed (27 = none),
+  // stop [B] = the caller's _stopwalking flag (non-zero = set); t_end = _t_end_footstep
+  double* lift0;
+  const double* stop;
+  int t_end;
 };
 cudaError_t foot_traj_launch(FootKParams P, cudaStream_t st);
 
@@ -170,6 +181,33 @@ struct RefInterpParams {
   double* out;                    // [9 + 3 (nh - 1)][B]
 };
 cudaError_t ref_interp_launch(RefInterpParams P, cudaStream_t st);
+
+// ---- the 40 Hz planner node (nlp_chain.cu): NLPRTControlClass around NLPClass; node state SoA [NLP_NODE_DOUBLES][B] ----
+constexpr int NLP_NODE_DOUBLES = 480;
+constexpr int NLP_NTD_MAX = 12;
+struct NlpKParams {
+  int B, walkdtime_max, t_end;
+  double dt, dtx, height_offset_time, half_hip_width, stepwidth0, mass, rad, ggg, z_c, height_offset, Wn;
+  double sh_w[NLP_NTD_MAX], ch_w[NLP_NTD_MAX];   // sinh / cosh(Wn dt jxx), jxx = 1..12: host libm
+  const double* squat;        // [3][squat_n]: z, vz, az of X_CoM_position_squat at walktime = column (host table)
+  int squat_n;
+  double* node;               // [NLP_NODE_DOUBLES][B]
+  const int* walkdtime;       // [B]
+  const int* start;           // [B] or null (= 1)
+  const int* cmd;             // [B] or null: 1 = StopWalking, 2 = StartWalking before this tick
+  const double* rfoot_fb;     // [3][B] or null (= 0)
+  const double* lfoot_fb;
+  int* tick;                  // [B] workspace: the planner tick of the robot, 0 = no planner tick this call
+  double* in;                 // [STEP_IN_DOUBLES][B] workspace: planner inputs
+  double* out38;              // [38][B] workspace: planner outputs
+  double* out18;              // [18][B] workspace: swing-foot outputs
+  int* right_support;         // [B] workspace
+  double* hz_co;              // [8][B] workspace
+  double* lipm;               // [6][B] workspace
+  double* msg;                // [100][B] /MPC/Gait
+};
+cudaError_t nlp_pre_launch(NlpKParams P, cudaStream_t st);
+cudaError_t nlp_post_launch(NlpKParams P, cudaStream_t st);
 
 // ---- the 100 Hz node around the body MPC (rt_chain.cu): state SoA [field][B], messages SoA [100][B] ----
 struct RtKParams {

@@ -442,6 +442,7 @@ __global__ void __launch_bounds__(SQP_THREADS, GO1_SQP_MINB) step_sqp_kernel(Ste
   const StepCfgDev& c = P.cfg;
   const double dt = c.dt, Wn = c.Wn;
   const int i = P.tick[b];
+  if (i < 1) return;          // no tick for this planner (the reference's i starts at 1): nothing is read or written
   // :702-704 Indexfind((i+1) dt, xyz0 = -1): first entry the time has not passed
   int j = NS;
 #pragma unroll
@@ -723,7 +724,12 @@ __device__ __forceinline__ void gj_inverse7_cols234(double (&a)[49], double (&ri
 
 // NLPClass::CoM_height_solve (NLPClass_sqp.cpp:2361-2473) for the samples i, i+1, i+2
 __device__ __forceinline__ void com_height_solve(int i, int bjx1, double ts1, double tx1, double f0, double f1, double hcom, double dt,
-                                                 double comz[3], double comvz[3], double comaz[3]) {
+                                                 double comz[3], double comvz[3], double comaz[3], double* co_out, size_t co_stride) {
+  if (co_out) {        // constant polynomial z = hcom unless the fit below replaces it
+#pragma unroll
+    for (int r = 0; r < 6; r++) co_out[(size_t)r * co_stride] = 0.0;
+    co_out[(size_t)6 * co_stride] = hcom; co_out[(size_t)7 * co_stride] = 0.0;
+  }
   if (bjx1 >= 2) {
     const double tp[3] = {0.0001, ts1 / 2 + 0.0001, ts1 + 0.0001};
     double A[49], Rinv[21];
@@ -747,6 +753,11 @@ __device__ __forceinline__ void com_height_solve(int i, int bjx1, double ts1, do
 #pragma unroll
       for (int c = 0; c < 3; c++) acc = __dadd_rn(acc, __dmul_rn(Rinv[3 * r + c], plan3[c]));
       co[r] = acc;
+    }
+    if (co_out) {
+#pragma unroll
+      for (int r = 0; r < 7; r++) co_out[(size_t)r * co_stride] = co[r];
+      co_out[(size_t)7 * co_stride] = round(tx1 / dt);
     }
 #pragma unroll
     for (int jxx = 1; jxx <= 3; jxx++) {
@@ -786,6 +797,7 @@ __global__ void __launch_bounds__(128, GO1_POST_MINB) step_height_kernel(StepKPa
   const StepCfgDev& c = P.cfg;
   const double dt = c.dt, Wn = c.Wn;
   const int i = P.tick[b];
+  if (i < 1) return;
   const double v2 = O[(size_t)0 * B], v3 = O[(size_t)1 * B];
   const int pv = (int)O[(size_t)28 * B];
   const int k_yu = (int)O[(size_t)29 * B];
@@ -811,7 +823,7 @@ __global__ void __launch_bounds__(128, GO1_POST_MINB) step_height_kernel(StepKPa
     } else {
       tx_b1 = ST(S_TX + b1 - 1);
     }
-    com_height_solve(i, bp <= NS ? bp : 0, ts_b1, tx_b1, fz_b2, fz_b1, c.hcom, dt, hz_z, hz_vz, hz_az);
+    com_height_solve(i, bp <= NS ? bp : 0, ts_b1, tx_b1, fz_b2, fz_b1, c.hcom, dt, hz_z, hz_vz, hz_az, P.hz_co ? P.hz_co + b : nullptr, B);
   }
   O[(size_t)2 * B] = hz_z[0]; O[(size_t)5 * B] = hz_vz[0]; O[(size_t)8 * B] = hz_az[0];
   O[(size_t)23 * B] = hz_az[1]; O[(size_t)26 * B] = hz_az[2];
@@ -837,6 +849,7 @@ __global__ void __launch_bounds__(128, 4) step_finish_kernel(StepKParams P) {
   const StepCfgDev& c = P.cfg;
   const double dt = c.dt, Wn = c.Wn;
   const int i = P.tick[b];
+  if (i < 1) return;
   // hand-over of the two kernels before
   double v[4];
   v[0] = O[(size_t)36 * B]; v[1] = O[(size_t)37 * B]; v[2] = O[(size_t)0 * B]; v[3] = O[(size_t)1 * B];
@@ -854,6 +867,10 @@ __global__ void __launch_bounds__(128, 4) step_finish_kernel(StepKParams P) {
   const double isx = comx_f - px, esx = v[0] * 0.5, visx = (esx - isx * v[2]) / (1 / Wn * v[3]);
   const double isy = comy_f - py, esy = v[1] * 0.5, visy = (esy - isy * v[2]) / (1 / Wn * v[3]);
   const double fx_next = px + v[0], fy_next = py + v[1];
+  if (P.lipm) {
+    double* LP = P.lipm + b;
+    LP[0] = isx; LP[B] = visx; LP[2 * B] = isy; LP[3 * B] = visy; LP[4 * B] = px; LP[5 * B] = py;
+  }
   // _ts(p-1) = ts_new and the running sum _tx(k) = _tx(k-1) + _ts(k-1) for k >= p (:906-909), in the reference's order;
   // in the same pass: the two index searches against the UPDATED table (:1031-1041) and the store of the new _tx
   // entries (every load of column k precedes its store: in-place safe)

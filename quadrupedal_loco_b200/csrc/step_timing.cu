@@ -169,6 +169,7 @@ __global__ void GO1_STEP_BOUNDS step_timing_kernel(StepKParams P) {
   const StepCfgDev& c = P.cfg;
   const double dt = c.dt, Wn = c.Wn;
   const int i = P.tick[b];
+  if (i < 1) return;          // no tick for this planner (warp-uniform in the warp-per-planner mapping)
   // The step tables _ts / _tx (27 entries each) are not copied into per-thread arrays (run-time indexed, i.e. local
   // memory, and searched by dependent loads): the searches run over the state's columns as independent coalesced
   // loads, the few entries a tick needs are fetched by index.

@@ -185,7 +185,7 @@ class StepTimingMPC {
     foot_state.assign(GO1MPC_FOOT_STATE_DOUBLES, 0.0);
     go1mpc_foot_default_state(ctx_->get(), foot_state.data());
     last_out38_.assign(GO1MPC_STEP_OUT_DOUBLES, 0.0);
-    _periond_i = _k_yu = _bjxx = _bjx1 = 0; right_support = 2;
+    _periond_i = _k_yu = _bjxx = _bjx1 = 0; right_support = 2; lift_zero_from = GO1MPC_FOOTSTEPS;
   }
   Vec<38> step_timing_opti_loop(int i, const Vec<18>& estimated_state, const Vec<3>& _Rfoot_location_feedback,
                                 const Vec<3>& _Lfoot_location_feedback, double /*lamda*/, bool /*_stopwalking*/) {
@@ -205,9 +205,10 @@ class StepTimingMPC {
   // NLPClass::Foot_trajectory_solve_mod2 (NLP/src/NLP/NLPClass_sqp.cpp:2039-2358): call it right after
   // step_timing_opti_loop with the same index, as NLPRTControlClass::rt_nlp_gait does.
   Vec<18> Foot_trajectory_solve_mod2(int j_index, bool _stopwalking) {
-    if (_stopwalking) throw std::runtime_error("Foot_trajectory_solve_mod2: the stop-walking branch is not provided");
     double out[GO1MPC_FOOT_OUT_DOUBLES];
-    int rc = go1mpc_foot_trajectory_batch_host(ctx_->get(), 1, &j_index, state.data(), last_out38_.data(), foot_state.data(), out, &right_support);
+    const double stop = _stopwalking ? 1.0 : 0.0;
+    int rc = go1mpc_foot_trajectory_stop_batch_host(ctx_->get(), 1, &j_index, state.data(), last_out38_.data(), foot_state.data(), out,
+                                                    &right_support, &lift_zero_from, &stop);
     if (rc != GO1MPC_OK) throw std::runtime_error(std::string("Foot_trajectory_solve_mod2: ") + go1mpc_last_error(ctx_->get()));
     Vec<18> r;
     for (int k = 0; k < 18; k++) r(k) = out[k];
@@ -215,11 +216,72 @@ class StepTimingMPC {
   }
   std::vector<double> state;          // the 202-double planner state (layout: go1mpc.h)
   std::vector<double> foot_state;     // the 32-double swing-foot window
+  double lift_zero_from = GO1MPC_FOOTSTEPS;   // first step whose _lift_height_ref a stop has zeroed (:2043-2048)
   int right_support = 2;
   int _periond_i, _k_yu, _bjxx, _bjx1, qp_status[5];
  private:
   double sw_ = 0.2535, sl_ = 0.075, sh_ = 0.0;
   std::vector<double> last_out38_;
+  std::shared_ptr<Context> ctx_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// NLPRTControlClass (NLP/src/NLPRTControl/NLPRTControlClass.h): the 40 Hz planner node.  WalkingReactStepping keeps the
+// reference's signature and returns the 100-slot /MPC/Gait vector; StartWalking / StopWalking act on the same flags.
+class GaitPlannerNode {
+ public:
+  explicit GaitPlannerNode(std::shared_ptr<Context> ctx = nullptr) : ctx_(ctx ? ctx : Context::shared()) {
+    state.assign(go1mpc_nlp_node_state_doubles(), 0.0);
+    go1mpc_nlp_node_default_state(ctx_->get(), state.data());
+    _walkdtime_max = go1mpc_nlp_walkdtime_max(ctx_->get());
+  }
+  // estimated_statex is accepted and ignored, as in the reference (rt_nlp_gait hands the planner its zero member, :446)
+  Vec<100> WalkingReactStepping(int walkdtime, bool start_mpc, const Vec<18>& /*estimated_statex*/,
+                                const Vec<3>& _Rfoot_location_feedbackx, const Vec<3>& _Lfoot_location_feedbackx) {
+    const int start = start_mpc ? 1 : 0;
+    Vec<100> msg;
+    int rc = go1mpc_nlp_node_tick_batch_host(ctx_->get(), 1, state.data(), &walkdtime, &start, nullptr, _Rfoot_location_feedbackx.v,
+                                             _Lfoot_location_feedbackx.v, msg.v);
+    if (rc != GO1MPC_OK) throw std::runtime_error(std::string("WalkingReactStepping: ") + go1mpc_last_error(ctx_->get()));
+    right_support = (int)state[GO1MPC_NLP_ROW_RIGHT_SUPPORT]; mpc_stop = (int)state[GO1MPC_NLP_ROW_MPC_STOP];
+    _t_int = (int)state[GO1MPC_NLP_ROW_T_INT];
+    return msg;
+  }
+  void StartWalking() {       // :400-414
+    if (state[GO1MPC_NLP_ROW_STOP] != 0.0) state[GO1MPC_NLP_ROW_START_AGAIN] = 1.0;
+    state[GO1MPC_NLP_ROW_STOP] = 0.0;
+  }
+  void StopWalking() {        // :416-432
+    if (!(state[GO1MPC_NLP_ROW_T_INT] < 10)) state[GO1MPC_NLP_ROW_STOP] = 1.0;
+  }
+  std::vector<double> state;  // the node's members, planner state and ZMP history (layout: go1mpc.h)
+  int right_support = 2, mpc_stop = 0, _t_int = 0, _walkdtime_max = 0;
+ private:
+  std::shared_ptr<Context> ctx_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// The 100 Hz node of rt_mpc_qp (RT/src/gait_fast.cpp:505-746): one pass of its main loop -- the latest /MPC/Gait message in,
+// the /rtMPC/traj message out -- with the PRMPCClass object and the loop's variables as members.
+class FastGaitNode {
+ public:
+  explicit FastGaitNode(int nh = 4, std::shared_ptr<Context> ctx = nullptr) : _nh(nh), ctx_(ctx ? ctx : Context::shared()) {
+    state.assign(go1mpc_rt_node_state_doubles(nh), 0.0);
+    go1mpc_rt_node_default_state(ctx_->get(), nh, state.data());
+    body_state.assign(go1mpc_body_out_stride(nh), 0.0);
+  }
+  Vec<100> tick(const Vec<100>& mpc_gait_msg, bool control_gait_on, const Vec<4>& bodyangle_state) {
+    const int ctrl = control_gait_on ? 1 : 0;
+    Vec<100> out;
+    int rc = go1mpc_rt_node_tick_batch_host(ctx_->get(), _nh, 1, state.data(), mpc_gait_msg.v, &ctrl, bodyangle_state.v,
+                                            body_state.data(), out.v);
+    if (rc != GO1MPC_OK) throw std::runtime_error(std::string("FastGaitNode::tick: ") + go1mpc_last_error(ctx_->get()));
+    return out;
+  }
+  int _nh;
+  std::vector<double> state;        // the loop's variables and the PRMPCClass members around the body MPC
+  std::vector<double> body_state;   // the body MPC's output record = its state
+ private:
   std::shared_ptr<Context> ctx_;
 };
 

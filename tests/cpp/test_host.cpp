@@ -95,6 +95,33 @@ int main() {
     printf("\"grf_ok\": [%d, %d],\n", okk[0], okk[1]);
   }
 
+  // --- the two MPC nodes in lock step, as mpc.cpp / gait_fast.cpp run them: NLPRTControlClass::WalkingReactStepping every 25 ms
+  //     (with a StopWalking at slow tick 260), the 100 Hz node consuming the latest message every 10 ms; first 400 slow ticks
+  {
+    GaitPlannerNode slow;
+    FastGaitNode fast(4);
+    Vec<18> est2; Vec<3> rf2, lf2; Vec<4> bs;
+    Vec<100> msg;
+    const int n_slow = 400;
+    static double slow_msgs[400 * 100], fast_msgs[1001 * 100];
+    int count = 0, nfast = 0;
+    for (int t_ms = 0; count < n_slow || t_ms % 25; t_ms += 5) {
+      if (t_ms % 25 == 0) {
+        count++;
+        if (count == 260) slow.StopWalking();
+        msg = slow.WalkingReactStepping(count, true, est2, rf2, lf2);
+        for (int k = 0; k < 100; k++) slow_msgs[(count - 1) * 100 + k] = msg(k);
+      }
+      if (t_ms % 10 == 0 && nfast < 1001) {
+        Vec<100> o = fast.tick(msg, true, bs);
+        for (int k = 0; k < 100; k++) fast_msgs[nfast * 100 + k] = o(k);
+        nfast++;
+      }
+    }
+    arr("node_slow", slow_msgs, n_slow * 100); arr("node_fast", fast_msgs, nfast * 100);
+    printf("\"node_nfast\": %d, \"node_right_support\": %d,\n", nfast, slow.right_support);
+  }
+
   // --- Kinematicclass: FK_g -> IK_g round trip, Jacobian side channel
   LegKinematics kin;
   Vec<3> bp, br, q, qi; bp(2) = 0.31; br(0) = 0.05; br(1) = -0.04; br(2) = 0.1; q(0) = 0.1; q(1) = 0.8; q(2) = -1.5;

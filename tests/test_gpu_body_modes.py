@@ -1,6 +1,7 @@
-"""The three device paths of the body-inclination MPC tick at horizon 10 -- the combined warp-per-instance
-kernel ("fast"), roll / pitch halves side by side in one warp ("split"), and the three-launch path with
-register-resident solver state ("tri") -- each forced through GO1MPC_BODY_MODE and checked against the CPU
+"""The device paths of the body-inclination MPC tick at horizon 10 -- the combined warp-per-instance
+kernel ("fast"), roll / pitch halves side by side in one warp ("split"), the three-launch path with
+register-resident solver state ("tri") and the any-horizon interleaved-halves kernel ("duo", body_duo.cu: what every
+horizon other than 4 / 10 runs) -- each forced through GO1MPC_BODY_MODE and checked against the CPU
 oracle of PRMPCClass::body_theta_mpc (RT/src/FastMPC/PRMPCClass.cpp:379-714) exactly like test_gpu_body.py:
 primal 1e-9 relative, identical ORDERED final active set and iteration counters (the split paths rebuild the
 reference's interleaving of the two halves from their logs), bit-exact phase indices.  Instances the split
@@ -17,7 +18,7 @@ from tests.test_gpu_body import run_gpu, run_oracle, assert_body_parity
 pytestmark = pytest.mark.gpu
 
 # "split" (body_split.cu) is an A/B variant: compiled into the library only with GO1MPC_BUILD_AB=1
-MODES = ["fast", "tri"] + (["split"] if os.environ.get("GO1MPC_BUILD_AB") == "1" else [])
+MODES = ["fast", "tri", "duo"] + (["split"] if os.environ.get("GO1MPC_BUILD_AB") == "1" else [])
 
 
 @pytest.fixture(params=MODES)
@@ -60,6 +61,8 @@ def test_modes_parity_large_perturbation_and_handover(handle, oracle):
     assert hard > 0, "workload has no infeasible instance"
     if mode == "fast":
         assert handed == 0
+    elif mode == "duo":
+        assert handed <= B // 50           # body_duo.cu solves infeasible instances itself; it hands over one rare corner only
     else:
         assert handed >= hard, (handed, hard)          # every non-converged instance went through the combined kernel
         assert handed <= hard + B // 50, (handed, hard)  # ... and (almost) only those
@@ -192,3 +195,35 @@ def test_two_devices_in_one_process(oracle):
             finally:
                 h.close()
                 os.environ.pop("GO1MPC_BODY_MODE", None)
+
+
+@pytest.mark.parametrize("nh,B", [(20, 1024), (40, 256), (33, 300), (7, 500)])
+def test_duo_horizons_large_perturbation(mpc, oracle, nh, B):
+    """Horizons other than 4 / 10 run body_duo.cu (cfg4: 20, 40): 2x perturbation -- drops, infeasible instances -- against
+    the oracle, ordered active set and counters included; the hand-over list stays (almost) empty."""
+    d = synth.body_mpc_inputs(B, nh, seed=synth.SEED_CFG3 + nh, scale=2.0)
+    h0 = mpc.body_handover_total()
+    out, diag = run_gpu(mpc, nh, d)
+    r = run_oracle(oracle, nh, d)
+    assert_body_parity(out, diag, r, nh, f"duo nh={nh}")
+    assert (r["iters"][:, 2] > 0).any(), "workload never drops a constraint"
+    assert mpc.body_handover_total() - h0 <= B // 50
+
+
+def test_dense_kernel_alone_still_matches(oracle):
+    """GO1MPC_FORCE_GENERIC=1: the dense warp-per-problem kernel (body_mpc.cu) on its own -- it is also the list-mode
+    fallback behind body_duo.cu."""
+    old = os.environ.get("GO1MPC_FORCE_GENERIC")
+    os.environ["GO1MPC_FORCE_GENERIC"] = "1"
+    h = q.Go1Mpc(0)
+    try:
+        for nh, B in ((16, 200), (10, 300)):
+            d = synth.body_mpc_inputs(B, nh, seed=synth.SEED_CFG3 + 3 * nh, scale=2.0)
+            out, diag = run_gpu(h, nh, d)
+            assert_body_parity(out, diag, run_oracle(oracle, nh, d), nh, f"dense nh={nh}")
+    finally:
+        h.close()
+        if old is None:
+            os.environ.pop("GO1MPC_FORCE_GENERIC", None)
+        else:
+            os.environ["GO1MPC_FORCE_GENERIC"] = old

@@ -65,6 +65,29 @@ def test_host_classes_reproduce_oracle(oracle):
     assert list(d["right_support"]) == list(g["replay_right_support"][1:121])
     foot = np.array(d["foot_out18"]).reshape(120, 18)
     assert np.abs(foot[:, :6] - g["replay_foot"][1:121, :6]).max() < 2e-6     # closed loop: see test_foot_trajectory_replay...
+    # the two nodes in lock step: slow messages vs the unmodified NLPRTControlClass up to the stop (tick 260), the stopped tail and
+    # the 100 Hz node's messages vs the oracle chains fed the same way
+    from tests.test_oracle_vs_ref import OracleNlpNode, OracleRtNode
+    gs = load("rt_node_ref.npz")
+    slow = np.array(d["node_slow"]).reshape(400, 100); fast = np.array(d["node_fast"]).reshape(d["node_nfast"], 100)
+    rel = lambda a, b: (np.abs(a - b) / np.maximum(1.0, np.abs(b))).max()
+    assert rel(slow[:259], gs["msgs"][1:260]) < 1e-9 and np.array_equal(slow[:259, [27, 97, 99]], gs["msgs"][1:260][:, [27, 97, 99]])
+    ns, nf = OracleNlpNode(oracle), OracleRtNode(oracle, 4)
+    want_slow = np.zeros((400, 100)); want_fast = []; msg = np.zeros(100); count = 0; t_ms = 0
+    while count < 400 or t_ms % 25:
+        if t_ms % 25 == 0:
+            count += 1
+            if count == 260:
+                ns.stop()
+            msg = ns.tick(count, 1, np.zeros(3), np.zeros(3)); want_slow[count - 1] = msg
+        if t_ms % 10 == 0 and len(want_fast) < 1001:
+            want_fast.append(nf.tick(msg))
+        t_ms += 5
+    want_fast = np.array(want_fast)
+    assert rel(slow, want_slow) < 1e-9 and slow[300:, [8, 11]].max() == 0.0            # lift heights zeroed after the stop
+    assert fast.shape == want_fast.shape and rel(fast, want_fast) < 1e-9
+    assert np.array_equal(fast[:, [27, 63, 98, 99]], want_fast[:, [27, 63, 98, 99]])
+    assert (np.abs(fast[:, 72:86]).sum(axis=1) > 0).sum() > 800                          # the body MPC really ran
     # Dynamiccclass chain: closed-form split -> force QP -> torque map, twice (pace, then trot from the first grf_opt)
     from tests.test_grf import oracle_grf, oracle_tau
     hom = np.array([0.1881, -0.1268, 0, 0.1881, 0.1268, 0, -0.1881, -0.1268, 0, -0.1881, 0.1268, 0])
