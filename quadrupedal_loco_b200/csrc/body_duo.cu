@@ -59,13 +59,18 @@ struct DuoShared {
   // slacks of one half (its 4 nh constraints), returns the lane's part of psi
   __device__ __forceinline__ double eval_half(int h, int lane) const {
     double psi = 0.0;
-    for (int lc = lane; lc < 4 * nh; lc += 32) {
-      const int bl = lc / nh, k = lc - bl * nh;
-      const int blk = (bl < 2) ? (2 * h + bl) : (4 + 2 * h + (bl - 2));
-      const int c = blk * nh + k;
-      const double sv = s_of(c);
-      S[c] = sv;
-      psi += fmin(0.0, sv);
+    const double* xx = X + h * nh;
+    const double* ppk = h ? ppsy : ppsx;
+    for (int k = lane; k < nh; k += 32) {
+      // one triangular product per horizon step serves the upper and the lower angle bound (same value as s_of)
+      double v = 0.0;
+      for (int j = 0; j <= k; j++) v = fma(ppu[j * nh + k], xx[j], v);
+      const double pk = ppk[k], xv = xx[k];
+      const double s0 = (thmax - pk) - v, s1 = v + (thmax + pk);
+      const double s2 = fma(-j_ini, xv, tq), s3 = fma(j_ini, xv, tq);
+      S[(2 * h) * nh + k] = s0; S[(2 * h + 1) * nh + k] = s1;
+      S[(4 + 2 * h) * nh + k] = s2; S[(5 + 2 * h) * nh + k] = s3;
+      psi += (fmin(0.0, s0) + fmin(0.0, s1)) + (fmin(0.0, s2) + fmin(0.0, s3));
     }
     return psi;
   }
@@ -285,7 +290,10 @@ __device__ __forceinline__ int duo_indexfind(const double* tx, double goal) {
   return j - 1;
 }
 
-constexpr int DUO_MAX_THREADS = 256;
+constexpr int DUO_MAX_THREADS = 128;
+#ifndef GO1_DUO_MINB
+#define GO1_DUO_MINB 4
+#endif
 
 }  // namespace
 
@@ -299,7 +307,7 @@ __host__ __device__ inline int duo_warp_doubles(int nh, int in_stride, int out_s
 }
 __host__ __device__ inline int duo_cta_doubles(int nh) { return (nh * nh + 6 * nh + 1) & ~1; }
 
-__global__ void __launch_bounds__(DUO_MAX_THREADS) body_duo_kernel(BodyKParams P) {
+__global__ void __launch_bounds__(DUO_MAX_THREADS, GO1_DUO_MINB) body_duo_kernel(BodyKParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* smem = reinterpret_cast<double*>(smem_raw);
   const int nh = P.nh, n = 2 * nh, m = 12 * nh;

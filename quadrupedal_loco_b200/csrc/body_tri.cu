@@ -957,6 +957,12 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
   memcpy(T.v, tab_host, sizeof(T.v));
   tri_setup_kernel<NH><<<blocks, TRI_SETUP_THREADS, ssmem, st>>>(P, T);
   int grid = (2 * P.B + WPC * 8 - 1) / (WPC * 8);
+  {
+    // A/B knob (GO1MPC_TRI_OCC = resident solve CTAs per SM the grid is sized for): smaller grids leave room for the solve
+    // kernels of other streams and give every group several halves to balance its iteration counts over
+    static const int occ_env = [] { const char* e = getenv("GO1MPC_TRI_OCC"); return e ? atoi(e) : 0; }();
+    if (occ_env > 0 && occ_env < occ) occ = occ_env;
+  }
   if (grid > sms * occ) grid = sms * occ;
   tri_solve_kernel<NH, WPC><<<grid, WPC * 32, smem, st>>>(P);
   tri_merge_kernel<NH><<<(P.B + TRI_MERGE_THREADS - 1) / TRI_MERGE_THREADS, TRI_MERGE_THREADS, msmem, st>>>(P);

@@ -6,9 +6,12 @@ import quadrupedal_loco_b200 as q
 from quadrupedal_loco_b200 import synth
 mpc = q.Go1Mpc(0); dev = torch.device("cuda", 0)
 stream = torch.cuda.ExternalStream(mpc.stream, device=dev)
-for nh in (4, 10, 20, 40):
-    for B in (4096, 32768):
-        d = synth.body_mpc_inputs(B, nh, seed=nh)
+NHS = [int(v) for v in os.environ.get('SWEEP_NH', '4,10,20,40').split(',')]
+BS = [int(v) for v in os.environ.get('SWEEP_B', '4096,32768').split(',')]
+SCALE = float(os.environ.get('SWEEP_SCALE', '1.0'))
+for nh in NHS:
+    for B in BS:
+        d = synth.body_mpc_inputs(B, nh, seed=nh, scale=SCALE)
         r = torch.from_numpy(q.pack_body_inputs(nh, d["tick"], d["tx"], d["theta"], d["bstate"], d["x_warm"], d["refs"])).to(dev)
         o = torch.zeros(B, q.body_out_stride(nh), dtype=torch.float64, device=dev)
         dg = torch.zeros(B, q.body_diag_stride(nh), dtype=torch.int32, device=dev)
