@@ -216,8 +216,9 @@ class ClockSampler:
     timed region runs; only samples taken between start() and stop() are kept."""
     REASONS = {8: "hw_slowdown", 64: "hw_thermal_slowdown", 32: "sw_thermal_slowdown", 4: "sw_power_cap"}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.002):
         self.index, self.samples, self.run, self.t, self.h = index, [], False, None, None
+        self.period = period
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -239,7 +240,7 @@ class ClockSampler:
                 self.samples.append((sm, pw, rs))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         if self.h is None:
@@ -286,6 +287,9 @@ def run_b200(a):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # every rank's host side (pinned buffers, feeder threads) lives on the NUMA node of its own GPU
+    from quadrupedal_loco_b200 import sharding as _sh
+    numa_note = _sh.pin_to_gpu_numa_node(local) if world > 1 else "single rank: not bound"
     dist = None
     if world > 1:
         # stdout carries exactly one JSON line: NCCL's own log lines (version banner, INFO when the caller asks for
@@ -398,9 +402,15 @@ def run_b200(a):
         enqueue_steps(K)
         chk(lib.go1mpc_graph_capture_end(hh, lane_ptr[0], ctypes.byref(graph)), "graph_capture_end")
     launches_per_K = mpc.launch_count - l_cap0
+    if graph:
+        # one untimed launch of the graph: uploads it to the device and brings every rank's GPU to its working clocks (the
+        # W warm-up steps of an idle GPU are a fraction of a millisecond); the timed launch below then starts warm on all ranks
+        chk(lib.go1mpc_graph_launch(hh, graph, lane_ptr[0]), "graph_launch")
+        torch.cuda.synchronize()
     enqueue_steps(W)                                   # warm-up: W untimed steps
     torch.cuda.synchronize()
-    clocks = ClockSampler(local)
+    # NVML polling takes driver locks shared by every process of the box: 2 ms period on one GPU, 10 ms when 8 ranks poll
+    clocks = ClockSampler(local, period=0.002 if world == 1 else 0.010)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
     clocks.start()
@@ -442,9 +452,20 @@ def run_b200(a):
     handed_over = mpc.body_handover_total(); guard_trips = mpc.body_guard_trips()
 
     t = torch.tensor([total_ms, solves_timed], dtype=torch.float64, device=dev)
+    ms_by_rank = [total_ms / K]
     if dist:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        ms_by_rank = [float(x[0].item()) / K for x in allt]
+        # clocks of every rank's GPU: lowest median SM clock, union of the throttle reasons
+        names = sorted(ClockSampler.REASONS.values())
+        c = torch.tensor([clk["sm_mhz"] or 0.0] + [1.0 if nm in clk["reasons"] else 0.0 for nm in names], dtype=torch.float64, device=dev)
+        cmin = c.clone(); dist.all_reduce(cmin, op=dist.ReduceOp.MIN)
+        cmax = c.clone(); dist.all_reduce(cmax, op=dist.ReduceOp.MAX)
+        clk = dict(clk, sm_mhz=float(cmin[0].item()), reasons=[nm for i, nm in enumerate(names) if cmax[1 + i].item() > 0],
+                   scope="all ranks: lowest median SM clock, union of reasons")
         total_ms_max, solves_all = float(tmax[0].item()), float(tsum[1].item())
     else:
         total_ms_max, solves_all = total_ms, solves_timed
@@ -630,7 +651,7 @@ def run_b200(a):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": p["scaling"], "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(a, world),
             "solves_per_step_per_gpu": solves_per_step, "robot_ticks_per_s": world * B * K / (total_ms_max * 1e-3),
-            "timed_region": ("one CUDA-graph launch of the K-step schedule (captured before the timed region)" if not a.no_graph
+            "timed_region": ("one CUDA-graph launch of the K-step schedule (captured, uploaded and launched once untimed before the W warm-up steps)" if not a.no_graph
                              else "host enqueue of the K steps") + f", steps dealt over {L} streams, {nrot} distinct input batches",
             "host_ms_in_timed_region": 1e3 * t_host,
             "latency_ms": {"p50": float(np.percentile(lat_ms, 50)), "p99": float(np.percentile(lat_ms, 99)),
@@ -666,7 +687,7 @@ def run_b200(a):
                        "body_mean_drop": float(mean_iters[2]), "body_mean_degen": float(mean_iters[3]),
                        "body_mean_l2a": float(mean_l2a), "sqp_solves_per_robot": float(np.mean(sqp_solves)) / B,
                        "sqp_converged_frac": float((sqp_status == 0).mean()), "sqp_infeasible_frac": float((sqp_status == 2).mean())},
-            "clocks": clk, "gpu_launches": int(launches), "e2e": e2e,
+            "clocks": clk, "ms_per_step_by_rank": ms_by_rank, "host_numa": numa_note, "gpu_launches": int(launches), "e2e": e2e,
         }
         if world == 1 and not a.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(a)

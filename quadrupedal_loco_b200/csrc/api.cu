@@ -1633,6 +1633,7 @@ int go1mpc_graph_capture_end(go1mpc_t* h, void* stream, void** graph_exec_out) {
   cudaError_t e = cudaGraphInstantiate(&ge, g, 0);
   cudaGraphDestroy(g);
   if (e != cudaSuccess) return cuda_fail(h, e, "cudaGraphInstantiate");
+  cudaGraphUpload(ge, stream ? (cudaStream_t)stream : h->stream);      // so that the first launch does not pay for it
   *graph_exec_out = (void*)ge;
   return GO1MPC_OK;
 }

@@ -80,3 +80,31 @@ class ResultGather:
             lo, hi = shard_range(B_total, r, self.world)
             keep.append(self.all[r, :hi - lo])
         return torch.cat(keep, dim=0)
+
+
+def pin_to_gpu_numa_node(device_index):
+    """Bind the calling process (all its present and future threads) to the CPU cores of the NUMA node the GPU hangs off, so
+    that the pinned host buffers it allocates afterwards are first-touched in memory local to that GPU's PCIe root and its
+    feeder threads run beside them.  Eight ranks streaming records over eight links otherwise meet on one socket's memory
+    controllers.  Linux sysfs only (no libnuma); returns a description of what was done, or of why nothing was."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        addr = f"{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{addr}/numa_node").read().strip())
+        if node < 0:
+            return f"GPU {device_index} ({addr}): no NUMA affinity reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"GPU {device_index} ({addr}): NUMA node {node} has no CPU this process may use"
+        os.sched_setaffinity(0, allowed)
+        return f"GPU {device_index} ({addr}): bound to NUMA node {node}, {len(allowed)} CPUs"
+    except Exception as e:                      # containers without sysfs PCI entries, non-Linux hosts
+        return f"not bound ({type(e).__name__}: {e})"
