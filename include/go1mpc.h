@@ -519,6 +519,23 @@ int go1mpc_graph_launch(go1mpc_t *h, void *graph_exec, void *stream);
 int go1mpc_graph_destroy(go1mpc_t *h, void *graph_exec);
 
 /* ---------------------------------------------------------------------------
+ * Signal filters of go1_servo's 1 kHz loop for B robots x C channels.  Replaces butterworthLPF::filter
+ * (GO1/Filter/butterworthLPF.cpp:104-121; init :82-100 = go1mpc_lpf_coefficients) -- 28 objects on slots of the /MPC/Gait
+ * message, servo.cpp:579-610,898-931 -- and ButterworthFilter::ForceFilter (GO1/Filter/butterworth_filter.cpp:37-69).
+ * coef      host, [C][6]: b0 b1 b2 a1 a2 a per channel (C <= 32 per call)
+ * in_d      [rows][B] SoA; channel c filters row in_rows_d[c] (device ints) or row c when in_rows_d is NULL -- so the channels
+ *           can be picked straight out of a [100][B] message buffer
+ * state_d   [5][C][B] SoA, in/out: call counter, y_p, y_pp, x_p, x_pp of every filter object; zero-initialise
+ *           (force filter: [6][C][B]: count, raw[2], filtered[3])
+ * out_d     [C][B]
+ * Bit-identical to the reference classes (tests/test_filters.py).
+ * ------------------------------------------------------------------------ */
+int go1mpc_lpf_coefficients(double fsampling, double fcutoff, double *coef6);
+int go1mpc_lpf_batch(go1mpc_t *h, int B, int C, const double *coef, const double *in_d, const int *in_rows_d, double *state_d,
+                     double *out_d, void *stream);
+int go1mpc_force_filter_batch(go1mpc_t *h, int B, int C, const double *in_d, double *state_d, double *out_d, void *stream);
+
+/* ---------------------------------------------------------------------------
  * The 40 Hz planner node of mosek_nlp_kmp for B robots: one call of NLPRTControlClass::WalkingReactStepping per robot,
  * /MPC/Gait message out.  Replaces NLP/NLPRTControl/NLPRTControlClass.cpp:191-396 (squat / walk / over / idle branches and the
  * 100-slot message layout :288-392), StartWalking / StopWalking :400-432, rt_nlp_gait :436-596 with everything it calls:

@@ -302,6 +302,15 @@ void orc_grf_joint_torques(const double Jaco[9], int swing, const double p_des[3
                            const double grav[3], double swing_kp, double swing_kd, double tau[3]);
 
 /* ------------------------------------------------------------------------
+ * Signal filters of go1_servo (filters.c): butterworthLPF (GO1/src/Filter/butterworthLPF.cpp:82-121) and
+ * ButterworthFilter::ForceFilter (butterworth_filter.cpp:37-69).  States are plain double arrays (layouts in filters.c).
+ * --------------------------------------------------------------------- */
+typedef struct { double b0, b1, b2, a1, a2, a; } orc_lpf_coef;
+void orc_lpf_init(double fsampling, double fcutoff, orc_lpf_coef *c);
+double orc_lpf_filter(const orc_lpf_coef *c, double state[5], double y);
+double orc_force_filter(double state[6], double input);
+
+/* ------------------------------------------------------------------------
  * Go1 leg kinematics (Kinematicclass, GO1/src/kinematics/Kinematics.cpp:29-304).
  * leg: 0 FR, 1 FL, 2 RR, 3 RL.  J is row-major 3x3 (the reference's Jacobian_kin
  * side channel after the call).  The IK functions return the number of Newton

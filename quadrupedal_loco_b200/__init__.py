@@ -9,7 +9,7 @@ from .binding import (  # noqa: F401
     Go1Mpc, Go1MpcError, load_library, library_path, body_in_stride, body_out_stride,
     body_diag_stride, pack_body_inputs, EXPORTED_SYMBOLS, QP_ITERS, BODY_DIAG_ACTIVE,
     STEP_STATE, STEP_IN, STEP_OUT, STEP_DIAG, BODY_TICK_OUT, body_tick_in_stride, split_body_record,
-    ControlTick, COMPACT_DOUBLES,
+    ControlTick, COMPACT_DOUBLES, lpf_coefficients,
 )
 from ._build import build  # noqa: F401
 
@@ -17,5 +17,5 @@ __all__ = [
     "Go1Mpc", "Go1MpcError", "load_library", "library_path", "build", "body_in_stride",
     "body_out_stride", "body_diag_stride", "pack_body_inputs", "EXPORTED_SYMBOLS", "QP_ITERS",
     "BODY_DIAG_ACTIVE", "STEP_STATE", "STEP_IN", "STEP_OUT", "STEP_DIAG", "BODY_TICK_OUT", "body_tick_in_stride",
-    "split_body_record", "ControlTick", "COMPACT_DOUBLES",
+    "split_body_record", "ControlTick", "COMPACT_DOUBLES", "lpf_coefficients",
 ]

@@ -1043,6 +1043,51 @@ int go1mpc_ref_interp_batch(go1mpc_t* h, int B, int nh, const int* walktime_d, d
   return GO1MPC_OK;
 }
 
+// ------------------------------------------------------------------ signal filters of the servo loop
+// coefficients of butterworthLPF::init (GO1/src/Filter/butterworthLPF.cpp:82-100), host libm; CPU-callable
+int go1mpc_lpf_coefficients(double fsampling, double fcutoff, double* coef6) {
+  if (!coef6 || !(fsampling > 0)) return GO1MPC_E_INVALID;
+  const double ff = fcutoff / fsampling;
+  const double ita = 1.0 / tan(3.14159265359 * ff);
+  const double q = sqrt(2.0);
+  const double qi = q * ita, ii = ita * ita;
+  const double b0 = 1.0 / (1.0 + qi + ii);
+  coef6[0] = b0; coef6[1] = 2 * b0; coef6[2] = b0;
+  const double t1 = 2.0 * (ii - 1.0);
+  coef6[3] = t1 * b0;
+  const double t2 = -(1.0 - qi + ii);
+  coef6[4] = t2 * b0;
+  const double w = 2.0 * 3.14159265359 * ff;
+  coef6[5] = w / (w + 1.0);
+  return GO1MPC_OK;
+}
+int go1mpc_lpf_batch(go1mpc_t* h, int B, int C, const double* coef, const double* in_d, const int* in_rows_d, double* state_d,
+                     double* out_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  if (B < 0 || C < 0 || !coef || !in_d || !state_d || !out_d) return fail(h, GO1MPC_E_INVALID, "lpf_batch: bad argument");
+  if (C > LPF_MAX_CHANNELS) return fail(h, GO1MPC_E_UNSUPPORTED, "lpf_batch: at most 32 channels per call");
+  if (B == 0 || C == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  LpfKParams P;
+  P.B = B; P.C = C;
+  for (int c = 0; c < C; c++) { const double* k = coef + 6 * c; P.coef[c] = LpfCoef{k[0], k[1], k[2], k[3], k[4], k[5]}; }
+  P.in = in_d; P.in_rows = in_rows_d; P.state = state_d; P.out = out_d;
+  CU(h, lpf_launch(P, h->sms, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+int go1mpc_force_filter_batch(go1mpc_t* h, int B, int C, const double* in_d, double* state_d, double* out_d, void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  if (B < 0 || C < 0 || !in_d || !state_d || !out_d) return fail(h, GO1MPC_E_INVALID, "force_filter_batch: bad argument");
+  if (B == 0 || C == 0) return GO1MPC_OK;
+  CU(h, cudaSetDevice(h->device));
+  CU(h, force_filter_launch(B, C, in_d, state_d, out_d, h->sms, stream ? (cudaStream_t)stream : h->stream));
+  h->launches++;
+  return GO1MPC_OK;
+}
+
 // ------------------------------------------------------------------ the 40 Hz planner node (message out)
 namespace {
 // reference constants of NLPRTControlClass / NLPClass (NLPRTControlClass.h:16-18, NLPClass.h:35-38, NLPClass_sqp.cpp:262)

@@ -182,6 +182,20 @@ struct RefInterpParams {
 };
 cudaError_t ref_interp_launch(RefInterpParams P, cudaStream_t st);
 
+// ---- signal filters of the servo loop (filters.cu) ----
+constexpr int LPF_MAX_CHANNELS = 32;
+struct LpfCoef { double b0, b1, b2, a1, a2, a; };
+struct LpfKParams {
+  int B, C;
+  LpfCoef coef[LPF_MAX_CHANNELS];
+  const double* in;        // [rows][B]: channel c reads row in_rows[c] (or row c when in_rows is null)
+  const int* in_rows;      // device, [C] or null
+  double* state;           // [5][C][B]
+  double* out;             // [C][B]
+};
+cudaError_t lpf_launch(LpfKParams P, int sms, cudaStream_t st);
+cudaError_t force_filter_launch(int B, int C, const double* in, double* state, double* out, int sms, cudaStream_t st);
+
 // ---- the 40 Hz planner node (nlp_chain.cu): NLPRTControlClass around NLPClass; node state SoA [NLP_NODE_DOUBLES][B] ----
 constexpr int NLP_NODE_DOUBLES = 480;
 constexpr int NLP_NTD_MAX = 12;

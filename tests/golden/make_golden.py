@@ -324,6 +324,33 @@ def gen_grf_tau(dl):
     print("grf_tau_ref.npz", N)
 
 
+def filter_inputs(seed=41, T=400, C=6):
+    rng = np.random.Generator(np.random.Philox(seed))
+    t = np.arange(T)[:, None]
+    return np.sin(0.013 * t * (1 + np.arange(C))) + 0.2 * rng.standard_normal((T, C)) + np.arange(C)
+
+
+def gen_filters(rf):
+    """butterworthLPF (the servo's (fs, fc) pairs: 1 kHz with 3 / 10 / 20 Hz cut-offs) and ButterworthFilter::ForceFilter of the
+    UNMODIFIED classes on seeded noisy signals."""
+    rf.ref_lpf_new.restype = ctypes.c_void_p; rf.ref_lpf_new.argtypes = [ctypes.c_double] * 2
+    rf.ref_lpf_filter.restype = ctypes.c_double; rf.ref_lpf_filter.argtypes = [ctypes.c_void_p, ctypes.c_double]
+    rf.ref_lpf_coefs.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    rf.ref_force_filter_new.restype = ctypes.c_void_p
+    rf.ref_force_filter.restype = ctypes.c_double; rf.ref_force_filter.argtypes = [ctypes.c_void_p, ctypes.c_double]
+    x = filter_inputs()
+    T, C = x.shape
+    fsfc = np.array([(1000.0, 3.0), (1000.0, 10.0), (1000.0, 20.0), (400.0, 5.0), (1000.0, 3.0), (200.0, 30.0)])
+    y = np.zeros((T, C)); coefs = np.zeros((C, 7)); yf = np.zeros((T, C))
+    for c in range(C):
+        h = ctypes.c_void_p(rf.ref_lpf_new(*fsfc[c])); rf.ref_lpf_coefs(h, P(coefs[c]))
+        g = ctypes.c_void_p(rf.ref_force_filter_new())
+        for t in range(T):
+            y[t, c] = rf.ref_lpf_filter(h, float(x[t, c])); yf[t, c] = rf.ref_force_filter(g, float(50 * x[t, c]))
+    np.savez_compressed(os.path.join(HERE, "filter_ref.npz"), x=x, fsfc=fsfc, coefs=coefs, lpf=y, force=yf)
+    print("filter_ref.npz", T, C)
+
+
 def nlp_node_scripts():
     """Scripted sequences for the 40 Hz node: (name, ticks, {tick: 'stop' | 'start'}, ticks with start_mpc = 0, foot-feedback seed)."""
     return [("walk_fb", 739, {}, (), 21),                     # cfg1 with noisy foot-location feedback, runs past the end
@@ -387,6 +414,8 @@ if __name__ == "__main__":
         gen_rt_foot(rtl)
     if not only or "rt_node" in only:
         gen_rt_node(rtl, ctypes.CDLL(nlp), ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so")))
+    if not only or "filters" in only:
+        gen_filters(ctypes.CDLL(ref_path("libref_filter.so")))
     if not only or "nlp_node" in only:
         gen_nlp_node(ctypes.CDLL(nlp))
     if not only or "grf_tau" in only:
