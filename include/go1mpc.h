@@ -131,6 +131,9 @@ int go1mpc_sm_count(const go1mpc_t *h);
 /* device-to-device copy on `stream` (NULL = the handle's): all per-instance state of this library
  * is plain SoA / record memory, so checkpointing or restoring a batch is a memcpy */
 int go1mpc_copy_device_async(go1mpc_t *h, void *dst_d, const void *src_d, size_t bytes, void *stream);
+/* The *_host_async entries order calls that share a device-resident buffer (planner state, body records) through a per-buffer
+ * event; call this before freeing such a buffer (waits for its last user, drops the bookkeeping). */
+int go1mpc_forget_buffer(go1mpc_t *h, const void *buf_d);
 /* wait for the handle's stream and for every pipelined *_host_async call */
 int go1mpc_synchronize(go1mpc_t *h);
 

@@ -1459,13 +1459,30 @@ int go1mpc_step_timing_step_batch_host_async(go1mpc_t* h, int n_sqp, int B, cons
   CU(h, cudaMemcpyAsync(di, in, ib, cudaMemcpyHostToDevice, L.stream));
   rc = go1mpc_step_timing_step_batch(h, n_sqp, B, (const int*)dt_, state_d, state_out_d, (const double*)di, (double*)do_, (int*)dd, L.stream);
   if (rc) return rc;
-  {
-    cudaEvent_t& ev = h->last_writer[(const void*)state_out_d];
+  // the buffer read and the buffer written: a later call on another lane that WRITES the state this call read must come after
+  // it too (write-after-read when state_out_d != state_d)
+  for (const void* key : {(const void*)state_out_d, (const void*)state_d}) {
+    cudaEvent_t& ev = h->last_writer[key];
     if (!ev) CU(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(h, cudaEventRecord(ev, L.stream));
+    if (state_out_d == state_d) break;
   }
   CU(h, cudaMemcpyAsync(out, do_, ob, cudaMemcpyDeviceToHost, L.stream));
   if (diag) CU(h, cudaMemcpyAsync(diag, dd, db, cudaMemcpyDeviceToHost, L.stream));
+  return GO1MPC_OK;
+}
+
+// The pipelined entries order calls that share a device-resident buffer through an event kept per buffer address; a caller that
+// frees such a buffer tells the handle, so that the entry does not outlive the allocation (and a new allocation at the same
+// address does not inherit it)
+int go1mpc_forget_buffer(go1mpc_t* h, const void* buf_d) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  auto it = h->last_writer.find(buf_d);
+  if (it != h->last_writer.end()) {
+    if (it->second) { cudaEventSynchronize(it->second); cudaEventDestroy(it->second); }
+    h->last_writer.erase(it);
+  }
   return GO1MPC_OK;
 }
 

@@ -328,9 +328,19 @@ __device__ __forceinline__ double q4sum(double v) {
 #ifndef GO1_TRI_WARPS
 #define GO1_TRI_WARPS 12
 #endif
+// A/B build knobs of the solve kernel: warps per CTA and, optionally, a register cap instead of the min-blocks bound
+// (GO1_TRI_WPC=2 GO1_TRI_MAXNREG=144: 7 CTAs of 2 warps = 14 warps per SM with 148 bytes of spills)
+#ifndef GO1_TRI_WPC
+#define GO1_TRI_WPC 4
+#endif
+#ifdef GO1_TRI_MAXNREG
+#define GO1_TRI_BOUNDS(WPC) __maxnreg__(GO1_TRI_MAXNREG)
+#else
+#define GO1_TRI_BOUNDS(WPC) __launch_bounds__(WPC * 32, GO1_TRI_WARPS / WPC)
+#endif
 
 template <int NH, int WPC>
-__global__ void __launch_bounds__(WPC * 32, GO1_TRI_WARPS / WPC) tri_solve_kernel(BodyKParams P) {
+__global__ void GO1_TRI_BOUNDS(WPC) tri_solve_kernel(BodyKParams P) {
   using D = TriDims<NH>;
   constexpr int RW = (NH + 3) / 4;          // rows of J per lane
   static_assert(RW >= 1 && RW <= 3 && NH % 2 == 0, "4 lanes per half, up to 3 rows of J per lane, rows moved 16 bytes at a time");
@@ -921,7 +931,7 @@ bool body_tri_supported(int nh) { return nh == 10 || nh == 4; }
 template <int NH>
 static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, int sms, cudaStream_t st) {
   using D = TriDims<NH>;
-  constexpr int WPC = 4;
+  constexpr int WPC = GO1_TRI_WPC;
   if (P.in_stride != D::IN || P.out_stride != D::OUT || P.tab_doubles != D::TAB) return cudaErrorInvalidValue;
   const int blocks = (P.B + TRI_SETUP_THREADS - 1) / TRI_SETUP_THREADS;
   const size_t ssmem = (size_t)TRI_SETUP_THREADS * D::IN * sizeof(double) + 16;
