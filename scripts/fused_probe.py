@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import quadrupedal_loco_b200 as q
 from tests.test_gpu_fused import make_inputs
 mpc = q.Go1Mpc(0); dev = torch.device("cuda", 0)
-for B, S in ((4096, 8), (65536, 2)):
+for B, S in ((4096, 8), (65536, 2), (131072, 2)):
     f64 = dict(dtype=torch.float64, device=dev); i32 = dict(dtype=torch.int32, device=dev)
     slots = []
     for s in range(S):
