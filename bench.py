@@ -49,6 +49,7 @@ PRESET_STEP_LAMDA = (0.25, 0.001, 0.025, 0.001)     # NLPClass_sqp.cpp:986-993 (
 # feasible (> 99 % at cfg2's amplitude, ~93 % at cfg3's 2x)
 PLANNER_MIX = dict(push_x=0.4, push_y=0.75, p_hi=16)
 PRESET_BODY_LAMDA = (0.2, 0.001, 0.2, 0.001)        # PRMPCClass.cpp:681-687 (commented preset)
+SENSOR_ROWS = 10       # e2e: planner input rows uploaded per tick (Go1ControlTick.step_in_rows)
 
 
 def parse():
@@ -497,6 +498,7 @@ def run_b200(a):
             t_.tx_d = R_tx[r].data_ptr(); t_.body_out_d = R_out[r].data_ptr()
             t_.compact_d = comp_d[ln].data_ptr()
             t_.compact = comp_h[ln].data_ptr() if not dist else None
+            t_.step_in_rows = SENSOR_ROWS       # the 10 sensor rows; external heights / terrain rows are zero in this workload
             ticks.append(t_)
         torch.cuda.synchronize()
 
@@ -607,11 +609,11 @@ def run_b200(a):
             te_ms, se_all = float(tm[0].item()), float(tsu[1].item())
         else:
             te_ms, se_all = float(te[0].item()), se
-        h2d = B * (tk_s * 8 + q.STEP_IN * 8 + 4)
+        h2d = B * (tk_s * 8 + SENSOR_ROWS * 8 + 4)
         d2h = (world * per if dist else B) * CD * 8
         e2e = {"value": se_all / (te_ms * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "bytes_def": "per rank H2D: tick (4 B) + 20 planner inputs + (9 + 9 nh) body-tick doubles per robot; D2H: 12-double result rows"
+               "bytes_def": "per rank H2D: tick (4 B) + the 10 planner sensor inputs (estimated CoM state, foot locations; flat ground) + (9 + 9 nh) body-tick doubles per robot; D2H: 12-double result rows"
                             + (" of ALL ranks, on rank 0 only (the other ranks ship theirs over NVLink)" if dist else ""),
                "gather_ms": gather_ms,
                "gather_def": ("NCCL gather of every rank's [%d][12] result rows into rank 0's device buffer + rank 0's D2H of the gathered "

@@ -476,7 +476,8 @@ int go1mpc_ref_interp_model(const Go1MpcConfig *cfg, double *inv16, int *t_end_f
  * planner tick (= go1mpc_step_timing_step_batch) and body-inclination MPC tick on the device-resident records
  * (= go1mpc_body_mpc_step_batch_resident_host_async) on ONE caller stream, then a 12-double result row per robot.
  * What the reference classes keep as members stays in HBM (planner state, _tx, _V_ini / stale results); what their
- * tick methods take as arguments moves up per call (tick, the 20 planner inputs, the 9+9nh body-tick doubles); what
+ * tick methods take as arguments moves up per call (tick, the 20 -- or 10, see step_in_rows -- planner inputs, the 9+9nh
+ * body-tick doubles); what
  * comes down is GO1MPC_COMPACT_DOUBLES per robot instead of Vec38 + Vec14 + diagnostics:
  *   [0,3) CoM x y z (Vec38 0..2)   [3,5) body roll, pitch   [5,7) body torques (Vec14 0..3)
  *   [7,9) next footstep x, y (Vec38 29, 31)   [9] step period (Vec38 35)
@@ -501,6 +502,10 @@ typedef struct {
   double *out38;                  /* host [38][B] or NULL */
   int *step_diag;                 /* host [60][B] or NULL */
   int *body_diag;                 /* host [B][go1mpc_body_diag_stride(nh)] or NULL */
+  int step_in_rows;               /* leading rows of step_in that are uploaded: 0 or 20 = all; 10 = the sensor rows only
+                                   * (estimated CoM state, foot locations; step_in is then host [10][B]).  Rows 10..19 -- the
+                                   * external CoM-height samples (read only with cfg.step.ext_height) and the terrain heights
+                                   * Zsc -- then read as zero: flat ground, the reference's own configuration */
 } Go1ControlTick;
 int go1mpc_control_tick_host_async(go1mpc_t *h, int B, const Go1ControlTick *t, void *stream);
 /* The pack kernel alone (device pointers; step_diag_d / body_diag_d may be NULL). */

@@ -243,7 +243,7 @@ class ControlTick(ctypes.Structure):
                 ("body_tick_in", ctypes.c_void_p), ("step_state_src_d", ctypes.c_void_p), ("step_state_d", ctypes.c_void_p),
                 ("tx_d", ctypes.c_void_p), ("body_out_d", ctypes.c_void_p), ("compact_d", ctypes.c_void_p),
                 ("compact", ctypes.c_void_p), ("out38", ctypes.c_void_p), ("step_diag", ctypes.c_void_p),
-                ("body_diag", ctypes.c_void_p)]
+                ("body_diag", ctypes.c_void_p), ("step_in_rows", ctypes.c_int)]
 
 
 def _ptr(a):

@@ -63,7 +63,7 @@ struct go1mpc {
   std::map<cudaStream_t, StreamCtl> ctl;
   // staging of go1mpc_control_tick_host_async, one set per caller stream (grown on demand): tick | step_in | body tick
   // records | expanded body records | out38 | planner diag | body diag
-  struct TickWs { DevBuf b[7]; };
+  struct TickWs { DevBuf b[7]; int zero_B = -1; };   // zero_B: batch size for which rows 10..19 of the planner inputs are known zero
   std::map<cudaStream_t, TickWs> tick_ws;
   cudaStream_t side = nullptr;     // side stream of the planner tick's out-of-place state copy
   double* squat_d = nullptr;       // X_CoM_position_squat table of the planner node (host libm), built on first use
@@ -1645,12 +1645,26 @@ int go1mpc_control_tick_host_async(go1mpc_t* h, int B, const Go1ControlTick* t, 
                            b * STEP_OUT_DOUBLES * sizeof(double), b * STEP_DIAG_INTS * sizeof(int), b * ds * sizeof(int)};
   void* d[7];
   int rc;
+  const int in_rows = (t->step_in_rows > 0 && t->step_in_rows < STEP_IN_DOUBLES) ? t->step_in_rows : STEP_IN_DOUBLES;
+  if (in_rows < STEP_IN_DOUBLES && (in_rows < 10 || h->cfg.step.ext_height))
+    return fail(h, GO1MPC_E_INVALID, "control_tick_host_async: step_in_rows must cover the 10 sensor rows, and all 20 with cfg.step.ext_height");
   for (int k = 0; k < 7; k++) {
-    if (bytes[k] > W.b[k].cap) CU(h, cudaStreamSynchronize(st));     // growing: earlier work on this stream may still use the old buffer
+    const bool grow = bytes[k] > W.b[k].cap;
+    if (grow) CU(h, cudaStreamSynchronize(st));     // growing: earlier work on this stream may still use the old buffer
     if ((rc = stage_buf2(h, W.b[k], bytes[k], &d[k]))) return rc;
+    if (grow && k == 1) W.zero_B = -1;
+  }
+  if (in_rows < STEP_IN_DOUBLES) {
+    // rows a partial upload does not carry read as zero (flat ground, no external heights): cleared once per batch size
+    if (W.zero_B != B) {
+      CU(h, cudaMemsetAsync((double*)d[1] + b * in_rows, 0, b * (STEP_IN_DOUBLES - in_rows) * sizeof(double), st));
+      W.zero_B = B;
+    }
+  } else {
+    W.zero_B = -1;
   }
   CU(h, cudaMemcpyAsync(d[0], t->tick, bytes[0], cudaMemcpyHostToDevice, st));
-  CU(h, cudaMemcpyAsync(d[1], t->step_in, bytes[1], cudaMemcpyHostToDevice, st));
+  CU(h, cudaMemcpyAsync(d[1], t->step_in, b * in_rows * sizeof(double), cudaMemcpyHostToDevice, st));
   CU(h, cudaMemcpyAsync(d[2], t->body_tick_in, bytes[2], cudaMemcpyHostToDevice, st));
   // planner tick: out of place from the pristine state when the caller gives one (replays of the same tick), else in place
   const double* src = t->step_state_src_d ? t->step_state_src_d : t->step_state_d;
