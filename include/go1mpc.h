@@ -596,6 +596,13 @@ int go1mpc_rt_node_default_state(go1mpc_t *h, int nh, double *state);
 int go1mpc_rt_node_tick_batch(go1mpc_t *h, int nh, int B, double *state_d, const double *msg_d, const int *ctrl_d,
                               const double *bodyangle_state_d, double *body_in_d, double *body_out_d, int *body_diag_d,
                               double *out100_d, int *active_d, void *stream);
+/* The same tick with the node's other two topics in their wire format (gait_fast.cpp:92-110, 519-527): ctl_msg_d [25][B] is
+ * /control2rtmpc/state -- slot 0 the control flag control_gait(0), slots 10, 11, 13, 14 the measured body angles / rates the
+ * MPC is fed (bodyangle_state) --, rt2nrt_msg_d [25][B] (or NULL) receives /rt2nrt/state: slot 0 = t_int, slots 1..24 = the
+ * control message's. */
+int go1mpc_rt_node_tick_msgs_batch(go1mpc_t *h, int nh, int B, double *state_d, const double *gait_msg_d, const double *ctl_msg_d,
+                                   double *body_in_d, double *body_out_d, int *body_diag_d, double *traj_msg_d,
+                                   double *rt2nrt_msg_d, void *stream);
 /* host buffers (synchronous); body_out [B][go1mpc_body_out_stride(nh)] is the body MPC's state, in/out */
 int go1mpc_rt_node_tick_batch_host(go1mpc_t *h, int nh, int B, double *state, const double *msg, const int *ctrl,
                                    const double *bodyangle_state, double *body_out, double *out100);

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_grf_force_opt_batch", "go1mpc_grf_force_distribution_batch", "go1mpc_grf_joint_torques_batch", "go1mpc_ref_interp_batch", "go1mpc_ref_interp_model",
     "go1mpc_control_tick_host_async", "go1mpc_pack_compact_batch", "go1mpc_stream_wait", "go1mpc_graph_capture_begin",
     "go1mpc_graph_capture_end", "go1mpc_graph_launch", "go1mpc_graph_destroy",
-    "go1mpc_rt_node_state_doubles", "go1mpc_rt_node_default_state", "go1mpc_rt_node_tick_batch",
+    "go1mpc_rt_node_state_doubles", "go1mpc_rt_node_default_state", "go1mpc_rt_node_tick_batch", "go1mpc_rt_node_tick_msgs_batch",
     "go1mpc_forget_buffer", "go1mpc_lpf_coefficients", "go1mpc_lpf_batch", "go1mpc_force_filter_batch",
     "go1mpc_nlp_node_state_doubles", "go1mpc_nlp_node_default_state", "go1mpc_nlp_walkdtime_max", "go1mpc_nlp_t_end_footstep",
     "go1mpc_nlp_node_tick_batch", "go1mpc_foot_trajectory_stop_batch", "go1mpc_nlp_node_tick_batch_host", "go1mpc_rt_node_tick_batch_host", "go1mpc_foot_trajectory_stop_batch_host",
@@ -138,6 +138,7 @@ def load_library():
     lib.go1mpc_rt_node_state_doubles.argtypes = [ctypes.c_int]
     lib.go1mpc_rt_node_default_state.argtypes = [vp, ctypes.c_int, vp]
     lib.go1mpc_rt_node_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 10
+    lib.go1mpc_rt_node_tick_msgs_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 9
     lib.go1mpc_forget_buffer.argtypes = [vp, vp]
     lib.go1mpc_lpf_coefficients.argtypes = [ctypes.c_double, ctypes.c_double, vp]
     lib.go1mpc_lpf_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 6
@@ -521,6 +522,12 @@ class Go1Mpc:
     def nlp_node_tick(self, B, state_d, walkdtime_d, msg_d, start_d=None, cmd_d=None, rfoot_fb_d=None, lfoot_fb_d=None, stream=None):
         self._check(self.lib.go1mpc_nlp_node_tick_batch(self.h, B, _ptr(state_d), _ptr(walkdtime_d), _ptr(start_d), _ptr(cmd_d),
                                                         _ptr(rfoot_fb_d), _ptr(lfoot_fb_d), _ptr(msg_d), stream), "nlp_node_tick_batch")
+
+    def rt_node_tick_msgs(self, nh, B, state_d, gait_msg_d, ctl_msg_d, body_in_d, body_out_d, traj_msg_d, rt2nrt_msg_d=None,
+                          body_diag_d=None, stream=None):
+        self._check(self.lib.go1mpc_rt_node_tick_msgs_batch(self.h, nh, B, _ptr(state_d), _ptr(gait_msg_d), _ptr(ctl_msg_d), _ptr(body_in_d),
+                                                            _ptr(body_out_d), _ptr(body_diag_d), _ptr(traj_msg_d), _ptr(rt2nrt_msg_d),
+                                                            stream), "rt_node_tick_msgs_batch")
 
     def measure_dfma_peak(self, ms=200):
         g = ctypes.c_double(0.0)

@@ -1290,9 +1290,29 @@ int go1mpc_rt_node_default_state(go1mpc_t* h, int nh, double* s) {
   for (int k = 0; k < W; k++) { fs[138 + 1 * W + k] = -sw[0]; fs[138 + 4 * W + k] = sw[0]; }
   return GO1MPC_OK;
 }
+namespace {
+int rt_node_enqueue(go1mpc_t* h, int nh, int B, double* state_d, const double* msg_d, const int* ctrl_d, const double* bodyangle_state_d,
+                    const double* ctl_msg_d, double* body_in_d, double* body_out_d, int* body_diag_d, double* out100_d,
+                    double* rt2nrt_d, int* active_d, void* stream);
+}
 int go1mpc_rt_node_tick_batch(go1mpc_t* h, int nh, int B, double* state_d, const double* msg_d, const int* ctrl_d,
                               const double* bodyangle_state_d, double* body_in_d, double* body_out_d, int* body_diag_d,
                               double* out100_d, int* active_d, void* stream) {
+  return rt_node_enqueue(h, nh, B, state_d, msg_d, ctrl_d, bodyangle_state_d, nullptr, body_in_d, body_out_d, body_diag_d, out100_d,
+                         nullptr, active_d, stream);
+}
+int go1mpc_rt_node_tick_msgs_batch(go1mpc_t* h, int nh, int B, double* state_d, const double* gait_msg_d, const double* ctl_msg_d,
+                                   double* body_in_d, double* body_out_d, int* body_diag_d, double* traj_msg_d, double* rt2nrt_msg_d,
+                                   void* stream) {
+  if (!h) return GO1MPC_E_INVALID;
+  if (!ctl_msg_d) return fail(h, GO1MPC_E_INVALID, "rt_node_tick_msgs_batch: bad argument");
+  return rt_node_enqueue(h, nh, B, state_d, gait_msg_d, nullptr, nullptr, ctl_msg_d, body_in_d, body_out_d, body_diag_d, traj_msg_d,
+                         rt2nrt_msg_d, nullptr, stream);
+}
+namespace {
+int rt_node_enqueue(go1mpc_t* h, int nh, int B, double* state_d, const double* msg_d, const int* ctrl_d, const double* bodyangle_state_d,
+                    const double* ctl_msg_d, double* body_in_d, double* body_out_d, int* body_diag_d, double* out100_d,
+                    double* rt2nrt_d, int* active_d, void* stream) {
   if (!h) return GO1MPC_E_INVALID;
   std::lock_guard<std::recursive_mutex> lk_(h->mu);
   if (B < 0 || !state_d || !msg_d || !body_in_d || !body_out_d || !out100_d) return fail(h, GO1MPC_E_INVALID, "rt_node_tick_batch: bad argument");
@@ -1308,6 +1328,7 @@ int go1mpc_rt_node_tick_batch(go1mpc_t* h, int nh, int B, double* state_d, const
   build_aaa_inv_mod(c.dt_slow, P.inv);
   P.state = state_d; P.msg = msg_d; P.ctrl = ctrl_d; P.bodyangle_state = bodyangle_state_d;
   P.body_in = body_in_d; P.body_out = body_out_d; P.out = out100_d; P.active = active_d;
+  P.ctl_msg = ctl_msg_d; P.rt2nrt = rt2nrt_d;
   CU(h, rt_pre_launch(P, st));
   h->launches++;
   int rc = go1mpc_body_mpc_step_batch(h, nh, B, body_in_d, body_out_d, body_diag_d, st);
@@ -1316,6 +1337,7 @@ int go1mpc_rt_node_tick_batch(go1mpc_t* h, int nh, int B, double* state_d, const
   h->launches++;
   return GO1MPC_OK;
 }
+}  // namespace
 
 // host form of the 100 Hz node: state / msg / body_out (the body MPC's state) are host SoA / record buffers
 int go1mpc_rt_node_tick_batch_host(go1mpc_t* h, int nh, int B, double* state, const double* msg, const int* ctrl,

@@ -236,6 +236,10 @@ struct RtKParams {
   double* body_out;               // [B][out_stride] the body MPC's output records = its state
   double* out;                    // [100][B] /rtMPC/traj
   int* active;                    // [B] or null: 1 where the fast tick ran (message slot 99 > 0)
+  // wire format of the node's other two topics (gait_fast.cpp:92-110, 519-527), optional: when ctl_msg is given it supplies the
+  // control flag (slot 0) and the measured body angles (slots 10, 11, 13, 14) instead of ctrl / bodyangle_state
+  const double* ctl_msg;          // [25][B] /control2rtmpc/state or null
+  double* rt2nrt;                 // [25][B] /rt2nrt/state or null: slot 0 = t_int, slots 1..24 = the control message's
 };
 cudaError_t rt_pre_launch(RtKParams P, cudaStream_t st);
 cudaError_t rt_post_launch(RtKParams P, cudaStream_t st);

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(128) rt_pre_kernel(RtKParams P) {
   const double dt_fast = P.dt_mpc, dt_slow = P.dt_slow;
   const int n_t_int = (int)floor(dt_slow / dt_fast);
   const double flag = MSG(99);
-  const bool ctrl = P.ctrl ? (P.ctrl[b] > 0) : true;
+  const bool ctrl = P.ctl_msg ? (P.ctl_msg[b] > 0) : (P.ctrl ? (P.ctrl[b] > 0) : true);
   bool active = false;
   double* rec = P.body_in + (size_t)b * P.in_stride;
   const double* bout = P.body_out + (size_t)b * P.out_stride;
@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(128) rt_pre_kernel(RtKParams P) {
   // ---- body-MPC input record (:568-620); an inactive robot gets a gated tick (0): its body state stays as it is ----
   for (int k = 0; k < NS; k++) rec[k] = tx[k];
   rec[27] = active ? N_(N_MPC) : 0.0;
-  for (int k = 0; k < 4; k++) { rec[28 + k] = bout[14 + k]; rec[32 + k] = P.bodyangle_state ? P.bodyangle_state[(size_t)k * B + b] : 0.0; }
+  for (int k = 0; k < 4; k++) { rec[28 + k] = bout[14 + k]; rec[32 + k] = P.ctl_msg ? P.ctl_msg[(size_t)(k < 2 ? 10 + k : 11 + k) * B + b]       // state_feedback(10, 11, 13, 14), :105-108
+                             : (P.bodyangle_state ? P.bodyangle_state[(size_t)k * B + b] : 0.0); }
   for (int k = 0; k < 2 * nh; k++) rec[36 + k] = bout[18 + k];
   double* rows = rec + 36 + 2 * nh;
   if (active) {
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(128) rt_post_kernel(RtKParams P) {
   double* O = P.out + b;
 #define N_(f) st[(size_t)(f) * B]
   const int o_foot = N_INTER + 4 * NI, o_rot = o_foot + 6 * (nh + 1), o_thx = o_rot + 6 * nh, o_bm = o_thx + 3;
-  const bool ctrl = P.ctrl ? (P.ctrl[b] > 0) : true;
+  const bool ctrl = P.ctl_msg ? (P.ctl_msg[b] > 0) : (P.ctrl ? (P.ctrl[b] > 0) : true);
   const bool active = ctrl && M[(size_t)99 * B] > 0;
   if (active) {
     const double* bout = P.body_out + (size_t)b * P.out_stride;
@@ -352,6 +353,12 @@ __global__ void __launch_bounds__(128) rt_post_kernel(RtKParams P) {
     O[(size_t)98 * B] = (double)(int)txv / 0.001;
   }
   O[(size_t)99 * B] = N_(N_LOOP);
+  if (P.rt2nrt) {
+    // /rt2nrt/state (:519-527): state_feedback = the control message with slot 0 replaced by t_int
+    double* R = P.rt2nrt + b;
+    R[0] = N_(N_TINT);
+    for (int k = 1; k < 25; k++) R[(size_t)k * B] = P.ctl_msg ? P.ctl_msg[(size_t)k * B + b] : 0.0;
+  }
 #undef N_
 }
 
