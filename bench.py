@@ -376,6 +376,12 @@ def run_b200(a):
     diag_all = diag_d.cpu().numpy()
     body_status = diag_all[:, :, 0]
     flops_per_batch = diag_all[:, :, 9].astype(np.float64).sum(axis=1)          # [nrot]
+    # the solve kernel's share: instances that entered the active-set loop (at least one add), their flops minus the
+    # factorisation / inverse / unconstrained minimiser (n^3/3 + n^3/3 + 2 n^2), which the setup kernel does
+    n_ = 2 * nh
+    setup_flops = float(n_ ** 3 // 3 + n_ ** 3 // 3 + 2 * n_ * n_)
+    entered = diag_all[:, :, 3] > 0
+    solve_flops_per_batch = ((diag_all[:, :, 9].astype(np.float64) - setup_flops) * entered).sum(axis=1)
     mean_iters = diag_all[:, :, 2:6].reshape(-1, 4).mean(axis=0)
     mean_l2a = diag_all[:, :, 8].mean()
     sdiag = sd_d.cpu().numpy()
@@ -449,6 +455,21 @@ def run_b200(a):
     lat_ms = timed(step, n_lat)
     body_ms = timed(launch_body, min(n_lat, 300))
     sqp_ms = timed(launch_sqp, min(n_lat, 300))
+    # per-kernel durations of the body tick's three launches (CUDA events recorded by the library around each launch of a lone
+    # call): the solve kernel is the dominant kernel of the step
+    phase_ms = None
+    try:
+        mpc.body_phase_timing(True)
+        acc = np.zeros(3); n_ph = min(n_lat, 100)
+        for i in range(n_ph):
+            launch_body(i)
+            acc += np.array(mpc.body_phase_ms())
+        mpc.body_phase_timing(False)
+        if acc[1] > 0:
+            phase_ms = acc / n_ph
+            solve_fl = float(np.mean(solve_flops_per_batch[np.arange(n_ph) % nrot]))
+    except Exception:
+        phase_ms = None
     clk = clocks.stop()
     handed_over = mpc.body_handover_total(); guard_trips = mpc.body_guard_trips()
 
@@ -633,8 +654,21 @@ def run_b200(a):
     if rank == 0:
         kern_ms = float(np.mean(body_ms))
         fl = float(np.mean(flops_per_batch[np.arange(len(body_ms)) % nrot]))
-        achieved_tf = fl / (kern_ms * 1e-3) / 1e12
+        call_tf = fl / (kern_ms * 1e-3) / 1e12
         peak_tf = dfma_gflops / 1e3
+        # dominant kernel = tri_solve_kernel when the three-launch path ran (phase events); else the whole call
+        if phase_ms is not None:
+            dom_name, dom_ms, dom_fl = f"tri_solve_kernel<{nh}, 4> (active-set iteration of the body-inclination MPC tick)", float(phase_ms[1]), solve_fl
+            dom_def = (f"mean duration of the solve kernel's launch inside a LONE body-tick call on {B} robots (CUDA events recorded by the library "
+                       f"around that launch on the launching stream, go1mpc_body_phase_timing; {min(n_lat, 100)} calls)")
+            dom_fdef = ("algorithmic flops of the dense reference algorithm's active-set loop (SURVEY.md 8d formula without its n^3/3 + n^3/3 + 2 n^2 "
+                        "set-up terms, n = 2 nh, m = 12 nh) of the instances that enter the loop, counted per problem on the device; the kernel "
+                        "exploits G = blockdiag(H, H) and executes fewer")
+        else:
+            dom_name, dom_ms, dom_fl = "body-inclination MPC tick (go1mpc_body_mpc_step_batch)", kern_ms, fl
+            dom_def = f"mean duration of a LONE call on {B} robots (CUDA events around exactly one call on the launching stream)"
+            dom_fdef = "algorithmic flops of the dense reference algorithm along each problem's path (SURVEY.md 8d formula), counted per problem on the device"
+        achieved_tf = dom_fl / (dom_ms * 1e-3) / 1e12
         io_bytes = B * ((in_s + out_s) * 8 + dg_s * 4)
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]; hbm_src = "measured (MEASURED_PEAKS.json)"
@@ -644,6 +678,10 @@ def run_b200(a):
             traffic = json.load(open(TRAFFIC_FILE)).get(f"{nh}:{B}")
         except Exception:
             traffic = None
+        traffic_call = None
+        if isinstance(traffic, dict):
+            traffic_call = traffic.get("body_tick_call")
+            traffic = traffic.get("tri_solve_kernel") if phase_ms is not None else traffic_call
         sqp_fl = float(np.mean(sqp_flops_per_batch))
         sqp_k_ms = float(np.mean(sqp_ms))
         step_flops = fl + sqp_fl
@@ -667,16 +705,19 @@ def run_b200(a):
                          "frac_step": step_flops / (ms_per_step * 1e-3) / 1e12 / peak_tf if peak_tf else None,
                          "frac_step_def": "algorithmic flops of BOTH ticks of one step / the timed ms_per_step / peak",
                          "traffic": traffic,
-                         "traffic_source": "profile constant: dram__bytes_read.sum + dram__bytes_write.sum of the body tick's kernels for one call, "
+                         "traffic_source": "profile constant: dram__bytes_read.sum + dram__bytes_write.sum of that kernel for one launch, "
                                            "ncu --set full, profiles/traffic.json (null: no capture at this batch size)",
-                         "kernel": "body-inclination MPC tick (go1mpc_body_mpc_step_batch)",
-                         "kernel_ms": kern_ms,
-                         "kernel_ms_def": f"mean duration of a LONE call on {B} robots (CUDA events around exactly one call on the launching "
-                                          f"stream, {len(body_ms)} calls, inputs rotating through > 2x L2)",
-                         "flops_per_launch": fl, "flops_per_solve": fl / B,
-                         "flops_def": "algorithmic flops of the dense reference algorithm along each problem's path "
-                                      "(SURVEY.md 8d formula, n = 2 nh, m = 12 nh, counted per problem on the device); the kernels exploit "
-                                      "G = blockdiag(H, H) and execute fewer",
+                         "kernel": dom_name,
+                         "kernel_ms": dom_ms,
+                         "kernel_ms_def": dom_def,
+                         "flops_per_launch": dom_fl, "flops_per_solve": dom_fl / B,
+                         "flops_def": dom_fdef,
+                         "body_tick_call": {"what": "the whole body-inclination MPC tick (go1mpc_body_mpc_step_batch: setup, solve, merge and the "
+                                                    "empty list-mode launch), LONE call, CUDA events around exactly one call",
+                                            "kernel_ms": kern_ms, "flops_per_launch": fl, "flops_per_solve": fl / B, "traffic": traffic_call,
+                                            "achieved": call_tf, "frac": call_tf / peak_tf if peak_tf else None,
+                                            "phases_ms": ({"tri_setup_kernel": float(phase_ms[0]), "tri_solve_kernel": float(phase_ms[1]),
+                                                           "tri_merge_kernel": float(phase_ms[2])} if phase_ms is not None else None)},
                          "peak_source": "measured live on this GPU: register-resident DFMA loop (go1mpc_measure_dfma_peak); "
                                         "MEASURED_PEAKS.json has no FP64 figure",
                          "hbm": {"achieved": io_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

@@ -607,6 +607,13 @@ int go1mpc_rt_node_tick_msgs_batch(go1mpc_t *h, int nh, int B, double *state_d, 
 int go1mpc_rt_node_tick_batch_host(go1mpc_t *h, int nh, int B, double *state, const double *msg, const int *ctrl,
                                    const double *bodyangle_state, double *body_out, double *out100);
 
+/* Per-kernel timing of the three-launch body tick (measurement aid for bench.py's roofline): while enabled, each
+ * go1mpc_body_mpc_step_batch call on that path records CUDA events around its setup / solve / merge launches;
+ * go1mpc_body_phase_ms waits for the last such call and returns the three durations in milliseconds.  Do not enable
+ * inside a graph capture. */
+int go1mpc_body_phase_timing(go1mpc_t *h, int enable);
+int go1mpc_body_phase_ms(go1mpc_t *h, float *ms3);
+
 /* Measured FP64 FMA throughput of the device (GFLOP/s, 2 flop per FMA) from a
  * register-resident DFMA loop: the roofline denominator bench.py reports
  * against.  Runs ~`ms` milliseconds. */

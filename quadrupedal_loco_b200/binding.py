@@ -27,7 +27,7 @@ EXPORTED_SYMBOLS = [
     "go1mpc_control_tick_host_async", "go1mpc_pack_compact_batch", "go1mpc_stream_wait", "go1mpc_graph_capture_begin",
     "go1mpc_graph_capture_end", "go1mpc_graph_launch", "go1mpc_graph_destroy",
     "go1mpc_rt_node_state_doubles", "go1mpc_rt_node_default_state", "go1mpc_rt_node_tick_batch", "go1mpc_rt_node_tick_msgs_batch",
-    "go1mpc_forget_buffer", "go1mpc_lpf_coefficients", "go1mpc_lpf_batch", "go1mpc_force_filter_batch",
+    "go1mpc_body_phase_timing", "go1mpc_body_phase_ms", "go1mpc_forget_buffer", "go1mpc_lpf_coefficients", "go1mpc_lpf_batch", "go1mpc_force_filter_batch",
     "go1mpc_nlp_node_state_doubles", "go1mpc_nlp_node_default_state", "go1mpc_nlp_walkdtime_max", "go1mpc_nlp_t_end_footstep",
     "go1mpc_nlp_node_tick_batch", "go1mpc_foot_trajectory_stop_batch", "go1mpc_nlp_node_tick_batch_host", "go1mpc_rt_node_tick_batch_host", "go1mpc_foot_trajectory_stop_batch_host",
     "go1mpc_grf_force_opt_batch_host", "go1mpc_grf_force_distribution_batch_host", "go1mpc_grf_joint_torques_batch_host", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
@@ -139,6 +139,8 @@ def load_library():
     lib.go1mpc_rt_node_default_state.argtypes = [vp, ctypes.c_int, vp]
     lib.go1mpc_rt_node_tick_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 10
     lib.go1mpc_rt_node_tick_msgs_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 9
+    lib.go1mpc_body_phase_timing.argtypes = [vp, ctypes.c_int]
+    lib.go1mpc_body_phase_ms.argtypes = [vp, vp]
     lib.go1mpc_forget_buffer.argtypes = [vp, vp]
     lib.go1mpc_lpf_coefficients.argtypes = [ctypes.c_double, ctypes.c_double, vp]
     lib.go1mpc_lpf_batch.argtypes = [vp, ctypes.c_int, ctypes.c_int] + [vp] * 6
@@ -495,6 +497,14 @@ class Go1Mpc:
         self._check(self.lib.go1mpc_rt_node_tick_batch(self.h, nh, B, _ptr(state_d), _ptr(msg_d), _ptr(ctrl_d), _ptr(bodyangle_state_d),
                                                        _ptr(body_in_d), _ptr(body_out_d), _ptr(body_diag_d), _ptr(out100_d),
                                                        _ptr(active_d), stream), "rt_node_tick_batch")
+
+    def body_phase_timing(self, enable):
+        self._check(self.lib.go1mpc_body_phase_timing(self.h, 1 if enable else 0), "body_phase_timing")
+
+    def body_phase_ms(self):
+        ms = (ctypes.c_float * 3)()
+        self._check(self.lib.go1mpc_body_phase_ms(self.h, ms), "body_phase_ms")
+        return [float(v) for v in ms]
 
     def forget_buffer(self, buf_d):
         self._check(self.lib.go1mpc_forget_buffer(self.h, _ptr(buf_d)), "forget_buffer")

@@ -66,6 +66,8 @@ struct go1mpc {
   struct TickWs { DevBuf b[7]; int zero_B = -1; };   // zero_B: batch size for which rows 10..19 of the planner inputs are known zero
   std::map<cudaStream_t, TickWs> tick_ws;
   cudaStream_t side = nullptr;     // side stream of the planner tick's out-of-place state copy
+  bool phase_timing = false;       // go1mpc_body_phase_timing: events around the three launches of the body tick
+  cudaEvent_t phase_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   double* squat_d = nullptr;       // X_CoM_position_squat table of the planner node (host libm), built on first use
   struct NlpWs { DevBuf b[7]; };   // workspace of go1mpc_nlp_node_tick_batch, one per caller stream
   std::map<cudaStream_t, NlpWs> nlp_ws;
@@ -326,6 +328,7 @@ void go1mpc_destroy(go1mpc_t* h) {
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   if (h->trtab_d) cudaFree(h->trtab_d);
   if (h->squat_d) cudaFree(h->squat_d);
+  for (cudaEvent_t e : h->phase_ev) if (e) cudaEventDestroy(e);
   for (auto& kv : h->nlp_ws) for (DevBuf& b : kv.second.b) if (b.p) cudaFree(b.p);
   for (auto& L : h->lanes) {
     for (DevBuf& b : L.stage) if (b.p) cudaFree(b.p);
@@ -481,7 +484,7 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
       P.tri_queue = (int*)(W.p + W.off[3]); P.tri_qctl = (int*)(W.p + W.qctl_off); P.tri_meta = (int*)(W.p + W.off[4]); P.tri_fr = (double*)(W.p + W.off[5]);
       int* fl = ctl + 2;
       P.flist_count = fl; P.flist = fl + 2; P.flist_cap = kFlistCap;
-      CU(h, body_tri_launch(P, M->tab_h.data(), h->sms, st));
+      CU(h, body_tri_launch(P, M->tab_h.data(), h->sms, st, h->phase_timing ? h->phase_ev : nullptr));
       CU(h, body_fast_launch(P, h->sms, st));   // list mode: what the merge kernel handed over (normally nothing)
       h->launches += 4;
       return GO1MPC_OK;
@@ -538,6 +541,26 @@ int go1mpc_body_mpc_step_batch(go1mpc_t* h, int nh, int B, const double* in_d, d
   }
   CU(h, body_mpc_launch(P, wpc, grid, smem, st));
   h->launches++;
+  return GO1MPC_OK;
+}
+
+// Per-kernel timing of the three-launch body tick (measurement aid): while enabled, every go1mpc_body_mpc_step_batch call that
+// takes the three-launch path records CUDA events around its setup / solve / merge launches; go1mpc_body_phase_ms waits for the
+// last call and returns the three durations.  Not for use inside a graph capture.
+int go1mpc_body_phase_timing(go1mpc_t* h, int enable) {
+  if (!h) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  CU(h, cudaSetDevice(h->device));
+  if (enable) for (cudaEvent_t& e : h->phase_ev) if (!e) CU(h, cudaEventCreate(&e));
+  h->phase_timing = enable != 0;
+  return GO1MPC_OK;
+}
+int go1mpc_body_phase_ms(go1mpc_t* h, float* ms3) {
+  if (!h || !ms3) return GO1MPC_E_INVALID;
+  std::lock_guard<std::recursive_mutex> lk_(h->mu);
+  if (!h->phase_ev[3]) return fail(h, GO1MPC_E_INVALID, "body_phase_ms: phase timing was never enabled");
+  CU(h, cudaEventSynchronize(h->phase_ev[3]));
+  for (int k = 0; k < 3; k++) CU(h, cudaEventElapsedTime(ms3 + k, h->phase_ev[k], h->phase_ev[k + 1]));
   return GO1MPC_OK;
 }
 

@@ -929,7 +929,7 @@ size_t body_tri_workspace_bytes(int nh, int B, size_t off[6]) {
 bool body_tri_supported(int nh) { return nh == 10 || nh == 4; }
 
 template <int NH>
-static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, int sms, cudaStream_t st) {
+static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, int sms, cudaStream_t st, cudaEvent_t* phase_ev) {
   using D = TriDims<NH>;
   constexpr int WPC = GO1_TRI_WPC;
   if (P.in_stride != D::IN || P.out_stride != D::OUT || P.tab_doubles != D::TAB) return cudaErrorInvalidValue;
@@ -965,7 +965,10 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
   }
   TriTab<NH> T;
   memcpy(T.v, tab_host, sizeof(T.v));
+  // phase_ev (optional, 4 events): recorded around the three launches, for bench.py's per-kernel roofline
+  if (phase_ev) cudaEventRecord(phase_ev[0], st);
   tri_setup_kernel<NH><<<blocks, TRI_SETUP_THREADS, ssmem, st>>>(P, T);
+  if (phase_ev) cudaEventRecord(phase_ev[1], st);
   int grid = (2 * P.B + WPC * 8 - 1) / (WPC * 8);
   {
     // A/B knob (GO1MPC_TRI_OCC = resident solve CTAs per SM the grid is sized for): smaller grids leave room for the solve
@@ -975,14 +978,16 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
   }
   if (grid > sms * occ) grid = sms * occ;
   tri_solve_kernel<NH, WPC><<<grid, WPC * 32, smem, st>>>(P);
+  if (phase_ev) cudaEventRecord(phase_ev[2], st);
   tri_merge_kernel<NH><<<(P.B + TRI_MERGE_THREADS - 1) / TRI_MERGE_THREADS, TRI_MERGE_THREADS, msmem, st>>>(P);
+  if (phase_ev) cudaEventRecord(phase_ev[3], st);
   return cudaGetLastError();
 }
 
-cudaError_t body_tri_launch(BodyKParams P, const double* tab_host, int sms, cudaStream_t st) {
+cudaError_t body_tri_launch(BodyKParams P, const double* tab_host, int sms, cudaStream_t st, cudaEvent_t* phase_ev) {
   switch (P.nh) {
-    case 4: return tri_launch_nh<4>(P, tab_host, sms, st);       // the reference's own horizon (PRMPCClass.h:34)
-    case 10: return tri_launch_nh<10>(P, tab_host, sms, st);
+    case 4: return tri_launch_nh<4>(P, tab_host, sms, st, phase_ev);       // the reference's own horizon (PRMPCClass.h:34)
+    case 10: return tri_launch_nh<10>(P, tab_host, sms, st, phase_ev);
     default: return cudaErrorInvalidValue;
   }
 }

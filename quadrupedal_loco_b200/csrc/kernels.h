@@ -42,7 +42,7 @@ cudaError_t body_fast_launch(BodyKParams P, int sms, cudaStream_t st);
 // three launches, register-resident solver state (body_tri.cu)
 bool body_tri_supported(int nh);
 size_t body_tri_workspace_bytes(int nh, int B, size_t off[6]);   // offsets: J | half state | half result | queue | meta | hand-over
-cudaError_t body_tri_launch(BodyKParams P, const double* tab_host, int sms, cudaStream_t st);
+cudaError_t body_tri_launch(BodyKParams P, const double* tab_host, int sms, cudaStream_t st, cudaEvent_t* phase_ev = nullptr);
 bool body_split_supported(int nh);
 cudaError_t body_split_launch(BodyKParams P, int sms, cudaStream_t st);
 
