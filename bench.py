@@ -66,6 +66,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="enqueue the timed steps from the host instead of one graph launch")
     ap.add_argument("--latency-samples", type=int, default=1000)
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="e2e, N > 1: how the result rows reach rank 0 -- NVLink peer-memory stores + flags (csrc/peer_gather.cu) or torch.distributed.gather")
+    ap.add_argument("--e2e-no-graph", action="store_true", help="e2e: enqueue every step's calls from the host instead of replaying one captured graph per batch slot")
+    ap.add_argument("--e2e-no-gather", action="store_true", help="DIAGNOSTIC: leave the gather to rank 0 out of the e2e leg (the number is then not the e2e metric)")
     return ap.parse_args()
 
 
@@ -505,8 +509,22 @@ def run_b200(a):
         R_out = torch.zeros(nrot, B, out_s, dtype=torch.float64, device=dev)
         R_out[:, :, 18:18 + 2 * nh] = torch.from_numpy(xw_np).to(dev).view(nrot, B, 2 * nh)
         ti_h = torch.from_numpy(tick_np).view(nrot, B, tk_s).pin_memory()
-        gathers = [sharding.ResultGather(per, CD, torch.float64, dev) if dist else None for _ in range(Le)]
+        # N > 1: the result rows of every rank go to rank 0 once per batch.  Default: each rank's tick stores its rows straight into
+        # rank 0's buffer over NVLink peer memory and raises a flag there (sharding.PeerGather); --gather nccl: torch.distributed.gather
+        pg, gathers, gather_kind = None, [None] * Le, None
+        if dist:
+            if a.gather == "peer":
+                try:
+                    pg = sharding.PeerGather(lib, local, per, CD, Le)
+                    gather_kind = "peer"
+                except Exception as ex:
+                    dbg(f"peer gather unavailable ({ex}); falling back to the NCCL gather")
+                    pg = None
+            if pg is None:
+                gathers = [sharding.ResultGather(per, CD, torch.float64, dev) for _ in range(Le)]
+                gather_kind = "nccl"
         comp_d = [g.local if g else torch.zeros(per, CD, dtype=torch.float64, device=dev) for g in gathers]
+        comp_ptr = [pg.dest(ln) if pg else comp_d[ln].data_ptr() for ln in range(Le)]
         host_rows = world * per if rank == 0 else 0
         comp_h = [torch.zeros(max(host_rows, 1), CD, dtype=torch.float64).pin_memory() for _ in range(Le)]
         ticks = []
@@ -517,20 +535,55 @@ def run_b200(a):
             t_.tick = tk_h[r].data_ptr(); t_.step_in = si_h[r].data_ptr(); t_.body_tick_in = ti_h[r].data_ptr()
             t_.step_state_src_d = P_st[r]; t_.step_state_d = P_sw[ln]
             t_.tx_d = R_tx[r].data_ptr(); t_.body_out_d = R_out[r].data_ptr()
-            t_.compact_d = comp_d[ln].data_ptr()
+            t_.compact_d = comp_ptr[ln]
             t_.compact = comp_h[ln].data_ptr() if not dist else None
             t_.step_in_rows = SENSOR_ROWS       # the 10 sensor rows; external heights / terrain rows are zero in this workload
             ticks.append(t_)
         torch.cuda.synchronize()
 
-        def e2e_step(i):
+        def e2e_enqueue(i):
             r, ln = i % nrot, i % Le
+            if pg and not a.e2e_no_gather:
+                pg.acquire(ln, lane_ptr[ln])                           # peers: device-side wait until rank 0 released the slot
             chk(lib.go1mpc_control_tick_host_async(hh, B, ctypes.byref(ticks[r + nrot * ln]), lane_ptr[ln]), "control_tick_host_async")
-            if dist:
-                with torch.cuda.stream(lanes[ln]):
-                    allrows = gathers[ln].gather()                     # NCCL, once per batch
+            if dist and not a.e2e_no_gather:
+                if pg:
+                    pg.publish(ln, lane_ptr[ln])                       # the tick's pack kernel wrote the rows into rank 0's block
                     if rank == 0:
-                        comp_h[ln].view(world, per, CD).copy_(allrows, non_blocking=True)
+                        pg.wait_all(ln, lane_ptr[ln])
+                        with torch.cuda.stream(lanes[ln]):
+                            comp_h[ln].view(world, per, CD).copy_(pg.block(ln), non_blocking=True)
+                        pg.release(ln, lane_ptr[ln])
+                else:
+                    with torch.cuda.stream(lanes[ln]):
+                        allrows = gathers[ln].gather()                     # NCCL, once per batch
+                        if rank == 0:
+                            comp_h[ln].view(world, per, CD).copy_(allrows, non_blocking=True)
+
+        # One CUDA graph per batch slot: the slot's whole call sequence (H2D copies from its pinned buffers, both ticks, the result
+        # rows to rank 0, rank 0's D2H) is captured ONCE through the ABI's capture helpers and replayed with one launch per step --
+        # the per-step host cost of ~15 CUDA calls is what bounds small per-GPU batches (0.14 ms per 4096-robot step on one GPU).
+        # Not with the NCCL gather (a collective enqueued by torch.distributed is not captured here).
+        e2e_graphs = None
+        if not a.e2e_no_graph and (pg is not None or not dist) and nrot % Le == 0:
+            e2e_enqueue(0); torch.cuda.synchronize()           # workspaces of every stream exist before anything is captured
+            for ln in range(Le):
+                e2e_enqueue(ln)
+            torch.cuda.synchronize()
+            e2e_graphs = []
+            for r in range(nrot):
+                ge = ctypes.c_void_p()
+                chk(lib.go1mpc_graph_capture_begin(hh, lane_ptr[r % Le]), "graph_capture_begin")
+                e2e_enqueue(r)
+                chk(lib.go1mpc_graph_capture_end(hh, lane_ptr[r % Le], ctypes.byref(ge)), "graph_capture_end")
+                e2e_graphs.append(ge)
+
+        def e2e_step(i):
+            if e2e_graphs is not None:
+                r = i % nrot
+                chk(lib.go1mpc_graph_launch(hh, e2e_graphs[r], lane_ptr[r % Le]), "graph_launch")
+            else:
+                e2e_enqueue(i)
 
         go = threading.Barrier(2)
         done = threading.Event()
@@ -581,26 +634,37 @@ def run_b200(a):
         ns = sdg[4]
         last = np.where(ns > 0, sdg[5 + 11 * np.clip(ns - 1, 0, 4), np.arange(B)], -1)
         want[:, 10] = last; want[:, 11] = bdg[:, 0]
-        if rank == 0:
+        if rank == 0 and not (dist and a.e2e_no_gather):
             got = comp_h[0].numpy()[:B]
             assert np.array_equal(got, want, equal_nan=True), "e2e result rows differ from the device-resident leg"
         gather_ms = None
-        if dist:
+        if dist and not a.e2e_no_gather:
             # digest check of the gather: sum over all ranks of the local rows == sum of what rank 0 received
             loc = torch.from_numpy(want).to(dev).nansum().reshape(1)
             dist.all_reduce(loc, op=dist.ReduceOp.SUM)
             if rank == 0:
                 tot = float(comp_h[0].view(world, per, CD).nansum().item())
                 assert abs(tot - float(loc.item())) <= 1e-6 * max(1.0, abs(tot)), "gathered rows do not add up to the ranks' rows"
-            # the gather alone: NCCL gather of the rows + rank 0's read-back, CUDA events, 50 repetitions
+            # the gather alone: the rows of one batch to rank 0 + rank 0's read-back, CUDA events, 50 repetitions
             g0 = torch.cuda.Event(enable_timing=True); g1 = torch.cuda.Event(enable_timing=True)
+            rows_src = torch.zeros(per, CD, dtype=torch.float64, device=dev)
+            dst_view = torch.as_tensor(sharding._DevView(pg.dest(0), (per, CD)), device=dev) if pg else None
             barrier()
             with torch.cuda.stream(lanes[0]):
                 g0.record(lanes[0])
                 for _ in range(50):
-                    allrows = gathers[0].gather()
-                    if rank == 0:
-                        comp_h[0].view(world, per, CD).copy_(allrows, non_blocking=True)
+                    if pg:
+                        pg.acquire(0, lane_ptr[0])
+                        dst_view.copy_(rows_src)                       # a device kernel storing the rows into rank 0's block
+                        pg.publish(0, lane_ptr[0])
+                        if rank == 0:
+                            pg.wait_all(0, lane_ptr[0])
+                            comp_h[0].view(world, per, CD).copy_(pg.block(0), non_blocking=True)
+                            pg.release(0, lane_ptr[0])
+                    else:
+                        allrows = gathers[0].gather()
+                        if rank == 0:
+                            comp_h[0].view(world, per, CD).copy_(allrows, non_blocking=True)
                 g1.record(lanes[0])
             g1.synchronize()
             gt = torch.tensor([g0.elapsed_time(g1) / 50], dtype=torch.float64, device=dev)
@@ -637,9 +701,14 @@ def run_b200(a):
                "bytes_def": "per rank H2D: tick (4 B) + the 10 planner sensor inputs (estimated CoM state, foot locations; flat ground) + (9 + 9 nh) body-tick doubles per robot; D2H: 12-double result rows"
                             + (" of ALL ranks, on rank 0 only (the other ranks ship theirs over NVLink)" if dist else ""),
                "gather_ms": gather_ms,
-               "gather_def": ("NCCL gather of every rank's [%d][12] result rows into rank 0's device buffer + rank 0's D2H of the gathered "
-                              "block, once per batch inside the timed region; gather_ms = that exchange alone (50 repetitions, CUDA events, "
-                              "max over ranks)" % per) if dist else None,
+               "gather": gather_kind,
+               "gather_def": ((("every rank's tick stores its [%d][12] result rows straight into rank 0's buffer over NVLink peer memory and "
+                                "raises a flag there (csrc/peer_gather.cu: no collective, no rendezvous); rank 0 waits for the flags on the "
+                                "device, then D2H of the gathered block" if gather_kind == "peer" else
+                                "NCCL gather (torch.distributed.gather) of every rank's [%d][12] result rows into rank 0's device buffer + rank "
+                                "0's D2H of the gathered block") % per)
+                              + ", once per batch inside the timed region; gather_ms = that exchange alone (50 repetitions, CUDA events, "
+                                "max over ranks)") if dist else None,
                "latency_ms": {"p50": float(lat_t[0].item()), "p99": float(lat_t[1].item()), "max": float(lat_t[2].item()),
                               "samples": n_le,
                               "what": f"one {B}-robot batch host to host through the same entry (enqueue, synchronize its stream), wall clock "
@@ -647,9 +716,12 @@ def run_b200(a):
                "steps": Ke, "ms_per_step": te_ms / Ke, "wall_ms_per_step": 1e3 * t_wall / Ke, "launches": e2e_launches,
                "api": "go1mpc_control_tick_host_async (pinned host buffers; per call on one of %d caller streams: H2D of the tick's arguments, "
                       "planner tick, body tick on the device-resident records, 12-double result row per robot%s); planner state, body step "
-                      "table and previous body output record resident on the device; one feeder thread, created and parked before the "
+                      "table and previous body output record resident on the device; %s; one feeder thread, created and parked before the "
                       "timed region; CUDA events recorded before its release and after the last stream has joined"
-                      % (Le, "; then one NCCL gather of the rows to rank 0 and rank 0's D2H" if dist else ", D2H of the rows")}
+                      % (Le, "; the rows go to rank 0 once per batch (see gather_def), then rank 0's D2H" if dist else ", D2H of the rows",
+                         "every batch slot's call sequence captured once (go1mpc_graph_capture_*) and replayed with ONE graph launch per step, "
+                         "copies included" if e2e_graphs is not None else "every call enqueued from the host each step"),
+               "graph_replay": e2e_graphs is not None}
 
     if rank == 0:
         kern_ms = float(np.mean(body_ms))

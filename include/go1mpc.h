@@ -513,6 +513,30 @@ int go1mpc_pack_compact_batch(go1mpc_t *h, int B, int nh, const double *out38_d,
                               const double *body_out_d, const int *body_diag_d, double *compact_d, void *stream);
 
 /* ---------------------------------------------------------------------------
+ * Once-per-batch gather of result rows to rank 0 over NVLink / NVSwitch peer memory, without a collective.
+ * Rank 0 owns `slots` blocks [world][rows_per_rank][row_doubles]; it exports an IPC blob the host program hands to the
+ * other ranks (one process per GPU); a peer maps the memory and lets its kernels write its rows straight into rank 0's
+ * block: go1mpc_gather_dest() is a valid compact_d for go1mpc_control_tick_host_async.  Per use of a slot, all on a stream:
+ *   peer:   acquire -> [tick writing to dest] -> publish
+ *   rank 0: [tick writing to dest] -> publish -> wait_all -> [read go1mpc_gather_block, e.g. D2H] -> release
+ * acquire / wait_all are single-thread device-side waits on flags in rank 0's memory (2 s time-out -> go1mpc_gather_status);
+ * no rank ever waits for another on the host.  Every rank must use a slot the same number of times, in the same order.
+ * ------------------------------------------------------------------------ */
+typedef struct go1mpc_gather go1mpc_gather_t;
+#define GO1MPC_GATHER_BLOB_BYTES 128
+int go1mpc_gather_create(int device, int rank, int world, int slots, int rows_per_rank, int row_doubles, go1mpc_gather_t **out);
+void go1mpc_gather_destroy(go1mpc_gather_t *g);
+int go1mpc_gather_export(go1mpc_gather_t *g, void *blob, int blob_bytes);          /* rank 0 */
+int go1mpc_gather_import(go1mpc_gather_t *g, const void *blob, int blob_bytes);    /* peers */
+double *go1mpc_gather_dest(go1mpc_gather_t *g, int slot);
+const double *go1mpc_gather_block(go1mpc_gather_t *g, int slot);                   /* rank 0 */
+int go1mpc_gather_acquire(go1mpc_gather_t *g, int slot, void *stream);
+int go1mpc_gather_publish(go1mpc_gather_t *g, int slot, void *stream);
+int go1mpc_gather_wait_all(go1mpc_gather_t *g, int slot, void *stream);            /* rank 0 */
+int go1mpc_gather_release(go1mpc_gather_t *g, int slot, void *stream);             /* rank 0 */
+int go1mpc_gather_status(go1mpc_gather_t *g, int *status);
+
+/* ---------------------------------------------------------------------------
  * Stream ordering and CUDA-graph capture.  Every *_batch entry only enqueues work on the stream it is given and
  * allocates nothing once that stream has been used with the same batch size, so a sequence of ticks dealt over several
  * streams can be captured once and replayed with one launch (launch-bound loops at small batches):

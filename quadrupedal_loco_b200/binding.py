@@ -27,7 +27,9 @@ EXPORTED_SYMBOLS = [
     "go1mpc_control_tick_host_async", "go1mpc_pack_compact_batch", "go1mpc_stream_wait", "go1mpc_graph_capture_begin",
     "go1mpc_graph_capture_end", "go1mpc_graph_launch", "go1mpc_graph_destroy",
     "go1mpc_rt_node_state_doubles", "go1mpc_rt_node_default_state", "go1mpc_rt_node_tick_batch", "go1mpc_rt_node_tick_msgs_batch",
-    "go1mpc_body_phase_timing", "go1mpc_body_phase_ms", "go1mpc_forget_buffer", "go1mpc_lpf_coefficients", "go1mpc_lpf_batch", "go1mpc_force_filter_batch",
+    "go1mpc_gather_create", "go1mpc_gather_destroy", "go1mpc_gather_export", "go1mpc_gather_import", "go1mpc_gather_dest",
+    "go1mpc_gather_block", "go1mpc_gather_acquire", "go1mpc_gather_publish", "go1mpc_gather_wait_all", "go1mpc_gather_release",
+    "go1mpc_gather_status", "go1mpc_body_phase_timing", "go1mpc_body_phase_ms", "go1mpc_forget_buffer", "go1mpc_lpf_coefficients", "go1mpc_lpf_batch", "go1mpc_force_filter_batch",
     "go1mpc_nlp_node_state_doubles", "go1mpc_nlp_node_default_state", "go1mpc_nlp_walkdtime_max", "go1mpc_nlp_t_end_footstep",
     "go1mpc_nlp_node_tick_batch", "go1mpc_foot_trajectory_stop_batch", "go1mpc_nlp_node_tick_batch_host", "go1mpc_rt_node_tick_batch_host", "go1mpc_foot_trajectory_stop_batch_host",
     "go1mpc_grf_force_opt_batch_host", "go1mpc_grf_force_distribution_batch_host", "go1mpc_grf_joint_torques_batch_host", "go1mpc_leg_fk_batch_host", "go1mpc_leg_ik_batch_host",
