@@ -565,6 +565,8 @@ def run_b200(a):
         # the per-step host cost of ~15 CUDA calls is what bounds small per-GPU batches (0.14 ms per 4096-robot step on one GPU).
         # Not with the NCCL gather (a collective enqueued by torch.distributed is not captured here).
         e2e_graphs = None
+        torch.cuda.synchronize()
+        barrier()                                              # the ranks enter the gather protocol together
         if not a.e2e_no_graph and (pg is not None or not dist) and nrot % Le == 0:
             e2e_enqueue(0); torch.cuda.synchronize()           # workspaces of every stream exist before anything is captured
             for ln in range(Le):
@@ -686,6 +688,9 @@ def run_b200(a):
         n_feed[0] = 0
         go.wait()
         th.join()
+        if pg is not None:
+            assert pg.status() == 0, "a device-side wait of the peer gather timed out"
+
         se = float(sum(B + sqp_solves[i % nrot] for i in range(Ke)))
         te = torch.tensor([ee0.elapsed_time(ee1), se], dtype=torch.float64, device=dev)
         if dist:

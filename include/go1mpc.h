@@ -519,7 +519,7 @@ int go1mpc_pack_compact_batch(go1mpc_t *h, int B, int nh, const double *out38_d,
  * block: go1mpc_gather_dest() is a valid compact_d for go1mpc_control_tick_host_async.  Per use of a slot, all on a stream:
  *   peer:   acquire -> [tick writing to dest] -> publish
  *   rank 0: [tick writing to dest] -> publish -> wait_all -> [read go1mpc_gather_block, e.g. D2H] -> release
- * acquire / wait_all are single-thread device-side waits on flags in rank 0's memory (2 s time-out -> go1mpc_gather_status);
+ * acquire / wait_all are single-thread device-side waits on flags in rank 0's memory (about 10 s time-out -> go1mpc_gather_status);
  * no rank ever waits for another on the host.  Every rank must use a slot the same number of times, in the same order.
  * ------------------------------------------------------------------------ */
 typedef struct go1mpc_gather go1mpc_gather_t;

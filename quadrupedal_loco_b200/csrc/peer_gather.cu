@@ -12,7 +12,7 @@
 //          block (D2H) -> go1mpc_gather_release (acknowledge: sequence number into the ack array the peers poll over NVLink)
 // Everything is stream ordered and the use counters advance on the device, so a tick with its gather calls can be captured
 // into a CUDA graph and replayed; the host never blocks and no rank waits for another on the host.  The waits are single-thread
-// kernels with a time-out (2 s of GPU clock): a rank that dies turns into an error code in `status`, not a hang.
+// kernels with a time-out (about 10 s of GPU clock): a rank that dies turns into an error code in `status`, not a hang.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
@@ -48,7 +48,7 @@ __global__ void pg_wait_kernel(const volatile unsigned* flag, int n, const unsig
   const long long t0 = clock64();
   for (int r = 0; r < n; r++) {
     while ((int)(flag[r] - seq) < 0) {
-      if (clock64() - t0 > 4000000000ll) { *status = 1; return; }
+      if (clock64() - t0 > 20000000000ll) { *status = 1; return; }
       __nanosleep(200);
     }
   }
