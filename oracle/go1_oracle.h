@@ -197,7 +197,7 @@ void orc_step_timing_batch(const orc_step_cfg *c, int B, const int *tick, double
  * Swing-foot trajectory of the step planner: NLPClass::Foot_trajectory_solve_mod2
  * (NLP/src/NLP/NLPClass_sqp.cpp:2039-2358) with solve_AAA_inv2 (:3633-3645), called
  * right after step_timing_opti_loop with the same tick (NLPRTControlClass.cpp:470).
- * Stop-walking (_stopwalking / ticks beyond _t_end_footstep) is not restated.
+ * The stop-walking branch (:2043-2048) is the caller's: it passes the lift height of the current step (nlp_node.c).
  * The reference keeps whole-walk arrays _R/Lfoot{x,y,z}; only a sliding window
  * is ever read, carried here as 32 doubles:
  *   [0,6)  R xyz, L xyz at tick j-1      [6,12)  values the arrays hold at j before this tick
