@@ -1216,6 +1216,8 @@ int go1mpc_nlp_node_tick_batch(go1mpc_t* h, int B, double* state_d, const int* w
     CU(h, cudaMemcpy(h->squat_d, tab, sizeof tab, cudaMemcpyHostToDevice));
   }
   // per-stream workspace: tick | in | out38 | out18 | right_support | hz_co | lipm
+  if (h->nlp_ws.size() >= 256 && h->nlp_ws.find(st) == h->nlp_ws.end())
+    return fail(h, GO1MPC_E_UNSUPPORTED, "nlp_node_tick_batch: more than 256 distinct streams used with one handle");
   go1mpc::NlpWs& W = h->nlp_ws[st];
   const size_t need[7] = {(size_t)B * sizeof(int), (size_t)B * STEP_IN_DOUBLES * sizeof(double), (size_t)B * STEP_OUT_DOUBLES * sizeof(double),
                           (size_t)B * FOOT_OUT_DOUBLES * sizeof(double), (size_t)B * sizeof(int), (size_t)B * 8 * sizeof(double),
