@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
   }
   bool act0 = false, act1 = false, flag0 = false, flag1 = false, tol0 = false, done = false;
   double f00 = 0.0, psi0 = 0.0;
-  if (b < P.B && !live) { tri_gated<NH>(P, b, rec); P.tri_meta[b] = 1; }
+  if (b < P.B && !live) tri_gated<NH>(P, b, rec);
+  bool need_merge = false;      // the instance has a queued half (or a flagged one): the merge kernel finishes it
   if (live) {
     const double* refs = rec + 36 + N;
     const int bjx1 = tri_index(rec, (i + 1) * dt), bjx2 = tri_index(rec, (i + NH) * dt);
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
         }
       }
     }
-    P.tri_meta[b] = done ? 1 : 0;
+    need_merge = !done;
     if (!done) {
       double2* frg = reinterpret_cast<double2*>(P.tri_fr + (size_t)b * D::FR);
 #pragma unroll
@@ -314,6 +315,14 @@ __global__ void __launch_bounds__(TRI_SETUP_THREADS) tri_setup_kernel(const __gr
     const unsigned below = (1u << lane) - 1u;
     if (act0) P.tri_queue[base + __popc(m0 & below)] = 2 * b;
     if (act1) P.tri_queue[base + n0 + __popc(m1b & below)] = 2 * b + 1;
+  }
+  // ---- list of the instances the merge kernel has to finish (compact: its CTAs are full whatever the finished share) ----
+  const unsigned mm = __ballot_sync(FULL_MASK, need_merge);
+  if (mm) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(P.tri_qctl + 3, __popc(mm));
+    base = __shfl_sync(FULL_MASK, base, 0);
+    if (need_merge) P.tri_meta[base + __popc(mm & ((1u << lane) - 1u))] = b;
   }
 }
 
@@ -834,10 +843,12 @@ __global__ void __launch_bounds__(TRI_MERGE_THREADS) tri_merge_kernel(BodyKParam
   double* sfr = sres + (size_t)2 * TRI_MERGE_THREADS * RSTR;
   uint64_t* bar = reinterpret_cast<uint64_t*>(sfr + (size_t)TRI_MERGE_THREADS * FSTR);
   const int tid = threadIdx.x;
-  const int b0 = blockIdx.x * TRI_MERGE_THREADS;
-  const int b = b0 + tid;
-  if (b == 0) { P.tri_qctl[0] = 0; P.tri_qctl[1] = 0; }    // queue counters for the next call on this stream
-  const bool mine = b < P.B && P.tri_meta[b < P.B ? b : 0] == 0;   // 1: finished by the setup kernel
+  const int idx = blockIdx.x * TRI_MERGE_THREADS + tid;
+  if (idx == 0) { P.tri_qctl[0] = 0; P.tri_qctl[1] = 0; }  // queue counters for the next call on this stream (the merge count
+                                                           // is cleared by a memset node behind this kernel: every CTA reads it)
+  const int cnt = *reinterpret_cast<volatile const int*>(P.tri_qctl + 3);
+  const bool mine = idx < cnt;                              // the setup kernel's list of unfinished instances, compact
+  const int b = mine ? P.tri_meta[idx] : 0;
   if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
   const int nmine = __syncthreads_count(mine);
   if (nmine == 0) return;
@@ -980,6 +991,7 @@ static cudaError_t tri_launch_nh(const BodyKParams& P, const double* tab_host, i
   tri_solve_kernel<NH, WPC><<<grid, WPC * 32, smem, st>>>(P);
   if (phase_ev) cudaEventRecord(phase_ev[2], st);
   tri_merge_kernel<NH><<<(P.B + TRI_MERGE_THREADS - 1) / TRI_MERGE_THREADS, TRI_MERGE_THREADS, msmem, st>>>(P);
+  cudaMemsetAsync(P.tri_qctl + 3, 0, sizeof(int), st);
   if (phase_ev) cudaEventRecord(phase_ev[3], st);
   return cudaGetLastError();
 }

@@ -23,8 +23,8 @@ struct BodyKParams {
   int flist_cap;
   // body_tri workspace (per stream): J per instance, state / result records per half, queue of active halves
   double *tri_jb, *tri_hs, *tri_res;
-  int *tri_queue, *tri_qctl;      // qctl: {queued, fetched, guard trips}
-  int* tri_meta;                  // per instance: 1 = finished by the setup kernel
+  int *tri_queue, *tri_qctl;      // qctl: {queued, fetched, guard trips, instances listed for the merge kernel}
+  int* tri_meta;                  // compact list of the instances the merge kernel finishes (count: tri_qctl[3])
   double* tri_fr;                 // per instance: what the merge kernel needs of the input record
   double dt_mpc, j_ini, mass, g, gama, theta_lim, torque_lim;
   double lamda[4];
