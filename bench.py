@@ -206,7 +206,7 @@ def run_reference(a):
     v = solves * steps / tot
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": W, "ms_per_step": 1e3 * tot / steps, "higher_is_better": True, "scaling": plan(a, 1)["scaling"],
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, 1),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(a, max(1, a.gpus)),   # the own arm's config at this N
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"each step = one pass over the {B}-robot {a.config} batch of one GPU at N = 1, statically split over {cores} "
                                        f"native threads (oracle/mt_pool.c; oracle/ C port at -O3 -march=native; host CPU only, the GPU count does not apply)"},
